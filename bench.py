@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""bench.py -- SPH particle-steps/sec of the full hot path (smoothing + neighbors + density + EOS + pressure force +
+gravity + integrate) on synthetic gas spheres, per BASELINE.json.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c4|c2|c1] [--impl ours|reference]
+
+Workloads (BASELINE.json configs): c3 = 1 048 576-particle sphere, tiled all-pairs gravity (default; the 1-GPU headline);
+c4 = 16 000 000-particle sphere, LBVH tree gravity; c1/c2 = the reference's own 3k / 10k scenes.
+One rank per GPU (torchrun for N > 1): targets are split by Morton range, positions are all-gathered over NCCL.
+
+Prints ONE JSON line (rank 0).  `value` = particles * K / max-over-ranks device time with the state resident in HBM;
+`e2e` = the same through the C ABI with HOST component arrays uploaded and downloaded every step;
+`roofline` = dominant kernel against its bound; `cpu_baseline` = the CPU oracle (port of the reference job path) on the
+box's host cores over a bounded sample.  `--impl reference` times only that CPU port (the reference itself is C#/Unity
+and cannot run here -- DESIGN.md).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "planetmodel-sph_b200"))
+
+import numpy as np  # noqa: E402
+
+METRIC = "sph_particle_steps_per_sec"
+UNIT = "particle-steps/s"
+DT = 1.0 / 60.0
+FLOP_PER_PAIR = 20.0          # conventional N-body count per ordered pair
+SPH_BYTES_BASE, SPH_BYTES_PER_NEIGHBOR = 368.0, 12.0   # algorithmic HBM bytes / particle-step
+
+
+def workload_config(name):
+    from sphb200 import ic
+    c = ic.make_config(name)
+    grav = {"c1": "particle", "c2": "tree", "c3": "particle", "c4": "tree"}[name]
+    return c, grav
+
+
+# ------------------------------------------------------------------------------------------------ clocks sampler
+class ClockSampler(threading.Thread):
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.rows = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.check_output(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                               "--format=csv,noheader,nounits"], timeout=5).decode().strip()
+                self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = []
+        for k, nm in ((3, "hw_slowdown"), (4, "hw_thermal_slowdown"), (5, "sw_thermal_slowdown"), (6, "sw_power_cap")):
+            if any(len(r) > k and r[k].lower().startswith("active") for r in self.rows):
+                reasons.append(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows else None,
+                "power_w_max": max(float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()) if self.rows else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU baseline
+def cpu_reference_sample(c, grav, seconds_budget=20.0):
+    """Time the oracle (CPU port of the reference job path) on a bounded sample of the workload and extrapolate the
+    per-step time: SPH passes on a contiguous subset of particles' worth of work, gravity on a sample of targets
+    against ALL sources.  Returns (particle_steps_per_sec, cores, sample_description, seconds_spent)."""
+    from oracle import oracle as orc
+    n = len(c["h"])
+    cores = orc.lib().orc_num_threads()
+    t_start = time.time()
+    # -- SPH passes (neighbor search via cell list = labelled variant of the reference's BVH broadphase, then the
+    #    literal filter/interaction/density/EOS/pressure-gradient arithmetic) on up to 262 144 particles
+    ns = min(n, 262144)
+    if ns < n:
+        r = np.linalg.norm(c["pos"], axis=1)
+        sel = np.argsort(r)[:ns]                      # a central ball: same number density, no extra surface
+    else:
+        sel = np.arange(n)
+    pos, h, m = c["pos"][sel].copy(), c["h"][sel].copy(), c["mass"][sel].copy()
+    t0 = time.time()
+    off, nbr = orc.neighbors(pos, h, "grid" if ns > 4096 else "brute")
+    rho, own = orc.density(pos, h, m, off, nbr)
+    P = orc.eos(rho)
+    gp = orc.pressure_grad(pos, h, m, rho, P, off, nbr)
+    t_sph = (time.time() - t0) / ns                   # seconds per particle
+    # -- gravity sample
+    if grav == "particle":
+        nt = max(64, min(n, int(2.0e9 * max(cores, 1) / 8 / n)))   # ~ a few seconds of pair work
+        t0 = time.time()
+        orc.gravity_direct(c["pos"], c["h"], c["mass"], i0=0, i1=nt)
+        t_grav = (time.time() - t0) / nt
+        gdesc = "direct gravity for %d targets x %d sources" % (nt, n)
+    else:
+        t0 = time.time()
+        nt = min(n, 200000)
+        g, _, _, _, _ = orc.tree_gravity(c["pos"], c["vel"], c["h"], c["mass"], DT)
+        t_grav = (time.time() - t0) / n
+        gdesc = "LBVH build + tree walk for all %d particles" % n
+    # integrate + smoothing update are O(N) trivial; timed on the subset
+    t0 = time.time()
+    orc.smoothing_update(h, own)
+    orc.integrate(pos, np.zeros_like(pos), rho, gp, np.zeros((ns, 4), np.float32), DT)
+    t_int = (time.time() - t0) / ns
+    per_particle = t_sph + t_grav + t_int
+    desc = "oracle (C++ port, OpenMP): neighbor+density+EOS+pressure on %d particles (%.1f neighbors avg), %s; per-particle " \
+           "times extrapolated to N=%d" % (ns, len(nbr) / ns, gdesc, n)
+    return 1.0 / per_particle, cores, desc, time.time() - t_start
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU job path (oracle port) on the host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    c, grav = workload_config(args.workload)
+    vals = []
+    for k in range(args.warmup + args.steps):
+        v, cores, desc, _ = cpu_reference_sample(c, grav, 10.0)
+        if k >= args.warmup:
+            vals.append(v)
+    v = float(np.mean(vals))
+    n = len(c["h"])
+    line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * n / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_desc(args.workload, n, grav, args.gpus),
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def workload_desc(name, n, grav, gpus):
+    return {"workload": "%s: %d-particle uniform gas sphere (reference scene density), %s gravity, dt=1/60, full step" %
+            (name, n, "tiled all-pairs" if grav == "particle" else "LBVH Barnes-Hut theta=0.7"),
+            "particles": n, "gravity": grav, "parallelism": "morton-range x%d" % gpus,
+            "l2_policy": "working set (>= 190 MB of SoA + lists at 1M) exceeds the 126 MB L2; no explicit flush"}
+
+
+# ------------------------------------------------------------------------------------------------ our arm
+def run_ours(args):
+    import torch
+    import sphb200
+    from sphb200 import dist as sdist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as td
+        td.init_process_group("nccl", device_id=torch.device("cuda", local))
+    c, grav = workload_config(args.workload)
+    n = len(c["h"])
+    impl = sphb200.GRAVITY_PARTICLE if grav == "particle" else sphb200.GRAVITY_TREE
+
+    eng = sdist.ShardedSimulation(n, device=local, rank=rank, world=world)
+    eng.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    sim = eng.sim
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as td
+            td.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also settles h towards ~50 own-support neighbors)
+    for _ in range(args.warmup):
+        eng.step(DT, impl)
+    barrier()
+    sim.enable_timing(True)
+    launches0 = sim.launch_count()
+    sampler = ClockSampler(local)
+    sampler.start()
+    stream = torch.cuda.current_stream()
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    pass_ms = {}
+    e0.record(stream)
+    for _ in range(args.steps):
+        eng.step(DT, impl)
+        for nm, ms in sim.timings():            # reads the CUDA events of the step just issued (all ranks alike)
+            pass_ms.setdefault(nm, []).append(ms)
+    e1.record(stream)
+    barrier()
+    sampler.stop_flag = True
+    ms_total = e0.elapsed_time(e1)
+    launches = sim.launch_count() - launches0
+    if world > 1:
+        import torch.distributed as td
+        t = torch.tensor([ms_total], device="cuda")
+        td.all_reduce(t, op=td.ReduceOp.MAX)
+        ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = n * args.steps / (ms_total * 1e-3)
+    sim.enable_timing(False)
+
+    # ---- e2e: host component arrays in, host component arrays out, every step (N = 1 path of the C ABI)
+    e2e = None
+    if world == 1:
+        e2e = measure_e2e(sim, c, impl, max(1, min(args.steps, 3)))
+
+    eng.gather_results()
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel
+    diag = sim.diagnostics()
+    kbar = diag["mean_neighbors"]
+    mean = {k: float(np.mean(v)) for k, v in pass_ms.items()}
+    fp32_peak = sim.fp32_peak_tflops()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+    sph_ms = sum(mean.get(k, 0.0) for k in ("smoothing_bounds", "keys_sort_permute_cells", "neighbors_density_eos",
+                                            "pressure_grad", "integrate"))
+    sph_bytes = (SPH_BYTES_BASE + SPH_BYTES_PER_NEIGHBOR * kbar) * n / world
+    hbm_passes = {"achieved": sph_bytes / (sph_ms * 1e-3) / 1e9 if sph_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
+                  "frac": (sph_bytes / (sph_ms * 1e-3) / 1e9 / hbm_peak) if sph_ms > 0 else None, "ms": sph_ms,
+                  "bytes_per_particle": SPH_BYTES_BASE + SPH_BYTES_PER_NEIGHBOR * kbar, "peak_source": hbm_src}
+    if grav == "particle":
+        gms = mean.get("gravity_allpairs", 0.0)
+        flops = FLOP_PER_PAIR * (n / world) * (n - 1)
+        ach = flops / (gms * 1e-3) / 1e12 if gms > 0 else None
+        roof = {"bound": "fp32", "kernel": "k_gravity_allpairs", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
+                "frac": ach / fp32_peak if ach else None, "traffic": None,
+                "note": "FP32 FMA-pipe bound (not a contraction: no tensor roof applies); peak = FMA microbenchmark measured "
+                        "in this run; flops = 20 per ordered pair (SURVEY 8d)", "ms": gms, "share_of_step": gms / ms_per_step}
+    else:
+        gms = mean.get("gravity_tree", 0.0)
+        inter = float(diag.get("mean_neighbors", 0))
+        roof = {"bound": "hbm", "kernel": "sph passes (keys/sort/permute/neighbors+density/pressure/integrate)",
+                "achieved": hbm_passes["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm_passes["frac"], "traffic": None,
+                "note": "tree walk is L2-latency/FP32 mixed (no single roof, SURVEY 8d): %.2f ms of the step" % gms, "ms": sph_ms,
+                "share_of_step": sph_ms / ms_per_step}
+    cpu_v, cores, desc, _ = cpu_reference_sample(c, grav)
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_desc(args.workload, n, grav, world), "clocks": sampler.summary(),
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "hbm_passes": hbm_passes,
+            "pass_ms": mean, "mean_neighbors": kbar, "fp32_peak_tflops_measured": fp32_peak,
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}}
+    print(json.dumps(line))
+
+
+def measure_e2e(sim, c, impl, steps):
+    """Drop-in usage: ECS owns the components on the host; every step uploads them (pinned) and reads all results back."""
+    import torch
+    import sphb200
+    n = len(c["h"])
+    host = {
+        "pos": torch.from_numpy(c["pos"].copy()).pin_memory(), "vel": torch.from_numpy(c["vel"].copy()).pin_memory(),
+        "mass": torch.from_numpy(c["mass"].copy()).pin_memory(),
+        "sm": torch.from_numpy(np.zeros(n * 7, np.float32)).pin_memory(),
+    }
+    sm = host["sm"].numpy().view(sphb200.ParticleSmoothing)
+    sm["influenceArea"] = c["h"]
+    outs = {f: torch.empty(n * w, dtype=torch.float32).pin_memory() for f, w in
+            ((sphb200.FIELD_TRANSLATION, 3), (sphb200.FIELD_VELOCITY, 3), (sphb200.FIELD_DENSITY, 1), (sphb200.FIELD_PRESSURE, 1),
+             (sphb200.FIELD_PRESSURE_GRAD, 3), (sphb200.FIELD_GRAVITY, 6))}
+    h2d = n * (12 + 12 + 4 + 4 + 4)
+    d2h = n * (12 + 12 + 8 + 4 + 4 + 12 + 24)
+
+    def one():
+        sim.upload(host["pos"].numpy().reshape(n, 3), host["vel"].numpy().reshape(n, 3), host["mass"].numpy(), sm)
+        sim.step(DT, impl)
+        for f, buf in outs.items():
+            w = buf.numel() // n
+            sim.download(f, buf.numpy().reshape(n, w) if w > 1 else buf.numpy())
+        sim.download(sphb200.FIELD_SMOOTHING, sm)
+        # feed the results back as next step's host state (what the ECS write-back does)
+        host["pos"].copy_(outs[sphb200.FIELD_TRANSLATION]); host["vel"].copy_(outs[sphb200.FIELD_VELOCITY])
+    one()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": steps,
+            "ms_per_step": 1e3 * dt / steps, "path": "sphb200_upload + sphb200_step + sphb200_download x7 (host arrays, pinned staging)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,198 @@
+/* sphb200.h -- C ABI of the B200-native SPH hot path (drop-in for PlanetModel-SPH's per-timestep systems).
+ *
+ * Every entry point is `extern "C"`, takes plain pointers / sizes, returns an int status (0 = ok, <0 = error)
+ * and never exposes torch or CUDA types.  Each one cites the reference interface it replaces
+ * (A/ = Assets/Scripts/, UP/ = UpstreamPackages/com.unity.physics@0.6.0-preview.3/Unity.Physics/).
+ * The C# P/Invoke binding a maintainer would add is shown in INTEGRATION.md.
+ *
+ * Threading: one host thread per handle; calls are asynchronous on the handle's CUDA stream except
+ * upload/download/sync/diagnostics which block.  Distinct handles are independent.
+ * Ownership: the library owns all device memory; host pointers are borrowed for the duration of a call.
+ * There is NO CPU fallback: every call fails with SPH_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef SPHB200_H
+#define SPHB200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define SPH_API __declspec(dllexport)
+#else
+#define SPH_API __attribute__((visibility("default")))
+#endif
+
+/* ---- status codes (reference: C# exceptions, KernelSystem.cs:102-105, GravityFieldSystem.cs:84-87,400-403) */
+enum {
+    SPH_OK = 0,
+    SPH_ERR_INVALID_ARG = -1,
+    SPH_ERR_CAPACITY = -2,          /* n > capacity, or > 2^24-2 in ref-compat (UP/Dynamics/Simulation/Scheduler.cs:26-31,41) */
+    SPH_ERR_NEIGHBOR_OVERFLOW = -3, /* some particle has more than max_neighbors neighbors; lists truncated */
+    SPH_ERR_CUDA = -4,
+    SPH_ERR_STATE = -5,             /* stage called out of order (e.g. pressure before build_neighbors) */
+    SPH_ERR_TREE_STACK = -6         /* traversal stack overflow in the LBVH walk */
+};
+
+/* ---- gravity implementation (GravityFieldSystem.cs:19-25 `GravityImpl`) */
+enum {
+    SPH_GRAVITY_TREE = 0,     /* GRAVITY_TREE_CPU: Barnes-Hut monopole, Bmax MAC (default in the reference) */
+    SPH_GRAVITY_PARTICLE = 1, /* GRAVITY_PARTICLE_CPU: O(N^2) direct sum */
+    SPH_GRAVITY_NONE = 2
+};
+
+/* ---- compile-time constants of the reference, as one POD (SURVEY.md section 5 "Config / flags") */
+typedef struct sph_Params {
+    float K;                /* EOS constant P = K rho^2           PressureFieldSystem.cs:31 (1000)  */
+    float G;                /* k_GravConstant                     GravityFieldSystem.cs:26  (1)     */
+    float theta;            /* k_Theta                            GravityFieldSystem.cs:228 (0.7)   */
+    float target_neighbors; /* TARGET_NEIGHBORS                   ParticleSmoothingSystem.cs:18 (50) */
+    int32_t max_neighbors;  /* neighbor-list capacity per particle (multiple of 32; default 128)    */
+    int32_t leaf_max;       /* bodies per tree leaf               BoundingVolumeHierarchy.cs:40-83 (4) */
+    int32_t aabb_mode;      /* 0 = MAC boxes are collider AABBs (quirk Q2, default), 1 = point bounds */
+    int32_t max_grid_bits;  /* cells per axis <= 2^bits, bits <= 8; 0 = choose from capacity          */
+    int32_t flags;          /* SPH_FLAG_* ; 0 = reference-compatible                                  */
+    int32_t reserved[3];
+} sph_Params;
+
+enum {
+    SPH_FLAG_FIX_KERNEL_DERIV_SIGN = 1 /* use -3q in KernelDeriv's inner branch (undo quirk Q1, SplineKernel.cs:135) */
+};
+
+/* ---- byte-exact mirrors of the reference components */
+typedef struct { float x, y, z; } sph_Translation;                        /* Unity.Transforms.Translation, 12 B */
+typedef struct { float linear[3]; float angular[3]; } sph_PhysicsVelocity; /* UP/ECS/Base/Components/PhysicsComponents.cs:79-90, 24 B */
+typedef struct { float value; } sph_ParticleMass;                          /* A/Components/DensityField.cs:4-7   */
+typedef struct { float value; } sph_ParticleDensity;                       /* A/Components/DensityField.cs:9-13  */
+typedef struct { float value; } sph_ParticlePressure;                      /* A/Components/PressureField.cs:4-7  */
+typedef struct { float value[3]; } sph_ParticlePressureGrad;               /* A/Components/PressureField.cs:9-12 */
+typedef struct {
+    float influenceArea;              /* h   */
+    float supportDomain;              /* 2h  */
+    float sphereColliderPosRadius[4]; /* debug: xyz = centre, w = radius (= 2h) */
+    int32_t neighbors;                /* debug: own-support neighbor count */
+} sph_ParticleSmoothing;                                                   /* A/Components/ParticleSmoothing.cs:28-31, 28 B */
+typedef struct {
+    float value[4];       /* xyz = grad(Phi), w = Phi */
+    int32_t numParticles; /* direct body interactions in the tree walk */
+    int32_t numApprox;    /* accepted node approximations */
+} sph_GravityField;                                                        /* A/Components/GravityField.cs:10-15, 24 B */
+typedef struct {
+    int32_t otherIndex, otherVersion; /* Entity Other */
+    float kernelThis[4];              /* xyz = grad_i W(r,h_i), w = W(r,h_i) */
+    float kernelSymmetric[4];
+} sph_ParticleInteraction;                                                 /* A/Components/Kernel.cs:6-10, 40 B */
+
+/* Grid/key parameters of the last neighbor build (specification shared with oracle/sph_oracle.cpp GridParams) */
+typedef struct sph_GridParams {
+    float min[3];
+    float cell;
+    float fine_scale;
+    int32_t bits;
+    float hmax;
+    float ext;
+} sph_GridParams;
+
+/* ---- per-particle fields for download / device_ptr */
+enum {
+    SPH_FIELD_TRANSLATION = 0,   /* sph_Translation           (natural stride 12) */
+    SPH_FIELD_VELOCITY = 1,      /* sph_PhysicsVelocity.linear (12 B written; natural stride 24) */
+    SPH_FIELD_MASS = 2,          /* 4  */
+    SPH_FIELD_SMOOTHING = 3,     /* sph_ParticleSmoothing if stride >= 28, else h only (4 B) */
+    SPH_FIELD_DENSITY = 4,       /* 4  */
+    SPH_FIELD_PRESSURE = 5,      /* 4  */
+    SPH_FIELD_PRESSURE_GRAD = 6, /* 12 */
+    SPH_FIELD_GRAVITY = 7,       /* sph_GravityField if stride >= 24, else float4 (16 B) */
+    SPH_FIELD_NEIGHBOR_COUNT = 8,/* int32: symmetric neighbor count (interaction buffer length) */
+    SPH_FIELD_COUNT_
+};
+
+typedef struct sphb200_ctx* sph_handle;
+
+/* Fill *p with the reference's constants. */
+SPH_API int sphb200_default_params(sph_Params* p);
+
+/* Create a simulation context on CUDA device `device` holding up to `capacity` particles.
+ * Replaces: World/system creation (OnCreate of the six systems, e.g. GravityFieldSystem.cs:39-46). */
+SPH_API int sphb200_create(const sph_Params* params, int64_t capacity, int device, sph_handle* out);
+SPH_API int sphb200_destroy(sph_handle h);
+/* Last error text of this handle (or of the failed create when h == NULL). */
+SPH_API const char* sphb200_last_error(sph_handle h);
+/* Run on an externally owned cudaStream_t (e.g. torch's current stream); NULL = the handle's own stream. */
+SPH_API int sphb200_set_stream(sph_handle h, void* cuda_stream);
+SPH_API int sphb200_sync(sph_handle h);
+
+/* Upload the per-particle components from host AoS arrays (strides in bytes; body index = array index).
+ * Replaces: BuildPhysicsWorld's entity->rigid-body gather (UP/ECS/Base/Systems/BuildPhysicsWorld.cs:389-469).
+ *   pos        -> sph_Translation          (Translation.Value)
+ *   vel        -> sph_PhysicsVelocity      (.linear read)
+ *   mass       -> sph_ParticleMass
+ *   smoothing  -> sph_ParticleSmoothing    (.influenceArea = h read; .neighbors read as last step's own-support count
+ *                                           when stride >= 28, else 0)
+ * Resets the resident order to body-index order. */
+SPH_API int sphb200_upload(sph_handle h, int64_t n, const void* pos, int pos_stride, const void* vel, int vel_stride,
+                           const void* mass, int mass_stride, const void* smoothing, int smoothing_stride);
+
+/* ---- stages, one per reference system ------------------------------------------ */
+/* ParticleSmoothingSystem.OnUpdate (ParticleSmoothingSystem.cs:19-87): h <- h*0.5*(1+(target/n)^(1/3)). */
+SPH_API int sphb200_smoothing_update(sph_handle h);
+/* KernelSystem.OnUpdate + BuildPhysicsWorld broadphase (KernelSystem.cs:93-231, Broadphase.cs:275-351):
+ * keys, radix sort, cell table, neighbor lists (exact Interacts + keep rule), and -- fused -- the density sum. */
+SPH_API int sphb200_build_neighbors(sph_handle h);
+/* GravityFieldSystem.OnUpdate (GravityFieldSystem.cs:62-74): impl = SPH_GRAVITY_*.  dt is needed because the
+ * reference's MAC boxes are swept by v*dt (quirk Q2). PARTICLE mode requires build_neighbors in this step. */
+SPH_API int sphb200_gravity(sph_handle h, int impl, float dt);
+/* DensityFieldSystem.OnUpdate (DensityFieldSystem.cs:38-56): publishes rho (summed inside build_neighbors). */
+SPH_API int sphb200_density(sph_handle h);
+/* PressureFieldSystem.OnUpdate (PressureFieldSystem.cs:30-70): P = K rho^2 and grad P. */
+SPH_API int sphb200_pressure(sph_handle h);
+/* Integrator.IntegratePosition + VelocitySystem.OnUpdate (Integrator.cs:98-101, VelocitySystem.cs:24-36). */
+SPH_API int sphb200_integrate(sph_handle h, float dt);
+/* One FixedStepSimulationSystemGroup tick: all of the above in the reference order. */
+SPH_API int sphb200_step(sph_handle h, float dt, int gravity_impl);
+
+/* Restrict the *target* particles of density/pressure/gravity/integrate to sorted slots [t0,t1) (multi-GPU:
+ * Morton-range ownership).  t1 < 0 = all.  Neighbor/tree structures are always built over all resident particles. */
+SPH_API int sphb200_set_target_range(sph_handle h, int64_t t0, int64_t t1);
+
+/* ---- results --------------------------------------------------------------------------------------------- */
+/* Download one field into a host AoS array in body-index order.
+ * Replaces: ExportPhysicsWorld (UP/ECS/Base/Systems/ExportPhysicsWorld.cs:130-161) and the component writes. */
+SPH_API int sphb200_download(sph_handle h, int field, void* dst, int stride);
+/* Neighbor lists as CSR in body-index space, each row ascending (canonical order).  offsets has n+1 entries.
+ * If total > cap only *total is set (call again).  Replaces reading DynamicBuffer<ParticleInteraction>.Other. */
+SPH_API int sphb200_download_neighbors(sph_handle h, int64_t* offsets, int32_t* nbr, int64_t cap, int64_t* total);
+/* Interaction records (KernelSystem.cs:305-334) for the same CSR layout; optional debugging/parity surface. */
+SPH_API int sphb200_download_interactions(sph_handle h, const int64_t* offsets, const int32_t* nbr,
+                                          sph_ParticleInteraction* out);
+/* Sorted slot -> body index, and the 30-bit Morton keys in sorted order (either pointer may be NULL). */
+SPH_API int sphb200_download_sort(sph_handle h, uint32_t* order, uint32_t* keys, sph_GridParams* grid);
+/* LBVH of the last tree-gravity call: 2n-1 nodes (internal 0..n-2, leaf slot s -> n-1+s). Any pointer may be NULL.
+ * child = int32[2] per node, range = int32[2] (first,last), moment = float[4] (cm, M), lo/hi = float[3]. */
+SPH_API int sphb200_download_tree(sph_handle h, int32_t* child, int32_t* range, float* moment, float* lo, float* hi);
+/* Conserved-quantity diagnostics (README.md:50-52 roadmap): out[0]=sum m, [1..3]=sum m v, [4..6]=sum m x cross v,
+ * [7]=E_kin, [8]=E_pot=0.5 sum m Phi, [9]=E_int=sum m K rho, [10]=mean symmetric neighbor count, [11]=max count */
+SPH_API int sphb200_diagnostics(sph_handle h, double* out12);
+
+/* ---- introspection ------------------------------------------------------------------------------------------ */
+SPH_API int sphb200_count(sph_handle h, int64_t* n, int64_t* capacity);
+SPH_API int sphb200_get_params(sph_handle h, sph_Params* out);
+/* Raw device pointer of an internal SoA array (sorted order) for zero-copy interop (NCCL through torch).
+ * names: "posh" float4(x,y,z,h), "velm" float4(v,m), "posm" float4(x,y,z,m), "rho", "press", "cvol" float,
+ * "gradp" float4, "grav" float4, "nown" int32, "orig" uint32 */
+SPH_API int sphb200_device_ptr(sph_handle h, const char* name, void** ptr, int64_t* bytes);
+/* Number of kernel launches issued by this library since create (bench.py's gpu_launches). */
+SPH_API int sphb200_launch_count(sph_handle h, int64_t* launches);
+/* Per-pass device times (ms) of the most recent step when timing is enabled.
+ * names[i] -> static strings; returns number of passes written (<= cap). */
+SPH_API int sphb200_enable_timing(sph_handle h, int enable);
+SPH_API int sphb200_get_timings(sph_handle h, const char** names, float* ms, int cap);
+/* FP32 FMA-pipe microbenchmark (roofline denominator for all-pairs gravity): returns TFLOP/s. */
+SPH_API int sphb200_fp32_peak(sph_handle h, double* tflops);
+SPH_API const char* sphb200_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHB200_H */

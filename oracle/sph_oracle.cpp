@@ -1,0 +1,694 @@
+// sph_oracle.cpp -- CPU ORACLE for the PlanetModel-SPH per-timestep hot path.
+//
+// *** TEST INFRASTRUCTURE ONLY. ***  Nothing in the product path (the sphb200 CUDA library, its C ABI,
+// the Python/C++ host mirrors) may link, import or call this file.  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs use it, and only as the checker / CPU baseline.
+//
+// What it is: an op-for-op fp32 restatement of the reference's C#/Burst job path (the reference cannot be
+// compiled here: no C#/Unity toolchain).  Each function cites the reference file:line it
+// follows.  Paths: A/ = /root/reference/Assets/Scripts/, UP/ = /root/reference/UpstreamPackages/
+// com.unity.physics@0.6.0-preview.3/Unity.Physics/.
+//
+// PARITY PINNING STATUS: the reference has *no* tests, fixtures or golden vectors for the SPH path
+// (A/Util/SplineKernel.cs:43 "TODO: learn to write tests in unity!").  The SPH arithmetic is therefore
+// "parity unpinned" against reference outputs; it is pinned instead by (i) the invariants the reference
+// states in its own comments (SplineKernel.cs:29-43), (ii) closed forms, (iii) an independent numpy
+// float32 restatement (tests/test_oracle_known_answers.py), and -- for the vendored Unity.Physics pieces that
+// DO have reference tests -- (iv) the known answers in UT/PlayModeTests (MotionTests.cs:50-91 ExpandAabb /
+// CalculateExpansion, SphereColliderTests.cs:81-118).
+//
+// Third-party arithmetic not in the tree (com.unity.mathematics 1.2.1) is restated as:
+//   math.dot(a,a) = a.x*a.x + a.y*a.y + a.z*a.z (left to right), math.length = sqrtf(dot), math.max = fmaxf,
+//   math.pow = correctly rounded powf (computed in double), Mathf.PI = 3.14159274f.
+// No FMA contraction (compile with -ffp-contract=off), IEEE-RN '/' and sqrt.
+//
+// Build: g++ -O2 -std=c++17 -fopenmp -ffp-contract=off -fno-fast-math -shared -fPIC (see oracle/Makefile).
+
+#include <cstdint>
+#include <cstring>
+#include <cmath>
+#include <vector>
+#include <algorithm>
+#include <numeric>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+#define ORC_API extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+const float kPI = 3.14159274f;  // UnityEngine.Mathf.PI (fp32)
+
+struct F3 { float x, y, z; };
+struct F4 { float x, y, z, w; };
+
+inline F3 sub3(F3 a, F3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline float dot3(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline F3 ld3(const float* p, int64_t i) { return {p[3 * i], p[3 * i + 1], p[3 * i + 2]}; }
+
+// A/Util/SplineKernel.cs:44
+inline float Kappa() { return 2.0f; }
+
+// A/Util/SplineKernel.cs:47-53
+inline bool Interacts(F3 r_i, F3 r_j, float size_i, float size_j) {
+    F3 d = sub3(r_i, r_j);
+    float size = fmaxf(size_i, size_j);
+    float distanceSq = dot3(d, d);
+    return distanceSq < size * size * Kappa() * Kappa();
+}
+
+// A/Util/SplineKernel.cs:55-89
+inline float Kernel(float distance, float size) {
+    float retval = 0.0f;
+    if (distance >= size * Kappa()) return retval;
+    float r_over_h = distance / size;
+    float pi_h_cube = kPI * size * size * size;
+    if (distance < size) {
+        float r_over_h_sq = r_over_h * r_over_h;
+        float numerator = 1.0f - 1.5f * r_over_h_sq + 0.75f * (r_over_h_sq * r_over_h);
+        retval = numerator / pi_h_cube;
+    } else {
+        float inner_term = 2.0f - r_over_h;
+        float numerator = inner_term * inner_term * inner_term;
+        float denominator = 4.0f * pi_h_cube;
+        retval = numerator / denominator;
+    }
+    return retval;
+}
+
+// A/Util/SplineKernel.cs:115-148.  fix_q1 = 0 reproduces the reference (quirk Q1: +3q in the inner branch).
+inline float KernelDeriv(float distance, float size, int fix_q1) {
+    float retval = 0.0f;
+    if (distance >= size * Kappa()) return retval;
+    float r_over_h = distance / size;
+    float pi_h_4th = kPI * size * size * size * size;
+    if (distance < size) {
+        float r_over_h_sq = r_over_h * r_over_h;
+        float lead = fix_q1 ? -3.0f : 3.0f;
+        float numerator = lead * r_over_h + 2.25f * r_over_h_sq;
+        retval = numerator / pi_h_4th;
+    } else {
+        float inner_term = 2.0f - r_over_h;
+        float numerator = -3.0f * inner_term * inner_term;
+        float denominator = 4.0f * pi_h_4th;
+        retval = numerator / denominator;
+    }
+    return retval;
+}
+
+// A/Util/SplineKernel.cs:102-111
+inline F4 KernelAndGradienti(F3 r_i, F3 r_j, float size, int fix_q1) {
+    F3 d = sub3(r_i, r_j);
+    float distance = sqrtf(dot3(d, d));
+    float s = KernelDeriv(distance, size, fix_q1) / distance;  // r==0 -> 0/0 = NaN (quirk Q9)
+    float kernel = Kernel(distance, size);
+    return {d.x * s, d.y * s, d.z * s, kernel};
+}
+
+struct Interaction { F4 kthis; F4 ksym; };
+
+// A/Systems/KernelSystem.cs:305-334
+inline Interaction CalculateInteraction(F3 r_i, F3 r_j, float h_i, float h_j, int fix_q1) {
+    F4 ki = KernelAndGradienti(r_i, r_j, h_i, fix_q1);
+    F4 kj = KernelAndGradienti(r_i, r_j, h_j, fix_q1);
+    Interaction it;
+    it.kthis = ki;
+    it.ksym = {(ki.x + kj.x) * 0.5f, (ki.y + kj.y) * 0.5f, (ki.z + kj.z) * 0.5f, (ki.w + kj.w) * 0.5f};
+    return it;
+}
+
+// Effective neighbor rule = FilterPairs predicate (KernelSystem.cs:617) AND keep rule (KernelSystem.cs:269,283).
+inline bool IsNeighbor(F3 r_i, F3 r_j, float h_i, float h_j) {
+    if (!Interacts(r_i, r_j, h_i, h_j)) return false;
+    Interaction it = CalculateInteraction(r_i, r_j, h_i, h_j, 0);
+    return it.ksym.w > 0.0f;
+}
+
+// A/Systems/GravityFieldSystem.cs:332-356
+inline F4 GravityContributionParticle(F3 r_i, F3 r_j, float m, float a, float G) {
+    F3 d = sub3(r_i, r_j);
+    float r = sqrtf(dot3(d, d));
+    float grav_mag_over_r, grav_potential;
+    if (r < a) {
+        float x = r / a;
+        float x_sq = x * x;
+        float x_cube = x_sq * x;
+        float x_5th = x_sq * x_cube;
+        grav_mag_over_r = (m / (a * a * a)) * (8.0f - 9.0f * x + 2.0f * x_cube);
+        grav_potential = -(m / a) * (2.4f - 4.0f * x_sq + 3.0f * x_cube - 0.4f * x_5th);
+    } else {
+        grav_mag_over_r = m / (r * r * r);
+        grav_potential = -(m / r);
+    }
+    return {G * (d.x * grav_mag_over_r), G * (d.y * grav_mag_over_r), G * (d.z * grav_mag_over_r),
+            G * grav_potential};
+}
+
+// A/Systems/GravityFieldSystem.cs:367-443  (GravitationalMoment)
+struct Moment {
+    F3 cm{0, 0, 0};
+    float m = 0;
+    // :398-411 Accumulate (P2M and M2M share it, :415-418)
+    void Accumulate(F3 c, float first) {
+        if (first != 0.0f) {
+            float newMoment = m + first;
+            F3 n;
+            n.x = (cm.x * m + c.x * first) / newMoment;
+            n.y = (cm.y * m + c.y * first) / newMoment;
+            n.z = (cm.z * m + c.z * first) / newMoment;
+            cm = n;
+            m = newMoment;
+        }
+    }
+    // :428-442 M2P
+    F4 GravityContribution(F3 r_i, float G) const {
+        F3 d = sub3(r_i, cm);
+        float r = sqrtf(dot3(d, d));
+        float g = m / (r * r * r);
+        float phi = -(m / r);
+        return {G * (d.x * g), G * (d.y * g), G * (d.z * g), G * phi};
+    }
+};
+
+struct Aabb { F3 lo, hi; };
+
+// A/Systems/GravityFieldSystem.cs:229-247
+inline bool AcceptApproximation(F3 r_i, const Moment& mo, const Aabb& bv, float theta) {
+    F3 d = sub3(r_i, mo.cm);
+    float r_sq = dot3(d, d);
+    F3 b;
+    b.x = fmaxf(bv.hi.x - mo.cm.x, mo.cm.x - bv.lo.x);
+    b.y = fmaxf(bv.hi.y - mo.cm.y, mo.cm.y - bv.lo.y);
+    b.z = fmaxf(bv.hi.z - mo.cm.z, mo.cm.z - bv.lo.z);
+    float bmax_sq = dot3(b, b);
+    return bmax_sq / r_sq < theta * theta;
+}
+
+// UP/Dynamics/Motion/Motion.cs:142-146 (MotionExpansion.ExpandAabb)
+inline Aabb ExpandAabb(Aabb a, F3 lin, float uni) {
+    Aabb o;
+    o.hi.x = fmaxf(a.hi.x, a.hi.x + lin.x) + uni;
+    o.hi.y = fmaxf(a.hi.y, a.hi.y + lin.y) + uni;
+    o.hi.z = fmaxf(a.hi.z, a.hi.z + lin.z) + uni;
+    o.lo.x = fminf(a.lo.x, a.lo.x + lin.x) - uni;
+    o.lo.y = fminf(a.lo.y, a.lo.y + lin.y) - uni;
+    o.lo.z = fminf(a.lo.z, a.lo.z + lin.z) - uni;
+    return o;
+}
+
+// Particle collider box as the broadphase prepares it (quirk Q2): sphere of radius 2h centred on x
+// (Physics_SphereCollider.cs:129-137), swept by v*dt with zero angular part (Motion.cs:117-122),
+// then Expand(margin = CollisionTolerance*0.5 = 0.05) (UP/Collision/World/Broadphase.cs:200, 757-761;
+// CollisionWorld.cs:32).  mode 1 = plain point bounds (non-reference option).
+inline Aabb ParticleBox(F3 x, float h, F3 v, float dt, int aabb_mode) {
+    Aabb a;
+    if (aabb_mode == 1) { a.lo = x; a.hi = x; return a; }
+    float rad = h * Kappa();
+    a.lo = {x.x - rad, x.y - rad, x.z - rad};
+    a.hi = {x.x + rad, x.y + rad, x.z + rad};
+    F3 lin = {v.x * dt, v.y * dt, v.z * dt};
+    a = ExpandAabb(a, lin, 0.0f);
+    const float margin = 0.1f * 0.5f;
+    a.lo = {a.lo.x - margin, a.lo.y - margin, a.lo.z - margin};
+    a.hi = {a.hi.x + margin, a.hi.y + margin, a.hi.z + margin};
+    return a;
+}
+
+inline Aabb Union(const Aabb& a, const Aabb& b) {
+    return {{fminf(a.lo.x, b.lo.x), fminf(a.lo.y, b.lo.y), fminf(a.lo.z, b.lo.z)},
+            {fmaxf(a.hi.x, b.hi.x), fmaxf(a.hi.y, b.hi.y), fmaxf(a.hi.z, b.hi.z)}};
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// Scalar entry points (known-answer tests)
+// ------------------------------------------------------------------------------------------------
+ORC_API float orc_kernel(float r, float h) { return Kernel(r, h); }
+ORC_API float orc_kernel_deriv(float r, float h, int fix_q1) { return KernelDeriv(r, h, fix_q1); }
+ORC_API int orc_interacts(const float* ri, const float* rj, float hi, float hj) {
+    return Interacts(ld3(ri, 0), ld3(rj, 0), hi, hj) ? 1 : 0;
+}
+ORC_API int orc_is_neighbor(const float* ri, const float* rj, float hi, float hj) {
+    return IsNeighbor(ld3(ri, 0), ld3(rj, 0), hi, hj) ? 1 : 0;
+}
+ORC_API void orc_kernel_and_gradient(const float* ri, const float* rj, float h, int fix_q1, float* out4) {
+    F4 k = KernelAndGradienti(ld3(ri, 0), ld3(rj, 0), h, fix_q1);
+    out4[0] = k.x; out4[1] = k.y; out4[2] = k.z; out4[3] = k.w;
+}
+// out8 = KernelThis(4), KernelSymmetric(4)
+ORC_API void orc_interaction(const float* ri, const float* rj, float hi, float hj, int fix_q1, float* out8) {
+    Interaction it = CalculateInteraction(ld3(ri, 0), ld3(rj, 0), hi, hj, fix_q1);
+    memcpy(out8, &it.kthis, 16);
+    memcpy(out8 + 4, &it.ksym, 16);
+}
+ORC_API void orc_gravity_pair(const float* ri, const float* rj, float m, float a, float G, float* out4) {
+    F4 g = GravityContributionParticle(ld3(ri, 0), ld3(rj, 0), m, a, G);
+    memcpy(out4, &g, 16);
+}
+// moment accumulate: cm_m[4] in/out
+ORC_API void orc_moment_accumulate(float* cm_m, const float* c, float m) {
+    Moment mo; mo.cm = {cm_m[0], cm_m[1], cm_m[2]}; mo.m = cm_m[3];
+    mo.Accumulate(ld3(c, 0), m);
+    cm_m[0] = mo.cm.x; cm_m[1] = mo.cm.y; cm_m[2] = mo.cm.z; cm_m[3] = mo.m;
+}
+ORC_API void orc_moment_m2p(const float* cm_m, const float* ri, float G, float* out4) {
+    Moment mo; mo.cm = {cm_m[0], cm_m[1], cm_m[2]}; mo.m = cm_m[3];
+    F4 g = mo.GravityContribution(ld3(ri, 0), G);
+    memcpy(out4, &g, 16);
+}
+ORC_API int orc_accept(const float* ri, const float* cm_m, const float* lo, const float* hi, float theta) {
+    Moment mo; mo.cm = {cm_m[0], cm_m[1], cm_m[2]}; mo.m = cm_m[3];
+    Aabb b{ld3(lo, 0), ld3(hi, 0)};
+    return AcceptApproximation(ld3(ri, 0), mo, b, theta) ? 1 : 0;
+}
+// UP/Dynamics/Motion/Motion.cs:117-122, 142-146 -- pinned by UT MotionTests.cs:50-91
+ORC_API void orc_expand_aabb(const float* lo, const float* hi, const float* lin, float uni, float* out_lo, float* out_hi) {
+    Aabb o = ExpandAabb({ld3(lo, 0), ld3(hi, 0)}, ld3(lin, 0), uni);
+    memcpy(out_lo, &o.lo, 12); memcpy(out_hi, &o.hi, 12);
+}
+ORC_API void orc_calculate_expansion(const float* linvel, const float* angvel, float angfactor, float dt, float* out_lin3, float* out_uni) {
+    out_lin3[0] = linvel[0] * dt; out_lin3[1] = linvel[1] * dt; out_lin3[2] = linvel[2] * dt;
+    F3 w = ld3(angvel, 0);
+    *out_uni = fminf(sqrtf(dot3(w, w)) * dt * angfactor, angfactor);
+}
+ORC_API void orc_particle_box(const float* x, float h, const float* v, float dt, int aabb_mode, float* out_lo, float* out_hi) {
+    Aabb o = ParticleBox(ld3(x, 0), h, ld3(v, 0), dt, aabb_mode);
+    memcpy(out_lo, &o.lo, 12); memcpy(out_hi, &o.hi, 12);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Smoothing-length controller   A/Systems/ParticleSmoothingSystem.cs:21-86
+// ------------------------------------------------------------------------------------------------
+// radius_ratio = math.pow(TARGET/(float)n, 1.0f/3.0f).  Unity.Mathematics/Burst pow is not in the tree;
+// restated as the correctly rounded fp32 power (double pow, one rounding).
+ORC_API float orc_radius_ratio(float target, int n) {
+    float ratio = target / (float)n;
+    return (float)pow((double)ratio, (double)(1.0f / 3.0f));
+}
+ORC_API void orc_smoothing_update(int64_t n, const float* h_prev, const int* n_own, float target, float* h_next) {
+    for (int64_t i = 0; i < n; i++) {
+        float h = h_prev[i];
+        if (n_own[i] != 0) {
+            float rr = orc_radius_ratio(target, n_own[i]);
+            h = h_prev[i] * 0.5f * (1.0f + rr);
+        }
+        h_next[i] = h;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Neighbor sets (ground truth: brute force; cell list for sizes brute force cannot reach).
+// Lists are CSR, per-particle neighbors in ascending index order (the canonical order; the reference's
+// BVH emission order -- KernelSystem.cs:262-287 -- is not reproducible by any other structure).
+// Returns total entries; if > cap nothing past cap is written (caller re-calls with a larger buffer).
+// ------------------------------------------------------------------------------------------------
+ORC_API int64_t orc_neighbors_brute(int64_t n, const float* pos, const float* h, int64_t* offsets, int32_t* nbr, int64_t cap) {
+    std::vector<int32_t> cnt(n, 0);
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; i++) {
+        F3 ri = ld3(pos, i); int c = 0;
+        for (int64_t j = 0; j < n; j++)
+            if (j != i && IsNeighbor(ri, ld3(pos, j), h[i], h[j])) c++;
+        cnt[i] = c;
+    }
+    offsets[0] = 0;
+    for (int64_t i = 0; i < n; i++) offsets[i + 1] = offsets[i] + cnt[i];
+    if (offsets[n] > cap) return offsets[n];
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t i = 0; i < n; i++) {
+        F3 ri = ld3(pos, i); int64_t o = offsets[i];
+        for (int64_t j = 0; j < n; j++)
+            if (j != i && IsNeighbor(ri, ld3(pos, j), h[i], h[j])) nbr[o++] = (int32_t)j;
+    }
+    return offsets[n];
+}
+
+// Cell list with cell edge >= 2*h_max*(1+1e-3): every pair that passes Interacts lies in adjacent cells.
+ORC_API int64_t orc_neighbors_grid(int64_t n, const float* pos, const float* h, int64_t* offsets, int32_t* nbr, int64_t cap) {
+    if (n == 0) { offsets[0] = 0; return 0; }
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}; double hmax = 0;
+    for (int64_t i = 0; i < n; i++) {
+        for (int k = 0; k < 3; k++) { lo[k] = std::min(lo[k], (double)pos[3 * i + k]); hi[k] = std::max(hi[k], (double)pos[3 * i + k]); }
+        hmax = std::max(hmax, (double)h[i]);
+    }
+    double cell = 2.0 * hmax * 1.001; if (!(cell > 0)) cell = 1.0;
+    int64_t dim[3];
+    for (int k = 0; k < 3; k++) { dim[k] = (int64_t)std::floor((hi[k] - lo[k]) / cell) + 1; }
+    while ((double)dim[0] * dim[1] * dim[2] > 64e6) { cell *= 1.26; for (int k = 0; k < 3; k++) dim[k] = (int64_t)std::floor((hi[k] - lo[k]) / cell) + 1; }
+    int64_t ncell = dim[0] * dim[1] * dim[2];
+    std::vector<int64_t> cid(n);
+    std::vector<int64_t> cstart(ncell + 1, 0);
+    for (int64_t i = 0; i < n; i++) {
+        int64_t c[3];
+        for (int k = 0; k < 3; k++) { c[k] = (int64_t)std::floor(((double)pos[3 * i + k] - lo[k]) / cell); c[k] = std::min(std::max(c[k], (int64_t)0), dim[k] - 1); }
+        cid[i] = (c[2] * dim[1] + c[1]) * dim[0] + c[0];
+        cstart[cid[i] + 1]++;
+    }
+    for (int64_t c = 0; c < ncell; c++) cstart[c + 1] += cstart[c];
+    std::vector<int32_t> members(n);
+    { std::vector<int64_t> fill(cstart.begin(), cstart.end() - 1);
+      for (int64_t i = 0; i < n; i++) members[fill[cid[i]]++] = (int32_t)i; }  // ascending i inside each cell
+    auto gather = [&](int64_t i, std::vector<int32_t>& out) {
+        out.clear();
+        int64_t c = cid[i]; int64_t cx = c % dim[0], cy = (c / dim[0]) % dim[1], cz = c / (dim[0] * dim[1]);
+        F3 ri = ld3(pos, i);
+        for (int64_t z = std::max<int64_t>(cz - 1, 0); z <= std::min(cz + 1, dim[2] - 1); z++)
+            for (int64_t y = std::max<int64_t>(cy - 1, 0); y <= std::min(cy + 1, dim[1] - 1); y++)
+                for (int64_t x = std::max<int64_t>(cx - 1, 0); x <= std::min(cx + 1, dim[0] - 1); x++) {
+                    int64_t cc = (z * dim[1] + y) * dim[0] + x;
+                    for (int64_t k = cstart[cc]; k < cstart[cc + 1]; k++) {
+                        int32_t j = members[k];
+                        if (j != i && IsNeighbor(ri, ld3(pos, j), h[i], h[j])) out.push_back(j);
+                    }
+                }
+        std::sort(out.begin(), out.end());
+    };
+    std::vector<int32_t> cnt(n);
+#pragma omp parallel
+    { std::vector<int32_t> tmp;
+#pragma omp for schedule(dynamic, 256)
+      for (int64_t i = 0; i < n; i++) { gather(i, tmp); cnt[i] = (int32_t)tmp.size(); } }
+    offsets[0] = 0;
+    for (int64_t i = 0; i < n; i++) offsets[i + 1] = offsets[i] + cnt[i];
+    if (offsets[n] > cap) return offsets[n];
+#pragma omp parallel
+    { std::vector<int32_t> tmp;
+#pragma omp for schedule(dynamic, 256)
+      for (int64_t i = 0; i < n; i++) { gather(i, tmp); std::copy(tmp.begin(), tmp.end(), nbr + offsets[i]); } }
+    return offsets[n];
+}
+
+// Materialised interaction buffer (DynamicBuffer<ParticleInteraction>, A/Components/Kernel.cs:5-16) for the
+// entries of one CSR list: kthis[4*e], ksym[4*e].
+ORC_API void orc_interactions(int64_t n, const float* pos, const float* h, const int64_t* offsets, const int32_t* nbr,
+                              int fix_q1, float* kthis, float* ksym) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t e = offsets[i]; e < offsets[i + 1]; e++) {
+            int32_t j = nbr[e];
+            Interaction it = CalculateInteraction(ld3(pos, i), ld3(pos, j), h[i], h[j], fix_q1);
+            memcpy(kthis + 4 * e, &it.kthis, 16);
+            memcpy(ksym + 4 * e, &it.ksym, 16);
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Density  A/Systems/DensityFieldSystem.cs:38-56 ; own-support count ParticleSmoothingSystem.cs:33-43
+// ------------------------------------------------------------------------------------------------
+ORC_API void orc_density(int64_t n, const float* pos, const float* h, const float* m, const int64_t* offsets,
+                         const int32_t* nbr, float* rho, int32_t* n_own) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < n; i++) {
+        float density = m[i] * Kernel(0.0f, h[i]);
+        int own = 0;
+        for (int64_t e = offsets[i]; e < offsets[i + 1]; e++) {
+            int32_t j = nbr[e];
+            Interaction it = CalculateInteraction(ld3(pos, i), ld3(pos, j), h[i], h[j], 0);
+            density += m[j] * it.ksym.w;
+            if (it.kthis.w > 0.0f) own++;
+        }
+        rho[i] = density;
+        if (n_own) n_own[i] = own;
+    }
+}
+
+// EOS  A/Systems/PressureFieldSystem.cs:30-34
+ORC_API void orc_eos(int64_t n, const float* rho, float K, float* P) {
+    for (int64_t i = 0; i < n; i++) P[i] = K * rho[i] * rho[i];
+}
+
+// Pressure gradient  A/Systems/PressureFieldSystem.cs:44-70
+ORC_API void orc_pressure_grad(int64_t n, const float* pos, const float* h, const float* m, const float* rho,
+                               const float* P, const int64_t* offsets, const int32_t* nbr, int fix_q1, float* gradP) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < n; i++) {
+        F3 g{0, 0, 0};
+        for (int64_t e = offsets[i]; e < offsets[i + 1]; e++) {
+            int32_t j = nbr[e];
+            Interaction it = CalculateInteraction(ld3(pos, i), ld3(pos, j), h[i], h[j], fix_q1);
+            float s = m[j] / rho[j] * P[j];
+            g.x += it.ksym.x * s; g.y += it.ksym.y * s; g.z += it.ksym.z * s;
+        }
+        gradP[3 * i] = g.x; gradP[3 * i + 1] = g.y; gradP[3 * i + 2] = g.z;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Direct gravity  A/Systems/GravityFieldSystem.cs:249-303 (targets i0..i1, all sources, self skipped).
+// accum_double = 0: literal fp32 sequential sum in index order (what the reference computes);
+//              = 1: same per-pair fp32 arithmetic, accumulated in double (summation-order-free yardstick).
+// ------------------------------------------------------------------------------------------------
+ORC_API void orc_gravity_direct(int64_t n, const float* pos, const float* h, const float* m, float G,
+                                int64_t i0, int64_t i1, int accum_double, float* grav4) {
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = i0; i < i1; i++) {
+        F3 ri = ld3(pos, i); float a = h[i];
+        if (accum_double) {
+            double s[4] = {0, 0, 0, 0};
+            for (int64_t j = 0; j < n; j++) {
+                if (j == i) continue;
+                F4 c = GravityContributionParticle(ri, ld3(pos, j), m[j], a, G);
+                s[0] += c.x; s[1] += c.y; s[2] += c.z; s[3] += c.w;
+            }
+            for (int k = 0; k < 4; k++) grav4[4 * (i - i0) + k] = (float)s[k];
+        } else {
+            F4 s{0, 0, 0, 0};
+            for (int64_t j = 0; j < n; j++) {
+                if (j == i) continue;
+                F4 c = GravityContributionParticle(ri, ld3(pos, j), m[j], a, G);
+                s.x += c.x; s.y += c.y; s.z += c.z; s.w += c.w;
+            }
+            memcpy(grav4 + 4 * (i - i0), &s, 16);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Integration: x += v*dt  (UP/Dynamics/Integrator/Integrator.cs:98-101, old v), then
+//              v += (-gradP/rho - gradPhi)*dt  (A/Systems/VelocitySystem.cs:24-36)
+// ------------------------------------------------------------------------------------------------
+ORC_API void orc_integrate(int64_t n, float* pos, float* vel, const float* rho, const float* gradP,
+                           const float* grav4, float dt) {
+    for (int64_t i = 0; i < n; i++)
+        for (int k = 0; k < 3; k++) {
+            float v = vel[3 * i + k];
+            pos[3 * i + k] = pos[3 * i + k] + v * dt;
+            float dvdt = -gradP[3 * i + k] / rho[i] - grav4[4 * i + k];
+            vel[3 * i + k] = v + dvdt * dt;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Spatial keys.  This part has no reference counterpart (it replaces the Unity.Physics broadphase); it is
+// the *specification* the CUDA key/sort kernels must match bit-for-bit ("sort orders bit-exact").
+// GridParams layout is shared with include/sphb200.h (sph_GridParams).
+// ------------------------------------------------------------------------------------------------
+struct GridParams {
+    float min[3];      // global AABB min of positions
+    float cell;        // cell edge (>= 2.002*h_max)
+    float fine_scale;  // 1024 / (cell * 2^bits)
+    int32_t bits;      // cells per axis = 2^bits
+    float hmax;
+    float ext;         // max extent over the three axes
+};
+
+static inline uint32_t expand10(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+
+ORC_API void orc_grid_params(int64_t n, const float* pos, const float* h, int max_bits, GridParams* g) {
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}; float hmax = 0.0f;
+    for (int64_t i = 0; i < n; i++) {
+        for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], pos[3 * i + k]); hi[k] = fmaxf(hi[k], pos[3 * i + k]); }
+        hmax = fmaxf(hmax, h[i]);
+    }
+    float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
+    float cell = hmax * 2.002f;
+    int bits = 0;
+    for (; bits < max_bits; bits++)
+        if (cell * (float)(1 << bits) > ext) break;
+    if (!(cell * (float)(1 << bits) > ext)) cell = (ext * 1.0001f) / (float)(1 << bits);
+    if (!(cell > 0.0f)) cell = 1.0f;
+    for (int k = 0; k < 3; k++) g->min[k] = lo[k];
+    g->cell = cell; g->bits = bits; g->hmax = hmax; g->ext = ext;
+    g->fine_scale = 1024.0f / (cell * (float)(1 << bits));
+}
+
+ORC_API void orc_morton_keys(int64_t n, const float* pos, const GridParams* g, uint32_t* keys) {
+    for (int64_t i = 0; i < n; i++) {
+        uint32_t q[3];
+        for (int k = 0; k < 3; k++) {
+            float s = (pos[3 * i + k] - g->min[k]) * g->fine_scale;
+            int v = (int)s;  // truncation; s >= 0
+            if (v < 0) v = 0; if (v > 1023) v = 1023;
+            q[k] = (uint32_t)v;
+        }
+        keys[i] = expand10(q[0]) | (expand10(q[1]) << 1) | (expand10(q[2]) << 2);
+    }
+}
+
+// stable ascending sort of (key, original index): order[k] = original index at sorted slot k
+ORC_API void orc_sort_order(int64_t n, const uint32_t* keys, uint32_t* order) {
+    std::iota(order, order + n, 0u);
+    std::stable_sort(order, order + n, [&](uint32_t a, uint32_t b) { return keys[a] < keys[b]; });
+}
+
+// ------------------------------------------------------------------------------------------------
+// LBVH over Morton-sorted particles (Karras 2012 binary radix tree) -- the structure that replaces the
+// Unity.Physics 4-ary BVH (UP/Collision/Geometry/BoundingVolumeHierarchy.cs:40-83) as the Barnes-Hut tree.
+// Node ids: internal 0..n-2 (root 0), leaf particle s -> n-1+s.  All arrays sized 2n-1.
+// A node whose particle range holds <= leaf_max particles plays the role of a reference *leaf node*
+// (<= 4 bodies, BoundingVolumeHierarchy.cs:57): it is never descended, its bodies are summed directly.
+// ------------------------------------------------------------------------------------------------
+static inline int delta_fn(const uint32_t* keys, int64_t n, int64_t i, int64_t j) {
+    if (j < 0 || j >= n) return -1;
+    uint32_t a = keys[i], b = keys[j];
+    if (a == b) return 32 + __builtin_clz((uint32_t)i ^ (uint32_t)j);  // i != j here
+    return __builtin_clz(a ^ b);
+}
+
+ORC_API void orc_lbvh_topology(int64_t n, const uint32_t* keys, int32_t* left, int32_t* right, int32_t* parent,
+                               int32_t* first, int32_t* last) {
+    // leaves
+    for (int64_t s = 0; s < n; s++) { first[n - 1 + s] = (int32_t)s; last[n - 1 + s] = (int32_t)s; left[n - 1 + s] = -1; right[n - 1 + s] = -1; }
+    if (n == 1) { parent[0] = -1; return; }
+    parent[0] = -1;
+    for (int64_t i = 0; i < n - 1; i++) {
+        int d = (delta_fn(keys, n, i, i + 1) - delta_fn(keys, n, i, i - 1)) > 0 ? 1 : -1;
+        int dmin = delta_fn(keys, n, i, i - d);
+        int64_t lmax = 2;
+        while (delta_fn(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+        int64_t l = 0;
+        for (int64_t t = lmax / 2; t >= 1; t /= 2)
+            if (delta_fn(keys, n, i, i + (l + t) * d) > dmin) l += t;
+        int64_t j = i + l * d;
+        int dnode = delta_fn(keys, n, i, j);
+        int64_t s = 0;
+        for (int64_t t = (l + 1) / 2;; t = (t + 1) / 2) {
+            if (delta_fn(keys, n, i, i + (s + t) * d) > dnode) s += t;
+            if (t == 1) break;
+        }
+        int64_t gamma = i + s * d + std::min(d, 0);
+        int64_t lo = std::min(i, j), hi = std::max(i, j);
+        int32_t lc = (lo == gamma) ? (int32_t)(n - 1 + gamma) : (int32_t)gamma;
+        int32_t rc = (hi == gamma + 1) ? (int32_t)(n - 1 + gamma + 1) : (int32_t)(gamma + 1);
+        left[i] = lc; right[i] = rc; parent[lc] = (int32_t)i; parent[rc] = (int32_t)i;
+        first[i] = (int32_t)lo; last[i] = (int32_t)hi;
+    }
+}
+
+// Moments + boxes for every node.  pos/vel/h/m are in *sorted* order.
+//  - nodes with count <= leaf_max: reference leaf rule -- running mass-weighted mean over the bodies in
+//    Data (= sorted) order from a zero moment (GravityFieldSystem.cs:398-411, 485-500)
+//  - larger nodes: Accumulate(left child), Accumulate(right child) (GravityFieldSystem.cs:513-521)
+//  - box = union of the particles' collider boxes (Q2) or points (aabb_mode 1); min/max is order-free.
+// mom4[4*node] = (cm.xyz, M); lo3/hi3[3*node].
+ORC_API void orc_lbvh_moments(int64_t n, const float* pos, const float* vel, const float* h, const float* m,
+                              const int32_t* left, const int32_t* right, const int32_t* first, const int32_t* last,
+                              int leaf_max, int aabb_mode, float dt, float* mom4, float* lo3, float* hi3) {
+    int64_t nn = 2 * n - 1;
+    std::vector<char> done(nn, 0);
+    // small nodes directly
+#pragma omp parallel for schedule(dynamic, 1024)
+    for (int64_t k = 0; k < nn; k++) {
+        int cnt = last[k] - first[k] + 1;
+        if (cnt > leaf_max) continue;
+        Moment mo; Aabb b{{INFINITY, INFINITY, INFINITY}, {-INFINITY, -INFINITY, -INFINITY}};
+        for (int s = first[k]; s <= last[k]; s++) {
+            mo.Accumulate(ld3(pos, s), m[s]);
+            b = Union(b, ParticleBox(ld3(pos, s), h[s], ld3(vel, s), dt, aabb_mode));
+        }
+        mom4[4 * k] = mo.cm.x; mom4[4 * k + 1] = mo.cm.y; mom4[4 * k + 2] = mo.cm.z; mom4[4 * k + 3] = mo.m;
+        memcpy(lo3 + 3 * k, &b.lo, 12); memcpy(hi3 + 3 * k, &b.hi, 12);
+        done[k] = 1;
+    }
+    // large nodes: post-order with an explicit stack (GravityFieldSystem.cs:465-539 pattern)
+    if (n >= 1 && !done[0]) {
+        std::vector<int32_t> stack; stack.push_back(0);
+        while (!stack.empty()) {
+            int32_t k = stack.back();
+            int32_t l = left[k], r = right[k];
+            if (done[l] && done[r]) {
+                stack.pop_back();
+                Moment mo;
+                mo.Accumulate({mom4[4 * l], mom4[4 * l + 1], mom4[4 * l + 2]}, mom4[4 * l + 3]);
+                mo.Accumulate({mom4[4 * r], mom4[4 * r + 1], mom4[4 * r + 2]}, mom4[4 * r + 3]);
+                mom4[4 * k] = mo.cm.x; mom4[4 * k + 1] = mo.cm.y; mom4[4 * k + 2] = mo.cm.z; mom4[4 * k + 3] = mo.m;
+                for (int c = 0; c < 3; c++) { lo3[3 * k + c] = fminf(lo3[3 * l + c], lo3[3 * r + c]); hi3[3 * k + c] = fmaxf(hi3[3 * l + c], hi3[3 * r + c]); }
+                done[k] = 1;
+            } else {
+                if (!done[l]) stack.push_back(l);
+                if (!done[r]) stack.push_back(r);
+            }
+        }
+    }
+}
+
+// Tree walk  A/Systems/GravityFieldSystem.cs:133-215 on the LBVH above.
+// Per target: explicit stack, pop; Accept -> M2P, numApprox++; else leaf (count<=leaf_max) -> P2P over its
+// bodies INCLUDING the target itself (quirk Q3), numParticles++ each; else push children (left then right;
+// LIFO pops right first, matching the reference's "push in Data order" :201-206).
+// Targets t0..t1 (sorted indices).  accum_double as in orc_gravity_direct.
+ORC_API void orc_tree_walk(int64_t n, const float* pos, const float* h, const float* m,
+                           const int32_t* left, const int32_t* right, const int32_t* first, const int32_t* last,
+                           const float* mom4, const float* lo3, const float* hi3,
+                           int leaf_max, float theta, float G, int64_t t0, int64_t t1, int accum_double,
+                           float* grav4, int32_t* num_particles, int32_t* num_approx) {
+#pragma omp parallel
+    {
+        std::vector<int32_t> stack; stack.reserve(256);
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t t = t0; t < t1; t++) {
+            F3 ri = ld3(pos, t); float a = h[t];
+            F4 g{0, 0, 0, 0}; double gd[4] = {0, 0, 0, 0};
+            int np = 0, na = 0;
+            stack.clear(); stack.push_back(0);
+            do {
+                int32_t k = stack.back(); stack.pop_back();
+                Moment mo; mo.cm = {mom4[4 * k], mom4[4 * k + 1], mom4[4 * k + 2]}; mo.m = mom4[4 * k + 3];
+                Aabb b{ld3(lo3, k), ld3(hi3, k)};
+                if (AcceptApproximation(ri, mo, b, theta)) {
+                    F4 c = mo.GravityContribution(ri, G);
+                    if (accum_double) { gd[0] += c.x; gd[1] += c.y; gd[2] += c.z; gd[3] += c.w; }
+                    else { g.x += c.x; g.y += c.y; g.z += c.z; g.w += c.w; }
+                    na++;
+                } else if (last[k] - first[k] + 1 <= leaf_max) {
+                    for (int s = first[k]; s <= last[k]; s++) {
+                        F4 c = GravityContributionParticle(ri, ld3(pos, s), m[s], a, G);
+                        if (accum_double) { gd[0] += c.x; gd[1] += c.y; gd[2] += c.z; gd[3] += c.w; }
+                        else { g.x += c.x; g.y += c.y; g.z += c.z; g.w += c.w; }
+                        np++;
+                    }
+                } else {
+                    stack.push_back(left[k]); stack.push_back(right[k]);
+                }
+            } while (!stack.empty());
+            if (accum_double) { g.x = (float)gd[0]; g.y = (float)gd[1]; g.z = (float)gd[2]; g.w = (float)gd[3]; }
+            memcpy(grav4 + 4 * (t - t0), &g, 16);
+            if (num_particles) num_particles[t - t0] = np;
+            if (num_approx) num_approx[t - t0] = na;
+        }
+    }
+}
+
+ORC_API int orc_num_threads() {
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+ORC_API void orc_set_num_threads(int t) {
+#ifdef _OPENMP
+    omp_set_num_threads(t);
+#else
+    (void)t;
+#endif
+}

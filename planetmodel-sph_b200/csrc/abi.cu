@@ -1,0 +1,543 @@
+// abi.cu -- the C ABI of libsphb200 (see include/sphb200.h for the contract and the reference citations).
+#include "ctx.cuh"
+#include <math.h>
+#include <string.h>
+#include <algorithm>
+#include <new>
+
+static std::string g_create_err;
+
+#define ARG_CHECK(c, cond, msg)                \
+    do {                                       \
+        if (!(cond)) {                         \
+            (c)->err = (msg);                  \
+            return SPH_ERR_INVALID_ARG;        \
+        }                                      \
+    } while (0)
+
+// ---- timing helpers --------------------------------------------------------------------------------------------
+static void pass_begin(sphb200_ctx* c) {
+    if (!c->timing) return;
+    if (!c->ev_created) {
+        for (int i = 0; i <= SPH_MAX_PASSES; i++) cudaEventCreate(&c->ev[i]);
+        c->ev_created = true;
+    }
+    c->npass = 0;
+    cudaEventRecord(c->ev[0], c->stream);
+}
+static void pass_mark(sphb200_ctx* c, const char* name) {
+    if (!c->timing || c->npass >= SPH_MAX_PASSES) return;
+    c->pass_name[c->npass] = name;
+    c->npass++;
+    cudaEventRecord(c->ev[c->npass], c->stream);
+}
+
+template <typename T>
+static cudaError_t dalloc(T** p, size_t count) {
+    return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+}
+
+extern "C" {
+
+const char* sphb200_version(void) { return "sphb200 0.1 (sm_100a)"; }
+
+int sphb200_default_params(sph_Params* p) {
+    if (!p) return SPH_ERR_INVALID_ARG;
+    memset(p, 0, sizeof(*p));
+    p->K = 1000.0f;            // PressureFieldSystem.cs:31
+    p->G = 1.0f;               // GravityFieldSystem.cs:26
+    p->theta = 0.7f;           // GravityFieldSystem.cs:228
+    p->target_neighbors = 50;  // ParticleSmoothingSystem.cs:18
+    p->max_neighbors = 128;
+    p->leaf_max = 4;           // <= 4 bodies per BVH leaf, BoundingVolumeHierarchy.cs:40-83
+    p->aabb_mode = 0;
+    p->max_grid_bits = 0;
+    p->flags = 0;
+    return SPH_OK;
+}
+
+int sphb200_destroy(sph_handle c) {
+    if (!c) return SPH_ERR_INVALID_ARG;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    for (int k = 0; k < 2; k++) { cudaFree(c->posh[k]); cudaFree(c->velm[k]); cudaFree(c->orig[k]); cudaFree(c->keys[k]); cudaFree(c->idx[k]); }
+    cudaFree(c->posm); cudaFree(c->cub_tmp); cudaFree(c->cell_start); cudaFree(c->cell_end); cudaFree(c->nlist);
+    cudaFree(c->ncount); cudaFree(c->nown); cudaFree(c->rho); cudaFree(c->press); cudaFree(c->cvol); cudaFree(c->gradp);
+    cudaFree(c->grav); cudaFree(c->npart); cudaFree(c->napprox); cudaFree(c->gpart); cudaFree(c->child); cudaFree(c->range);
+    cudaFree(c->parent); cudaFree(c->flag); cudaFree(c->mom); cudaFree(c->nlo); cudaFree(c->nhi); cudaFree(c->bounds);
+    cudaFree(c->grid_d); cudaFree(c->err_d); cudaFree(c->rr_table); cudaFree(c->diag_d); cudaFree(c->stage_d);
+    if (c->err_h) cudaFreeHost(c->err_h);
+    if (c->stage_h) cudaFreeHost(c->stage_h);
+    if (c->ev_created) for (int i = 0; i <= SPH_MAX_PASSES; i++) cudaEventDestroy(c->ev[i]);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return SPH_OK;
+}
+
+int sphb200_create(const sph_Params* params, int64_t capacity, int device, sph_handle* out) {
+    if (!out) return SPH_ERR_INVALID_ARG;
+    *out = nullptr;
+    sph_Params p;
+    if (params) p = *params; else sphb200_default_params(&p);
+    if (capacity <= 0 || capacity > 0x7fffff00LL / 2) { g_create_err = "capacity out of range"; return SPH_ERR_CAPACITY; }
+    if (p.max_neighbors <= 0 || p.max_neighbors % 32 != 0 || p.max_neighbors > 1024) { g_create_err = "max_neighbors must be a multiple of 32 in [32,1024]"; return SPH_ERR_INVALID_ARG; }
+    if (p.leaf_max < 1 || p.leaf_max > 64) { g_create_err = "leaf_max must be in [1,64]"; return SPH_ERR_INVALID_ARG; }
+    if (p.max_grid_bits < 0 || p.max_grid_bits > 8) { g_create_err = "max_grid_bits must be in [0,8]"; return SPH_ERR_INVALID_ARG; }
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) { g_create_err = std::string("no CUDA device (no CPU fallback exists): ") + cudaGetErrorString(e); return SPH_ERR_CUDA; }
+    if (device < 0 || device >= ndev) { g_create_err = "bad device index"; return SPH_ERR_INVALID_ARG; }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) { g_create_err = "device is not sm_100-class (library is built for sm_100a only)"; return SPH_ERR_CUDA; }
+    sphb200_ctx* c = new (std::nothrow) sphb200_ctx();
+    if (!c) return SPH_ERR_CUDA;
+    c->p = p; c->device = device; c->cap = capacity; c->sm_count = prop.multiProcessorCount;
+    int bits = p.max_grid_bits;
+    if (bits == 0) {  // ~2 cells per particle at most
+        bits = (int)floor(log2(2.0 * (double)capacity) / 3.0);
+        bits = std::min(std::max(bits, 1), 8);
+    }
+    c->grid_bits_max = bits;
+    c->ncell_max = (size_t)1 << (3 * bits);
+    c->gpart_splits = 8;
+    size_t cap = (size_t)capacity, nn = 2 * cap;
+    bool ok = cudaSetDevice(device) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    c->stream = c->own_stream;
+    for (int k = 0; k < 2 && ok; k++) {
+        ok = ok && dalloc(&c->posh[k], cap) == cudaSuccess && dalloc(&c->velm[k], cap) == cudaSuccess &&
+             dalloc(&c->orig[k], cap) == cudaSuccess && dalloc(&c->keys[k], cap) == cudaSuccess && dalloc(&c->idx[k], cap) == cudaSuccess;
+    }
+    c->cub_bytes = sph_sort_temp_bytes(capacity);
+    c->stage_bytes = std::max<size_t>(cap * 9 * 4, (cap + 1) * 8);
+    ok = ok && dalloc(&c->posm, cap) == cudaSuccess && cudaMalloc(&c->cub_tmp, std::max<size_t>(c->cub_bytes, 16)) == cudaSuccess &&
+         dalloc(&c->cell_start, c->ncell_max) == cudaSuccess && dalloc(&c->cell_end, c->ncell_max) == cudaSuccess &&
+         dalloc(&c->nlist, cap * (size_t)p.max_neighbors) == cudaSuccess && dalloc(&c->ncount, cap) == cudaSuccess &&
+         dalloc(&c->nown, cap) == cudaSuccess && dalloc(&c->rho, cap) == cudaSuccess && dalloc(&c->press, cap) == cudaSuccess &&
+         dalloc(&c->cvol, cap) == cudaSuccess && dalloc(&c->gradp, cap) == cudaSuccess && dalloc(&c->grav, cap) == cudaSuccess &&
+         dalloc(&c->npart, cap) == cudaSuccess && dalloc(&c->napprox, cap) == cudaSuccess &&
+         dalloc(&c->gpart, cap * (size_t)c->gpart_splits) == cudaSuccess && dalloc(&c->child, nn) == cudaSuccess &&
+         dalloc(&c->range, nn) == cudaSuccess && dalloc(&c->parent, nn) == cudaSuccess && dalloc(&c->flag, nn) == cudaSuccess &&
+         dalloc(&c->mom, nn) == cudaSuccess && dalloc(&c->nlo, nn) == cudaSuccess && dalloc(&c->nhi, nn) == cudaSuccess &&
+         dalloc(&c->bounds, 8) == cudaSuccess && dalloc(&c->grid_d, 1) == cudaSuccess && dalloc(&c->err_d, ERR_SLOTS) == cudaSuccess &&
+         dalloc(&c->rr_table, SPH_RR_TABLE) == cudaSuccess && dalloc(&c->diag_d, 16) == cudaSuccess &&
+         cudaMalloc(&c->stage_d, c->stage_bytes) == cudaSuccess && cudaMallocHost((void**)&c->err_h, ERR_SLOTS * sizeof(int32_t)) == cudaSuccess &&
+         cudaMallocHost(&c->stage_h, c->stage_bytes) == cudaSuccess;
+    if (!ok) {
+        g_create_err = std::string("allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+        sphb200_destroy(c);
+        return SPH_ERR_CUDA;
+    }
+    // radius-ratio table: correctly rounded fp32 pow(target/n, 1/3f) (ParticleSmoothingSystem.cs:49-50); the same
+    // expression as the oracle's orc_radius_ratio, so the controller is bit-identical on both sides.
+    std::vector<float> rr(SPH_RR_TABLE, 1.0f);
+    for (int k = 1; k < SPH_RR_TABLE; k++) {
+        float ratio = p.target_neighbors / (float)k;
+        rr[k] = (float)pow((double)ratio, (double)(1.0f / 3.0f));
+    }
+    uint32_t b0[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0, 0, 0};
+    ok = cudaMemcpy(c->rr_table, rr.data(), SPH_RR_TABLE * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemcpy(c->bounds, b0, sizeof(b0), cudaMemcpyHostToDevice) == cudaSuccess &&
+         cudaMemset(c->err_d, 0, ERR_SLOTS * sizeof(int32_t)) == cudaSuccess &&
+         cudaMemset(c->nown, 0, cap * sizeof(int32_t)) == cudaSuccess;
+    if (!ok) { g_create_err = "initialisation failed"; sphb200_destroy(c); return SPH_ERR_CUDA; }
+    *out = c;
+    return SPH_OK;
+}
+
+const char* sphb200_last_error(sph_handle c) { return c ? c->err.c_str() : g_create_err.c_str(); }
+
+int sphb200_set_stream(sph_handle c, void* s) {
+    if (!c) return SPH_ERR_INVALID_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return SPH_OK;
+}
+
+int sphb200_sync(sph_handle c) {
+    if (!c) return SPH_ERR_INVALID_ARG;
+    SPH_CK(c, cudaSetDevice(c->device));
+    SPH_CK(c, cudaStreamSynchronize(c->stream));
+    return SPH_OK;
+}
+
+int sphb200_count(sph_handle c, int64_t* n, int64_t* cap) {
+    if (!c) return SPH_ERR_INVALID_ARG;
+    if (n) *n = c->n;
+    if (cap) *cap = c->cap;
+    return SPH_OK;
+}
+int sphb200_get_params(sph_handle c, sph_Params* out) {
+    if (!c || !out) return SPH_ERR_INVALID_ARG;
+    *out = c->p;
+    out->max_grid_bits = c->grid_bits_max;
+    return SPH_OK;
+}
+int sphb200_launch_count(sph_handle c, int64_t* l) {
+    if (!c || !l) return SPH_ERR_INVALID_ARG;
+    *l = c->launches;
+    return SPH_OK;
+}
+int sphb200_enable_timing(sph_handle c, int en) {
+    if (!c) return SPH_ERR_INVALID_ARG;
+    c->timing = en != 0;
+    c->npass = 0;
+    return SPH_OK;
+}
+int sphb200_get_timings(sph_handle c, const char** names, float* ms, int cap) {
+    if (!c) return SPH_ERR_INVALID_ARG;
+    if (!c->timing || c->npass == 0) return 0;
+    cudaSetDevice(c->device);
+    cudaEventSynchronize(c->ev[c->npass]);
+    int k = 0;
+    for (; k < c->npass && k < cap; k++) {
+        if (names) names[k] = c->pass_name[k];
+        float t = 0;
+        cudaEventElapsedTime(&t, c->ev[k], c->ev[k + 1]);
+        if (ms) ms[k] = t;
+    }
+    return k;
+}
+int sphb200_fp32_peak(sph_handle c, double* tf) {
+    if (!c || !tf) return SPH_ERR_INVALID_ARG;
+    SPH_CK(c, cudaSetDevice(c->device));
+    return sph_fp32_peak(c, tf);
+}
+
+int sphb200_set_target_range(sph_handle c, int64_t t0, int64_t t1) {
+    if (!c) return SPH_ERR_INVALID_ARG;
+    ARG_CHECK(c, t0 >= 0, "t0 < 0");
+    c->t0 = t0;
+    c->t1 = t1;
+    return SPH_OK;
+}
+
+// ---- upload ---------------------------------------------------------------------------------------------------------
+int sphb200_upload(sph_handle c, int64_t n, const void* pos, int pos_stride, const void* vel, int vel_stride, const void* mass,
+                   int mass_stride, const void* smoothing, int smoothing_stride) {
+    if (!c) return SPH_ERR_INVALID_ARG;
+    ARG_CHECK(c, n >= 0, "n < 0");
+    if (n > c->cap) { c->err = "n exceeds capacity"; return SPH_ERR_CAPACITY; }
+    ARG_CHECK(c, n == 0 || (pos && vel && mass && smoothing), "null component array");
+    ARG_CHECK(c, pos_stride >= 12 && vel_stride >= 12 && mass_stride >= 4 && smoothing_stride >= 4, "stride too small");
+    SPH_CK(c, cudaSetDevice(c->device));
+    SPH_CK(c, cudaStreamSynchronize(c->stream));
+    c->n = n;
+    c->cur = 0;
+    c->resident = true; c->lists_valid = c->pressure_valid = c->gravity_valid = c->tree_valid = c->h_updated = false;
+    c->sorted_valid = c->lists_fresh = false;
+    if (n == 0) return SPH_OK;
+    float* st = (float*)c->stage_h;
+    float* P = st; float* V = st + 3 * n; float* M = st + 6 * n; float* H = st + 7 * n; int32_t* NO = (int32_t*)(st + 8 * n);
+    bool has_nown = smoothing_stride >= (int)sizeof(sph_ParticleSmoothing);
+    const char* pp = (const char*)pos; const char* vp = (const char*)vel; const char* mp = (const char*)mass; const char* sp = (const char*)smoothing;
+    if (pos_stride == 12) memcpy(P, pp, (size_t)n * 12);
+    else for (int64_t i = 0; i < n; i++) memcpy(P + 3 * i, pp + (size_t)i * pos_stride, 12);
+    if (vel_stride == 12) memcpy(V, vp, (size_t)n * 12);
+    else for (int64_t i = 0; i < n; i++) memcpy(V + 3 * i, vp + (size_t)i * vel_stride, 12);
+    if (mass_stride == 4) memcpy(M, mp, (size_t)n * 4);
+    else for (int64_t i = 0; i < n; i++) memcpy(M + i, mp + (size_t)i * mass_stride, 4);
+    if (smoothing_stride == 4) memcpy(H, sp, (size_t)n * 4);
+    else for (int64_t i = 0; i < n; i++) memcpy(H + i, sp + (size_t)i * smoothing_stride, 4);
+    if (has_nown) for (int64_t i = 0; i < n; i++) memcpy(NO + i, sp + (size_t)i * smoothing_stride + 24, 4);
+    SPH_CK(c, cudaMemcpyAsync(c->stage_d, c->stage_h, (size_t)n * 9 * 4, cudaMemcpyHostToDevice, c->stream));
+    int rc = sph_launch_pack_upload(c, n, has_nown);
+    if (rc) return rc;
+    SPH_CK(c, cudaStreamSynchronize(c->stream));
+    return SPH_OK;
+}
+
+// ---- stages ----------------------------------------------------------------------------------------------------------
+static int check_errflags(sphb200_ctx* c) {
+    SPH_CK(c, cudaMemcpyAsync(c->err_h, c->err_d, ERR_SLOTS * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    SPH_CK(c, cudaStreamSynchronize(c->stream));
+    if (c->err_h[ERR_TREE_STACK]) { c->err = "LBVH traversal stack overflow"; return SPH_ERR_TREE_STACK; }
+    if (c->err_h[ERR_NEIGHBOR_OVERFLOW]) {
+        c->err = "neighbor list overflow: a particle has " + std::to_string(c->err_h[ERR_NEIGHBOR_OVERFLOW]) +
+                 " neighbors > max_neighbors=" + std::to_string(c->p.max_neighbors) + " (lists truncated)";
+        return SPH_ERR_NEIGHBOR_OVERFLOW;
+    }
+    return SPH_OK;
+}
+
+#define NEED_RESIDENT(c)                                                  \
+    do {                                                                  \
+        if (!(c)) return SPH_ERR_INVALID_ARG;                             \
+        if (!(c)->resident) { (c)->err = "no particles uploaded"; return SPH_ERR_STATE; } \
+        SPH_CK(c, cudaSetDevice((c)->device));                            \
+    } while (0)
+
+int sphb200_smoothing_update(sph_handle c) {
+    NEED_RESIDENT(c);
+    if (c->n == 0) return SPH_OK;
+    int rc = sph_launch_smoothing_bounds(c, true);
+    if (rc) return rc;
+    c->h_updated = true;
+    c->sorted_valid = c->lists_fresh = c->pressure_valid = c->gravity_valid = false;
+    return SPH_OK;
+}
+
+static int ensure_sorted(sphb200_ctx* c) {
+    if (c->sorted_valid) return SPH_OK;  // sorted for the current positions already
+    int rc;
+    if (!c->h_updated) { rc = sph_launch_smoothing_bounds(c, false); if (rc) return rc; c->h_updated = true; }
+    rc = sph_launch_sort_and_cells(c);
+    if (rc) return rc;
+    c->sorted_valid = true;
+    c->lists_valid = c->lists_fresh = c->tree_valid = false;  // slot indices changed
+    return SPH_OK;
+}
+
+int sphb200_build_neighbors(sph_handle c) {
+    NEED_RESIDENT(c);
+    if (c->n == 0) return SPH_OK;
+    SPH_CK(c, cudaMemsetAsync(c->err_d, 0, ERR_SLOTS * sizeof(int32_t), c->stream));
+    int rc = ensure_sorted(c);
+    if (rc) return rc;
+    rc = sph_launch_neighbors_density(c);
+    if (rc) return rc;
+    c->lists_valid = c->lists_fresh = true;
+    c->pressure_valid = false;
+    return SPH_OK;
+}
+
+int sphb200_gravity(sph_handle c, int impl, float dt) {
+    NEED_RESIDENT(c);
+    if (c->n == 0) return SPH_OK;
+    c->last_dt = dt;
+    if (impl == SPH_GRAVITY_NONE) {
+        SPH_CK(c, cudaMemsetAsync(c->grav, 0, (size_t)c->n * sizeof(float4), c->stream));
+        SPH_CK(c, cudaMemsetAsync(c->npart, 0, (size_t)c->n * sizeof(int32_t), c->stream));
+        SPH_CK(c, cudaMemsetAsync(c->napprox, 0, (size_t)c->n * sizeof(int32_t), c->stream));
+        c->gravity_valid = true;
+        return SPH_OK;
+    }
+    if (impl == SPH_GRAVITY_PARTICLE) {
+        if (!c->lists_fresh) { c->err = "direct gravity needs this step's neighbor lists (softened near-pair correction): call build_neighbors first"; return SPH_ERR_STATE; }
+        int rc = sph_launch_gravity_allpairs(c);
+        if (rc) return rc;
+        rc = sph_launch_gravity_near(c);
+        if (rc) return rc;
+        c->gravity_valid = true;
+        return SPH_OK;
+    }
+    if (impl == SPH_GRAVITY_TREE) {
+        int rc = ensure_sorted(c);
+        if (rc) return rc;
+        rc = sph_launch_gravity_tree(c, dt);
+        if (rc) return rc;
+        c->gravity_valid = true;
+        return SPH_OK;
+    }
+    c->err = "unknown gravity impl";
+    return SPH_ERR_INVALID_ARG;
+}
+
+int sphb200_density(sph_handle c) {
+    NEED_RESIDENT(c);
+    if (!c->lists_fresh && c->n > 0) { c->err = "density needs build_neighbors in this step (the sum is fused into it)"; return SPH_ERR_STATE; }
+    return SPH_OK;
+}
+
+int sphb200_pressure(sph_handle c) {
+    NEED_RESIDENT(c);
+    if (c->n == 0) return SPH_OK;
+    if (!c->lists_fresh) { c->err = "pressure needs build_neighbors in this step"; return SPH_ERR_STATE; }
+    int rc = sph_launch_pressure(c);
+    if (rc) return rc;
+    c->pressure_valid = true;
+    return SPH_OK;
+}
+
+int sphb200_integrate(sph_handle c, float dt) {
+    NEED_RESIDENT(c);
+    if (c->n == 0) return SPH_OK;
+    if (!c->pressure_valid || !c->gravity_valid) { c->err = "integrate needs pressure and gravity of this step"; return SPH_ERR_STATE; }
+    int rc = sph_launch_integrate(c, dt);
+    if (rc) return rc;
+    // positions moved: neighbor/tree structures belong to the old positions; they stay downloadable until the next
+    // sort but no longer feed any compute stage
+    c->h_updated = c->sorted_valid = c->lists_fresh = c->pressure_valid = c->gravity_valid = false;
+    return SPH_OK;
+}
+
+int sphb200_step(sph_handle c, float dt, int impl) {
+    NEED_RESIDENT(c);
+    if (c->n == 0) return SPH_OK;
+    int rc;
+    pass_begin(c);
+    if ((rc = sphb200_smoothing_update(c))) return rc;
+    pass_mark(c, "smoothing_bounds");
+    SPH_CK(c, cudaMemsetAsync(c->err_d, 0, ERR_SLOTS * sizeof(int32_t), c->stream));
+    if ((rc = ensure_sorted(c))) return rc;
+    pass_mark(c, "keys_sort_permute_cells");
+    if ((rc = sph_launch_neighbors_density(c))) return rc;
+    c->lists_valid = c->lists_fresh = true;
+    pass_mark(c, "neighbors_density_eos");
+    if ((rc = sphb200_gravity(c, impl, dt))) return rc;
+    pass_mark(c, impl == SPH_GRAVITY_TREE ? "gravity_tree" : (impl == SPH_GRAVITY_PARTICLE ? "gravity_allpairs" : "gravity_none"));
+    if ((rc = sphb200_pressure(c))) return rc;
+    pass_mark(c, "pressure_grad");
+    if ((rc = sphb200_integrate(c, dt))) return rc;
+    pass_mark(c, "integrate");
+    return SPH_OK;
+}
+
+// ---- download --------------------------------------------------------------------------------------------------------
+int sphb200_download(sph_handle c, int field, void* dst, int stride) {
+    NEED_RESIDENT(c);
+    ARG_CHECK(c, dst || c->n == 0, "null dst");
+    if (c->n == 0) return SPH_OK;
+    int eb = 0;
+    int rc = sph_launch_unpack_field(c, field, &eb);
+    if (rc) { if (rc == SPH_ERR_INVALID_ARG) c->err = "unknown field"; return rc; }
+    int64_t n = c->n;
+    SPH_CK(c, cudaMemcpyAsync(c->stage_h, c->stage_d, (size_t)n * eb, cudaMemcpyDeviceToHost, c->stream));
+    rc = check_errflags(c);  // also synchronises
+    const char* src = (const char*)c->stage_h;
+    char* d = (char*)dst;
+    switch (field) {
+        case SPH_FIELD_SMOOTHING: {
+            ARG_CHECK(c, stride >= 4, "stride too small");
+            bool full = stride >= (int)sizeof(sph_ParticleSmoothing);
+            for (int64_t i = 0; i < n; i++) {
+                float h; int32_t no;
+                memcpy(&h, src + 8 * i, 4); memcpy(&no, src + 8 * i + 4, 4);
+                if (full) {
+                    sph_ParticleSmoothing s;
+                    s.influenceArea = h; s.supportDomain = 2.0f * h;  // ParticleSmoothing.cs:16-23
+                    s.sphereColliderPosRadius[0] = s.sphereColliderPosRadius[1] = s.sphereColliderPosRadius[2] = 0.f;
+                    s.sphereColliderPosRadius[3] = 2.0f * h;
+                    s.neighbors = no;
+                    memcpy(d + (size_t)i * stride, &s, sizeof(s));
+                } else memcpy(d + (size_t)i * stride, &h, 4);
+            }
+            break;
+        }
+        case SPH_FIELD_GRAVITY: {
+            ARG_CHECK(c, stride >= 16, "stride too small");
+            int w = stride >= 24 ? 24 : 16;
+            for (int64_t i = 0; i < n; i++) memcpy(d + (size_t)i * stride, src + 24 * i, w);
+            break;
+        }
+        default: {
+            ARG_CHECK(c, stride >= eb, "stride too small");
+            if (stride == eb) memcpy(d, src, (size_t)n * eb);
+            else for (int64_t i = 0; i < n; i++) memcpy(d + (size_t)i * stride, src + (size_t)i * eb, eb);
+        }
+    }
+    return rc;
+}
+
+int sphb200_download_neighbors(sph_handle c, int64_t* offsets, int32_t* nbr, int64_t cap, int64_t* total) {
+    NEED_RESIDENT(c);
+    ARG_CHECK(c, offsets && total, "null argument");
+    if (!c->lists_valid && c->n > 0) { c->err = "no neighbor lists"; return SPH_ERR_STATE; }
+    int64_t n = c->n;
+    offsets[0] = 0;
+    if (n == 0) { *total = 0; return SPH_OK; }
+    int eb;
+    int rc = sph_launch_unpack_field(c, SPH_FIELD_NEIGHBOR_COUNT, &eb);
+    if (rc) return rc;
+    SPH_CK(c, cudaMemcpyAsync(c->stage_h, c->stage_d, (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    SPH_CK(c, cudaStreamSynchronize(c->stream));
+    const int32_t* cnt = (const int32_t*)c->stage_h;
+    int kmax = c->p.max_neighbors;
+    for (int64_t i = 0; i < n; i++) offsets[i + 1] = offsets[i] + std::min(cnt[i], kmax);
+    *total = offsets[n];
+    if (*total > cap || !nbr) return check_errflags(c);
+    memcpy(c->stage_h, offsets, (size_t)(n + 1) * 8);
+    SPH_CK(c, cudaMemcpyAsync(c->stage_d, c->stage_h, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    int32_t* rows_d = nullptr;
+    SPH_CK(c, cudaMalloc((void**)&rows_d, std::max<int64_t>(*total, 1) * 4));
+    rc = sph_launch_neighbor_rows_sorted(c, rows_d);
+    if (rc == SPH_OK) {
+        cudaError_t e = cudaMemcpyAsync(nbr, rows_d, (size_t)*total * 4, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = SPH_ERR_CUDA; }
+    }
+    cudaFree(rows_d);
+    if (rc) return rc;
+    return check_errflags(c);
+}
+
+int sphb200_download_interactions(sph_handle c, const int64_t* offsets, const int32_t* nbr, sph_ParticleInteraction* out) {
+    NEED_RESIDENT(c);
+    ARG_CHECK(c, offsets && (nbr || offsets[c->n] == 0) && (out || offsets[c->n] == 0), "null argument");
+    int64_t n = c->n, total = offsets[n];
+    if (n == 0 || total == 0) return SPH_OK;
+    int64_t* off_d = nullptr; int32_t* nbr_d = nullptr; sph_ParticleInteraction* out_d = nullptr;
+    int rc = SPH_OK;
+    if (cudaMalloc((void**)&off_d, (n + 1) * 8) != cudaSuccess || cudaMalloc((void**)&nbr_d, total * 4) != cudaSuccess ||
+        cudaMalloc((void**)&out_d, total * sizeof(sph_ParticleInteraction)) != cudaSuccess) {
+        c->err = "allocation failed"; rc = SPH_ERR_CUDA;
+    }
+    if (!rc) {
+        cudaMemcpyAsync(off_d, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream);
+        cudaMemcpyAsync(nbr_d, nbr, total * 4, cudaMemcpyHostToDevice, c->stream);
+        rc = sph_launch_interactions(c, total, off_d, nbr_d, out_d);
+    }
+    if (!rc) {
+        cudaError_t e = cudaMemcpyAsync(out, out_d, total * sizeof(sph_ParticleInteraction), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = SPH_ERR_CUDA; }
+    }
+    cudaFree(off_d); cudaFree(nbr_d); cudaFree(out_d);
+    return rc;
+}
+
+int sphb200_download_sort(sph_handle c, uint32_t* order, uint32_t* keys, sph_GridParams* grid) {
+    NEED_RESIDENT(c);
+    int64_t n = c->n;
+    if (order && n) SPH_CK(c, cudaMemcpyAsync(order, c->orig[c->cur], (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (keys && n) SPH_CK(c, cudaMemcpyAsync(keys, c->keys[1], (size_t)n * 4, cudaMemcpyDeviceToHost, c->stream));
+    if (grid) SPH_CK(c, cudaMemcpyAsync(grid, c->grid_d, sizeof(sph_GridParams), cudaMemcpyDeviceToHost, c->stream));
+    SPH_CK(c, cudaStreamSynchronize(c->stream));
+    return SPH_OK;
+}
+
+int sphb200_download_tree(sph_handle c, int32_t* child, int32_t* range, float* moment, float* lo, float* hi) {
+    NEED_RESIDENT(c);
+    if (!c->tree_valid) { c->err = "no tree: call gravity(SPH_GRAVITY_TREE) first"; return SPH_ERR_STATE; }
+    int64_t nn = 2 * c->n - 1;
+    if (nn <= 0) return SPH_OK;
+    if (child) SPH_CK(c, cudaMemcpyAsync(child, c->child, (size_t)nn * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (range) SPH_CK(c, cudaMemcpyAsync(range, c->range, (size_t)nn * 8, cudaMemcpyDeviceToHost, c->stream));
+    if (moment) SPH_CK(c, cudaMemcpyAsync(moment, c->mom, (size_t)nn * 16, cudaMemcpyDeviceToHost, c->stream));
+    std::vector<float4> tmp;
+    if (lo || hi) {
+        tmp.resize((size_t)nn);
+        for (int pass = 0; pass < 2; pass++) {
+            float* dstp = pass == 0 ? lo : hi;
+            if (!dstp) continue;
+            SPH_CK(c, cudaMemcpyAsync(tmp.data(), pass == 0 ? c->nlo : c->nhi, (size_t)nn * 16, cudaMemcpyDeviceToHost, c->stream));
+            SPH_CK(c, cudaStreamSynchronize(c->stream));
+            for (int64_t k = 0; k < nn; k++) { dstp[3 * k] = tmp[k].x; dstp[3 * k + 1] = tmp[k].y; dstp[3 * k + 2] = tmp[k].z; }
+        }
+    }
+    SPH_CK(c, cudaStreamSynchronize(c->stream));
+    return SPH_OK;
+}
+
+int sphb200_diagnostics(sph_handle c, double* out12) {
+    NEED_RESIDENT(c);
+    ARG_CHECK(c, out12, "null out");
+    if (c->n == 0) { for (int k = 0; k < 12; k++) out12[k] = 0; return SPH_OK; }
+    return sph_launch_diagnostics(c, out12);
+}
+
+int sphb200_device_ptr(sph_handle c, const char* name, void** ptr, int64_t* bytes) {
+    if (!c || !name || !ptr) return SPH_ERR_INVALID_ARG;
+    struct { const char* nm; void* p; size_t el; } tab[] = {
+        {"posh", c->posh[c->cur], 16}, {"velm", c->velm[c->cur], 16}, {"posm", c->posm, 16}, {"rho", c->rho, 4},
+        {"press", c->press, 4}, {"cvol", c->cvol, 4}, {"gradp", c->gradp, 16}, {"grav", c->grav, 16}, {"nown", c->nown, 4},
+        {"orig", c->orig[c->cur], 4}, {"ncount", c->ncount, 4},
+    };
+    for (auto& t : tab)
+        if (strcmp(t.nm, name) == 0) { *ptr = t.p; if (bytes) *bytes = (int64_t)(t.el * (size_t)c->cap); return SPH_OK; }
+    c->err = std::string("unknown array name: ") + name;
+    return SPH_ERR_INVALID_ARG;
+}
+
+}  // extern "C"

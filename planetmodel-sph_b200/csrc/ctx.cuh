@@ -1,0 +1,156 @@
+// ctx.cuh -- internal context + helpers of libsphb200 (not part of the public ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/sphb200.h"
+
+#define SPH_MAX_PASSES 24
+#define SPH_RR_TABLE 4096          // radius-ratio table entries (own-support count 1..4095)
+#define SPH_TREE_STACK 160         // per-warp traversal stack entries
+#define SPH_BODY_CAP 16777214      // 2^24-2, UP/Dynamics/Simulation/Scheduler.cs:26-31,41 (quirk Q12)
+
+enum { ERR_NEIGHBOR_OVERFLOW = 0, ERR_TREE_STACK = 1, ERR_SLOTS = 4 };
+
+struct sphb200_ctx {
+    sph_Params p{};
+    int device = 0;
+    int sm_count = 148;
+    int64_t cap = 0, n = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+
+    // resident SoA state, sorted (Morton) order after build_neighbors; ping-pong through the permute
+    float4* posh[2] = {nullptr, nullptr};  // x,y,z,h
+    float4* velm[2] = {nullptr, nullptr};  // vx,vy,vz,m
+    uint32_t* orig[2] = {nullptr, nullptr};  // sorted slot -> body index
+    int cur = 0;
+    float4* posm = nullptr;                // x,y,z,m (gravity sources)
+
+    uint32_t* keys[2] = {nullptr, nullptr};
+    uint32_t* idx[2] = {nullptr, nullptr};
+    void* cub_tmp = nullptr;
+    size_t cub_bytes = 0;
+    uint32_t* cell_start = nullptr;
+    uint32_t* cell_end = nullptr;
+    int grid_bits_max = 0;
+    size_t ncell_max = 0;
+
+    uint32_t* nlist = nullptr;   // [cap][max_neighbors] sorted-slot indices
+    int32_t* ncount = nullptr;   // symmetric neighbor count
+    int32_t* nown = nullptr;     // own-support count (KernelThis.w > 0)
+    float* rho = nullptr;
+    float* press = nullptr;
+    float* cvol = nullptr;       // (m/rho)*P
+    float4* gradp = nullptr;
+    float4* grav = nullptr;
+    int32_t* npart = nullptr;
+    int32_t* napprox = nullptr;
+    float4* gpart = nullptr;     // all-pairs partial sums [splits][n]
+    int gpart_splits = 0;
+
+    // LBVH (2n-1 nodes)
+    int2* child = nullptr;
+    int2* range = nullptr;
+    int32_t* parent = nullptr;
+    int32_t* flag = nullptr;
+    float4* mom = nullptr;
+    float4* nlo = nullptr;       // xyz = box min, w = first (int bits)
+    float4* nhi = nullptr;       // xyz = box max, w = last  (int bits)
+
+    uint32_t* bounds = nullptr;  // 8 ordered-uint floats: min xyz, max xyz, hmax
+    sph_GridParams* grid_d = nullptr;
+    sph_GridParams grid_h{};
+    int32_t* err_d = nullptr;
+    int32_t* err_h = nullptr;    // pinned
+    float* rr_table = nullptr;
+    double* diag_d = nullptr;
+
+    void* stage_d = nullptr;     // upload/download staging (device)
+    void* stage_h = nullptr;     // pinned host staging
+    size_t stage_bytes = 0;
+
+    bool resident = false, lists_valid = false, pressure_valid = false, gravity_valid = false, tree_valid = false;
+    bool h_updated = false;      // bounds/grid params computed for the current positions and h
+    bool sorted_valid = false;   // sort + cell table match the current positions and h
+    bool lists_fresh = false;    // neighbor lists/density belong to the current positions and h
+    int64_t t0 = 0, t1 = -1;
+    int64_t launches = 0;
+    float last_dt = 0.f;
+
+    // timing
+    bool timing = false;
+    int npass = 0;
+    const char* pass_name[SPH_MAX_PASSES];
+    cudaEvent_t ev[SPH_MAX_PASSES + 1];
+    bool ev_created = false;
+
+    std::string err;
+};
+
+#define SPH_CK(ctx, call)                                                                            \
+    do {                                                                                             \
+        cudaError_t e__ = (call);                                                                    \
+        if (e__ != cudaSuccess) {                                                                    \
+            (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+            return SPH_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+#define SPH_LAUNCH_CHECK(ctx)                                                                        \
+    do {                                                                                             \
+        (ctx)->launches++;                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                                        \
+        if (e__ != cudaSuccess) {                                                                    \
+            (ctx)->err = std::string("kernel launch: ") + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + std::to_string(__LINE__); \
+            return SPH_ERR_CUDA;                                                                     \
+        }                                                                                            \
+    } while (0)
+
+static inline int sph_div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- device helpers ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t f2ord(float f) {
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(uint32_t u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+__device__ __forceinline__ uint32_t expand10(uint32_t v) {
+    v &= 0x3ffu;
+    v = (v | (v << 16)) & 0x030000FFu;
+    v = (v | (v << 8)) & 0x0300F00Fu;
+    v = (v | (v << 4)) & 0x030C30C3u;
+    v = (v | (v << 2)) & 0x09249249u;
+    return v;
+}
+__device__ __forceinline__ uint32_t compact10(uint32_t v) {
+    v &= 0x09249249u;
+    v = (v | (v >> 2)) & 0x030C30C3u;
+    v = (v | (v >> 4)) & 0x0300F00Fu;
+    v = (v | (v >> 8)) & 0x030000FFu;
+    v = (v | (v >> 16)) & 0x3ffu;
+    return v;
+}
+// exact (non-contracted) squared distance in the reference's order: dx*dx + dy*dy + dz*dz
+__device__ __forceinline__ float dot3_rn(float x, float y, float z) {
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+// ---- kernel launchers (one translation unit each) -----------------------------------------------------------
+int sph_launch_smoothing_bounds(sphb200_ctx* c, bool update_h);
+int sph_launch_sort_and_cells(sphb200_ctx* c);
+int sph_launch_neighbors_density(sphb200_ctx* c);
+int sph_launch_pressure(sphb200_ctx* c);
+int sph_launch_gravity_near(sphb200_ctx* c);
+int sph_launch_integrate(sphb200_ctx* c, float dt);
+int sph_launch_gravity_allpairs(sphb200_ctx* c);
+int sph_launch_gravity_tree(sphb200_ctx* c, float dt);
+int sph_launch_diagnostics(sphb200_ctx* c, double* out12);
+int sph_launch_pack_upload(sphb200_ctx* c, int64_t n, bool has_nown);
+int sph_launch_unpack_field(sphb200_ctx* c, int field, int* elem_bytes);
+int sph_launch_neighbor_rows_sorted(sphb200_ctx* c, int32_t* rows_d);
+int sph_launch_interactions(sphb200_ctx* c, int64_t total, const int64_t* offsets_d, const int32_t* nbr_d, sph_ParticleInteraction* out_d);
+int sph_fp32_peak(sphb200_ctx* c, double* tflops);
+size_t sph_sort_temp_bytes(int64_t cap);

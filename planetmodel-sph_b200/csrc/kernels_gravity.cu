@@ -1,0 +1,175 @@
+// kernels_gravity.cu -- all-pairs (direct-sum) self-gravity: shared-memory-tiled FP32 FMA kernel.
+//
+// Replaces: GravityFieldSystem.OnUpdateParticle + GravityContributionParticle
+// (A/Systems/GravityFieldSystem.cs:249-303, 332-356): for every target i, sum over all j != i of
+//   r <  a=h_i : d * (m/a^3)(8 - 9x + 2x^3),  phi = -(m/a)(2.4 - 4x^2 + 3x^3 - 0.4x^5),  x = r/a   (Dyer & Ip)
+//   r >= a     : d * m/r^3,                   phi = -m/r
+//
+// B200 mapping: FP32 FMA-pipe bound (no tensor cores: not a contraction).  The inner loop is branch-free:
+// it evaluates the Newtonian law with r^2 capped from below at a^2 (one FMNMX), which makes the self pair and every
+// pair inside the softening radius finite and smooth.  The difference "softened - capped" for the few pairs with
+// r < h_i (all of them are in i's SPH neighbor list, since r < h_i < 2 max(h_i,h_j)) is added by the pressure kernel
+// (kernels_sph.cu, add_grav), and the capped self term is removed in the reduce kernel.  15 issue slots per pair.
+// Summation: per-tile fp32 partials (256 sources) added into a running sum, then a fixed-order reduction over the
+// source splits -- deterministic, and ~sqrt(256) times tighter than one 10^6-term fp32 chain.
+#include "ctx.cuh"
+
+namespace {
+
+constexpr int AP_THREADS = 256;
+constexpr int AP_TPT = 2;     // targets per thread
+constexpr int AP_TILE = 256;  // sources per shared-memory tile
+
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__global__ void __launch_bounds__(AP_THREADS) k_gravity_allpairs(const float4* __restrict__ src, int n_src, int src_per_split,
+                                                                 const float4* __restrict__ posh, int t0, int t1,
+                                                                 float4* __restrict__ part) {
+    __shared__ float4 tile[AP_TILE];
+    const int nt = t1 - t0;
+    const int tid = threadIdx.x;
+    const int tb = blockIdx.x * (AP_THREADS * AP_TPT);
+    float xi[AP_TPT], yi[AP_TPT], zi[AP_TPT], a2[AP_TPT];
+    float AX[AP_TPT], AY[AP_TPT], AZ[AP_TPT], PH[AP_TPT];
+#pragma unroll
+    for (int k = 0; k < AP_TPT; k++) {
+        int t = tb + k * AP_THREADS + tid;
+        float4 p = posh[t0 + min(t, nt - 1)];
+        xi[k] = p.x; yi[k] = p.y; zi[k] = p.z; a2[k] = p.w * p.w;
+        AX[k] = AY[k] = AZ[k] = PH[k] = 0.f;
+    }
+    const int s0 = blockIdx.y * src_per_split;
+    const int s1 = min(s0 + src_per_split, n_src);
+    for (int base = s0; base < s1; base += AP_TILE) {
+        int idx = base + tid;
+        // padding source: zero mass, far away (contributes exactly 0)
+        tile[tid] = idx < s1 ? src[idx] : make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.f);
+        __syncthreads();
+        float ax[AP_TPT], ay[AP_TPT], az[AP_TPT], ph[AP_TPT];
+#pragma unroll
+        for (int k = 0; k < AP_TPT; k++) ax[k] = ay[k] = az[k] = ph[k] = 0.f;
+#pragma unroll 8
+        for (int j = 0; j < AP_TILE; j++) {
+            float4 s = tile[j];
+#pragma unroll
+            for (int k = 0; k < AP_TPT; k++) {
+                float dx = xi[k] - s.x, dy = yi[k] - s.y, dz = zi[k] - s.z;
+                float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                r2 = fmaxf(r2, a2[k]);
+                float rinv = rsqrt_approx(r2);
+                float mr = s.w * rinv;
+                float g = mr * (rinv * rinv);
+                ax[k] = fmaf(dx, g, ax[k]);
+                ay[k] = fmaf(dy, g, ay[k]);
+                az[k] = fmaf(dz, g, az[k]);
+                ph[k] += mr;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < AP_TPT; k++) { AX[k] += ax[k]; AY[k] += ay[k]; AZ[k] += az[k]; PH[k] += ph[k]; }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int k = 0; k < AP_TPT; k++) {
+        int t = tb + k * AP_THREADS + tid;
+        if (t < nt) part[(size_t)blockIdx.y * nt + t] = make_float4(AX[k], AY[k], AZ[k], PH[k]);
+    }
+}
+
+// Fixed-order sum over the source splits; removes the capped self term (-m_i/a_i), applies G and the sign of Phi.
+__global__ void __launch_bounds__(256) k_gravity_reduce(const float4* __restrict__ part, int splits, const float4* __restrict__ posh,
+                                                        const float4* __restrict__ posm, int t0, int t1, float G,
+                                                        float4* __restrict__ grav, int32_t* __restrict__ npart,
+                                                        int32_t* __restrict__ napprox) {
+    int nt = t1 - t0;
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nt) return;
+    float4 s = part[t];
+    for (int k = 1; k < splits; k++) {
+        float4 q = part[(size_t)k * nt + t];
+        s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
+    }
+    float h = posh[t0 + t].w;
+    float self = posm[t0 + t].w * rsqrt_approx(h * h);
+    grav[t0 + t] = make_float4(G * s.x, G * s.y, G * s.z, -G * (s.w - self));
+    npart[t0 + t] = 0;
+    napprox[t0 + t] = 0;
+}
+
+// FP32 FMA-pipe microbenchmark: 8 independent chains per thread.
+__global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a, float b) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; k++) v[k] = (float)(threadIdx.x + k);
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int k = 0; k < 8; k++) v[k] = fmaf(v[k], a, b);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; k++) s += v[k];
+    if (s == 12345.678f) out[0] = s;  // never true; keeps the chains alive
+}
+
+}  // namespace
+
+int sph_launch_gravity_allpairs(sphb200_ctx* c) {
+    int t0 = (int)c->t0;
+    int t1 = (c->t1 < 0 || c->t1 > c->n) ? (int)c->n : (int)c->t1;
+    int nt = t1 - t0;
+    if (nt <= 0) return SPH_OK;
+    int n = (int)c->n;
+    int tblocks = sph_div_up(nt, AP_THREADS * AP_TPT);
+    // enough blocks for >= ~6 waves of 8 resident CTAs/SM, bounded by the partial-sum buffer (cap * gpart_splits float4)
+    int want = c->sm_count * 8 * 6;
+    int splits = sph_div_up(want, tblocks);
+    int64_t mem_splits = (int64_t)c->cap * c->gpart_splits / nt;
+    if (splits > mem_splits) splits = (int)mem_splits;
+    int max_by_src = sph_div_up(n, AP_TILE);
+    if (splits > max_by_src) splits = max_by_src;
+    if (splits > 65535) splits = 65535;
+    if (splits < 1) splits = 1;
+    int per = sph_div_up(n, splits);
+    per = sph_div_up(per, AP_TILE) * AP_TILE;
+    splits = sph_div_up(n, per);
+    dim3 grid(tblocks, splits);
+    k_gravity_allpairs<<<grid, AP_THREADS, 0, c->stream>>>(c->posm, n, per, c->posh[c->cur], t0, t1, c->gpart);
+    SPH_LAUNCH_CHECK(c);
+    k_gravity_reduce<<<sph_div_up(nt, 256), 256, 0, c->stream>>>(c->gpart, splits, c->posh[c->cur], c->posm, t0, t1, c->p.G, c->grav,
+                                                                c->npart, c->napprox);
+    SPH_LAUNCH_CHECK(c);
+    return SPH_OK;
+}
+
+int sph_fp32_peak(sphb200_ctx* c, double* tflops) {
+    cudaEvent_t e0, e1;
+    SPH_CK(c, cudaEventCreate(&e0));
+    SPH_CK(c, cudaEventCreate(&e1));
+    int blocks = c->sm_count * 8, iters = 4096;
+    float* out = (float*)c->diag_d;
+    k_fma_peak<<<blocks, 256, 0, c->stream>>>(out, 64, 1.0001f, 0.5f);  // warm-up
+    SPH_LAUNCH_CHECK(c);
+    double best = 0;
+    for (int rep = 0; rep < 5; rep++) {
+        SPH_CK(c, cudaEventRecord(e0, c->stream));
+        k_fma_peak<<<blocks, 256, 0, c->stream>>>(out, iters, 1.0001f, 0.5f);
+        SPH_LAUNCH_CHECK(c);
+        SPH_CK(c, cudaEventRecord(e1, c->stream));
+        SPH_CK(c, cudaEventSynchronize(e1));
+        float ms = 0;
+        SPH_CK(c, cudaEventElapsedTime(&ms, e0, e1));
+        double flops = 2.0 * 64.0 * (double)iters * 256.0 * (double)blocks;
+        double tf = flops / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    *tflops = best;
+    return SPH_OK;
+}

@@ -1,0 +1,542 @@
+// kernels_sph.cu -- neighbor lists + density + EOS (fused), pressure gradient, integration, upload/download packing.
+//
+// Replaces: KernelSystem.FilterPairs / CalculateInteractionJob (A/Systems/KernelSystem.cs:234-335, 583-633),
+// SplineKernel (A/Util/SplineKernel.cs), DensityFieldSystem (A/Systems/DensityFieldSystem.cs:38-56),
+// PressureFieldSystem (A/Systems/PressureFieldSystem.cs:30-70), Integrator.IntegratePosition
+// (UP/Dynamics/Integrator/Integrator.cs:98-101) and VelocitySystem (A/Systems/VelocitySystem.cs:24-36).
+//
+// Numerics contract: *membership* (which j is a neighbor of i, which neighbor is inside i's own support) replays the
+// reference's fp32 op sequence exactly (non-contracted __f*_rn intrinsics, IEEE sqrt); *values* (W, grad W, sums) use
+// fast arithmetic (reciprocal multiplies, rsqrt, FMA, warp-tree sums) and are held to <= 1e-5 relative by the tests.
+#include "ctx.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr float kPI = 3.14159274f;          // Mathf.PI
+constexpr float kInvPI = 0.318309886f;
+constexpr unsigned FULL = 0xffffffffu;
+
+// ---- exact reference arithmetic (SplineKernel.cs:55-89, 115-148), used for edge decisions and the debug surface
+__device__ __forceinline__ float kernel_exact(float distance, float size) {
+    if (distance >= __fmul_rn(size, 2.0f)) return 0.0f;
+    float q = __fdiv_rn(distance, size);
+    float pi_h_cube = __fmul_rn(__fmul_rn(__fmul_rn(kPI, size), size), size);
+    if (distance < size) {
+        float q2 = __fmul_rn(q, q);
+        float num = __fadd_rn(__fsub_rn(1.0f, __fmul_rn(1.5f, q2)), __fmul_rn(0.75f, __fmul_rn(q2, q)));
+        return __fdiv_rn(num, pi_h_cube);
+    }
+    float t = __fsub_rn(2.0f, q);
+    float num = __fmul_rn(__fmul_rn(t, t), t);
+    return __fdiv_rn(num, __fmul_rn(4.0f, pi_h_cube));
+}
+__device__ __forceinline__ float kernel_deriv_exact(float distance, float size, int fix_q1) {
+    if (distance >= __fmul_rn(size, 2.0f)) return 0.0f;
+    float q = __fdiv_rn(distance, size);
+    float pi_h_4th = __fmul_rn(__fmul_rn(__fmul_rn(__fmul_rn(kPI, size), size), size), size);
+    if (distance < size) {
+        float q2 = __fmul_rn(q, q);
+        float lead = fix_q1 ? -3.0f : 3.0f;
+        float num = __fadd_rn(__fmul_rn(lead, q), __fmul_rn(2.25f, q2));
+        return __fdiv_rn(num, pi_h_4th);
+    }
+    float t = __fsub_rn(2.0f, q);
+    float num = __fmul_rn(__fmul_rn(-3.0f, t), t);
+    return __fdiv_rn(num, __fmul_rn(4.0f, pi_h_4th));
+}
+
+// ---- fast value arithmetic
+// M4 spline via the identity 4(1 - 1.5q^2 + 0.75q^3) = (2-q)^3 - 4(1-q)^3 (branch-free), norm = 1/(pi h^3)
+__device__ __forceinline__ float w_fast(float r, float hinv) {
+    float q = r * hinv;
+    float t1 = fmaxf(2.0f - q, 0.0f), t2 = fmaxf(1.0f - q, 0.0f);
+    float c = hinv * hinv * hinv * (0.25f * kInvPI);
+    return c * (t1 * t1 * t1 - 4.0f * (t2 * t2 * t2));
+}
+// (dW/dr)/r with the reference's inner branch (quirk Q1: +3q unless lead = -3):
+//   q<1 : (lead*q + 2.25 q^2)/(pi h^4)/r = (lead + 2.25 q) / (pi h^5);   1<=q<2 : -0.75 (2-q)^2 /(pi h^4) / r
+__device__ __forceinline__ float dwr_fast(float r, float rinv, float hinv, float lead) {
+    float q = r * hinv;
+    float h2 = hinv * hinv;
+    float c4 = h2 * h2 * kInvPI;
+    float t = 2.0f - q;
+    float inner = (lead + 2.25f * q) * hinv * c4;
+    float outer = -0.75f * t * t * c4 * rinv;
+    return q < 1.0f ? inner : (q < 2.0f ? outer : 0.0f);
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1: neighbor lists + density + EOS.  One warp per target particle; the 27 neighbor cells of the target's cell are
+// split over four 8-lane groups, lanes stride over the (contiguous, sorted) particles of a cell with coalesced
+// float4 loads; survivors are compacted into the target's list row with ballot/popc.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int K1_WARPS = 8;
+constexpr int K1_TPW = 4;  // consecutive targets per warp (L1 reuse of the neighbor cells)
+
+__global__ void __launch_bounds__(K1_WARPS * 32) k_neighbors_density(
+    const float4* __restrict__ posh, const float4* __restrict__ posm, const uint32_t* __restrict__ keys,
+    const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, const sph_GridParams* __restrict__ g,
+    int t0, int t1, int kmax, float Keos, uint32_t* __restrict__ nlist, int32_t* __restrict__ ncount,
+    int32_t* __restrict__ nown, float* __restrict__ rho, float* __restrict__ press, float* __restrict__ cvol,
+    int32_t* __restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    const int warp = (blockIdx.x * K1_WARPS + (threadIdx.x >> 5));
+    const int bits = g->bits;
+    const int shift = 3 * (10 - bits);
+    const int dim = 1 << bits;
+    const int grp = lane >> 3, sl = lane & 7;
+
+    for (int tt = 0; tt < K1_TPW; tt++) {
+        int t = t0 + warp * K1_TPW + tt;
+        if (t >= t1) return;
+        const float4 pi = posh[t];
+        const float hi = pi.w;
+        const float hi2 = __fmul_rn(hi, 2.0f);
+        const float hinv_i = 1.0f / hi;
+        uint32_t ck = keys[t] >> shift;
+        int cx = (int)compact10(ck), cy = (int)compact10(ck >> 1), cz = (int)compact10(ck >> 2);
+        uint32_t s_l = 0, e_l = 0;
+        if (lane < 27) {
+            int nx = cx + (lane % 3) - 1, ny = cy + ((lane / 3) % 3) - 1, nz = cz + (lane / 9) - 1;
+            if (nx >= 0 && ny >= 0 && nz >= 0 && nx < dim && ny < dim && nz < dim) {
+                uint32_t nk = expand10((uint32_t)nx) | (expand10((uint32_t)ny) << 1) | (expand10((uint32_t)nz) << 2);
+                s_l = cell_start[nk];
+                e_l = cell_end[nk];
+            }
+        }
+        float rho_l = 0.f;
+        int own_l = 0;
+        int count = 0;
+        uint32_t* row = nlist + (size_t)t * kmax;
+        for (int round = 0; round < 7; round++) {
+            int c = round * 4 + grp;
+            uint32_t s = __shfl_sync(FULL, s_l, c & 31), e = __shfl_sync(FULL, e_l, c & 31);
+            if (c >= 27) { s = 0; e = 0; }
+            uint32_t j = s + sl;
+            while (__any_sync(FULL, j < e)) {
+                bool keep = false, in_i = false;
+                float r = 0.f, hj = 1.f;
+                if (j < e && j != (uint32_t)t) {
+                    float4 pj = posh[j];
+                    hj = pj.w;
+                    float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
+                    float d2 = dot3_rn(dx, dy, dz);
+                    float sz = fmaxf(hi, hj);
+                    // SplineKernel.Interacts (SplineKernel.cs:47-53): d2 < size*size*Kappa*Kappa
+                    if (d2 < __fmul_rn(__fmul_rn(__fmul_rn(sz, sz), 2.0f), 2.0f)) {
+                        r = __fsqrt_rn(d2);
+                        if (sz < 1.0e5f) {
+                            // keep rule KernelSymmetric.w > 0 (KernelSystem.cs:269,283): with h < 1e5 no underflow is
+                            // possible, so W(r,h) > 0 <=> r < 2h (SplineKernel.cs:62)
+                            in_i = r < hi2;
+                            keep = in_i || (r < __fmul_rn(hj, 2.0f));
+                        } else {
+                            float wi = kernel_exact(r, hi), wj = kernel_exact(r, hj);
+                            in_i = wi > 0.0f;
+                            keep = __fmul_rn(__fadd_rn(wi, wj), 0.5f) > 0.0f;
+                        }
+                    }
+                }
+                unsigned bal = __ballot_sync(FULL, keep);
+                if (keep) {
+                    float hinv_j = __fdividef(1.0f, hj);
+                    float wsym = 0.5f * (w_fast(r, hinv_i) + w_fast(r, hinv_j));
+                    float mj = posm[j].w;
+                    rho_l = fmaf(mj, wsym, rho_l);
+                    own_l += in_i ? 1 : 0;
+                    int slot = count + __popc(bal & ((1u << lane) - 1u));
+                    if (slot < kmax) row[slot] = j;
+                }
+                count += __popc(bal);
+                j += 8;
+            }
+        }
+        float rsum = warp_sum(rho_l);
+        int own = warp_sum_i(own_l);
+        if (lane == 0) {
+            // self term m_i * Kernel(0,h_i) (DensityFieldSystem.cs:45), exact: 1/(pi h^3)
+            float mi = posm[t].w;
+            float w0 = __fdiv_rn(1.0f, __fmul_rn(__fmul_rn(__fmul_rn(kPI, hi), hi), hi));
+            float d = __fadd_rn(__fmul_rn(mi, w0), rsum);
+            float P = __fmul_rn(__fmul_rn(Keos, d), d);  // PressureFieldSystem.cs:31-33
+            rho[t] = d;
+            press[t] = P;
+            cvol[t] = __fmul_rn(__fdiv_rn(mi, d), P);    // m_j / rho_j * P_j (PressureFieldSystem.cs:65)
+            ncount[t] = count;
+            nown[t] = own;
+            if (count > kmax) atomicMax(&err[ERR_NEIGHBOR_OVERFLOW], count);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2: pressure gradient over the materialised lists (16 lanes per target).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int K2_LPT = 16;
+
+__global__ void __launch_bounds__(256) k_pressure_grad(const float4* __restrict__ posh, const float* __restrict__ cvol,
+                                                       const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
+                                                       int t0, int t1, int kmax, float lead, float4* __restrict__ gradp) {
+    const int sub = threadIdx.x & (K2_LPT - 1);
+    const int t = t0 + (blockIdx.x * blockDim.x + threadIdx.x) / K2_LPT;
+    const bool live = t < t1;
+    float ax = 0.f, ay = 0.f, az = 0.f;
+    if (live) {
+        const float4 pi = posh[t];
+        const float hinv_i = 1.0f / pi.w;
+        const int cnt = min(ncount[t], kmax);
+        const uint32_t* row = nlist + (size_t)t * kmax;
+        for (int k = sub; k < cnt; k += K2_LPT) {
+            uint32_t j = row[k];
+            float4 pj = posh[j];
+            float cj = cvol[j];
+            float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+            float r2 = dx * dx + dy * dy + dz * dz;
+            float rinv = r2 > 0.f ? rsqrtf(r2) : 0.f;   // coincident distinct particles: gradient 0 (reference: NaN, quirk Q9)
+            float r = r2 * rinv;
+            float hinv_j = __fdividef(1.0f, pj.w);
+            float s = 0.5f * (dwr_fast(r, rinv, hinv_i, lead) + dwr_fast(r, rinv, hinv_j, lead)) * cj;
+            ax = fmaf(dx, s, ax); ay = fmaf(dy, s, ay); az = fmaf(dz, s, az);
+        }
+    }
+#pragma unroll
+    for (int o = K2_LPT / 2; o > 0; o >>= 1) {
+        ax += __shfl_xor_sync(FULL, ax, o); ay += __shfl_xor_sync(FULL, ay, o); az += __shfl_xor_sync(FULL, az, o);
+    }
+    if (live && sub == 0) gradp[t] = make_float4(ax, ay, az, 0.f);
+}
+
+// Near-pair correction of the all-pairs gravity kernel (kernels_gravity.cu): for neighbors with r < a = h_i add
+// "Dyer & Ip softened law minus the capped Newtonian value the all-pairs kernel already summed"
+// (GravityFieldSystem.cs:340-347).  Every such pair is in i's list because r < h_i < 2 max(h_i,h_j).
+__global__ void __launch_bounds__(256) k_gravity_near(const float4* __restrict__ posh, const float4* __restrict__ posm,
+                                                      const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
+                                                      int t0, int t1, int kmax, float G, float4* __restrict__ grav) {
+    const int sub = threadIdx.x & (K2_LPT - 1);
+    const int t = t0 + (blockIdx.x * blockDim.x + threadIdx.x) / K2_LPT;
+    const bool live = t < t1;
+    float gx = 0.f, gy = 0.f, gz = 0.f, gp = 0.f;
+    if (live) {
+        const float4 pi = posh[t];
+        const float hinv_i = 1.0f / pi.w;
+        const float a2 = pi.w * pi.w;
+        const int cnt = min(ncount[t], kmax);
+        const uint32_t* row = nlist + (size_t)t * kmax;
+        for (int k = sub; k < cnt; k += K2_LPT) {
+            uint32_t j = row[k];
+            float4 pj = posm[j];
+            float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
+            float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));   // same expression as the all-pairs kernel
+            if (r2 < a2) {
+                float r = r2 > 0.f ? r2 * rsqrtf(r2) : 0.f;
+                float x = r * hinv_i, x2 = x * x, x3 = x2 * x;
+                float ma = pj.w * hinv_i;
+                float mg = ma * hinv_i * hinv_i * (7.0f - 9.0f * x + 2.0f * x3);
+                gx = fmaf(dx, mg, gx); gy = fmaf(dy, mg, gy); gz = fmaf(dz, mg, gz);
+                gp -= ma * (1.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
+            }
+        }
+    }
+#pragma unroll
+    for (int o = K2_LPT / 2; o > 0; o >>= 1) {
+        gx += __shfl_xor_sync(FULL, gx, o); gy += __shfl_xor_sync(FULL, gy, o);
+        gz += __shfl_xor_sync(FULL, gz, o); gp += __shfl_xor_sync(FULL, gp, o);
+    }
+    if (live && sub == 0) {
+        float4 g0 = grav[t];
+        grav[t] = make_float4(g0.x + G * gx, g0.y + G * gy, g0.z + G * gz, g0.w + G * gp);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Integrate: x += v*dt (old v), v += (-gradP/rho - gradPhi)*dt ; exact op order of the reference.
+// ------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_integrate(float4* __restrict__ posh, float4* __restrict__ velm,
+                                                   const float* __restrict__ rho, const float4* __restrict__ gradp,
+                                                   const float4* __restrict__ grav, int t0, int t1, float dt) {
+    int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= t1) return;
+    float4 p = posh[t], v = velm[t], gp = gradp[t], g = grav[t];
+    float d = rho[t];
+    p.x = __fadd_rn(p.x, __fmul_rn(v.x, dt));
+    p.y = __fadd_rn(p.y, __fmul_rn(v.y, dt));
+    p.z = __fadd_rn(p.z, __fmul_rn(v.z, dt));
+    float ax = __fsub_rn(__fdiv_rn(-gp.x, d), g.x);
+    float ay = __fsub_rn(__fdiv_rn(-gp.y, d), g.y);
+    float az = __fsub_rn(__fdiv_rn(-gp.z, d), g.z);
+    v.x = __fadd_rn(v.x, __fmul_rn(ax, dt));
+    v.y = __fadd_rn(v.y, __fmul_rn(ay, dt));
+    v.z = __fadd_rn(v.z, __fmul_rn(az, dt));
+    posh[t] = p;
+    velm[t] = v;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Upload / download packing
+// ------------------------------------------------------------------------------------------------------------
+// staging (device): pos[3n] vel[3n] mass[n] h[n] nown[n]
+__global__ void __launch_bounds__(256) k_pack_upload(const float* __restrict__ st, int n, int has_nown, float4* __restrict__ posh,
+                                                     float4* __restrict__ velm, uint32_t* __restrict__ orig,
+                                                     int32_t* __restrict__ nown) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* pos = st;
+    const float* vel = st + 3 * (size_t)n;
+    const float* mass = st + 6 * (size_t)n;
+    const float* h = st + 7 * (size_t)n;
+    const int32_t* no = (const int32_t*)(st + 8 * (size_t)n);
+    posh[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], h[i]);
+    velm[i] = make_float4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], mass[i]);
+    orig[i] = (uint32_t)i;
+    nown[i] = has_nown ? no[i] : 0;
+}
+
+__global__ void __launch_bounds__(256) k_unpack_field(int field, int n, const uint32_t* __restrict__ orig,
+                                                      const float4* __restrict__ posh, const float4* __restrict__ velm,
+                                                      const float* __restrict__ rho, const float* __restrict__ press,
+                                                      const float4* __restrict__ gradp, const float4* __restrict__ grav,
+                                                      const int32_t* __restrict__ npart, const int32_t* __restrict__ napprox,
+                                                      const int32_t* __restrict__ ncount, const int32_t* __restrict__ nown,
+                                                      float* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    size_t b = orig[i];
+    switch (field) {
+        case SPH_FIELD_TRANSLATION: { float4 p = posh[i]; out[3 * b] = p.x; out[3 * b + 1] = p.y; out[3 * b + 2] = p.z; break; }
+        case SPH_FIELD_VELOCITY: { float4 v = velm[i]; out[3 * b] = v.x; out[3 * b + 1] = v.y; out[3 * b + 2] = v.z; break; }
+        case SPH_FIELD_MASS: out[b] = velm[i].w; break;
+        case SPH_FIELD_SMOOTHING: out[2 * b] = posh[i].w; ((int32_t*)out)[2 * b + 1] = nown[i]; break;
+        case SPH_FIELD_DENSITY: out[b] = rho[i]; break;
+        case SPH_FIELD_PRESSURE: out[b] = press[i]; break;
+        case SPH_FIELD_PRESSURE_GRAD: { float4 q = gradp[i]; out[3 * b] = q.x; out[3 * b + 1] = q.y; out[3 * b + 2] = q.z; break; }
+        case SPH_FIELD_GRAVITY: {
+            float4 q = grav[i];
+            out[6 * b] = q.x; out[6 * b + 1] = q.y; out[6 * b + 2] = q.z; out[6 * b + 3] = q.w;
+            ((int32_t*)out)[6 * b + 4] = npart[i]; ((int32_t*)out)[6 * b + 5] = napprox[i];
+            break;
+        }
+        case SPH_FIELD_NEIGHBOR_COUNT: ((int32_t*)out)[b] = ncount[i]; break;
+    }
+}
+
+// One warp per sorted slot: map the list row to body indices, bitonic-sort ascending, write at offsets[body].
+__global__ void __launch_bounds__(128) k_neighbor_rows(const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
+                                                       const uint32_t* __restrict__ orig, const int64_t* __restrict__ offsets,
+                                                       int n, int kmax, int p2, int32_t* __restrict__ nbr) {
+    extern __shared__ uint32_t sm[];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    int t = blockIdx.x * 4 + w;
+    if (t >= n) return;
+    uint32_t* a = sm + (size_t)w * p2;
+    int cnt = min(ncount[t], kmax);
+    for (int k = lane; k < p2; k += 32) a[k] = k < cnt ? orig[nlist[(size_t)t * kmax + k]] : 0xffffffffu;
+    __syncwarp();
+    for (int size = 2; size <= p2; size <<= 1)
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int k = lane; k < p2; k += 32) {
+                int partner = k ^ stride;
+                if (partner > k) {
+                    bool up = (k & size) == 0;
+                    uint32_t x = a[k], y = a[partner];
+                    if ((x > y) == up) { a[k] = y; a[partner] = x; }
+                }
+            }
+            __syncwarp();
+        }
+    int64_t o = offsets[orig[t]];
+    for (int k = lane; k < cnt; k += 32) nbr[o + k] = (int32_t)a[k];
+}
+
+__global__ void __launch_bounds__(256) k_inverse_map(const uint32_t* __restrict__ orig, int n, uint32_t* __restrict__ inv) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) inv[orig[i]] = (uint32_t)i;
+}
+
+// Debug/parity surface: the reference's interaction record, computed with the exact op sequence
+// (KernelSystem.cs:305-334, SplineKernel.cs:102-111).  One thread per body.
+__global__ void __launch_bounds__(128) k_interactions(const float4* __restrict__ posh, const uint32_t* __restrict__ inv, int n,
+                                                      const int64_t* __restrict__ offsets, const int32_t* __restrict__ nbr,
+                                                      int fix_q1, sph_ParticleInteraction* __restrict__ out) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n) return;
+    float4 pi = posh[inv[b]];
+    for (int64_t e = offsets[b]; e < offsets[b + 1]; e++) {
+        int jb = nbr[e];
+        float4 pj = posh[inv[jb]];
+        float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
+        float dist = __fsqrt_rn(dot3_rn(dx, dy, dz));
+        float si = __fdiv_rn(kernel_deriv_exact(dist, pi.w, fix_q1), dist);
+        float sj = __fdiv_rn(kernel_deriv_exact(dist, pj.w, fix_q1), dist);
+        float wi = kernel_exact(dist, pi.w), wj = kernel_exact(dist, pj.w);
+        float ki[4] = {__fmul_rn(dx, si), __fmul_rn(dy, si), __fmul_rn(dz, si), wi};
+        float kj[4] = {__fmul_rn(dx, sj), __fmul_rn(dy, sj), __fmul_rn(dz, sj), wj};
+        sph_ParticleInteraction it;
+        it.otherIndex = jb; it.otherVersion = 1;
+        for (int k = 0; k < 4; k++) { it.kernelThis[k] = ki[k]; it.kernelSymmetric[k] = __fmul_rn(__fadd_rn(ki[k], kj[k]), 0.5f); }
+        out[e] = it;
+    }
+}
+
+// Diagnostics: block reduce in double, one atomicAdd per block per quantity.
+__global__ void __launch_bounds__(256) k_diagnostics(const float4* __restrict__ posh, const float4* __restrict__ velm,
+                                                     const float* __restrict__ rho, const float4* __restrict__ grav,
+                                                     const int32_t* __restrict__ ncount, int n, float Keos, double* __restrict__ out,
+                                                     int* __restrict__ maxcount) {
+    double v[11] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int mc = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        float4 p = posh[i], u = velm[i];
+        double m = u.w;
+        v[0] += m;
+        v[1] += m * u.x; v[2] += m * u.y; v[3] += m * u.z;
+        v[4] += m * ((double)p.y * u.z - (double)p.z * u.y);
+        v[5] += m * ((double)p.z * u.x - (double)p.x * u.z);
+        v[6] += m * ((double)p.x * u.y - (double)p.y * u.x);
+        v[7] += 0.5 * m * ((double)u.x * u.x + (double)u.y * u.y + (double)u.z * u.z);
+        v[8] += 0.5 * m * (double)grav[i].w;
+        v[9] += m * (double)Keos * (double)rho[i];
+        v[10] += (double)ncount[i];
+        mc = max(mc, ncount[i]);
+    }
+    __shared__ double s[11][8];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int k = 0; k < 11; k++) {
+        double x = v[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+        if (lane == 0) s[k][w] = x;
+    }
+    for (int o = 16; o > 0; o >>= 1) mc = max(mc, __shfl_xor_sync(FULL, mc, o));
+    if (lane == 0) atomicMax(maxcount, mc);
+    __syncthreads();
+    if (threadIdx.x < 11) {
+        double x = 0;
+        for (int j = 0; j < 8; j++) x += s[threadIdx.x][j];
+        atomicAdd(&out[threadIdx.x], x);
+    }
+}
+
+}  // namespace
+
+// ---- launchers ------------------------------------------------------------------------------------------------
+static inline void target_range(sphb200_ctx* c, int& t0, int& t1) {
+    t0 = (int)c->t0;
+    t1 = (c->t1 < 0 || c->t1 > c->n) ? (int)c->n : (int)c->t1;
+    if (t0 > t1) t0 = t1;
+}
+
+int sph_launch_neighbors_density(sphb200_ctx* c) {
+    int t0, t1; target_range(c, t0, t1);
+    int nt = t1 - t0;
+    if (nt <= 0) return SPH_OK;
+    int per_block = K1_WARPS * K1_TPW;
+    k_neighbors_density<<<sph_div_up(nt, per_block), K1_WARPS * 32, 0, c->stream>>>(
+        c->posh[c->cur], c->posm, c->keys[1], c->cell_start, c->cell_end, c->grid_d, t0, t1, c->p.max_neighbors, c->p.K,
+        c->nlist, c->ncount, c->nown, c->rho, c->press, c->cvol, c->err_d);
+    SPH_LAUNCH_CHECK(c);
+    return SPH_OK;
+}
+
+int sph_launch_pressure(sphb200_ctx* c) {
+    int t0, t1; target_range(c, t0, t1);
+    int nt = t1 - t0;
+    if (nt <= 0) return SPH_OK;
+    float lead = (c->p.flags & SPH_FLAG_FIX_KERNEL_DERIV_SIGN) ? -3.0f : 3.0f;
+    int tpb = 256 / K2_LPT;
+    k_pressure_grad<<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->cvol, c->nlist, c->ncount, t0, t1,
+                                                                c->p.max_neighbors, lead, c->gradp);
+    SPH_LAUNCH_CHECK(c);
+    return SPH_OK;
+}
+
+int sph_launch_gravity_near(sphb200_ctx* c) {
+    int t0, t1; target_range(c, t0, t1);
+    int nt = t1 - t0;
+    if (nt <= 0) return SPH_OK;
+    int tpb = 256 / K2_LPT;
+    k_gravity_near<<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->posm, c->nlist, c->ncount, t0, t1,
+                                                               c->p.max_neighbors, c->p.G, c->grav);
+    SPH_LAUNCH_CHECK(c);
+    return SPH_OK;
+}
+
+int sph_launch_integrate(sphb200_ctx* c, float dt) {
+    int t0, t1; target_range(c, t0, t1);
+    int nt = t1 - t0;
+    if (nt <= 0) return SPH_OK;
+    k_integrate<<<sph_div_up(nt, 256), 256, 0, c->stream>>>(c->posh[c->cur], c->velm[c->cur], c->rho, c->gradp, c->grav, t0, t1, dt);
+    SPH_LAUNCH_CHECK(c);
+    return SPH_OK;
+}
+
+int sph_launch_pack_upload(sphb200_ctx* c, int64_t n, bool has_nown) {
+    k_pack_upload<<<sph_div_up(n, 256), 256, 0, c->stream>>>((const float*)c->stage_d, (int)n, has_nown ? 1 : 0, c->posh[0],
+                                                            c->velm[0], c->orig[0], c->nown);
+    SPH_LAUNCH_CHECK(c);
+    return SPH_OK;
+}
+
+int sph_launch_unpack_field(sphb200_ctx* c, int field, int* elem_bytes) {
+    static const int words[SPH_FIELD_COUNT_] = {3, 3, 1, 2, 1, 1, 3, 6, 1};
+    if (field < 0 || field >= SPH_FIELD_COUNT_) return SPH_ERR_INVALID_ARG;
+    *elem_bytes = words[field] * 4;
+    int n = (int)c->n;
+    k_unpack_field<<<sph_div_up(n, 256), 256, 0, c->stream>>>(field, n, c->orig[c->cur], c->posh[c->cur], c->velm[c->cur], c->rho,
+                                                             c->press, c->gradp, c->grav, c->npart, c->napprox, c->ncount,
+                                                             c->nown, (float*)c->stage_d);
+    SPH_LAUNCH_CHECK(c);
+    return SPH_OK;
+}
+
+// offsets_d: int64[n+1] in body order (device); rows_d: int32[total]
+int sph_launch_neighbor_rows_sorted(sphb200_ctx* c, int32_t* rows_d) {
+    int n = (int)c->n;
+    int kmax = c->p.max_neighbors;
+    int p2 = 32;
+    while (p2 < kmax) p2 <<= 1;
+    const int64_t* offsets_d = (const int64_t*)c->stage_d;
+    k_neighbor_rows<<<sph_div_up(n, 4), 128, 4 * p2 * sizeof(uint32_t), c->stream>>>(c->nlist, c->ncount, c->orig[c->cur], offsets_d, n,
+                                                                                    kmax, p2, rows_d);
+    SPH_LAUNCH_CHECK(c);
+    return SPH_OK;
+}
+
+int sph_launch_interactions(sphb200_ctx* c, int64_t total, const int64_t* offsets_d, const int32_t* nbr_d,
+                            sph_ParticleInteraction* out_d) {
+    (void)total;
+    int n = (int)c->n;
+    uint32_t* inv = c->idx[0];  // scratch (free outside build_neighbors)
+    k_inverse_map<<<sph_div_up(n, 256), 256, 0, c->stream>>>(c->orig[c->cur], n, inv);
+    SPH_LAUNCH_CHECK(c);
+    k_interactions<<<sph_div_up(n, 128), 128, 0, c->stream>>>(c->posh[c->cur], inv, n, offsets_d, nbr_d,
+                                                             (c->p.flags & SPH_FLAG_FIX_KERNEL_DERIV_SIGN) ? 1 : 0, out_d);
+    SPH_LAUNCH_CHECK(c);
+    return SPH_OK;
+}
+
+int sph_launch_diagnostics(sphb200_ctx* c, double* out12) {
+    int n = (int)c->n;
+    SPH_CK(c, cudaMemsetAsync(c->diag_d, 0, 16 * sizeof(double), c->stream));
+    int* maxc = (int*)(c->diag_d + 12);
+    int blocks = min(sph_div_up(n, 256), c->sm_count * 4);
+    k_diagnostics<<<blocks, 256, 0, c->stream>>>(c->posh[c->cur], c->velm[c->cur], c->rho, c->grav, c->ncount, n, c->p.K, c->diag_d, maxc);
+    SPH_LAUNCH_CHECK(c);
+    double tmp[16];
+    SPH_CK(c, cudaMemcpyAsync(tmp, c->diag_d, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    SPH_CK(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 10; k++) out12[k] = tmp[k];
+    out12[10] = n > 0 ? tmp[10] / n : 0.0;
+    out12[11] = (double)(*(int*)&tmp[12]);
+    return SPH_OK;
+}

@@ -1,0 +1,258 @@
+// kernels_tree.cu -- Barnes-Hut tree gravity on an LBVH built over the Morton-sorted particles.
+//
+// Replaces: the Unity.Physics 4-ary broadphase BVH used as a Barnes-Hut tree
+// (UP/Collision/Geometry/BoundingVolumeHierarchy.cs:40-83, ...Builder.cs:416-467), GenerateMomentsSTJob
+// (A/Systems/GravityFieldSystem.cs:453-555), the per-particle tree walk (:133-215), the Bmax MAC (:229-247) and
+// the moment arithmetic (:367-443).  Tree *shape* is not a parity target; what is kept exactly is
+// the reference's moment/MAC arithmetic and walk semantics, executed on this LBVH.  oracle/sph_oracle.cpp
+// (orc_lbvh_topology / orc_lbvh_moments / orc_tree_walk) builds the identical tree on the CPU.
+//
+// Node ids: internal 0..n-2 (root 0), leaf of sorted slot s -> n-1+s.  A node holding <= leaf_max particles plays
+// the role of a reference leaf node (never descended; bodies summed directly, including the target itself, Q3).
+//
+// Walk mapping: one warp = 32 consecutive (spatially coherent) sorted targets sharing ONE traversal stack in shared
+// memory; each stack entry carries the mask of lanes still descending that subtree, so every lane sees exactly the
+// node sequence of its private depth-first walk (per-particle MAC, same summation order as the oracle) while node
+// loads are warp-uniform broadcasts and control flow is warp-coherent.
+#include "ctx.cuh"
+#include <math.h>
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+__device__ __forceinline__ int delta_fn(const uint32_t* __restrict__ keys, int n, int i, int j) {
+    if (j < 0 || j >= n) return -1;
+    uint32_t a = keys[i], b = keys[j];
+    return a == b ? 32 + __clz((uint32_t)i ^ (uint32_t)j) : __clz(a ^ b);
+}
+
+// Karras (2012) binary radix tree over (key, slot) -- integer-only, identical to orc_lbvh_topology.
+__global__ void __launch_bounds__(256) k_lbvh_topology(const uint32_t* __restrict__ keys, int n, int2* __restrict__ child,
+                                                       int2* __restrict__ range, int32_t* __restrict__ parent) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    child[n - 1 + i] = make_int2(-1, -1);
+    range[n - 1 + i] = make_int2(i, i);
+    if (i == 0) parent[0] = -1;
+    if (i >= n - 1) return;
+    int d = (delta_fn(keys, n, i, i + 1) - delta_fn(keys, n, i, i - 1)) > 0 ? 1 : -1;
+    int dmin = delta_fn(keys, n, i, i - d);
+    int lmax = 2;
+    while (delta_fn(keys, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax / 2; t >= 1; t /= 2)
+        if (delta_fn(keys, n, i, i + (l + t) * d) > dmin) l += t;
+    int j = i + l * d;
+    int dnode = delta_fn(keys, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) / 2;; t = (t + 1) / 2) {
+        if (delta_fn(keys, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t == 1) break;
+    }
+    int gamma = i + s * d + min(d, 0);
+    int lo = min(i, j), hi = max(i, j);
+    int lc = (lo == gamma) ? (n - 1 + gamma) : gamma;
+    int rc = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+    child[i] = make_int2(lc, rc);
+    range[i] = make_int2(lo, hi);
+    parent[lc] = i;
+    parent[rc] = i;
+}
+
+// GravitationalMoment.Accumulate (GravityFieldSystem.cs:398-411), exact op order
+__device__ __forceinline__ void moment_accumulate(float4& mo, float cx, float cy, float cz, float first) {
+    if (first != 0.0f) {
+        float nm = __fadd_rn(mo.w, first);
+        mo.x = __fdiv_rn(__fadd_rn(__fmul_rn(mo.x, mo.w), __fmul_rn(cx, first)), nm);
+        mo.y = __fdiv_rn(__fadd_rn(__fmul_rn(mo.y, mo.w), __fmul_rn(cy, first)), nm);
+        mo.z = __fdiv_rn(__fadd_rn(__fmul_rn(mo.z, mo.w), __fmul_rn(cz, first)), nm);
+        mo.w = nm;
+    }
+}
+
+// Moments + MAC boxes.  Small nodes (<= leaf_max bodies) are evaluated directly from their particle range (reference
+// leaf rule); larger nodes are finished bottom-up by the second thread to arrive (fixed left-then-right order).
+__global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ posh, const float4* __restrict__ velm, int n,
+                                                    const int2* __restrict__ child, const int2* __restrict__ range,
+                                                    const int32_t* __restrict__ parent, int leaf_max, int aabb_mode, float dt,
+                                                    int32_t* __restrict__ flag, float4* mom, float4* nlo, float4* nhi) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 2 * n - 1) return;
+    int2 rg = range[k];
+    if (rg.y - rg.x + 1 > leaf_max) return;
+    float4 mo = make_float4(0.f, 0.f, 0.f, 0.f);
+    float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+    const float margin = 0.1f * 0.5f;  // CollisionTolerance * 0.5 (Broadphase.cs:200, CollisionWorld.cs:32)
+    for (int s = rg.x; s <= rg.y; s++) {
+        float4 p = posh[s], v = velm[s];
+        moment_accumulate(mo, p.x, p.y, p.z, v.w);
+        float x[3] = {p.x, p.y, p.z}, vel[3] = {v.x, v.y, v.z};
+        for (int c = 0; c < 3; c++) {
+            float bl, bh;
+            if (aabb_mode == 1) { bl = x[c]; bh = x[c]; }
+            else {
+                // sphere AABB radius 2h (Physics_SphereCollider.cs:129-137), swept by v*dt (Motion.cs:142-146), +-margin
+                float rad = __fmul_rn(p.w, 2.0f);
+                bl = __fsub_rn(x[c], rad); bh = __fadd_rn(x[c], rad);
+                float lin = __fmul_rn(vel[c], dt);
+                bh = __fadd_rn(fmaxf(bh, __fadd_rn(bh, lin)), 0.0f);
+                bl = __fsub_rn(fminf(bl, __fadd_rn(bl, lin)), 0.0f);
+                bl = __fsub_rn(bl, margin); bh = __fadd_rn(bh, margin);
+            }
+            lo[c] = fminf(lo[c], bl); hi[c] = fmaxf(hi[c], bh);
+        }
+    }
+    mom[k] = mo;
+    nlo[k] = make_float4(lo[0], lo[1], lo[2], __int_as_float(rg.x));
+    nhi[k] = make_float4(hi[0], hi[1], hi[2], __int_as_float(rg.y));
+    int cur = k;
+    while (true) {
+        int p = parent[cur];
+        if (p < 0) break;
+        int2 prg = range[p];
+        if (prg.y - prg.x + 1 <= leaf_max) break;  // parent is a small node, evaluated by its own thread
+        __threadfence();
+        if (atomicAdd(&flag[p], 1) == 0) break;    // first arrival: sibling not ready yet
+        int2 ch = child[p];
+        float4 ml = __ldcg(&mom[ch.x]), mr = __ldcg(&mom[ch.y]);
+        float4 ll = __ldcg(&nlo[ch.x]), lr = __ldcg(&nlo[ch.y]);
+        float4 hl = __ldcg(&nhi[ch.x]), hr = __ldcg(&nhi[ch.y]);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        moment_accumulate(acc, ml.x, ml.y, ml.z, ml.w);  // GravityFieldSystem.cs:513-521, children in Data order
+        moment_accumulate(acc, mr.x, mr.y, mr.z, mr.w);
+        mom[p] = acc;
+        nlo[p] = make_float4(fminf(ll.x, lr.x), fminf(ll.y, lr.y), fminf(ll.z, lr.z), __int_as_float(prg.x));
+        nhi[p] = make_float4(fmaxf(hl.x, hr.x), fmaxf(hl.y, hr.y), fmaxf(hl.z, hr.z), __int_as_float(prg.y));
+        cur = p;
+    }
+}
+
+constexpr int TW_WARPS = 8;
+
+__global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __restrict__ posh, const float4* __restrict__ posm,
+                                                             const int2* __restrict__ child, const float4* __restrict__ mom,
+                                                             const float4* __restrict__ nlo, const float4* __restrict__ nhi,
+                                                             int t0, int t1, int leaf_max, float theta2, float G,
+                                                             float4* __restrict__ grav, int32_t* __restrict__ npart,
+                                                             int32_t* __restrict__ napprox, int32_t* __restrict__ err) {
+    __shared__ int2 stack[TW_WARPS][SPH_TREE_STACK];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int t = t0 + (blockIdx.x * TW_WARPS + w) * 32 + lane;
+    const bool active = t < t1;
+    const float4 pi = posh[active ? t : (t1 - 1)];
+    const float a = pi.w, a2 = a * a, ainv = 1.0f / a;
+    float gx = 0.f, gy = 0.f, gz = 0.f, gp = 0.f;
+    int np = 0, na = 0;
+    unsigned m0 = __ballot_sync(FULL, active);
+    if (m0 == 0) return;
+    int sp = 0;
+    if (lane == 0) stack[w][0] = make_int2(0, (int)m0);
+    sp = 1;
+    __syncwarp();
+    while (sp > 0) {
+        int2 e = stack[w][--sp];
+        __syncwarp();
+        const int k = e.x;
+        const unsigned mask = (unsigned)e.y;
+        const float4 mo = __ldg(&mom[k]);
+        const float4 lo = __ldg(&nlo[k]);
+        const float4 hi = __ldg(&nhi[k]);
+        const bool mine = (mask >> lane) & 1u;
+        // AcceptApproximation (GravityFieldSystem.cs:229-247), exact op order
+        float dx = __fsub_rn(pi.x, mo.x), dy = __fsub_rn(pi.y, mo.y), dz = __fsub_rn(pi.z, mo.z);
+        float r_sq = dot3_rn(dx, dy, dz);
+        float bx = fmaxf(__fsub_rn(hi.x, mo.x), __fsub_rn(mo.x, lo.x));
+        float by = fmaxf(__fsub_rn(hi.y, mo.y), __fsub_rn(mo.y, lo.y));
+        float bz = fmaxf(__fsub_rn(hi.z, mo.z), __fsub_rn(mo.z, lo.z));
+        float b_sq = dot3_rn(bx, by, bz);
+        const bool acc = mine && (__fdiv_rn(b_sq, r_sq) < theta2);
+        if (acc) {
+            // GravitationalMoment.GravityContribution (M2P, :428-442)
+            float rinv = rsqrt_approx(r_sq);
+            float mr = mo.w * rinv;
+            float g = mr * rinv * rinv;
+            gx = fmaf(dx, g, gx); gy = fmaf(dy, g, gy); gz = fmaf(dz, g, gz);
+            gp -= mr;
+            na++;
+        }
+        const unsigned rej = __ballot_sync(FULL, mine && !acc);
+        if (rej == 0) continue;
+        const int first = __float_as_int(lo.w), last = __float_as_int(hi.w);
+        if (last - first + 1 <= leaf_max) {
+            const bool open = (rej >> lane) & 1u;
+            for (int s = first; s <= last; s++) {
+                const float4 pj = __ldg(&posm[s]);
+                if (open) {
+                    // GravityContributionParticle (:332-356), a = h_i; includes s == t (quirk Q3)
+                    float ex = pi.x - pj.x, ey = pi.y - pj.y, ez = pi.z - pj.z;
+                    float r2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+                    float g, ph;
+                    if (r2 < a2) {
+                        float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
+                        float x = r * ainv, x2 = x * x, x3 = x2 * x;
+                        float ma = pj.w * ainv;
+                        g = ma * ainv * ainv * (8.0f - 9.0f * x + 2.0f * x3);
+                        ph = -ma * (2.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
+                    } else {
+                        float rinv = rsqrt_approx(r2);
+                        float mr = pj.w * rinv;
+                        g = mr * rinv * rinv;
+                        ph = -mr;
+                    }
+                    gx = fmaf(ex, g, gx); gy = fmaf(ey, g, gy); gz = fmaf(ez, g, gz);
+                    gp += ph;
+                    np++;
+                }
+            }
+        } else {
+            if (sp + 2 > SPH_TREE_STACK) {
+                if (lane == 0) atomicExch(&err[ERR_TREE_STACK], 1);
+                break;
+            }
+            const int2 ch = __ldg(&child[k]);
+            if (lane == 0) {
+                stack[w][sp] = make_int2(ch.x, (int)rej);      // left pushed first ...
+                stack[w][sp + 1] = make_int2(ch.y, (int)rej);  // ... right popped first (GravityFieldSystem.cs:201-206)
+            }
+            sp += 2;
+            __syncwarp();
+        }
+    }
+    if (active) {
+        grav[t] = make_float4(G * gx, G * gy, G * gz, G * gp);
+        npart[t] = np;
+        napprox[t] = na;
+    }
+}
+
+}  // namespace
+
+int sph_launch_gravity_tree(sphb200_ctx* c, float dt) {
+    int n = (int)c->n;
+    int t0 = (int)c->t0;
+    int t1 = (c->t1 < 0 || c->t1 > c->n) ? n : (int)c->t1;
+    if (n <= 0) return SPH_OK;
+    SPH_CK(c, cudaMemsetAsync(c->flag, 0, (size_t)n * sizeof(int32_t), c->stream));
+    k_lbvh_topology<<<sph_div_up(n, 256), 256, 0, c->stream>>>(c->keys[1], n, c->child, c->range, c->parent);
+    SPH_LAUNCH_CHECK(c);
+    k_lbvh_nodes<<<sph_div_up(2 * (int64_t)n - 1, 256), 256, 0, c->stream>>>(c->posh[c->cur], c->velm[c->cur], n, c->child, c->range,
+                                                                            c->parent, c->p.leaf_max, c->p.aabb_mode, dt, c->flag,
+                                                                            c->mom, c->nlo, c->nhi);
+    SPH_LAUNCH_CHECK(c);
+    c->tree_valid = true;
+    int nt = t1 - t0;
+    if (nt <= 0) return SPH_OK;
+    float theta2 = c->p.theta * c->p.theta;  // fp32 product, as k_Theta*k_Theta (GravityFieldSystem.cs:246)
+    k_tree_walk<<<sph_div_up(nt, TW_WARPS * 32), TW_WARPS * 32, 0, c->stream>>>(c->posh[c->cur], c->posm, c->child, c->mom, c->nlo,
+                                                                               c->nhi, t0, t1, c->p.leaf_max, theta2, c->p.G,
+                                                                               c->grav, c->npart, c->napprox, c->err_d);
+    SPH_LAUNCH_CHECK(c);
+    return SPH_OK;
+}

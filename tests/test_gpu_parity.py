@@ -1,0 +1,366 @@
+"""GPU parity tests proper: libsphb200 (through its C ABI) vs the CPU oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): neighbor sets and sort orders bit-exact; density, pressure, pressure gradient,
+acceleration within 1e-5 relative per particle (vector quantities: |delta| <= 1e-5 |v| + floor); tree gravity
+code-parity on the same LBVH; aggregates (momentum/energy drift) against the oracle's own drift over N steps.
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5
+
+
+def vec_close(got, ref, rtol=RTOL, floor=1e-9, what=""):
+    scale = np.linalg.norm(ref, axis=1, keepdims=True)
+    err = np.abs(got - ref)
+    bad = err > rtol * scale + floor
+    assert not bad.any(), "%s: %d components off, worst rel %.3e" % (what, bad.sum(), (err / (scale + 1e-30)).max())
+
+
+def make_sim(n, **kw):
+    import sphb200
+    return sphb200.Simulation(n, **kw)
+
+
+def run_gpu_step(c, dt, impl, **kw):
+    import sphb200
+    sim = make_sim(len(c["h"]), **kw)
+    sim.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    sim.step(dt, impl)
+    return sim
+
+
+def oracle_step(orc, c, dt, gravity, sim, n_own=None, **kw):
+    ref = orc.State(c["pos"], c["vel"], c["mass"], c["h"], n_own)
+    p = sim.effective_params()
+    orc.step(ref, dt, gravity=gravity, max_bits=p.max_grid_bits, leaf_max=p.leaf_max, aabb_mode=p.aabb_mode,
+             accum_double=True, **kw)
+    return ref
+
+
+def compare_step(orc, sim, ref, gravity):
+    got = sim.download_all()
+    off, nbr = sim.download_neighbors()
+    np.testing.assert_array_equal(off, ref.offsets)
+    np.testing.assert_array_equal(nbr, ref.nbr)                       # neighbor sets: bit-exact
+    np.testing.assert_array_equal(got["count"], np.diff(ref.offsets))
+    np.testing.assert_array_equal(got["n_own"], ref.n_own)
+    np.testing.assert_array_equal(got["h"], ref.h)                    # controller is bit-exact by construction
+    np.testing.assert_allclose(got["rho"], ref.rho, rtol=RTOL)
+    np.testing.assert_allclose(got["P"], ref.P, rtol=2 * RTOL)
+    vec_close(got["gradP"], ref.gradP, what="gradP", floor=1e-7 * np.abs(ref.gradP).max())
+    if gravity != "none":
+        vec_close(got["grav"][:, :3], ref.grav[:, :3], what="gradPhi")
+        np.testing.assert_allclose(got["grav"][:, 3], ref.grav[:, 3], rtol=RTOL)
+    if gravity == "tree":
+        np.testing.assert_array_equal(got["num_particles"], ref.num_particles)
+        np.testing.assert_array_equal(got["num_approx"], ref.num_approx)
+    np.testing.assert_allclose(got["pos"], ref.pos, rtol=1e-6, atol=1e-6)
+    acc_scale = np.abs(ref.vel - 0).max() + 1e-12
+    np.testing.assert_allclose(got["vel"], ref.vel, rtol=RTOL, atol=2e-5 * acc_scale)
+    return got
+
+
+# ------------------------------------------------------------------ config C1: 3k sphere, direct gravity, one step
+def test_c1_single_step_direct(orc):
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_config("c1")
+    sim = run_gpu_step(c, 1 / 60, sphb200.GRAVITY_PARTICLE)
+    ref = oracle_step(orc, c, 1 / 60, "direct", sim)
+    compare_step(orc, sim, ref, "direct")
+    # the literal fp32 sequential sum of the reference is itself ~1e-6 from the fp64-accumulated yardstick at 3k
+    lit = orc.gravity_direct(c["pos"], c["h"], c["mass"], accum_double=False)
+    vec_close(sim.download_all()["grav"][:, :3], lit[:, :3], what="gradPhi vs literal fp32 chain")
+
+
+def test_c1_settled_h_direct(orc):
+    """Same, after the smoothing-length controller has converged (mean ~56 neighbors, h spread 4x)."""
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_config("c1")
+    s = orc.State(c["pos"], c["vel"], c["mass"], c["h"])
+    for _ in range(25):
+        orc.step(s, 1 / 60, gravity="none")
+        s.pos[:] = c["pos"]; s.vel[:] = 0
+    c2 = dict(pos=c["pos"], vel=c["vel"], mass=c["mass"], h=s.h)
+    sim = run_gpu_step(c2, 1 / 60, sphb200.GRAVITY_PARTICLE)
+    ref = oracle_step(orc, c2, 1 / 60, "direct", sim)
+    got = compare_step(orc, sim, ref, "direct")
+    assert 45 < got["count"].mean() < 70
+
+
+# ------------------------------------------------------------------ sort order / keys / grid parameters: bit-exact
+@pytest.mark.parametrize("n", [1, 2, 33, 1000, 20000])
+def test_sort_order_and_keys_bit_exact(orc, n):
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_sphere(n, seed=100 + n)
+    sim = make_sim(n)
+    sim.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    sim.build_neighbors()
+    order, keys, g = sim.download_sort()
+    p = sim.effective_params()
+    go = orc.grid_params(c["pos"], c["h"], p.max_grid_bits)
+    for f in ("cell", "fine_scale", "bits", "hmax", "ext"):
+        assert getattr(g, f) == getattr(go, f), f
+    assert list(g.min) == list(go.min)
+    ko = orc.morton_keys(c["pos"], go)
+    oo = orc.sort_order(ko)
+    np.testing.assert_array_equal(order, oo)
+    np.testing.assert_array_equal(keys, ko[oo])
+
+
+# ------------------------------------------------------------------ config C2 regime: 10k, variable h, tree gravity
+def test_c2_tree_code_parity_same_lbvh(orc):
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_config("c2")
+    c["vel"] = (np.random.default_rng(1).normal(0, 0.5, c["pos"].shape)).astype(np.float32)  # exercise the swept boxes (Q2)
+    dt = 0.02
+    sim = run_gpu_step(c, dt, sphb200.GRAVITY_TREE)
+    p = sim.effective_params()
+    # the LBVH itself: topology exact, moments and boxes bit-exact
+    g_ref, npart, napp, tree, order = orc.tree_gravity(c["pos"], c["vel"], c["h"], c["mass"], dt, p.theta, p.G, p.leaf_max,
+                                                       p.aabb_mode, p.max_grid_bits, accum_double=True)
+    t = sim.download_tree()
+    np.testing.assert_array_equal(t["child"][:, 0], tree.left)
+    np.testing.assert_array_equal(t["child"][:, 1], tree.right)
+    np.testing.assert_array_equal(t["range"][:, 0], tree.first)
+    np.testing.assert_array_equal(t["range"][:, 1], tree.last)
+    reach = np.zeros(len(tree.left), bool)                   # nodes the walk can visit (not strictly inside a leaf bucket)
+    stack = [0]
+    while stack:
+        k = stack.pop(); reach[k] = True
+        if tree.last[k] - tree.first[k] + 1 > p.leaf_max:
+            stack += [tree.left[k], tree.right[k]]
+    np.testing.assert_array_equal(t["mom"][reach], tree.mom[reach])
+    np.testing.assert_array_equal(t["lo"][reach], tree.lo[reach])
+    np.testing.assert_array_equal(t["hi"][reach], tree.hi[reach])
+    ref = oracle_step(orc, c, dt, "tree", sim)
+    got = compare_step(orc, sim, ref, "tree")
+    # accuracy envelope vs the direct sum (monopole, theta = 0.7): report-level check
+    gd = orc.gravity_direct(c["pos"], c["h"], c["mass"], accum_double=True)
+    err = np.linalg.norm(got["grav"][:, :3] - gd[:, :3], axis=1) / np.linalg.norm(gd[:, :3], axis=1)
+    assert np.median(err) < 0.03
+
+
+def test_c2_multistep_drift_matches_oracle(orc):
+    """P2: 20 steps of the C2 regime; trajectories are compared through aggregates and their drift."""
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_sphere(4000, seed=9)
+    dt = 0.01
+    sim = make_sim(4000)
+    sim.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    ref = orc.State(c["pos"], c["vel"], c["mass"], c["h"])
+    p = sim.effective_params()
+    for _ in range(20):
+        sim.step(dt, sphb200.GRAVITY_TREE)
+        orc.step(ref, dt, gravity="tree", max_bits=p.max_grid_bits, leaf_max=p.leaf_max, aabb_mode=p.aabb_mode)
+    got = sim.download_all()
+    d = sim.diagnostics()
+    m = ref.mass.astype(np.float64)
+    mom_ref = (m[:, None] * ref.vel).sum(0)
+    ekin_ref = 0.5 * (m * (ref.vel.astype(np.float64) ** 2).sum(1)).sum()
+    vscale = np.sqrt((ref.vel.astype(np.float64) ** 2).sum(1).mean()) * m.sum()
+    assert np.all(np.abs(d["momentum"] - mom_ref) < 1e-3 * vscale)   # same (non-zero, quirk Q5) momentum drift
+    assert d["e_kin"] == pytest.approx(ekin_ref, rel=1e-3)
+    assert got["h"].mean() == pytest.approx(ref.h.mean(), rel=1e-4)
+    assert got["count"].mean() == pytest.approx(np.diff(ref.offsets).mean(), rel=1e-3)
+    # most particles still agree closely after 20 steps (a few diverge once a neighbor flips at an edge)
+    rel = np.linalg.norm(got["pos"] - ref.pos, axis=1) / 50.0
+    assert np.median(rel) < 1e-6
+
+
+def test_resync_per_step_error_does_not_grow(orc):
+    """P3: every step, the oracle state is loaded into the GPU and one step is compared at full tolerance."""
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_sphere(3000, seed=21)
+    dt = 0.02
+    ref = orc.State(c["pos"], c["vel"], c["mass"], c["h"])
+    sim = make_sim(3000)
+    p = sim.effective_params()
+    for k in range(6):
+        sm = np.zeros(3000, sphb200.ParticleSmoothing)
+        sm["influenceArea"] = ref.h; sm["neighbors"] = ref.n_own
+        sim.upload(ref.pos, ref.vel, ref.mass, sm)
+        sim.step(dt, sphb200.GRAVITY_TREE)
+        orc.step(ref, dt, gravity="tree", max_bits=p.max_grid_bits, leaf_max=p.leaf_max, aabb_mode=p.aabb_mode,
+                 accum_double=True)
+        compare_step(orc, sim, ref, "tree")
+
+
+# ------------------------------------------------------------------ stage API == fused step; component-struct strides
+def test_stage_calls_match_fused_step_and_struct_layouts(orc):
+    import sphb200
+    from sphb200 import ic, systems
+    c = ic.make_sphere(2000, seed=3)
+    a = run_gpu_step(c, 0.02, sphb200.GRAVITY_TREE).download_all()
+    w = systems.World(2000, dt=0.02)
+    w.set_particles(c["pos"], c["vel"], c["mass"], c["h"])
+    systems.FixedStepSimulationSystemGroup(w, sphb200.GRAVITY_TREE).Update()
+    w.export()
+    np.testing.assert_array_equal(np.stack([w.Translation["x"], w.Translation["y"], w.Translation["z"]], 1), a["pos"])
+    np.testing.assert_array_equal(w.PhysicsVelocity["linear"], a["vel"])
+    np.testing.assert_array_equal(w.PhysicsVelocity["angular"], 0)
+    np.testing.assert_array_equal(w.ParticleDensity, a["rho"])
+    np.testing.assert_array_equal(w.ParticlePressure, a["P"])
+    np.testing.assert_array_equal(w.ParticlePressureGrad, a["gradP"])
+    np.testing.assert_array_equal(w.GravityField["value"], a["grav"])
+    np.testing.assert_array_equal(w.GravityField["numApprox"], a["num_approx"])
+    np.testing.assert_array_equal(w.ParticleSmoothing["supportDomain"], 2 * w.ParticleSmoothing["influenceArea"])
+    np.testing.assert_array_equal(w.ParticleSmoothing["neighbors"], a["n_own"])
+
+
+def test_interaction_records_bit_exact(orc):
+    """The optional DynamicBuffer<ParticleInteraction> surface replays the reference arithmetic op for op."""
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_sphere(1500, seed=8)
+    c["h"] = (c["h"] * 1.8).astype(np.float32)
+    sim = make_sim(1500)
+    sim.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    sim.build_neighbors()
+    off, nbr = sim.download_neighbors()
+    rec = sim.download_interactions(off, nbr)
+    kthis = np.zeros((len(nbr), 4), np.float32); ksym = np.zeros((len(nbr), 4), np.float32)
+    orc.lib().orc_interactions(1500, c["pos"], c["h"], off, nbr, 0, kthis, ksym)
+    np.testing.assert_array_equal(rec["otherIndex"], nbr)
+    np.testing.assert_array_equal(rec["kernelThis"], kthis)
+    np.testing.assert_array_equal(rec["kernelSymmetric"], ksym)
+
+
+# ------------------------------------------------------------------ edge cases
+def test_edge_empty_single_pair_and_coincident(orc):
+    import sphb200
+    sim = make_sim(16)
+    z3 = np.zeros((0, 3), np.float32); z1 = np.zeros(0, np.float32)
+    sim.upload(z3, z3, z1, z1)                                  # empty input
+    sim.step(0.01, sphb200.GRAVITY_TREE)
+    assert len(sim.download(sphb200.FIELD_DENSITY)) == 0
+    # one particle: only self terms
+    one = dict(pos=np.array([[1, 2, 3]], np.float32), vel=np.zeros((1, 3), np.float32), mass=np.array([2.0], np.float32),
+               h=np.array([1.5], np.float32))
+    for impl, name in ((sphb200.GRAVITY_TREE, "tree"), (sphb200.GRAVITY_PARTICLE, "direct")):
+        sim.upload(one["pos"], one["vel"], one["mass"], one["h"])
+        sim.step(0.01, impl)
+        ref = oracle_step(orc, one, 0.01, name, sim)
+        compare_step(orc, sim, ref, name)
+    # coincident distinct particles (quirk Q9): the reference's gradient is NaN there; sets/density/gravity still match
+    rng = np.random.default_rng(0)
+    base = rng.uniform(-3, 3, (8, 3)).astype(np.float32)
+    c = dict(pos=np.concatenate([base, base]), vel=np.zeros((16, 3), np.float32), mass=np.full(16, 0.3, np.float32),
+             h=np.full(16, 0.8, np.float32))
+    sim.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    sim.step(0.01, sphb200.GRAVITY_PARTICLE)
+    ref = oracle_step(orc, c, 0.01, "direct", sim)
+    off, nbr = sim.download_neighbors()
+    np.testing.assert_array_equal(nbr, ref.nbr)
+    got = sim.download_all()
+    np.testing.assert_allclose(got["rho"], ref.rho, rtol=RTOL)
+    vec_close(got["grav"][:, :3], ref.grav[:, :3], what="grav coincident", floor=1e-7)
+    assert np.isnan(ref.gradP).any() and np.isfinite(got["gradP"]).all()   # documented guard instead of NaN
+
+
+def test_edge_high_h_contrast_and_boundary_ulps(orc):
+    """Small-h particles must still find large-h neighbors (max(h_i,h_j) rule), and pairs within an ulp of the
+    support edge must be classified exactly like the reference."""
+    import sphb200
+    rng = np.random.default_rng(5)
+    n = 3000
+    pos = rng.uniform(-10, 10, (n, 3)).astype(np.float32)
+    h = np.where(rng.random(n) < 0.05, 3.0, 0.35).astype(np.float32)   # 8.6x contrast
+    # plant pairs exactly at / one ulp inside / one ulp outside d = 2*max(h)
+    for k, (hk, off) in enumerate([(0.35, 0), (0.35, -1), (0.35, 1), (3.0, 0), (3.0, -1), (3.0, 1)]):
+        i, j = 2 * k, 2 * k + 1
+        d = np.float32(2.0) * np.float32(hk)
+        for _ in range(abs(off)):
+            d = np.nextafter(d, np.float32(0 if off < 0 else 100))
+        pos[i] = (20 + 10 * k, 0, 0); pos[j] = (20 + 10 * k + d, 0, 0)
+        h[i] = hk; h[j] = hk
+    c = dict(pos=pos, vel=np.zeros((n, 3), np.float32), mass=np.full(n, 0.01, np.float32), h=h)
+    sim = run_gpu_step(c, 0.01, sphb200.GRAVITY_NONE, max_neighbors=512)
+    ref = oracle_step(orc, c, 0.01, "none", sim)
+    compare_step(orc, sim, ref, "none")
+
+
+def test_errors_capacity_overflow_state(orc):
+    import sphb200
+    from sphb200 import ic
+    sim = make_sim(100, max_neighbors=32)
+    c = ic.make_sphere(200, seed=1)
+    with pytest.raises(sphb200.SphError) as e:
+        sim.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    assert e.value.code == sphb200.SPH_ERR_CAPACITY
+    c = ic.make_sphere(100, radius=5.0, particle_radius=6.0, seed=1)       # everyone neighbors everyone: 99 > 32
+    sim.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    with pytest.raises(sphb200.SphError) as e:
+        sim.pressure()                                                     # stage out of order
+    assert e.value.code == sphb200.SPH_ERR_STATE
+    sim.step(0.01, sphb200.GRAVITY_NONE)
+    with pytest.raises(sphb200.SphError) as e:
+        sim.download(sphb200.FIELD_DENSITY)
+    assert e.value.code == sphb200.SPH_ERR_NEIGHBOR_OVERFLOW
+    rho = sim.download(sphb200.FIELD_DENSITY, allow_overflow=True)        # density itself is still complete
+    o, nb = orc.neighbors(c["pos"], c["h"])
+    ref_rho, _ = orc.density(c["pos"], c["h"], c["mass"], o, nb)
+    np.testing.assert_allclose(rho, ref_rho, rtol=RTOL)
+    with pytest.raises(sphb200.SphError):
+        sphb200.Simulation(10, max_neighbors=33)
+
+
+# ------------------------------------------------------------------ BASELINE sizes: size-independent properties
+def test_c3_size_properties_1m():
+    """1M-particle sphere (config C3 geometry): sortedness, list symmetry, density positivity, agreement of the tree
+    with the tiled all-pairs kernel on a target sub-range, zero net self-force of pairwise Newtonian gravity."""
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_config("c3")
+    n = len(c["h"])
+    sim = make_sim(n)
+    sim.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    sim.step(1 / 60, sphb200.GRAVITY_TREE)
+    order, keys, g = sim.download_sort()
+    assert np.all(np.diff(keys.astype(np.int64)) >= 0)
+    assert np.array_equal(np.sort(order), np.arange(n, dtype=np.uint32))      # a permutation
+    cnt = sim.download(sphb200.FIELD_NEIGHBOR_COUNT)
+    off, nbr = sim.download_neighbors()
+    assert off[-1] == cnt.sum()
+    rows = np.repeat(np.arange(n, dtype=np.int64), np.diff(off))
+    fwd = rows * n + nbr; bwd = nbr.astype(np.int64) * n + rows
+    assert np.array_equal(np.sort(fwd), np.sort(bwd))                          # j in N(i) <=> i in N(j)
+    rho = sim.download(sphb200.FIELD_DENSITY)
+    assert np.all(rho > 0) and np.all(np.isfinite(rho))
+    tree = sim.download(sphb200.FIELD_GRAVITY)["value"].copy()
+    # all-pairs on the same state for a slice of targets, compared with the tree result there
+    sim.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    sim.smoothing_update(); sim.build_neighbors()
+    sim.set_target_range(0, 8192)
+    sim.gravity(sphb200.GRAVITY_PARTICLE, 1 / 60)
+    direct = sim.download(sphb200.FIELD_GRAVITY)["value"]
+    order2, _, _ = sim.download_sort()
+    sel = order2[:8192]
+    err = np.linalg.norm(tree[sel, :3] - direct[sel, :3], axis=1) / np.linalg.norm(direct[sel, :3], axis=1)
+    assert np.median(err) < 0.03 and np.percentile(err, 99) < 0.2
+    m = c["mass"].astype(np.float64)
+    net = (m[:, None] * tree[:, :3]).sum(0)
+    assert np.linalg.norm(net) < 2e-2 * (m * np.linalg.norm(tree[:, :3], axis=1)).sum()
+
+
+def test_allpairs_sampled_targets_vs_oracle_64k(orc):
+    """All-pairs kernel at 65 536 particles: 512 sampled targets against the fp64-accumulated oracle."""
+    import sphb200
+    from sphb200 import ic
+    n = 65536
+    c = ic.make_sphere(n, radius=ic.scaled_radius(n), total_mass=100.0 * n / 3000, seed=77)
+    sim = run_gpu_step(c, 1 / 60, sphb200.GRAVITY_PARTICLE)
+    got = sim.download(sphb200.FIELD_GRAVITY)["value"]
+    idx = np.random.default_rng(0).choice(n, 512, replace=False)
+    for i in idx[:512:8]:
+        ref = orc.gravity_direct(c["pos"], c["h"], c["mass"], i0=int(i), i1=int(i) + 1, accum_double=True)[0]
+        assert np.linalg.norm(got[i, :3] - ref[:3]) <= RTOL * np.linalg.norm(ref[:3])
+        assert got[i, 3] == pytest.approx(ref[3], rel=RTOL)

@@ -1,0 +1,380 @@
+"""Pins the CPU oracle (oracle/sph_oracle.cpp).
+
+The reference has NO tests for its SPH path (SplineKernel.cs:43 "TODO: learn to write tests in unity!"), so the oracle
+is pinned by (a) the invariants the reference states in its own comments (SplineKernel.cs:29-43), (b) closed forms of
+the formulas it implements, (c) an independent float32 numpy restatement written from the reference source, and
+(d) for the vendored Unity.Physics pieces, the known answers of the reference's own NUnit tests
+(UT = UpstreamPackages/com.unity.physics@0.6.0-preview.3/Tests/PlayModeTests):
+    UT/Dynamics/Motion/MotionTests.cs:50-91   CalculateExpansion / MaxDistance / ExpandAabb
+    UT/Collision/Colliders/SphereColliderTests.cs:81-118   sphere AABB = centre +- radius
+    UT/Collision/Geometry/BoundingVolumeHierarchyBuilderTests.cs:86-106 + Builder.cs:864-902  BVH integrity invariant
+"""
+import math
+import numpy as np
+import pytest
+
+f32 = np.float32
+PI32 = f32(3.14159274)
+
+
+# ------------------------------------------------------------------ independent numpy float32 restatement
+def np_kernel(r, h):
+    r = f32(r); h = f32(h)
+    if r >= h * f32(2.0):
+        return f32(0.0)
+    q = r / h
+    c = PI32 * h * h * h
+    if r < h:
+        q2 = q * q
+        return (f32(1.0) - f32(1.5) * q2 + f32(0.75) * (q2 * q)) / c
+    t = f32(2.0) - q
+    return (t * t * t) / (f32(4.0) * c)
+
+
+def np_kernel_deriv(r, h):
+    r = f32(r); h = f32(h)
+    if r >= h * f32(2.0):
+        return f32(0.0)
+    q = r / h
+    c4 = PI32 * h * h * h * h
+    if r < h:
+        return (f32(3.0) * q + f32(2.25) * (q * q)) / c4   # quirk Q1: +3q
+    t = f32(2.0) - q
+    return (f32(-3.0) * t * t) / (f32(4.0) * c4)
+
+
+def np_gravity_pair(ri, rj, m, a):
+    d = (np.asarray(ri, f32) - np.asarray(rj, f32)).astype(f32)
+    r = np.sqrt(f32(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]))
+    m = f32(m); a = f32(a)
+    if r < a:
+        x = r / a; x2 = x * x; x3 = x2 * x; x5 = x2 * x3
+        g = (m / (a * a * a)) * (f32(8.0) - f32(9.0) * x + f32(2.0) * x3)
+        p = -(m / a) * (f32(2.4) - f32(4.0) * x2 + f32(3.0) * x3 - f32(0.4) * x5)
+    else:
+        g = m / (r * r * r)
+        p = -(m / r)
+    return np.array([d[0] * g, d[1] * g, d[2] * g, p], f32)
+
+
+# ------------------------------------------------------------------ kernel invariants (SplineKernel.cs:29-43)
+@pytest.mark.parametrize("h", [0.37, 1.0, 2.5, 3.75, 9.5, 123.0])
+def test_kernel_compact_support_and_values(orc, h):
+    h = float(f32(h))
+    assert orc.kernel(2.0 * h, h) == 0.0                      # "Kernel(Kappa()*h, h) = 0" SplineKernel.cs:42
+    assert orc.kernel(2.5 * h, h) == 0.0
+    assert orc.kernel(0.0, h) == pytest.approx(1.0 / (math.pi * h ** 3), rel=3e-7)
+    assert orc.kernel(h, h) == pytest.approx(1.0 / (4.0 * math.pi * h ** 3), rel=3e-7)
+    below = float(np.nextafter(f32(2.0 * h), f32(0)))
+    assert orc.kernel(below, h) > 0.0                         # strictly positive just inside the support
+
+
+def test_kernel_normalisation(orc):
+    # 4 pi int_0^{2h} W r^2 dr = 1  (SplineKernel.cs:30-31)
+    for h in (0.5, 2.5, 7.0):
+        r = np.linspace(0, 2 * h, 20001)
+        w = np.array([orc.kernel(float(f32(x)), float(f32(h))) for x in r], np.float64)
+        integral = 4 * np.pi * np.trapezoid(w * r * r, r)
+        assert integral == pytest.approx(1.0, abs=2e-5)
+
+
+def test_kernel_matches_independent_restatement_bitwise(orc):
+    rng = np.random.default_rng(7)
+    for _ in range(4000):
+        h = f32(rng.uniform(0.3, 10)); r = f32(rng.uniform(0, 2.3) * h)
+        assert orc.kernel(float(r), float(h)) == float(np_kernel(r, h))
+        assert orc.kernel_deriv(float(r), float(h)) == float(np_kernel_deriv(r, h))
+
+
+def test_kernel_derivative_quirk_q1_and_fix(orc):
+    h = 2.0
+    # reference inner branch has +3q (SplineKernel.cs:135): positive derivative, jump at r = h
+    assert orc.kernel_deriv(0.5 * h, h) > 0
+    assert orc.kernel_deriv(0.5 * h, h, 1) < 0
+    inner = orc.kernel_deriv(float(np.nextafter(f32(h), f32(0))), h) * math.pi * h ** 4
+    outer = orc.kernel_deriv(h, h) * math.pi * h ** 4
+    assert inner == pytest.approx(5.25, rel=1e-5) and outer == pytest.approx(-0.75, rel=1e-5)
+    # with the sign fixed the derivative is the analytic one: finite difference of W
+    for q in (0.2, 0.7, 1.3, 1.9):
+        r = q * h; e = 1e-3
+        fd = (orc.kernel(r + e, h) - orc.kernel(r - e, h)) / (2 * e)
+        assert orc.kernel_deriv(r, h, 1) == pytest.approx(fd, rel=2e-3, abs=1e-7)
+
+
+def test_kernel_gradient_direction_and_symmetry(orc):
+    ri = np.array([1.0, 2.0, 3.0], f32); rj = np.array([2.5, 1.0, 3.5], f32)
+    kt_ij, ks_ij = orc.interaction(ri, rj, 1.5, 2.0)
+    kt_ji, ks_ji = orc.interaction(rj, ri, 2.0, 1.5)
+    assert ks_ij[3] == ks_ji[3]                               # W even (SplineKernel.cs:38)
+    np.testing.assert_array_equal(ks_ij[:3], -ks_ji[:3])      # gradient odd
+    d = ri - rj
+    r = np.sqrt(f32(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]))
+    s = np_kernel_deriv(r, 1.5) / r
+    np.testing.assert_array_equal(kt_ij[:3], (d * s).astype(f32))
+    assert kt_ij[3] == np_kernel(r, 1.5)
+
+
+def test_coincident_particles_nan_quirk_q9(orc):
+    p = np.array([1.0, 1.0, 1.0], f32)
+    kt, ks = orc.interaction(p, p, 1.0, 1.0)
+    assert np.isnan(kt[0]) and ks[3] > 0                      # 0/0 gradient, kept by the w>0 test
+
+
+def test_interacts_predicate_uses_larger_h_strictly(orc):
+    L = orc.lib()
+    ri = np.zeros(3, f32)
+    # d^2 < (max h)^2 * 4, strict (SplineKernel.cs:47-53)
+    assert L.orc_interacts(ri, np.array([3.9, 0, 0], f32), 1.0, 2.0) == 1
+    assert L.orc_interacts(ri, np.array([4.0, 0, 0], f32), 1.0, 2.0) == 0
+    assert L.orc_interacts(ri, np.array([2.1, 0, 0], f32), 1.0, 1.0) == 0
+    # keep rule: inside the predicate but W rounds out -> dropped; here both agree
+    assert L.orc_is_neighbor(ri, np.array([3.9, 0, 0], f32), 1.0, 2.0) == 1
+
+
+# ------------------------------------------------------------------ gravity law (GravityFieldSystem.cs:332-356)
+def test_gravity_pair_closed_forms(orc):
+    ri = np.zeros(3, f32)
+    m, a = 3.0, 2.0
+    # Newtonian branch
+    g = orc.gravity_pair(np.array([4.0, 0, 0], f32), ri, m, a)
+    assert g[0] == pytest.approx(m / 16.0, rel=1e-6) and g[3] == pytest.approx(-m / 4.0, rel=1e-6)
+    # continuity at x = 1: 8-9+2 = 1 and 2.4-4+3-0.4 = 1
+    inside = orc.gravity_pair(np.array([float(np.nextafter(f32(a), f32(0))), 0, 0], f32), ri, m, a)
+    outside = orc.gravity_pair(np.array([a, 0, 0], f32), ri, m, a)
+    np.testing.assert_allclose(inside, outside, rtol=3e-6)
+    # centre: zero field, Phi(0) = -2.4 m/a
+    c = orc.gravity_pair(ri, ri, m, a)
+    assert c[0] == 0 and c[3] == pytest.approx(-2.4 * m / a, rel=1e-6)
+
+
+def test_gravity_pair_matches_independent_restatement_bitwise(orc):
+    rng = np.random.default_rng(3)
+    for _ in range(3000):
+        ri = rng.uniform(-5, 5, 3).astype(f32); rj = rng.uniform(-5, 5, 3).astype(f32)
+        m = float(f32(rng.uniform(0.01, 3))); a = float(f32(rng.uniform(0.1, 6)))
+        np.testing.assert_array_equal(orc.gravity_pair(ri, rj, m, a), np_gravity_pair(ri, rj, m, a))
+
+
+def test_uniform_sphere_field(orc):
+    # g(r) = G M r / R^3 inside a uniform sphere, to sampling noise
+    import sphb200.ic as ic
+    c = ic.make_sphere(6000, radius=50, total_mass=100, seed=5)
+    g = orc.gravity_direct(c["pos"], c["h"], c["mass"], accum_double=True)
+    r = np.linalg.norm(c["pos"], axis=1)
+    sel = (r > 10) & (r < 40)
+    gr = (g[sel, :3] * c["pos"][sel]).sum(1) / r[sel]          # grad Phi . r_hat (points outward)
+    expect = 100.0 * r[sel] / 50.0 ** 3
+    assert np.median(gr / expect) == pytest.approx(1.0, abs=0.05)
+
+
+# ------------------------------------------------------------------ moments and MAC (GravityFieldSystem.cs:229-247, 398-442)
+def test_moment_accumulate_is_mass_weighted_mean(orc):
+    L = orc.lib()
+    mo = np.zeros(4, f32)
+    pts = np.array([[1, 0, 0], [3, 0, 0], [0, 4, 0]], f32); ms = [1.0, 1.0, 2.0]
+    for p, m in zip(pts, ms):
+        L.orc_moment_accumulate(mo, p, m)
+    assert mo[3] == 4.0
+    np.testing.assert_allclose(mo[:3], [1.0, 2.0, 0.0], rtol=1e-6)
+    before = mo.copy()
+    L.orc_moment_accumulate(mo, np.array([9, 9, 9], f32), 0.0)  # zero mass is ignored (:404)
+    np.testing.assert_array_equal(mo, before)
+
+
+def test_m2p_is_newtonian(orc):
+    L = orc.lib()
+    out = np.zeros(4, f32)
+    L.orc_moment_m2p(np.array([0, 0, 0, 5.0], f32), np.array([0, 10.0, 0], f32), 1.0, out)
+    np.testing.assert_allclose(out, [0, 5.0 / 100.0, 0, -0.5], rtol=1e-6)
+
+
+def test_mac_bmax_algebra(orc):
+    L = orc.lib()
+    cm = np.array([0, 0, 0, 1.0], f32); lo = np.array([-1, -1, -1], f32); hi = np.array([1, 1, 1], f32)
+    # bmax^2 = 3; accept iff 3/d^2 < 0.7f*0.7f  <=> d > sqrt(3)/0.7 = 2.474...
+    assert L.orc_accept(np.array([2.48, 0, 0], f32), cm, lo, hi, 0.7) == 1
+    assert L.orc_accept(np.array([2.47, 0, 0], f32), cm, lo, hi, 0.7) == 0
+    # off-centre CM: bmax uses the farther face per axis
+    cm2 = np.array([0.5, 0, 0, 1.0], f32)
+    d = math.sqrt(1.5 ** 2 + 1 + 1) / 0.7
+    assert L.orc_accept(np.array([0.5 + d * 1.001, 0, 0], f32), cm2, lo, hi, 0.7) == 1
+    assert L.orc_accept(np.array([0.5 + d * 0.999, 0, 0], f32), cm2, lo, hi, 0.7) == 0
+    # field point at the CM never accepts (inf / NaN compare false)
+    assert L.orc_accept(np.array([0, 0, 0], f32), cm, lo, hi, 0.7) == 0
+
+
+# ------------------------------------------------------------------ reference's own NUnit known answers
+def test_motion_expansion_known_answers_from_reference_tests(orc):
+    L = orc.lib()
+    lin = np.zeros(3, f32); uni = np.zeros(1, f32)
+    # MotionTests.cs:50-65 MotionVelocityCalculateExpansionTest
+    L.orc_calculate_expansion(np.array([2, 1, 5], f32), np.array([3, 4, 5], f32), 1.2, f32(1.0 / 60.0), lin, uni)
+    np.testing.assert_array_equal(lin, np.array([1.0 / 30.0, 1.0 / 60.0, 1.0 / 12.0], f32))
+    assert uni[0] == pytest.approx(math.sqrt(2.0) / 10.0, rel=1e-5)
+    # MotionTests.cs:79-91 MotionExpansionSweepAabbTest
+    lo = np.zeros(3, f32); hi = np.zeros(3, f32)
+    L.orc_expand_aabb(np.array([-10, -10, -10], f32), np.array([10, 10, 10], f32), np.array([2, 3, 4], f32), 5.0, lo, hi)
+    np.testing.assert_array_equal(lo, [-15, -15, -15]); np.testing.assert_array_equal(hi, [17, 18, 19])
+
+
+def test_particle_collider_box(orc):
+    L = orc.lib()
+    lo = np.zeros(3, f32); hi = np.zeros(3, f32)
+    # sphere AABB = centre +- radius (SphereColliderTests.cs:81-118), radius = 2h, then +-0.05 margin, no sweep
+    L.orc_particle_box(np.array([1, 2, 3], f32), 1.5, np.zeros(3, f32), 0.02, 0, lo, hi)
+    np.testing.assert_allclose(lo, [1 - 3.05, 2 - 3.05, 3 - 3.05], rtol=1e-6)
+    np.testing.assert_allclose(hi, [1 + 3.05, 2 + 3.05, 3 + 3.05], rtol=1e-6)
+    # swept by v*dt on the leading side only (Motion.cs:142-146)
+    L.orc_particle_box(np.array([0, 0, 0], f32), 1.0, np.array([10, -10, 0], f32), 0.1, 0, lo, hi)
+    np.testing.assert_allclose(hi, [3.05, 2.05, 2.05], rtol=1e-6)
+    np.testing.assert_allclose(lo, [-2.05, -3.05, -2.05], rtol=1e-6)
+    L.orc_particle_box(np.array([1, 2, 3], f32), 1.5, np.zeros(3, f32), 0.02, 1, lo, hi)
+    np.testing.assert_array_equal(lo, [1, 2, 3]); np.testing.assert_array_equal(hi, [1, 2, 3])
+
+
+# ------------------------------------------------------------------ smoothing controller (ParticleSmoothingSystem.cs:46-59)
+def test_smoothing_controller(orc):
+    h = np.array([2.0, 2.0, 2.0, 2.0], f32)
+    out = orc.smoothing_update(h, np.array([50, 0, 400, 6], np.int32), 50.0)
+    assert out[0] == 2.0                                      # fixed point at n = 50
+    assert out[1] == 2.0                                      # n = 0 leaves h unchanged (quirk Q8)
+    assert out[2] == pytest.approx(2.0 * 0.5 * (1 + 0.5), rel=1e-6)
+    assert out[3] == pytest.approx(2.0 * 0.5 * (1 + (50 / 6) ** (1 / 3)), rel=1e-6)
+
+
+# ------------------------------------------------------------------ neighbor sets
+def test_neighbors_brute_equals_grid_and_is_symmetric(orc):
+    import sphb200.ic as ic
+    c = ic.make_sphere(2500, seed=11)
+    h = (c["h"] * 2.0).astype(f32)
+    o1, n1 = orc.neighbors(c["pos"], h, "brute")
+    o2, n2 = orc.neighbors(c["pos"], h, "grid")
+    np.testing.assert_array_equal(o1, o2); np.testing.assert_array_equal(n1, n2)
+    pairs = set()
+    for i in range(len(h)):
+        row = n1[o1[i]:o1[i + 1]]
+        assert np.all(np.diff(row) > 0)                       # canonical ascending order
+        pairs.update((i, int(j)) for j in row)
+    assert all((j, i) in pairs for (i, j) in pairs)           # max(h_i,h_j) rule is symmetric
+
+
+def test_two_particle_hand_computed_step(orc):
+    # two equal particles on the x axis, r = 1.5 h: every quantity by hand from the formulas
+    h = 2.0; r = 3.0; m = 0.5
+    pos = np.array([[0, 0, 0], [r, 0, 0]], f32); vel = np.zeros((2, 3), f32)
+    s = orc.State(pos, vel, np.full(2, m, f32), np.full(2, h, f32))
+    dt = 0.01
+    orc.step(s, dt, gravity="direct")
+    W0 = 1 / (math.pi * h ** 3); q = r / h
+    W = (2 - q) ** 3 / (4 * math.pi * h ** 3)
+    rho = m * W0 + m * W
+    assert s.rho[0] == pytest.approx(rho, rel=1e-6) and s.rho[1] == pytest.approx(rho, rel=1e-6)
+    P = 1000 * rho * rho
+    assert s.P[0] == pytest.approx(P, rel=1e-6)
+    dW = -3 * (2 - q) ** 2 / (4 * math.pi * h ** 4)
+    gradP0 = (-r) * (dW / r) * (m / rho) * P                  # d = r_0 - r_1 = -r
+    assert s.gradP[0, 0] == pytest.approx(gradP0, rel=1e-5) and s.gradP[1, 0] == pytest.approx(-gradP0, rel=1e-5)
+    g0 = -r * m / r ** 3                                      # grad Phi at particle 0 (r >= h: Newtonian)
+    assert s.grav[0, 0] == pytest.approx(g0, rel=1e-6) and s.grav[0, 3] == pytest.approx(-m / r, rel=1e-6)
+    v0 = (-gradP0 / rho - g0) * dt
+    assert s.vel[0, 0] == pytest.approx(v0, rel=1e-5) and s.vel[1, 0] == pytest.approx(-v0, rel=1e-5)
+    np.testing.assert_array_equal(s.pos, pos)                  # x += v_n dt with v_n = 0
+    assert list(s.n_own) == [1, 1]
+
+
+# ------------------------------------------------------------------ keys / sort / LBVH
+def test_morton_keys_and_sort(orc):
+    import sphb200.ic as ic
+    c = ic.make_sphere(5000, seed=2)
+    g = orc.grid_params(c["pos"], c["h"], 6)
+    assert g.cell >= 2.0 * c["h"].max() and g.cell * (1 << g.bits) > g.ext
+    keys = orc.morton_keys(c["pos"], g)
+    assert keys.max() < (1 << 30)
+    order = orc.sort_order(keys)
+    ks = keys[order]
+    assert np.all(np.diff(ks.astype(np.int64)) >= 0)
+    same = np.diff(ks.astype(np.int64)) == 0
+    assert np.all(np.diff(order.astype(np.int64))[same] > 0)   # stable: ties by body index
+    # neighbors always live in adjacent cells of the 2^bits grid (the superset guarantee the GPU search relies on)
+    shift = 3 * (10 - g.bits)
+
+    def cell_xyz(k):
+        k = int(k) >> shift
+        return [sum(((k >> (3 * b + a)) & 1) << b for b in range(10)) for a in range(3)]
+    o, nb = orc.neighbors(c["pos"], c["h"], "grid")
+    rng = np.random.default_rng(0)
+    for i in rng.integers(0, 5000, 300):
+        ci = cell_xyz(keys[i])
+        for j in nb[o[i]:o[i + 1]]:
+            cj = cell_xyz(keys[j])
+            assert max(abs(a - b) for a, b in zip(ci, cj)) <= 1
+
+
+def _check_tree(t, n, leaf_max):
+    """BVH integrity invariant of the reference (Builder.cs:864-902 CheckIntegrity): every child box is inside its
+    parent's box, every body is reachable exactly once, ranges partition."""
+    seen = np.zeros(n, np.int32)
+    stack = [0]
+    while stack:
+        k = stack.pop()
+        if k >= n - 1:
+            seen[k - (n - 1)] += 1
+            continue
+        l, r = t.left[k], t.right[k]
+        assert t.first[k] == t.first[l] and t.last[k] == t.last[r] and t.last[l] + 1 == t.first[r]
+        for c in (l, r):
+            assert t.parent[c] == k
+            assert np.all(t.lo[c] >= t.lo[k]) and np.all(t.hi[c] <= t.hi[k])
+        stack += [l, r]
+    assert np.all(seen == 1)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 10, 100, 1000])
+def test_lbvh_integrity(orc, n):
+    # sizes of BoundingVolumeHierarchyBuilderTests.cs:86-106 (BuildTree N in {2,10,100,1000}) plus the degenerate ones
+    import sphb200.ic as ic
+    c = ic.make_sphere(n, seed=n)
+    g = orc.grid_params(c["pos"], c["h"], 5)
+    keys = orc.morton_keys(c["pos"], g)
+    order = orc.sort_order(keys).astype(np.int64)
+    t = orc.lbvh_build(keys[order], c["pos"][order], c["vel"][order], c["h"][order], c["mass"][order], 4, 0, 0.02)
+    _check_tree(t, n, 4)
+    assert t.mom[0, 3] == pytest.approx(c["mass"].sum(), rel=1e-5)          # total mass conserved by M2M
+    cm = (c["pos"] * c["mass"][:, None]).sum(0) / c["mass"].sum()
+    np.testing.assert_allclose(t.mom[0, :3], cm, atol=2e-3)
+    # root box contains every collider box (quirk Q2: boxes are +-(2h+0.05) around the particles)
+    assert np.all(t.lo[0] <= (c["pos"] - 2 * c["h"][:, None] - 0.05).min(0) + 1e-4)
+
+
+def test_lbvh_duplicate_keys(orc):
+    # 2N particles in coincident pairs (the reference's BuildTreeAndOverlap fixture, BuilderTests.cs:428-461):
+    # identical Morton keys must still give a valid tree, and each pair must see each other as neighbors
+    rng = np.random.default_rng(1)
+    base = rng.uniform(-20, 20, (300, 3)).astype(f32)
+    pos = np.concatenate([base, base]); n = len(pos)
+    h = np.full(n, 0.05, f32); m = np.ones(n, f32); vel = np.zeros((n, 3), f32)
+    g = orc.grid_params(pos, h, 8)
+    keys = orc.morton_keys(pos, g)
+    order = orc.sort_order(keys).astype(np.int64)
+    t = orc.lbvh_build(keys[order], pos[order], vel[order], h[order], m[order], 4, 0, 0.0)
+    _check_tree(t, n, 4)
+    o, nb = orc.neighbors(pos, h, "brute")
+    assert len(nb) == n                                       # exactly N coincident pairs -> 2N directed entries
+    for i in range(300):
+        assert list(nb[o[i]:o[i + 1]]) == [i + 300]
+
+
+def test_tree_gravity_converges_to_direct_sum(orc):
+    import sphb200.ic as ic
+    c = ic.make_sphere(2000, seed=4)
+    gd = orc.gravity_direct(c["pos"], c["h"], c["mass"], accum_double=True)
+    # theta -> 0: every node is opened, the walk is the direct sum plus the self potential (quirk Q3)
+    gt, npart, napp, _, _ = orc.tree_gravity(c["pos"], c["vel"], c["h"], c["mass"], 0.02, theta=1e-6, accum_double=True)
+    assert napp.sum() == 0 and np.all(npart == 2000)
+    np.testing.assert_allclose(gt[:, :3], gd[:, :3], rtol=2e-5, atol=1e-7)
+    self_phi = -2.4 * c["mass"] / c["h"]
+    np.testing.assert_allclose(gt[:, 3], gd[:, 3] + self_phi, rtol=2e-5)
+    # theta = 0.7 monopole: percent-level accuracy, far fewer interactions
+    gt7, npart7, napp7, _, _ = orc.tree_gravity(c["pos"], c["vel"], c["h"], c["mass"], 0.02, theta=0.7, accum_double=True)
+    err = np.linalg.norm(gt7[:, :3] - gd[:, :3], axis=1) / np.linalg.norm(gd[:, :3], axis=1)
+    assert np.median(err) < 0.03 and (npart7 + napp7).mean() < 600
