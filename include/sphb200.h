@@ -48,7 +48,7 @@ typedef struct sph_Params {
     float G;                /* k_GravConstant                     GravityFieldSystem.cs:26  (1)     */
     float theta;            /* k_Theta                            GravityFieldSystem.cs:228 (0.7)   */
     float target_neighbors; /* TARGET_NEIGHBORS                   ParticleSmoothingSystem.cs:18 (50) */
-    int32_t max_neighbors;  /* neighbor-list capacity per particle (multiple of 32; default 128)    */
+    int32_t max_neighbors;  /* neighbor-list capacity per particle (multiple of 32; default 256)    */
     int32_t leaf_max;       /* bodies per tree leaf               BoundingVolumeHierarchy.cs:40-83 (4) */
     int32_t aabb_mode;      /* 0 = MAC boxes are collider AABBs (quirk Q2, default), 1 = point bounds */
     int32_t max_grid_bits;  /* cells per axis <= 2^bits, bits <= 8; 0 = choose from capacity          */
@@ -121,6 +121,8 @@ SPH_API int sphb200_destroy(sph_handle h);
 SPH_API const char* sphb200_last_error(sph_handle h);
 /* Run on an externally owned cudaStream_t (e.g. torch's current stream); NULL = the handle's own stream. */
 SPH_API int sphb200_set_stream(sph_handle h, void* cuda_stream);
+/* Blocks until the handle's stream is idle; returns sticky asynchronous errors of the steps issued since the last
+ * neighbor build (SPH_ERR_NEIGHBOR_OVERFLOW, SPH_ERR_TREE_STACK). */
 SPH_API int sphb200_sync(sph_handle h);
 
 /* Upload the per-particle components from host AoS arrays (strides in bytes; body index = array index).

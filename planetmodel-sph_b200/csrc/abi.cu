@@ -48,7 +48,7 @@ int sphb200_default_params(sph_Params* p) {
     p->G = 1.0f;               // GravityFieldSystem.cs:26
     p->theta = 0.7f;           // GravityFieldSystem.cs:228
     p->target_neighbors = 50;  // ParticleSmoothingSystem.cs:18
-    p->max_neighbors = 128;
+    p->max_neighbors = 256;
     p->leaf_max = 4;           // <= 4 bodies per BVH leaf, BoundingVolumeHierarchy.cs:40-83
     p->aabb_mode = 0;
     p->max_grid_bits = 0;
@@ -155,11 +155,12 @@ int sphb200_set_stream(sph_handle c, void* s) {
     return SPH_OK;
 }
 
+static int check_errflags(sphb200_ctx* c);
+
 int sphb200_sync(sph_handle c) {
     if (!c) return SPH_ERR_INVALID_ARG;
     SPH_CK(c, cudaSetDevice(c->device));
-    SPH_CK(c, cudaStreamSynchronize(c->stream));
-    return SPH_OK;
+    return check_errflags(c);  // synchronises the stream and reports sticky asynchronous errors (list overflow, ...)
 }
 
 int sphb200_count(sph_handle c, int64_t* n, int64_t* cap) {
@@ -227,6 +228,8 @@ int sphb200_upload(sph_handle c, int64_t n, const void* pos, int pos_stride, con
     c->cur = 0;
     c->resident = true; c->lists_valid = c->pressure_valid = c->gravity_valid = c->tree_valid = c->h_updated = false;
     c->sorted_valid = c->lists_fresh = false;
+    // asynchronous error flags are sticky from one upload to the next (results after an overflow are tainted)
+    SPH_CK(c, cudaMemsetAsync(c->err_d, 0, ERR_SLOTS * sizeof(int32_t), c->stream));
     if (n == 0) return SPH_OK;
     float* st = (float*)c->stage_h;
     float* P = st; float* V = st + 3 * n; float* M = st + 6 * n; float* H = st + 7 * n; int32_t* NO = (int32_t*)(st + 8 * n);
@@ -292,7 +295,6 @@ static int ensure_sorted(sphb200_ctx* c) {
 int sphb200_build_neighbors(sph_handle c) {
     NEED_RESIDENT(c);
     if (c->n == 0) return SPH_OK;
-    SPH_CK(c, cudaMemsetAsync(c->err_d, 0, ERR_SLOTS * sizeof(int32_t), c->stream));
     int rc = ensure_sorted(c);
     if (rc) return rc;
     rc = sph_launch_neighbors_density(c);
@@ -369,7 +371,6 @@ int sphb200_step(sph_handle c, float dt, int impl) {
     pass_begin(c);
     if ((rc = sphb200_smoothing_update(c))) return rc;
     pass_mark(c, "smoothing_bounds");
-    SPH_CK(c, cudaMemsetAsync(c->err_d, 0, ERR_SLOTS * sizeof(int32_t), c->stream));
     if ((rc = ensure_sorted(c))) return rc;
     pass_mark(c, "keys_sort_permute_cells");
     if ((rc = sph_launch_neighbors_density(c))) return rc;

@@ -183,8 +183,10 @@ class Simulation:
         def stride(a, natural):
             if a.dtype.names:
                 return a.dtype.itemsize
-            a2 = a.reshape(len(a), -1)
             assert a.dtype == np.float32, "float32 arrays required"
+            if len(a) == 0:
+                return natural
+            a2 = a.reshape(len(a), -1)
             assert a2.shape[1] * 4 >= natural
             return a2.shape[1] * 4
         n = len(mass)
