@@ -168,6 +168,8 @@ def run_ours(args):
         import torch.distributed as td
         td.init_process_group("nccl", device_id=torch.device("cuda", local))
     c, grav = workload_config(args.workload)
+    if args.gravity:
+        grav = args.gravity
     n = len(c["h"])
     impl = sphb200.GRAVITY_PARTICLE if grav == "particle" else sphb200.GRAVITY_TREE
 
@@ -320,6 +322,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--gravity", default=None, choices=["tree", "particle"], help="override the workload's gravity path")
     ap.add_argument("--kernels-only", action="store_true", help="skip the e2e and CPU-baseline legs (ncu profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":

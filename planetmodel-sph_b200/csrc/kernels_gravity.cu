@@ -17,8 +17,8 @@
 namespace {
 
 constexpr int AP_THREADS = 256;
-constexpr int AP_TPT = 2;     // targets per thread
-constexpr int AP_TILE = 256;  // sources per shared-memory tile
+constexpr int AP_TPT = 4;     // targets per thread (one LDS.128 feeds 4 pair evaluations)
+constexpr int AP_TILE = 256;  // sources per shared-memory tile (= inner fp32 partial-sum length)
 
 __device__ __forceinline__ float rsqrt_approx(float x) {
     float y;
@@ -26,17 +26,20 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     return y;
 }
 
+// Source tiles are double-buffered in shared memory (one barrier per tile; the next tile's global load is in flight
+// during the math), read back as warp-uniform LDS.128 broadcasts through a running pointer kept in a vector register.
+template <int TPT>
 __global__ void __launch_bounds__(AP_THREADS) k_gravity_allpairs(const float4* __restrict__ src, int n_src, int src_per_split,
                                                                  const float4* __restrict__ posh, int t0, int t1,
                                                                  float4* __restrict__ part) {
-    __shared__ float4 tile[AP_TILE];
+    __shared__ float4 tile[2][AP_TILE];
     const int nt = t1 - t0;
     const int tid = threadIdx.x;
-    const int tb = blockIdx.x * (AP_THREADS * AP_TPT);
-    float xi[AP_TPT], yi[AP_TPT], zi[AP_TPT], a2[AP_TPT];
-    float AX[AP_TPT], AY[AP_TPT], AZ[AP_TPT], PH[AP_TPT];
+    const int tb = blockIdx.x * (AP_THREADS * TPT);
+    float xi[TPT], yi[TPT], zi[TPT], a2[TPT];
+    float AX[TPT], AY[TPT], AZ[TPT], PH[TPT];
 #pragma unroll
-    for (int k = 0; k < AP_TPT; k++) {
+    for (int k = 0; k < TPT; k++) {
         int t = tb + k * AP_THREADS + tid;
         float4 p = posh[t0 + min(t, nt - 1)];
         xi[k] = p.x; yi[k] = p.y; zi[k] = p.z; a2[k] = p.w * p.w;
@@ -44,37 +47,47 @@ __global__ void __launch_bounds__(AP_THREADS) k_gravity_allpairs(const float4* _
     }
     const int s0 = blockIdx.y * src_per_split;
     const int s1 = min(s0 + src_per_split, n_src);
-    for (int base = s0; base < s1; base += AP_TILE) {
-        int idx = base + tid;
-        // padding source: zero mass, far away (contributes exactly 0)
-        tile[tid] = idx < s1 ? src[idx] : make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.f);
+    const int ntiles = (s1 - s0 + AP_TILE - 1) / AP_TILE;
+    // padding source: zero mass, far away (contributes exactly 0)
+    const float4 pad = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.f);
+    int zero;
+    asm volatile("mov.u32 %0, 0;" : "=r"(zero));   // opaque: keeps the tile pointer in a vector register
+    float4 nxt = (s0 + tid < s1) ? src[s0 + tid] : pad;
+    for (int it = 0; it < ntiles; it++) {
+        float4* buf = tile[it & 1];
+        buf[tid] = nxt;
         __syncthreads();
-        float ax[AP_TPT], ay[AP_TPT], az[AP_TPT], ph[AP_TPT];
+        int nidx = s0 + (it + 1) * AP_TILE + tid;
+        nxt = (nidx < s1) ? src[nidx] : pad;
+        float ax[TPT], ay[TPT], az[TPT], ph[TPT];
 #pragma unroll
-        for (int k = 0; k < AP_TPT; k++) ax[k] = ay[k] = az[k] = ph[k] = 0.f;
-#pragma unroll 8
-        for (int j = 0; j < AP_TILE; j++) {
-            float4 s = tile[j];
+        for (int k = 0; k < TPT; k++) ax[k] = ay[k] = az[k] = ph[k] = 0.f;
+        const float4* tp = buf + zero;
+#pragma unroll 1
+        for (int j = 0; j < AP_TILE; j += 8, tp += 8) {
 #pragma unroll
-            for (int k = 0; k < AP_TPT; k++) {
-                float dx = xi[k] - s.x, dy = yi[k] - s.y, dz = zi[k] - s.z;
-                float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                r2 = fmaxf(r2, a2[k]);
-                float rinv = rsqrt_approx(r2);
-                float mr = s.w * rinv;
-                float g = mr * (rinv * rinv);
-                ax[k] = fmaf(dx, g, ax[k]);
-                ay[k] = fmaf(dy, g, ay[k]);
-                az[k] = fmaf(dz, g, az[k]);
-                ph[k] += mr;
+            for (int u = 0; u < 8; u++) {
+                const float4 s = tp[u];
+#pragma unroll
+                for (int k = 0; k < TPT; k++) {
+                    float dx = xi[k] - s.x, dy = yi[k] - s.y, dz = zi[k] - s.z;
+                    float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    r2 = fmaxf(r2, a2[k]);
+                    float rinv = rsqrt_approx(r2);
+                    float mr = s.w * rinv;
+                    float g = mr * (rinv * rinv);
+                    ax[k] = fmaf(dx, g, ax[k]);
+                    ay[k] = fmaf(dy, g, ay[k]);
+                    az[k] = fmaf(dz, g, az[k]);
+                    ph[k] += mr;
+                }
             }
         }
 #pragma unroll
-        for (int k = 0; k < AP_TPT; k++) { AX[k] += ax[k]; AY[k] += ay[k]; AZ[k] += az[k]; PH[k] += ph[k]; }
-        __syncthreads();
+        for (int k = 0; k < TPT; k++) { AX[k] += ax[k]; AY[k] += ay[k]; AZ[k] += az[k]; PH[k] += ph[k]; }
     }
 #pragma unroll
-    for (int k = 0; k < AP_TPT; k++) {
+    for (int k = 0; k < TPT; k++) {
         int t = tb + k * AP_THREADS + tid;
         if (t < nt) part[(size_t)blockIdx.y * nt + t] = make_float4(AX[k], AY[k], AZ[k], PH[k]);
     }
@@ -139,7 +152,7 @@ int sph_launch_gravity_allpairs(sphb200_ctx* c) {
     per = sph_div_up(per, AP_TILE) * AP_TILE;
     splits = sph_div_up(n, per);
     dim3 grid(tblocks, splits);
-    k_gravity_allpairs<<<grid, AP_THREADS, 0, c->stream>>>(c->posm, n, per, c->posh[c->cur], t0, t1, c->gpart);
+    k_gravity_allpairs<AP_TPT><<<grid, AP_THREADS, 0, c->stream>>>(c->posm, n, per, c->posh[c->cur], t0, t1, c->gpart);
     SPH_LAUNCH_CHECK(c);
     k_gravity_reduce<<<sph_div_up(nt, 256), 256, 0, c->stream>>>(c->gpart, splits, c->posh[c->cur], c->posm, t0, t1, c->p.G, c->grav,
                                                                 c->npart, c->napprox);
