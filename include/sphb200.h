@@ -86,12 +86,14 @@ typedef struct {
 
 /* Grid/key parameters of the last neighbor build (specification shared with oracle/sph_oracle.cpp GridParams) */
 typedef struct sph_GridParams {
-    float min[3];
-    float cell;
-    float fine_scale;
-    int32_t bits;
+    float min[3];       /* global AABB min of the positions */
+    float cell;         /* cell edge = max(2.002*href, 2.002*hmax/4, ext*1.0001/2^bits_max) */
+    float fine_scale;   /* 1024 / (cell * 2^bits): positions -> 10-bit fine Morton coordinates */
+    int32_t bits;       /* cells per axis = 2^bits */
     float hmax;
-    float ext;
+    float ext;          /* largest AABB extent */
+    float href;         /* typical h: float whose bit pattern is the mean bit pattern of all h (deterministic) */
+    int32_t stencil;    /* S: interacting pairs lie within S cells of each other on every axis (S*cell >= 2.002*hmax) */
 } sph_GridParams;
 
 /* ---- per-particle fields for download / device_ptr */

@@ -24,7 +24,7 @@ i64p = np.ctypeslib.ndpointer(np.int64, flags="C_CONTIGUOUS")
 
 class GridParams(C.Structure):
     _fields_ = [("min", C.c_float * 3), ("cell", C.c_float), ("fine_scale", C.c_float), ("bits", C.c_int32),
-                ("hmax", C.c_float), ("ext", C.c_float)]
+                ("hmax", C.c_float), ("ext", C.c_float), ("href", C.c_float), ("stencil", C.c_int32)]
 
 
 def build(force=False):

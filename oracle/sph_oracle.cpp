@@ -326,6 +326,7 @@ ORC_API int64_t orc_neighbors_brute(int64_t n, const float* pos, const float* h,
 }
 
 // Cell list with cell edge >= 2*h_max*(1+1e-3): every pair that passes Interacts lies in adjacent cells.
+// (Independent of the GPU's grid: this is the ground truth for larger N, itself checked against brute force.)
 ORC_API int64_t orc_neighbors_grid(int64_t n, const float* pos, const float* h, int64_t* offsets, int32_t* nbr, int64_t cap) {
     if (n == 0) { offsets[0] = 0; return 0; }
     double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300}; double hmax = 0;
@@ -487,11 +488,13 @@ ORC_API void orc_integrate(int64_t n, float* pos, float* vel, const float* rho, 
 // ------------------------------------------------------------------------------------------------
 struct GridParams {
     float min[3];      // global AABB min of positions
-    float cell;        // cell edge (>= 2.002*h_max)
+    float cell;        // cell edge
     float fine_scale;  // 1024 / (cell * 2^bits)
     int32_t bits;      // cells per axis = 2^bits
     float hmax;
     float ext;         // max extent over the three axes
+    float href;        // typical h (mean of the fp32 bit patterns, reinterpreted)
+    int32_t stencil;   // S
 };
 
 static inline uint32_t expand10(uint32_t v) {
@@ -503,21 +506,35 @@ static inline uint32_t expand10(uint32_t v) {
     return v;
 }
 
+static const int kStencilMax = 4;
+
+// Cell edge: 2.002 x a *typical* h (not h_max, which would inflate every cell by the tail of the h distribution);
+// pairs with a large h are covered by a stencil of S cells per axis, S*cell >= 2.002*h_max, S <= 4.
+// The typical h must be order-independent to be reproducible on the GPU: it is the float whose bit pattern is the
+// integer mean of all h bit patterns (monotone in h, between the geometric and arithmetic means).
 ORC_API void orc_grid_params(int64_t n, const float* pos, const float* h, int max_bits, GridParams* g) {
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY}; float hmax = 0.0f;
+    uint64_t bitsum = 0;
     for (int64_t i = 0; i < n; i++) {
         for (int k = 0; k < 3; k++) { lo[k] = fminf(lo[k], pos[3 * i + k]); hi[k] = fmaxf(hi[k], pos[3 * i + k]); }
         hmax = fmaxf(hmax, h[i]);
+        uint32_t u; memcpy(&u, &h[i], 4); bitsum += u;
     }
+    uint32_t ub = n > 0 ? (uint32_t)(bitsum / (uint64_t)n) : 0u;
+    float href; memcpy(&href, &ub, 4);
     float ext = fmaxf(fmaxf(hi[0] - lo[0], hi[1] - lo[1]), hi[2] - lo[2]);
-    float cell = hmax * 2.002f;
+    float reach = hmax * 2.002f;
+    float cell = href * 2.002f;
+    if (!(cell * (float)kStencilMax >= reach)) cell = reach / (float)kStencilMax;
     int bits = 0;
     for (; bits < max_bits; bits++)
         if (cell * (float)(1 << bits) > ext) break;
     if (!(cell * (float)(1 << bits) > ext)) cell = (ext * 1.0001f) / (float)(1 << bits);
     if (!(cell > 0.0f)) cell = 1.0f;
+    int S = 1;
+    while (S < kStencilMax && !(cell * (float)S >= reach)) S++;
     for (int k = 0; k < 3; k++) g->min[k] = lo[k];
-    g->cell = cell; g->bits = bits; g->hmax = hmax; g->ext = ext;
+    g->cell = cell; g->bits = bits; g->hmax = hmax; g->ext = ext; g->href = href; g->stencil = S;
     g->fine_scale = 1024.0f / (cell * (float)(1 << bits));
 }
 

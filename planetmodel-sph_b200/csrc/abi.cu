@@ -61,10 +61,10 @@ int sphb200_destroy(sph_handle c) {
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     for (int k = 0; k < 2; k++) { cudaFree(c->posh[k]); cudaFree(c->velm[k]); cudaFree(c->orig[k]); cudaFree(c->keys[k]); cudaFree(c->idx[k]); }
-    cudaFree(c->posm); cudaFree(c->cub_tmp); cudaFree(c->cell_start); cudaFree(c->cell_end); cudaFree(c->nlist);
+    cudaFree(c->posm); cudaFree(c->cub_tmp); cudaFree(c->cell_start); cudaFree(c->cell_end); cudaFree(c->cell_hmax); cudaFree(c->nlist);
     cudaFree(c->ncount); cudaFree(c->nown); cudaFree(c->rho); cudaFree(c->press); cudaFree(c->cvol); cudaFree(c->gradp);
     cudaFree(c->grav); cudaFree(c->npart); cudaFree(c->napprox); cudaFree(c->gpart); cudaFree(c->child); cudaFree(c->range);
-    cudaFree(c->parent); cudaFree(c->flag); cudaFree(c->mom); cudaFree(c->nlo); cudaFree(c->nhi); cudaFree(c->bounds);
+    cudaFree(c->parent); cudaFree(c->flag); cudaFree(c->mom); cudaFree(c->nlo); cudaFree(c->nhi); cudaFree(c->packed); cudaFree(c->bounds);
     cudaFree(c->grid_d); cudaFree(c->err_d); cudaFree(c->rr_table); cudaFree(c->diag_d); cudaFree(c->stage_d);
     if (c->err_h) cudaFreeHost(c->err_h);
     if (c->stage_h) cudaFreeHost(c->stage_h);
@@ -111,15 +111,15 @@ int sphb200_create(const sph_Params* params, int64_t capacity, int device, sph_h
     c->cub_bytes = sph_sort_temp_bytes(capacity);
     c->stage_bytes = std::max<size_t>(cap * 9 * 4, (cap + 1) * 8);
     ok = ok && dalloc(&c->posm, cap) == cudaSuccess && cudaMalloc(&c->cub_tmp, std::max<size_t>(c->cub_bytes, 16)) == cudaSuccess &&
-         dalloc(&c->cell_start, c->ncell_max) == cudaSuccess && dalloc(&c->cell_end, c->ncell_max) == cudaSuccess &&
+         dalloc(&c->cell_start, c->ncell_max) == cudaSuccess && dalloc(&c->cell_end, c->ncell_max) == cudaSuccess && dalloc(&c->cell_hmax, c->ncell_max) == cudaSuccess &&
          dalloc(&c->nlist, cap * (size_t)p.max_neighbors) == cudaSuccess && dalloc(&c->ncount, cap) == cudaSuccess &&
          dalloc(&c->nown, cap) == cudaSuccess && dalloc(&c->rho, cap) == cudaSuccess && dalloc(&c->press, cap) == cudaSuccess &&
          dalloc(&c->cvol, cap) == cudaSuccess && dalloc(&c->gradp, cap) == cudaSuccess && dalloc(&c->grav, cap) == cudaSuccess &&
          dalloc(&c->npart, cap) == cudaSuccess && dalloc(&c->napprox, cap) == cudaSuccess &&
          dalloc(&c->gpart, cap * (size_t)c->gpart_splits) == cudaSuccess && dalloc(&c->child, nn) == cudaSuccess &&
          dalloc(&c->range, nn) == cudaSuccess && dalloc(&c->parent, nn) == cudaSuccess && dalloc(&c->flag, nn) == cudaSuccess &&
-         dalloc(&c->mom, nn) == cudaSuccess && dalloc(&c->nlo, nn) == cudaSuccess && dalloc(&c->nhi, nn) == cudaSuccess &&
-         dalloc(&c->bounds, 8) == cudaSuccess && dalloc(&c->grid_d, 1) == cudaSuccess && dalloc(&c->err_d, ERR_SLOTS) == cudaSuccess &&
+         dalloc(&c->mom, nn) == cudaSuccess && dalloc(&c->nlo, nn) == cudaSuccess && dalloc(&c->nhi, nn) == cudaSuccess && dalloc(&c->packed, 2 * nn) == cudaSuccess &&
+         dalloc(&c->bounds, 16) == cudaSuccess && dalloc(&c->grid_d, 1) == cudaSuccess && dalloc(&c->err_d, ERR_SLOTS) == cudaSuccess &&
          dalloc(&c->rr_table, SPH_RR_TABLE) == cudaSuccess && dalloc(&c->diag_d, 16) == cudaSuccess &&
          cudaMalloc(&c->stage_d, c->stage_bytes) == cudaSuccess && cudaMallocHost((void**)&c->err_h, ERR_SLOTS * sizeof(int32_t)) == cudaSuccess &&
          cudaMallocHost(&c->stage_h, c->stage_bytes) == cudaSuccess;
@@ -135,7 +135,7 @@ int sphb200_create(const sph_Params* params, int64_t capacity, int device, sph_h
         float ratio = p.target_neighbors / (float)k;
         rr[k] = (float)pow((double)ratio, (double)(1.0f / 3.0f));
     }
-    uint32_t b0[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0, 0, 0};
+    uint32_t b0[16] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     ok = cudaMemcpy(c->rr_table, rr.data(), SPH_RR_TABLE * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemcpy(c->bounds, b0, sizeof(b0), cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemset(c->err_d, 0, ERR_SLOTS * sizeof(int32_t)) == cudaSuccess &&

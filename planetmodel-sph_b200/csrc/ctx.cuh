@@ -33,6 +33,7 @@ struct sphb200_ctx {
     size_t cub_bytes = 0;
     uint32_t* cell_start = nullptr;
     uint32_t* cell_end = nullptr;
+    uint32_t* cell_hmax = nullptr;  // max h per cell (fp32 bit pattern)
     int grid_bits_max = 0;
     size_t ncell_max = 0;
 
@@ -57,8 +58,9 @@ struct sphb200_ctx {
     float4* mom = nullptr;
     float4* nlo = nullptr;       // xyz = box min, w = first (int bits)
     float4* nhi = nullptr;       // xyz = box max, w = last  (int bits)
+    float4* packed = nullptr;    // walk nodes, 2 float4 per node: (cm, M), (Bmax^2, a, b, -)
 
-    uint32_t* bounds = nullptr;  // 8 ordered-uint floats: min xyz, max xyz, hmax
+    uint32_t* bounds = nullptr;  // [0..6] ordered-uint floats: min xyz, max xyz, hmax; [8..9] u64 sum of h bit patterns
     sph_GridParams* grid_d = nullptr;
     sph_GridParams grid_h{};
     int32_t* err_d = nullptr;

@@ -29,6 +29,7 @@ __global__ void __launch_bounds__(256) k_smoothing_bounds(float4* __restrict__ p
                                                           uint32_t* __restrict__ bounds) {
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     float hmax = 0.f;
+    unsigned long long bitsum = 0ull;  // sum of the fp32 bit patterns of h: integer, hence order-independent
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
         float4 p = posh[i];
         if (update_h) {
@@ -42,7 +43,11 @@ __global__ void __launch_bounds__(256) k_smoothing_bounds(float4* __restrict__ p
         lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
         hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
         hmax = fmaxf(hmax, p.w);
+        bitsum += __float_as_uint(p.w);
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bitsum += __shfl_xor_sync(0xffffffffu, bitsum, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd((unsigned long long*)(bounds + 8), bitsum);
     __shared__ float s[7][8];
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     float v[7] = {warp_min(lo[0]), warp_min(lo[1]), warp_min(lo[2]), warp_max(hi[0]), warp_max(hi[1]), warp_max(hi[2]), warp_max(hmax)};
@@ -59,22 +64,30 @@ __global__ void __launch_bounds__(256) k_smoothing_bounds(float4* __restrict__ p
 }
 
 // One thread: bounds -> grid parameters (mirror of orc_grid_params), then re-arm the bounds accumulator.
-__global__ void k_grid_setup(uint32_t* bounds, sph_GridParams* g, int max_bits) {
+__global__ void k_grid_setup(uint32_t* bounds, sph_GridParams* g, int max_bits, int n) {
     float lo[3], hi[3];
     for (int k = 0; k < 3; k++) { lo[k] = ord2f(bounds[k]); hi[k] = ord2f(bounds[3 + k]); }
     float hmax = ord2f(bounds[6]);
+    unsigned long long bitsum = *(unsigned long long*)(bounds + 8);
+    float href = __uint_as_float(n > 0 ? (uint32_t)(bitsum / (unsigned long long)n) : 0u);
     float ext = fmaxf(fmaxf(__fsub_rn(hi[0], lo[0]), __fsub_rn(hi[1], lo[1])), __fsub_rn(hi[2], lo[2]));
-    float cell = __fmul_rn(hmax, 2.002f);
+    const int kStencilMax = 4;
+    float reach = __fmul_rn(hmax, 2.002f);
+    float cell = __fmul_rn(href, 2.002f);
+    if (!(__fmul_rn(cell, (float)kStencilMax) >= reach)) cell = __fdiv_rn(reach, (float)kStencilMax);
     int bits = 0;
     for (; bits < max_bits; bits++)
         if (__fmul_rn(cell, (float)(1 << bits)) > ext) break;
     if (!(__fmul_rn(cell, (float)(1 << bits)) > ext)) cell = __fdiv_rn(__fmul_rn(ext, 1.0001f), (float)(1 << bits));
     if (!(cell > 0.0f)) cell = 1.0f;
+    int S = 1;
+    while (S < kStencilMax && !(__fmul_rn(cell, (float)S) >= reach)) S++;
     g->min[0] = lo[0]; g->min[1] = lo[1]; g->min[2] = lo[2];
-    g->cell = cell; g->bits = bits; g->hmax = hmax; g->ext = ext;
+    g->cell = cell; g->bits = bits; g->hmax = hmax; g->ext = ext; g->href = href; g->stencil = S;
     g->fine_scale = __fdiv_rn(1024.0f, __fmul_rn(cell, (float)(1 << bits)));
     bounds[0] = bounds[1] = bounds[2] = 0xffffffffu;
     bounds[3] = bounds[4] = bounds[5] = bounds[6] = 0u;
+    bounds[8] = bounds[9] = 0u;
 }
 
 __global__ void __launch_bounds__(256) k_keys(const float4* __restrict__ posh, const sph_GridParams* __restrict__ g, int n,
@@ -97,7 +110,8 @@ __global__ void __launch_bounds__(256) k_permute_cells(const uint32_t* __restric
                                                        const uint32_t* __restrict__ orig_in, float4* __restrict__ posh_out,
                                                        float4* __restrict__ velm_out, uint32_t* __restrict__ orig_out,
                                                        float4* __restrict__ posm, const sph_GridParams* __restrict__ g, int n,
-                                                       uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_end) {
+                                                       uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_end,
+                                                       uint32_t* __restrict__ cell_hmax) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t src = idx[i];
@@ -111,6 +125,7 @@ __global__ void __launch_bounds__(256) k_permute_cells(const uint32_t* __restric
     uint32_t ck = keys[i] >> shift;
     if (i == 0 || (keys[i - 1] >> shift) != ck) cell_start[ck] = (uint32_t)i;
     if (i == n - 1 || (keys[i + 1] >> shift) != ck) cell_end[ck] = (uint32_t)(i + 1);
+    atomicMax(&cell_hmax[ck], __float_as_uint(p.w));   // h > 0: the bit pattern orders like the value
 }
 
 }  // namespace
@@ -127,7 +142,7 @@ int sph_launch_smoothing_bounds(sphb200_ctx* c, bool update_h) {
     int blocks = min(sph_div_up(n, 256), c->sm_count * 8);
     k_smoothing_bounds<<<blocks, 256, 0, c->stream>>>(c->posh[c->cur], c->nown, c->rr_table, n, update_h ? 1 : 0, c->bounds);
     SPH_LAUNCH_CHECK(c);
-    k_grid_setup<<<1, 1, 0, c->stream>>>(c->bounds, c->grid_d, c->grid_bits_max);
+    k_grid_setup<<<1, 1, 0, c->stream>>>(c->bounds, c->grid_d, c->grid_bits_max, n);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;
 }
@@ -143,9 +158,10 @@ int sph_launch_sort_and_cells(sphb200_ctx* c) {
     size_t ncell = c->ncell_max;
     SPH_CK(c, cudaMemsetAsync(c->cell_start, 0, ncell * sizeof(uint32_t), c->stream));
     SPH_CK(c, cudaMemsetAsync(c->cell_end, 0, ncell * sizeof(uint32_t), c->stream));
+    SPH_CK(c, cudaMemsetAsync(c->cell_hmax, 0, ncell * sizeof(uint32_t), c->stream));
     k_permute_cells<<<sph_div_up(n, 256), 256, 0, c->stream>>>(c->keys[1], c->idx[1], c->posh[in], c->velm[in], c->orig[in],
                                                                c->posh[out], c->velm[out], c->orig[out], c->posm, c->grid_d, n,
-                                                               c->cell_start, c->cell_end);
+                                                               c->cell_start, c->cell_end, c->cell_hmax);
     SPH_LAUNCH_CHECK(c);
     c->cur = out;
     return SPH_OK;

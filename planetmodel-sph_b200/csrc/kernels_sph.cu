@@ -1,4 +1,5 @@
-// kernels_sph.cu -- neighbor lists + density + EOS (fused), pressure gradient, integration, upload/download packing.
+// kernels_sph.cu -- pressure gradient, near-pair gravity correction, integration, upload/download packing, diagnostics
+// (the fused neighbor-list + density + EOS kernel lives in kernels_neighbors.cu).
 //
 // Replaces: KernelSystem.FilterPairs / CalculateInteractionJob (A/Systems/KernelSystem.cs:234-335, 583-633),
 // SplineKernel (A/Util/SplineKernel.cs), DensityFieldSystem (A/Systems/DensityFieldSystem.cs:38-56),
@@ -75,110 +76,6 @@ __device__ __forceinline__ int warp_sum_i(int v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
     return v;
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// K1: neighbor lists + density + EOS.  One warp per target particle; the 27 neighbor cells of the target's cell are
-// split over four 8-lane groups, lanes stride over the (contiguous, sorted) particles of a cell with coalesced
-// float4 loads; survivors are compacted into the target's list row with ballot/popc.
-// ------------------------------------------------------------------------------------------------------------
-constexpr int K1_WARPS = 8;
-constexpr int K1_TPW = 4;  // consecutive targets per warp (L1 reuse of the neighbor cells)
-
-__global__ void __launch_bounds__(K1_WARPS * 32) k_neighbors_density(
-    const float4* __restrict__ posh, const float4* __restrict__ posm, const uint32_t* __restrict__ keys,
-    const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, const sph_GridParams* __restrict__ g,
-    int t0, int t1, int kmax, float Keos, uint32_t* __restrict__ nlist, int32_t* __restrict__ ncount,
-    int32_t* __restrict__ nown, float* __restrict__ rho, float* __restrict__ press, float* __restrict__ cvol,
-    int32_t* __restrict__ err) {
-    const int lane = threadIdx.x & 31;
-    const int warp = (blockIdx.x * K1_WARPS + (threadIdx.x >> 5));
-    const int bits = g->bits;
-    const int shift = 3 * (10 - bits);
-    const int dim = 1 << bits;
-    const int grp = lane >> 3, sl = lane & 7;
-
-    for (int tt = 0; tt < K1_TPW; tt++) {
-        int t = t0 + warp * K1_TPW + tt;
-        if (t >= t1) return;
-        const float4 pi = posh[t];
-        const float hi = pi.w;
-        const float hi2 = __fmul_rn(hi, 2.0f);
-        const float hinv_i = 1.0f / hi;
-        uint32_t ck = keys[t] >> shift;
-        int cx = (int)compact10(ck), cy = (int)compact10(ck >> 1), cz = (int)compact10(ck >> 2);
-        uint32_t s_l = 0, e_l = 0;
-        if (lane < 27) {
-            int nx = cx + (lane % 3) - 1, ny = cy + ((lane / 3) % 3) - 1, nz = cz + (lane / 9) - 1;
-            if (nx >= 0 && ny >= 0 && nz >= 0 && nx < dim && ny < dim && nz < dim) {
-                uint32_t nk = expand10((uint32_t)nx) | (expand10((uint32_t)ny) << 1) | (expand10((uint32_t)nz) << 2);
-                s_l = cell_start[nk];
-                e_l = cell_end[nk];
-            }
-        }
-        float rho_l = 0.f;
-        int own_l = 0;
-        int count = 0;
-        uint32_t* row = nlist + (size_t)t * kmax;
-        for (int round = 0; round < 7; round++) {
-            int c = round * 4 + grp;
-            uint32_t s = __shfl_sync(FULL, s_l, c & 31), e = __shfl_sync(FULL, e_l, c & 31);
-            if (c >= 27) { s = 0; e = 0; }
-            uint32_t j = s + sl;
-            while (__any_sync(FULL, j < e)) {
-                bool keep = false, in_i = false;
-                float r = 0.f, hj = 1.f;
-                if (j < e && j != (uint32_t)t) {
-                    float4 pj = posh[j];
-                    hj = pj.w;
-                    float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
-                    float d2 = dot3_rn(dx, dy, dz);
-                    float sz = fmaxf(hi, hj);
-                    // SplineKernel.Interacts (SplineKernel.cs:47-53): d2 < size*size*Kappa*Kappa
-                    if (d2 < __fmul_rn(__fmul_rn(__fmul_rn(sz, sz), 2.0f), 2.0f)) {
-                        r = __fsqrt_rn(d2);
-                        if (sz < 1.0e5f) {
-                            // keep rule KernelSymmetric.w > 0 (KernelSystem.cs:269,283): with h < 1e5 no underflow is
-                            // possible, so W(r,h) > 0 <=> r < 2h (SplineKernel.cs:62)
-                            in_i = r < hi2;
-                            keep = in_i || (r < __fmul_rn(hj, 2.0f));
-                        } else {
-                            float wi = kernel_exact(r, hi), wj = kernel_exact(r, hj);
-                            in_i = wi > 0.0f;
-                            keep = __fmul_rn(__fadd_rn(wi, wj), 0.5f) > 0.0f;
-                        }
-                    }
-                }
-                unsigned bal = __ballot_sync(FULL, keep);
-                if (keep) {
-                    float hinv_j = __fdividef(1.0f, hj);
-                    float wsym = 0.5f * (w_fast(r, hinv_i) + w_fast(r, hinv_j));
-                    float mj = posm[j].w;
-                    rho_l = fmaf(mj, wsym, rho_l);
-                    own_l += in_i ? 1 : 0;
-                    int slot = count + __popc(bal & ((1u << lane) - 1u));
-                    if (slot < kmax) row[slot] = j;
-                }
-                count += __popc(bal);
-                j += 8;
-            }
-        }
-        float rsum = warp_sum(rho_l);
-        int own = warp_sum_i(own_l);
-        if (lane == 0) {
-            // self term m_i * Kernel(0,h_i) (DensityFieldSystem.cs:45), exact: 1/(pi h^3)
-            float mi = posm[t].w;
-            float w0 = __fdiv_rn(1.0f, __fmul_rn(__fmul_rn(__fmul_rn(kPI, hi), hi), hi));
-            float d = __fadd_rn(__fmul_rn(mi, w0), rsum);
-            float P = __fmul_rn(__fmul_rn(Keos, d), d);  // PressureFieldSystem.cs:31-33
-            rho[t] = d;
-            press[t] = P;
-            cvol[t] = __fmul_rn(__fdiv_rn(mi, d), P);    // m_j / rho_j * P_j (PressureFieldSystem.cs:65)
-            ncount[t] = count;
-            nown[t] = own;
-            if (count > kmax) atomicMax(&err[ERR_NEIGHBOR_OVERFLOW], count);
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -434,18 +331,6 @@ static inline void target_range(sphb200_ctx* c, int& t0, int& t1) {
     t0 = (int)c->t0;
     t1 = (c->t1 < 0 || c->t1 > c->n) ? (int)c->n : (int)c->t1;
     if (t0 > t1) t0 = t1;
-}
-
-int sph_launch_neighbors_density(sphb200_ctx* c) {
-    int t0, t1; target_range(c, t0, t1);
-    int nt = t1 - t0;
-    if (nt <= 0) return SPH_OK;
-    int per_block = K1_WARPS * K1_TPW;
-    k_neighbors_density<<<sph_div_up(nt, per_block), K1_WARPS * 32, 0, c->stream>>>(
-        c->posh[c->cur], c->posm, c->keys[1], c->cell_start, c->cell_end, c->grid_d, t0, t1, c->p.max_neighbors, c->p.K,
-        c->nlist, c->ncount, c->nown, c->rho, c->press, c->cvol, c->err_d);
-    SPH_LAUNCH_CHECK(c);
-    return SPH_OK;
 }
 
 int sph_launch_pressure(sphb200_ctx* c) {

@@ -13,7 +13,9 @@
 // Walk mapping: one warp = 32 consecutive (spatially coherent) sorted targets sharing ONE traversal stack in shared
 // memory; each stack entry carries the mask of lanes still descending that subtree, so every lane sees exactly the
 // node sequence of its private depth-first walk (per-particle MAC, same summation order as the oracle) while node
-// loads are warp-uniform broadcasts and control flow is warp-coherent.
+// loads are warp-uniform broadcasts and control flow is warp-coherent.  The walk reads a packed 32-byte node
+// (centre of mass, mass, Bmax^2, children / body range): Bmax^2 depends only on the node, so it is evaluated once in
+// the build with the reference's exact op sequence instead of once per (target, node) visit.
 #include "ctx.cuh"
 #include <math.h>
 
@@ -24,6 +26,11 @@ constexpr unsigned FULL = 0xffffffffu;
 __device__ __forceinline__ float rsqrt_approx(float x) {
     float y;
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
 
@@ -77,12 +84,28 @@ __device__ __forceinline__ void moment_accumulate(float4& mo, float cx, float cy
     }
 }
 
+// Packed walk node: [2k] = (cm.xyz, M), [2k+1] = (Bmax^2, a, b, -) with (a,b) = (left,right) for nodes that are
+// descended and (first, -count) for leaf buckets.  Bmax^2 with the op order of AcceptApproximation (:235-243).
+__device__ __forceinline__ void pack_node(float4* __restrict__ packed, int k, float4 mo, const float lo[3], const float hi[3],
+                                          int2 ch, int2 rg, int leaf_max) {
+    float bx = fmaxf(__fsub_rn(hi[0], mo.x), __fsub_rn(mo.x, lo[0]));
+    float by = fmaxf(__fsub_rn(hi[1], mo.y), __fsub_rn(mo.y, lo[1]));
+    float bz = fmaxf(__fsub_rn(hi[2], mo.z), __fsub_rn(mo.z, lo[2]));
+    float b_sq = dot3_rn(bx, by, bz);
+    int cnt = rg.y - rg.x + 1;
+    int a = cnt <= leaf_max ? rg.x : ch.x;
+    int b = cnt <= leaf_max ? -cnt : ch.y;
+    packed[2 * (size_t)k] = mo;
+    packed[2 * (size_t)k + 1] = make_float4(b_sq, __int_as_float(a), __int_as_float(b), 0.f);
+}
+
 // Moments + MAC boxes.  Small nodes (<= leaf_max bodies) are evaluated directly from their particle range (reference
 // leaf rule); larger nodes are finished bottom-up by the second thread to arrive (fixed left-then-right order).
 __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ posh, const float4* __restrict__ velm, int n,
                                                     const int2* __restrict__ child, const int2* __restrict__ range,
                                                     const int32_t* __restrict__ parent, int leaf_max, int aabb_mode, float dt,
-                                                    int32_t* __restrict__ flag, float4* mom, float4* nlo, float4* nhi) {
+                                                    int32_t* __restrict__ flag, float4* mom, float4* nlo, float4* nhi,
+                                                    float4* __restrict__ packed) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= 2 * n - 1) return;
     int2 rg = range[k];
@@ -112,6 +135,7 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
     mom[k] = mo;
     nlo[k] = make_float4(lo[0], lo[1], lo[2], __int_as_float(rg.x));
     nhi[k] = make_float4(hi[0], hi[1], hi[2], __int_as_float(rg.y));
+    pack_node(packed, k, mo, lo, hi, child[k], rg, leaf_max);
     int cur = k;
     while (true) {
         int p = parent[cur];
@@ -127,9 +151,12 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         moment_accumulate(acc, ml.x, ml.y, ml.z, ml.w);  // GravityFieldSystem.cs:513-521, children in Data order
         moment_accumulate(acc, mr.x, mr.y, mr.z, mr.w);
+        float plo[3] = {fminf(ll.x, lr.x), fminf(ll.y, lr.y), fminf(ll.z, lr.z)};
+        float phi[3] = {fmaxf(hl.x, hr.x), fmaxf(hl.y, hr.y), fmaxf(hl.z, hr.z)};
         mom[p] = acc;
-        nlo[p] = make_float4(fminf(ll.x, lr.x), fminf(ll.y, lr.y), fminf(ll.z, lr.z), __int_as_float(prg.x));
-        nhi[p] = make_float4(fmaxf(hl.x, hr.x), fmaxf(hl.y, hr.y), fmaxf(hl.z, hr.z), __int_as_float(prg.y));
+        nlo[p] = make_float4(plo[0], plo[1], plo[2], __int_as_float(prg.x));
+        nhi[p] = make_float4(phi[0], phi[1], phi[2], __int_as_float(prg.y));
+        pack_node(packed, p, acc, plo, phi, ch, prg, leaf_max);
         cur = p;
     }
 }
@@ -137,93 +164,92 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
 constexpr int TW_WARPS = 8;
 
 __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __restrict__ posh, const float4* __restrict__ posm,
-                                                             const int2* __restrict__ child, const float4* __restrict__ mom,
-                                                             const float4* __restrict__ nlo, const float4* __restrict__ nhi,
-                                                             int t0, int t1, int leaf_max, float theta2, float G,
-                                                             float4* __restrict__ grav, int32_t* __restrict__ npart,
+                                                             const float4* __restrict__ packed, int t0, int t1, float theta2,
+                                                             float G, float4* __restrict__ grav, int32_t* __restrict__ npart,
                                                              int32_t* __restrict__ napprox, int32_t* __restrict__ err) {
     __shared__ int2 stack[TW_WARPS][SPH_TREE_STACK];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int t = t0 + (blockIdx.x * TW_WARPS + w) * 32 + lane;
     const bool active = t < t1;
     const float4 pi = posh[active ? t : (t1 - 1)];
-    const float a = pi.w, a2 = a * a, ainv = 1.0f / a;
+    const float a2 = pi.w * pi.w, ainv = 1.0f / pi.w;
+    // band around theta^2 inside which the fast reciprocal test is not trusted and the exact division decides
+    const float band = theta2 * 8.0e-6f;
     float gx = 0.f, gy = 0.f, gz = 0.f, gp = 0.f;
     int np = 0, na = 0;
-    unsigned m0 = __ballot_sync(FULL, active);
-    if (m0 == 0) return;
+    unsigned mask = __ballot_sync(FULL, active);
+    if (mask == 0) return;
+    int2* st = stack[w];
     int sp = 0;
-    if (lane == 0) stack[w][0] = make_int2(0, (int)m0);
-    sp = 1;
-    __syncwarp();
-    while (sp > 0) {
-        int2 e = stack[w][--sp];
-        __syncwarp();
-        const int k = e.x;
-        const unsigned mask = (unsigned)e.y;
-        const float4 mo = __ldg(&mom[k]);
-        const float4 lo = __ldg(&nlo[k]);
-        const float4 hi = __ldg(&nhi[k]);
+    int k = 0;
+    while (true) {
+        const float4 A = __ldg(&packed[2 * (size_t)k]);
+        const float4 B = __ldg(&packed[2 * (size_t)k + 1]);
         const bool mine = (mask >> lane) & 1u;
-        // AcceptApproximation (GravityFieldSystem.cs:229-247), exact op order
-        float dx = __fsub_rn(pi.x, mo.x), dy = __fsub_rn(pi.y, mo.y), dz = __fsub_rn(pi.z, mo.z);
-        float r_sq = dot3_rn(dx, dy, dz);
-        float bx = fmaxf(__fsub_rn(hi.x, mo.x), __fsub_rn(mo.x, lo.x));
-        float by = fmaxf(__fsub_rn(hi.y, mo.y), __fsub_rn(mo.y, lo.y));
-        float bz = fmaxf(__fsub_rn(hi.z, mo.z), __fsub_rn(mo.z, lo.z));
-        float b_sq = dot3_rn(bx, by, bz);
-        const bool acc = mine && (__fdiv_rn(b_sq, r_sq) < theta2);
+        // AcceptApproximation (GravityFieldSystem.cs:229-247): bmax_sq / r_sq < theta^2, r_sq with the exact op order
+        const float dx = __fsub_rn(pi.x, A.x), dy = __fsub_rn(pi.y, A.y), dz = __fsub_rn(pi.z, A.z);
+        const float r_sq = dot3_rn(dx, dy, dz);
+        const float q = B.x * rcp_approx(r_sq);
+        bool acc = q < theta2;
+        if (fabsf(q - theta2) < band) acc = __fdiv_rn(B.x, r_sq) < theta2;   // rare: the IEEE quotient decides
+        acc = acc && mine;
         if (acc) {
             // GravitationalMoment.GravityContribution (M2P, :428-442)
             float rinv = rsqrt_approx(r_sq);
-            float mr = mo.w * rinv;
+            float mr = A.w * rinv;
             float g = mr * rinv * rinv;
             gx = fmaf(dx, g, gx); gy = fmaf(dy, g, gy); gz = fmaf(dz, g, gz);
             gp -= mr;
             na++;
         }
         const unsigned rej = __ballot_sync(FULL, mine && !acc);
-        if (rej == 0) continue;
-        const int first = __float_as_int(lo.w), last = __float_as_int(hi.w);
-        if (last - first + 1 <= leaf_max) {
+        const int ia = __float_as_int(B.y), ib = __float_as_int(B.z);
+        if (rej != 0 && ib >= 0) {
+            // descend: right child now, left child later (LIFO order of GravityFieldSystem.cs:201-206)
+            if (sp >= SPH_TREE_STACK) {
+                if (lane == 0) atomicExch(&err[ERR_TREE_STACK], 1);
+                break;
+            }
+            if (lane == 0) st[sp] = make_int2(ia, (int)rej);
+            sp++;
+            k = ib;
+            mask = rej;
+            continue;
+        }
+        if (rej != 0) {
+            // leaf bucket: bodies first .. first+count-1, summed directly; includes the target itself (quirk Q3)
             const bool open = (rej >> lane) & 1u;
-            for (int s = first; s <= last; s++) {
+            const int cnt = -ib;
+            // a body can be inside the softening radius a = h_i only if |p - cm| < a + Bmax, i.e. r_sq < 2 (a^2 + Bmax^2)
+            const bool soft = __any_sync(FULL, open && r_sq < 2.0f * (a2 + B.x));
+            for (int s = ia; s < ia + cnt; s++) {
                 const float4 pj = __ldg(&posm[s]);
+                // GravityContributionParticle (:332-356), a = h_i
+                float ex = pi.x - pj.x, ey = pi.y - pj.y, ez = pi.z - pj.z;
+                float r2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+                float rinv = rsqrt_approx(fmaxf(r2, a2));
+                float mr = pj.w * rinv;
+                float g = mr * rinv * rinv, ph = -mr;
+                if (soft && r2 < a2) {
+                    float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
+                    float x = r * ainv, x2 = x * x, x3 = x2 * x;
+                    float ma = pj.w * ainv;
+                    g = ma * ainv * ainv * (8.0f - 9.0f * x + 2.0f * x3);
+                    ph = -ma * (2.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
+                }
                 if (open) {
-                    // GravityContributionParticle (:332-356), a = h_i; includes s == t (quirk Q3)
-                    float ex = pi.x - pj.x, ey = pi.y - pj.y, ez = pi.z - pj.z;
-                    float r2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-                    float g, ph;
-                    if (r2 < a2) {
-                        float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
-                        float x = r * ainv, x2 = x * x, x3 = x2 * x;
-                        float ma = pj.w * ainv;
-                        g = ma * ainv * ainv * (8.0f - 9.0f * x + 2.0f * x3);
-                        ph = -ma * (2.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
-                    } else {
-                        float rinv = rsqrt_approx(r2);
-                        float mr = pj.w * rinv;
-                        g = mr * rinv * rinv;
-                        ph = -mr;
-                    }
                     gx = fmaf(ex, g, gx); gy = fmaf(ey, g, gy); gz = fmaf(ez, g, gz);
                     gp += ph;
                     np++;
                 }
             }
-        } else {
-            if (sp + 2 > SPH_TREE_STACK) {
-                if (lane == 0) atomicExch(&err[ERR_TREE_STACK], 1);
-                break;
-            }
-            const int2 ch = __ldg(&child[k]);
-            if (lane == 0) {
-                stack[w][sp] = make_int2(ch.x, (int)rej);      // left pushed first ...
-                stack[w][sp + 1] = make_int2(ch.y, (int)rej);  // ... right popped first (GravityFieldSystem.cs:201-206)
-            }
-            sp += 2;
-            __syncwarp();
         }
+        if (sp == 0) break;
+        __syncwarp();
+        const int2 e = st[--sp];
+        __syncwarp();
+        k = e.x;
+        mask = (unsigned)e.y;
     }
     if (active) {
         grav[t] = make_float4(G * gx, G * gy, G * gz, G * gp);
@@ -244,15 +270,14 @@ int sph_launch_gravity_tree(sphb200_ctx* c, float dt) {
     SPH_LAUNCH_CHECK(c);
     k_lbvh_nodes<<<sph_div_up(2 * (int64_t)n - 1, 256), 256, 0, c->stream>>>(c->posh[c->cur], c->velm[c->cur], n, c->child, c->range,
                                                                             c->parent, c->p.leaf_max, c->p.aabb_mode, dt, c->flag,
-                                                                            c->mom, c->nlo, c->nhi);
+                                                                            c->mom, c->nlo, c->nhi, c->packed);
     SPH_LAUNCH_CHECK(c);
     c->tree_valid = true;
     int nt = t1 - t0;
     if (nt <= 0) return SPH_OK;
     float theta2 = c->p.theta * c->p.theta;  // fp32 product, as k_Theta*k_Theta (GravityFieldSystem.cs:246)
-    k_tree_walk<<<sph_div_up(nt, TW_WARPS * 32), TW_WARPS * 32, 0, c->stream>>>(c->posh[c->cur], c->posm, c->child, c->mom, c->nlo,
-                                                                               c->nhi, t0, t1, c->p.leaf_max, theta2, c->p.G,
-                                                                               c->grav, c->npart, c->napprox, c->err_d);
+    k_tree_walk<<<sph_div_up(nt, TW_WARPS * 32), TW_WARPS * 32, 0, c->stream>>>(c->posh[c->cur], c->posm, c->packed, t0, t1, theta2,
+                                                                               c->p.G, c->grav, c->npart, c->napprox, c->err_d);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;
 }

@@ -38,7 +38,7 @@ class Params(C.Structure):
 
 class GridParams(C.Structure):
     _fields_ = [("min", C.c_float * 3), ("cell", C.c_float), ("fine_scale", C.c_float), ("bits", C.c_int32),
-                ("hmax", C.c_float), ("ext", C.c_float)]
+                ("hmax", C.c_float), ("ext", C.c_float), ("href", C.c_float), ("stencil", C.c_int32)]
 
 
 # byte-exact mirrors of the reference components (include/sphb200.h)

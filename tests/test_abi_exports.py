@@ -34,7 +34,7 @@ def test_default_params_are_the_reference_constants():
     assert p.theta == np.float32(0.7)   # GravityFieldSystem.cs:228
     assert p.target_neighbors == 50  # ParticleSmoothingSystem.cs:18
     assert p.leaf_max == 4 and p.aabb_mode == 0 and p.flags == 0
-    assert C.sizeof(sphb200.Params) == 48 and C.sizeof(sphb200.GridParams) == 32
+    assert C.sizeof(sphb200.Params) == 48 and C.sizeof(sphb200.GridParams) == 40
 
 
 def test_component_struct_layouts():
@@ -62,7 +62,7 @@ def test_header_struct_sizes_match_python_mirrors(tmp_path):
     exe = tmp_path / "sz"
     subprocess.check_call(["/usr/bin/gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
     out = subprocess.check_output([str(exe)]).split()
-    assert [int(x) for x in out] == [12, 24, 28, 24, 40, 48, 32, 24, 16]
+    assert [int(x) for x in out] == [12, 24, 28, 24, 40, 48, 40, 24, 16]
 
 
 def test_no_gpu_means_loud_failure_not_fallback():

@@ -51,12 +51,16 @@ def compare_step(orc, sim, ref, gravity):
     np.testing.assert_allclose(got["rho"], ref.rho, rtol=RTOL)
     np.testing.assert_allclose(got["P"], ref.P, rtol=2 * RTOL)
     vec_close(got["gradP"], ref.gradP, what="gradP", floor=1e-7 * np.abs(ref.gradP).max())
-    if gravity != "none":
-        vec_close(got["grav"][:, :3], ref.grav[:, :3], what="gradPhi")
-        np.testing.assert_allclose(got["grav"][:, 3], ref.grav[:, 3], rtol=RTOL)
     if gravity == "tree":
+        # identical MAC decisions: every particle sums exactly the oracle's set of bodies and node approximations
         np.testing.assert_array_equal(got["num_particles"], ref.num_particles)
         np.testing.assert_array_equal(got["num_approx"], ref.num_approx)
+    if gravity != "none":
+        # |delta| <= 1e-5 |g_i|, with an absolute floor of 1e-6 x the median field for particles whose net field
+        # nearly cancels (centre of the sphere): there the sum is ill-conditioned for ANY fp32 summation order
+        gfloor = 1e-6 * np.median(np.linalg.norm(ref.grav[:, :3], axis=1))
+        vec_close(got["grav"][:, :3], ref.grav[:, :3], what="gradPhi", floor=gfloor)
+        np.testing.assert_allclose(got["grav"][:, 3], ref.grav[:, 3], rtol=RTOL)
     np.testing.assert_allclose(got["pos"], ref.pos, rtol=1e-6, atol=1e-6)
     acc_scale = np.abs(ref.vel - 0).max() + 1e-12
     np.testing.assert_allclose(got["vel"], ref.vel, rtol=RTOL, atol=2e-5 * acc_scale)
@@ -104,7 +108,7 @@ def test_sort_order_and_keys_bit_exact(orc, n):
     order, keys, g = sim.download_sort()
     p = sim.effective_params()
     go = orc.grid_params(c["pos"], c["h"], p.max_grid_bits)
-    for f in ("cell", "fine_scale", "bits", "hmax", "ext"):
+    for f in ("cell", "fine_scale", "bits", "hmax", "ext", "href", "stencil"):
         assert getattr(g, f) == getattr(go, f), f
     assert list(g.min) == list(go.min)
     ko = orc.morton_keys(c["pos"], go)

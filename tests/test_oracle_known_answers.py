@@ -287,7 +287,8 @@ def test_morton_keys_and_sort(orc):
     import sphb200.ic as ic
     c = ic.make_sphere(5000, seed=2)
     g = orc.grid_params(c["pos"], c["h"], 6)
-    assert g.cell >= 2.0 * c["h"].max() and g.cell * (1 << g.bits) > g.ext
+    assert g.cell * g.stencil >= 2.002 * c["h"].max() * (1 - 1e-6) and g.cell * (1 << g.bits) > g.ext
+    assert 1 <= g.stencil <= 4 and c["h"].min() <= g.href <= c["h"].max()
     keys = orc.morton_keys(c["pos"], g)
     assert keys.max() < (1 << 30)
     order = orc.sort_order(keys)
@@ -295,7 +296,7 @@ def test_morton_keys_and_sort(orc):
     assert np.all(np.diff(ks.astype(np.int64)) >= 0)
     same = np.diff(ks.astype(np.int64)) == 0
     assert np.all(np.diff(order.astype(np.int64))[same] > 0)   # stable: ties by body index
-    # neighbors always live in adjacent cells of the 2^bits grid (the superset guarantee the GPU search relies on)
+    # neighbors always live within `stencil` cells of each other (the superset guarantee the GPU search relies on)
     shift = 3 * (10 - g.bits)
 
     def cell_xyz(k):
@@ -307,7 +308,7 @@ def test_morton_keys_and_sort(orc):
         ci = cell_xyz(keys[i])
         for j in nb[o[i]:o[i + 1]]:
             cj = cell_xyz(keys[j])
-            assert max(abs(a - b) for a, b in zip(ci, cj)) <= 1
+            assert max(abs(a - b) for a, b in zip(ci, cj)) <= g.stencil
 
 
 def _check_tree(t, n, leaf_max):
