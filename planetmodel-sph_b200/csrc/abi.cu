@@ -533,7 +533,7 @@ int sphb200_device_ptr(sph_handle c, const char* name, void** ptr, int64_t* byte
     struct { const char* nm; void* p; size_t el; } tab[] = {
         {"posh", c->posh[c->cur], 16}, {"velm", c->velm[c->cur], 16}, {"posm", c->posm, 16}, {"rho", c->rho, 4},
         {"press", c->press, 4}, {"cvol", c->cvol, 4}, {"gradp", c->gradp, 16}, {"grav", c->grav, 16}, {"nown", c->nown, 4},
-        {"orig", c->orig[c->cur], 4}, {"ncount", c->ncount, 4},
+        {"orig", c->orig[c->cur], 4}, {"ncount", c->ncount, 4}, {"npart", c->npart, 4}, {"napprox", c->napprox, 4},
     };
     for (auto& t : tab)
         if (strcmp(t.nm, name) == 0) { *ptr = t.p; if (bytes) *bytes = (int64_t)(t.el * (size_t)c->cap); return SPH_OK; }

@@ -61,9 +61,15 @@ class ShardedSimulation:
         self.sim = Simulation(self.cap, device=device, **params)
         self.device = device
         self._views = {}
+        self.stream = None
+        self.timing = False
+        self._marks = []
         if world > 1:
+            # kernels and NCCL collectives must be ordered on ONE stream: a dedicated torch stream whose handle the
+            # library adopts (torch's legacy default stream has handle 0, which the C ABI reads as "own stream")
             import torch
-            self.sim.set_stream(torch.cuda.current_stream().cuda_stream)
+            self.stream = torch.cuda.Stream(device=device)
+            self.sim.set_stream(self.stream.cuda_stream)
 
     def upload(self, pos, vel, mass, h):
         self.sim.upload(pos, vel, mass, h)      # every rank uploads the full set (replicated state)
@@ -83,22 +89,60 @@ class ShardedSimulation:
         if self.world == 1:
             s.step(dt, impl)
             return
-        from . import GRAVITY_PARTICLE
+        import torch
+        with torch.cuda.stream(self.stream):
+            self._step_sharded(dt, impl)
+
+    def _mark(self, name):
+        if self.timing:
+            import torch
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record(self.stream)
+            self._marks.append((name, ev))
+
+    def _step_sharded(self, dt, impl):
+        from . import GRAVITY_TREE, GRAVITY_PARTICLE
+        s = self.sim
         t0, t1 = shard_range(self.n, self.rank, self.world)
+        self._marks = []
+        self._mark("begin")
         s.set_target_range(t0, t1)
         s.smoothing_update()                    # all N (needs everyone's own-support counts: gathered last step)
         s.build_neighbors()                     # global sort + cell table (redundant), lists + density for [t0,t1)
+        self._mark("smoothing_sort_neighbors_density_eos")
         allgather_slices(self._view("cvol", 1), self.rank, self.world)
+        self._mark("allgather_cvol")
         s.gravity(impl, dt)                     # sources: all N (posm / LBVH are global), targets [t0,t1)
+        self._mark({GRAVITY_TREE: "gravity_tree", GRAVITY_PARTICLE: "gravity_allpairs"}.get(impl, "gravity_none"))
         s.pressure()
+        self._mark("pressure_grad")
         s.integrate(dt)
+        self._mark("integrate")
         allgather_slices(self._view("posh", 4), self.rank, self.world)
         allgather_slices(self._view("velm", 4), self.rank, self.world)
         allgather_slices(self._view("nown", 1), self.rank, self.world)
+        self._mark("allgather_state")
+
+    def enable_timing(self, on=True):
+        self.timing = bool(on)
+        if self.world == 1:
+            self.sim.enable_timing(on)
+
+    def timings(self):
+        """[(pass, ms)] of the most recent step (synchronises that step)."""
+        if self.world == 1:
+            return self.sim.timings()
+        if not self._marks:
+            return []
+        self._marks[-1][1].synchronize()
+        return [(self._marks[i][0], self._marks[i - 1][1].elapsed_time(self._marks[i][1])) for i in range(1, len(self._marks))]
 
     def gather_results(self):
         """Make the per-step result fields complete on every rank (for downloads/diagnostics)."""
         if self.world == 1:
             return
-        for name, w in (("rho", 1), ("press", 1), ("gradp", 4), ("grav", 4), ("ncount", 1)):
-            allgather_slices(self._view(name, w), self.rank, self.world)
+        import torch
+        with torch.cuda.stream(self.stream):
+            for name, w in (("rho", 1), ("press", 1), ("gradp", 4), ("grav", 4), ("ncount", 1), ("npart", 1), ("napprox", 1)):
+                allgather_slices(self._view(name, w), self.rank, self.world)
+        self.stream.synchronize()
