@@ -63,7 +63,7 @@ int sphb200_destroy(sph_handle c) {
     for (int k = 0; k < 2; k++) { cudaFree(c->posh[k]); cudaFree(c->velm[k]); cudaFree(c->orig[k]); cudaFree(c->keys[k]); cudaFree(c->idx[k]); }
     cudaFree(c->posm); cudaFree(c->cub_tmp); cudaFree(c->cell_start); cudaFree(c->cell_end); cudaFree(c->cell_hmax); cudaFree(c->nlist);
     cudaFree(c->ncount); cudaFree(c->nown); cudaFree(c->rho); cudaFree(c->press); cudaFree(c->cvol); cudaFree(c->gradp);
-    cudaFree(c->grav); cudaFree(c->npart); cudaFree(c->napprox); cudaFree(c->gpart); cudaFree(c->child); cudaFree(c->range);
+    cudaFree(c->grav); cudaFree(c->npart); cudaFree(c->napprox); cudaFree(c->gpart); cudaFree(c->tbox); cudaFree(c->child); cudaFree(c->range);
     cudaFree(c->parent); cudaFree(c->flag); cudaFree(c->mom); cudaFree(c->nlo); cudaFree(c->nhi); cudaFree(c->packed); cudaFree(c->bounds);
     cudaFree(c->grid_d); cudaFree(c->err_d); cudaFree(c->rr_table); cudaFree(c->diag_d); cudaFree(c->stage_d);
     if (c->err_h) cudaFreeHost(c->err_h);
@@ -116,7 +116,7 @@ int sphb200_create(const sph_Params* params, int64_t capacity, int device, sph_h
          dalloc(&c->nown, cap) == cudaSuccess && dalloc(&c->rho, cap) == cudaSuccess && dalloc(&c->press, cap) == cudaSuccess &&
          dalloc(&c->cvol, cap) == cudaSuccess && dalloc(&c->gradp, cap) == cudaSuccess && dalloc(&c->grav, cap) == cudaSuccess &&
          dalloc(&c->npart, cap) == cudaSuccess && dalloc(&c->napprox, cap) == cudaSuccess &&
-         dalloc(&c->gpart, cap * (size_t)c->gpart_splits) == cudaSuccess && dalloc(&c->child, nn) == cudaSuccess &&
+         dalloc(&c->gpart, cap * (size_t)c->gpart_splits) == cudaSuccess && dalloc(&c->tbox, 2 * (cap / 256 + 2)) == cudaSuccess && dalloc(&c->child, nn) == cudaSuccess &&
          dalloc(&c->range, nn) == cudaSuccess && dalloc(&c->parent, nn) == cudaSuccess && dalloc(&c->flag, nn) == cudaSuccess &&
          dalloc(&c->mom, nn) == cudaSuccess && dalloc(&c->nlo, nn) == cudaSuccess && dalloc(&c->nhi, nn) == cudaSuccess && dalloc(&c->packed, 2 * nn) == cudaSuccess &&
          dalloc(&c->bounds, 16) == cudaSuccess && dalloc(&c->grid_d, 1) == cudaSuccess && dalloc(&c->err_d, ERR_SLOTS) == cudaSuccess &&
@@ -244,6 +244,9 @@ int sphb200_upload(sph_handle c, int64_t n, const void* pos, int pos_stride, con
     if (smoothing_stride == 4) memcpy(H, sp, (size_t)n * 4);
     else for (int64_t i = 0; i < n; i++) memcpy(H + i, sp + (size_t)i * smoothing_stride, 4);
     if (has_nown) for (int64_t i = 0; i < n; i++) memcpy(NO + i, sp + (size_t)i * smoothing_stride + 24, 4);
+    c->equal_mass = true;
+    c->common_mass = M[0];
+    for (int64_t i = 1; i < n && c->equal_mass; i++) c->equal_mass = (M[i] == M[0]);
     SPH_CK(c, cudaMemcpyAsync(c->stage_d, c->stage_h, (size_t)n * 9 * 4, cudaMemcpyHostToDevice, c->stream));
     int rc = sph_launch_pack_upload(c, n, has_nown);
     if (rc) return rc;

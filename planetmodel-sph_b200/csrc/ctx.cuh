@@ -47,6 +47,9 @@ struct sphb200_ctx {
     float4* grav = nullptr;
     int32_t* npart = nullptr;
     int32_t* napprox = nullptr;
+    float4* tbox = nullptr;      // all-pairs: bounding box (lo, hi) of every 256-source tile
+    bool equal_mass = false;     // every uploaded particle has the same mass (ParticleAuthoring.cs:208)
+    float common_mass = 0.f;
     float4* gpart = nullptr;     // all-pairs partial sums [splits][n]
     int gpart_splits = 0;
 

@@ -5,20 +5,28 @@
 //   r <  a=h_i : d * (m/a^3)(8 - 9x + 2x^3),  phi = -(m/a)(2.4 - 4x^2 + 3x^3 - 0.4x^5),  x = r/a   (Dyer & Ip)
 //   r >= a     : d * m/r^3,                   phi = -m/r
 //
-// B200 mapping: FP32 FMA-pipe bound (no tensor cores: not a contraction).  The inner loop is branch-free:
-// it evaluates the Newtonian law with r^2 capped from below at a^2 (one FMNMX), which makes the self pair and every
-// pair inside the softening radius finite and smooth.  The difference "softened - capped" for the few pairs with
-// r < h_i (all of them are in i's SPH neighbor list, since r < h_i < 2 max(h_i,h_j)) is added by the pressure kernel
-// (kernels_sph.cu, add_grav), and the capped self term is removed in the reduce kernel.  15 issue slots per pair.
+// B200 mapping: FP32 FMA-pipe bound (no tensor cores: not a contraction), so the design goal is the fewest issue
+// slots per pair.  The inner loop is branch-free Newtonian:
+//   * sources are Morton-sorted, so a 256-source tile is spatially compact; a tile whose box does not touch the box of
+//     the block's targets grown by their softening radii is FAR (r >= h_i for every pair) and runs the bare loop;
+//   * the few NEAR tiles (they also hold the self pair) run the same loop with r^2 capped from below at h_i^2 by one
+//     FMNMX -- finite and smooth; the exact "softened minus capped" difference for pairs with r < h_i (all of them are
+//     in i's SPH neighbor list, r < h_i < 2 max(h_i,h_j)) is added afterwards by k_gravity_near (kernels_sph.cu) and
+//     the capped self term is removed in k_gravity_reduce;
+//   * when every particle has the same mass (the reference spawner, ParticleAuthoring.cs:208) the mass multiply
+//     leaves the loop (EQM variant) and is applied once in the reduce.
+// Issue slots per pair (SASS): 13.4 far/equal-mass ... 15.4 near/general; measured rates in profiles/README.md.
 // Summation: per-tile fp32 partials (256 sources) added into a running sum, then a fixed-order reduction over the
 // source splits -- deterministic, and ~sqrt(256) times tighter than one 10^6-term fp32 chain.
 #include "ctx.cuh"
+#include <math.h>
 
 namespace {
 
 constexpr int AP_THREADS = 256;
 constexpr int AP_TPT = 4;     // targets per thread (one LDS.128 feeds 4 pair evaluations)
 constexpr int AP_TILE = 256;  // sources per shared-memory tile (= inner fp32 partial-sum length)
+constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float rsqrt_approx(float x) {
     float y;
@@ -26,63 +34,135 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     return y;
 }
 
+// Bounding box of every 256-source tile (2 float4 per tile: lo, hi).
+__global__ void __launch_bounds__(AP_TILE) k_tile_boxes(const float4* __restrict__ src, int n, float4* __restrict__ tbox) {
+    __shared__ float s[6][AP_TILE / 32];
+    int i = min(blockIdx.x * AP_TILE + threadIdx.x, n - 1);
+    float4 p = src[i];
+    float v[6] = {p.x, p.y, p.z, p.x, p.y, p.z};
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            v[k] = fminf(v[k], __shfl_xor_sync(FULL, v[k], o));
+            v[3 + k] = fmaxf(v[3 + k], __shfl_xor_sync(FULL, v[3 + k], o));
+        }
+    }
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0)
+        for (int k = 0; k < 6; k++) s[k][w] = v[k];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float r[6];
+        for (int k = 0; k < 6; k++) {
+            r[k] = s[k][0];
+            for (int j = 1; j < AP_TILE / 32; j++) r[k] = k < 3 ? fminf(r[k], s[k][j]) : fmaxf(r[k], s[k][j]);
+        }
+        tbox[2 * blockIdx.x] = make_float4(r[0], r[1], r[2], 0.f);
+        tbox[2 * blockIdx.x + 1] = make_float4(r[3], r[4], r[5], 0.f);
+    }
+}
+
+template <int TPT, bool CAP, bool EQM>
+__device__ __forceinline__ void tile_loop(const float4* __restrict__ tp, const float (&xi)[TPT], const float (&yi)[TPT],
+                                          const float (&zi)[TPT], const float (&a2)[TPT], float (&ax)[TPT], float (&ay)[TPT],
+                                          float (&az)[TPT], float (&ph)[TPT]) {
+#pragma unroll 1
+    for (int j = 0; j < AP_TILE; j += 8, tp += 8) {
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const float4 s = tp[u];
+#pragma unroll
+            for (int k = 0; k < TPT; k++) {
+                float dx = xi[k] - s.x, dy = yi[k] - s.y, dz = zi[k] - s.z;
+                float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                if (CAP) r2 = fmaxf(r2, a2[k]);
+                float rinv = rsqrt_approx(r2);
+                float g;
+                if (EQM) {
+                    g = rinv * rinv * rinv;
+                    ph[k] += rinv;
+                } else {
+                    float mr = s.w * rinv;
+                    g = mr * (rinv * rinv);
+                    ph[k] += mr;
+                }
+                ax[k] = fmaf(dx, g, ax[k]);
+                ay[k] = fmaf(dy, g, ay[k]);
+                az[k] = fmaf(dz, g, az[k]);
+            }
+        }
+    }
+}
+
 // Source tiles are double-buffered in shared memory (one barrier per tile; the next tile's global load is in flight
-// during the math), read back as warp-uniform LDS.128 broadcasts through a running pointer kept in a vector register.
-template <int TPT>
+// during the math) and read back as warp-uniform LDS.128 broadcasts.
+template <int TPT, bool EQM>
 __global__ void __launch_bounds__(AP_THREADS) k_gravity_allpairs(const float4* __restrict__ src, int n_src, int src_per_split,
-                                                                 const float4* __restrict__ posh, int t0, int t1,
-                                                                 float4* __restrict__ part) {
+                                                                 const float4* __restrict__ tbox, const float4* __restrict__ posh,
+                                                                 int t0, int t1, float4* __restrict__ part) {
     __shared__ float4 tile[2][AP_TILE];
+    __shared__ float4 tb_lo[2], tb_hi[2];
+    __shared__ float ebox[6][AP_THREADS / 32];
     const int nt = t1 - t0;
     const int tid = threadIdx.x;
     const int tb = blockIdx.x * (AP_THREADS * TPT);
     float xi[TPT], yi[TPT], zi[TPT], a2[TPT];
     float AX[TPT], AY[TPT], AZ[TPT], PH[TPT];
+    float e[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
     for (int k = 0; k < TPT; k++) {
         int t = tb + k * AP_THREADS + tid;
         float4 p = posh[t0 + min(t, nt - 1)];
         xi[k] = p.x; yi[k] = p.y; zi[k] = p.z; a2[k] = p.w * p.w;
         AX[k] = AY[k] = AZ[k] = PH[k] = 0.f;
+        // box of the block's targets grown by their softening radii (+0.1% against rounding)
+        float a = p.w * 1.001f;
+        e[0] = fminf(e[0], p.x - a); e[1] = fminf(e[1], p.y - a); e[2] = fminf(e[2], p.z - a);
+        e[3] = fmaxf(e[3], p.x + a); e[4] = fmaxf(e[4], p.y + a); e[5] = fmaxf(e[5], p.z + a);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            e[k] = fminf(e[k], __shfl_xor_sync(FULL, e[k], o));
+            e[3 + k] = fmaxf(e[3 + k], __shfl_xor_sync(FULL, e[3 + k], o));
+        }
+    }
+    if ((tid & 31) == 0)
+        for (int k = 0; k < 6; k++) ebox[k][tid >> 5] = e[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 6; k++) {
+        float r = ebox[k][0];
+#pragma unroll
+        for (int j = 1; j < AP_THREADS / 32; j++) r = k < 3 ? fminf(r, ebox[k][j]) : fmaxf(r, ebox[k][j]);
+        e[k] = r;
     }
     const int s0 = blockIdx.y * src_per_split;
     const int s1 = min(s0 + src_per_split, n_src);
     const int ntiles = (s1 - s0 + AP_TILE - 1) / AP_TILE;
-    // padding source: zero mass, far away (contributes exactly 0)
-    const float4 pad = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.f);
-    int zero;
-    asm volatile("mov.u32 %0, 0;" : "=r"(zero));   // opaque: keeps the tile pointer in a vector register
+    const int tile0 = s0 / AP_TILE;
+    // padding source: zero mass (EQM: weight folded into position), far away: contributes exactly 0
+    const float4 pad = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);
     float4 nxt = (s0 + tid < s1) ? src[s0 + tid] : pad;
+    float4 nbx = tid < 2 ? tbox[2 * tile0 + tid] : pad;
     for (int it = 0; it < ntiles; it++) {
         float4* buf = tile[it & 1];
         buf[tid] = nxt;
+        if (tid == 0) tb_lo[it & 1] = nbx;
+        if (tid == 1) tb_hi[it & 1] = nbx;
         __syncthreads();
         int nidx = s0 + (it + 1) * AP_TILE + tid;
         nxt = (nidx < s1) ? src[nidx] : pad;
+        if (tid < 2 && it + 1 < ntiles) nbx = tbox[2 * (tile0 + it + 1) + tid];
+        const float4 lo = tb_lo[it & 1], hi = tb_hi[it & 1];
+        const bool far = lo.x > e[3] || lo.y > e[4] || lo.z > e[5] || hi.x < e[0] || hi.y < e[1] || hi.z < e[2];
         float ax[TPT], ay[TPT], az[TPT], ph[TPT];
 #pragma unroll
         for (int k = 0; k < TPT; k++) ax[k] = ay[k] = az[k] = ph[k] = 0.f;
-        const float4* tp = buf + zero;
-#pragma unroll 1
-        for (int j = 0; j < AP_TILE; j += 8, tp += 8) {
-#pragma unroll
-            for (int u = 0; u < 8; u++) {
-                const float4 s = tp[u];
-#pragma unroll
-                for (int k = 0; k < TPT; k++) {
-                    float dx = xi[k] - s.x, dy = yi[k] - s.y, dz = zi[k] - s.z;
-                    float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                    r2 = fmaxf(r2, a2[k]);
-                    float rinv = rsqrt_approx(r2);
-                    float mr = s.w * rinv;
-                    float g = mr * (rinv * rinv);
-                    ax[k] = fmaf(dx, g, ax[k]);
-                    ay[k] = fmaf(dy, g, ay[k]);
-                    az[k] = fmaf(dz, g, az[k]);
-                    ph[k] += mr;
-                }
-            }
-        }
+        if (far) tile_loop<TPT, false, EQM>(buf, xi, yi, zi, a2, ax, ay, az, ph);
+        else tile_loop<TPT, true, EQM>(buf, xi, yi, zi, a2, ax, ay, az, ph);
 #pragma unroll
         for (int k = 0; k < TPT; k++) { AX[k] += ax[k]; AY[k] += ay[k]; AZ[k] += az[k]; PH[k] += ph[k]; }
     }
@@ -93,10 +173,11 @@ __global__ void __launch_bounds__(AP_THREADS) k_gravity_allpairs(const float4* _
     }
 }
 
-// Fixed-order sum over the source splits; removes the capped self term (-m_i/a_i), applies G and the sign of Phi.
+// Fixed-order sum over the source splits; removes the capped self term, applies the common mass (EQM), G and the sign
+// of Phi.
 __global__ void __launch_bounds__(256) k_gravity_reduce(const float4* __restrict__ part, int splits, const float4* __restrict__ posh,
-                                                        const float4* __restrict__ posm, int t0, int t1, float G,
-                                                        float4* __restrict__ grav, int32_t* __restrict__ npart,
+                                                        const float4* __restrict__ posm, int t0, int t1, float G, float wscale,
+                                                        int eqm, float4* __restrict__ grav, int32_t* __restrict__ npart,
                                                         int32_t* __restrict__ napprox) {
     int nt = t1 - t0;
     int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -107,8 +188,9 @@ __global__ void __launch_bounds__(256) k_gravity_reduce(const float4* __restrict
         s.x += q.x; s.y += q.y; s.z += q.z; s.w += q.w;
     }
     float h = posh[t0 + t].w;
-    float self = posm[t0 + t].w * rsqrt_approx(h * h);
-    grav[t0 + t] = make_float4(G * s.x, G * s.y, G * s.z, -G * (s.w - self));
+    float self = (eqm ? 1.0f : posm[t0 + t].w) * rsqrt_approx(h * h);   // the self pair always sits in a capped tile
+    float gs = G * wscale;
+    grav[t0 + t] = make_float4(gs * s.x, gs * s.y, gs * s.z, -gs * (s.w - self));
     npart[t0 + t] = 0;
     napprox[t0 + t] = 0;
 }
@@ -139,8 +221,8 @@ int sph_launch_gravity_allpairs(sphb200_ctx* c) {
     if (nt <= 0) return SPH_OK;
     int n = (int)c->n;
     int tblocks = sph_div_up(nt, AP_THREADS * AP_TPT);
-    // enough blocks for >= ~6 waves of 8 resident CTAs/SM, bounded by the partial-sum buffer (cap * gpart_splits float4)
-    int want = c->sm_count * 8 * 6;
+    // enough blocks for >= ~12 waves of 3 resident CTAs/SM, bounded by the partial-sum buffer (cap * gpart_splits float4)
+    int want = c->sm_count * 3 * 12;
     int splits = sph_div_up(want, tblocks);
     int64_t mem_splits = (int64_t)c->cap * c->gpart_splits / nt;
     if (splits > mem_splits) splits = (int)mem_splits;
@@ -151,10 +233,16 @@ int sph_launch_gravity_allpairs(sphb200_ctx* c) {
     int per = sph_div_up(n, splits);
     per = sph_div_up(per, AP_TILE) * AP_TILE;
     splits = sph_div_up(n, per);
-    dim3 grid(tblocks, splits);
-    k_gravity_allpairs<AP_TPT><<<grid, AP_THREADS, 0, c->stream>>>(c->posm, n, per, c->posh[c->cur], t0, t1, c->gpart);
+    k_tile_boxes<<<sph_div_up(n, AP_TILE), AP_TILE, 0, c->stream>>>(c->posm, n, c->tbox);
     SPH_LAUNCH_CHECK(c);
-    k_gravity_reduce<<<sph_div_up(nt, 256), 256, 0, c->stream>>>(c->gpart, splits, c->posh[c->cur], c->posm, t0, t1, c->p.G, c->grav,
+    dim3 grid(tblocks, splits);
+    if (c->equal_mass)
+        k_gravity_allpairs<AP_TPT, true><<<grid, AP_THREADS, 0, c->stream>>>(c->posm, n, per, c->tbox, c->posh[c->cur], t0, t1, c->gpart);
+    else
+        k_gravity_allpairs<AP_TPT, false><<<grid, AP_THREADS, 0, c->stream>>>(c->posm, n, per, c->tbox, c->posh[c->cur], t0, t1, c->gpart);
+    SPH_LAUNCH_CHECK(c);
+    k_gravity_reduce<<<sph_div_up(nt, 256), 256, 0, c->stream>>>(c->gpart, splits, c->posh[c->cur], c->posm, t0, t1, c->p.G,
+                                                                c->equal_mass ? c->common_mass : 1.0f, c->equal_mass ? 1 : 0, c->grav,
                                                                 c->npart, c->napprox);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;

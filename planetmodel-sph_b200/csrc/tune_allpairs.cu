@@ -1,0 +1,143 @@
+// tune_allpairs.cu -- standalone tuning harness for the all-pairs inner loop (not part of libsphb200.so).
+// Build: nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo tune_allpairs.cu -o tune_allpairs
+// Prints ms and "20 flop/pair" TFLOP/s for a set of loop variants on N random particles; used to pick the shipped
+// configuration of k_gravity_allpairs (results recorded in profiles/README.md).
+#include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+template <int TPT, int THREADS, int UNROLL, bool CAP, bool EQM, bool POT, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_ap(const float4* __restrict__ src, int n_src, int src_per_split,
+                                                      const float4* __restrict__ posh, int nt, float4* __restrict__ part) {
+    constexpr int TILE = THREADS > 256 ? THREADS : 256;
+    __shared__ float4 tile[2][TILE];
+    const int tid = threadIdx.x;
+    const int tb = blockIdx.x * (THREADS * TPT);
+    float xi[TPT], yi[TPT], zi[TPT], a2[TPT];
+    float AX[TPT], AY[TPT], AZ[TPT], PH[TPT];
+#pragma unroll
+    for (int k = 0; k < TPT; k++) {
+        int t = tb + k * THREADS + tid;
+        float4 p = posh[min(t, nt - 1)];
+        xi[k] = p.x; yi[k] = p.y; zi[k] = p.z; a2[k] = p.w * p.w;
+        AX[k] = AY[k] = AZ[k] = PH[k] = 0.f;
+    }
+    const int s0 = blockIdx.y * src_per_split;
+    const int s1 = min(s0 + src_per_split, n_src);
+    const int ntiles = (s1 - s0 + TILE - 1) / TILE;
+    const float4 pad = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.f);
+    float4 nxt[TILE / THREADS];
+#pragma unroll
+    for (int q = 0; q < TILE / THREADS; q++) { int i = s0 + q * THREADS + tid; nxt[q] = i < s1 ? src[i] : pad; }
+    for (int it = 0; it < ntiles; it++) {
+        float4* buf = tile[it & 1];
+#pragma unroll
+        for (int q = 0; q < TILE / THREADS; q++) buf[q * THREADS + tid] = nxt[q];
+        __syncthreads();
+#pragma unroll
+        for (int q = 0; q < TILE / THREADS; q++) { int i = s0 + (it + 1) * TILE + q * THREADS + tid; nxt[q] = i < s1 ? src[i] : pad; }
+        float ax[TPT], ay[TPT], az[TPT], ph[TPT];
+#pragma unroll
+        for (int k = 0; k < TPT; k++) ax[k] = ay[k] = az[k] = ph[k] = 0.f;
+        const float4* tp = buf;
+#pragma unroll 1
+        for (int j = 0; j < TILE; j += UNROLL, tp += UNROLL) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const float4 s = tp[u];
+#pragma unroll
+                for (int k = 0; k < TPT; k++) {
+                    float dx = xi[k] - s.x, dy = yi[k] - s.y, dz = zi[k] - s.z;
+                    float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    if (CAP) r2 = fmaxf(r2, a2[k]);
+                    float rinv = rsqrt_approx(r2);
+                    float g;
+                    if (EQM) {
+                        g = rinv * rinv * rinv;
+                        if (POT) ph[k] += rinv;
+                    } else {
+                        float mr = s.w * rinv;
+                        g = mr * (rinv * rinv);
+                        if (POT) ph[k] += mr;
+                    }
+                    ax[k] = fmaf(dx, g, ax[k]);
+                    ay[k] = fmaf(dy, g, ay[k]);
+                    az[k] = fmaf(dz, g, az[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < TPT; k++) { AX[k] += ax[k]; AY[k] += ay[k]; AZ[k] += az[k]; PH[k] += ph[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < TPT; k++) {
+        int t = tb + k * THREADS + tid;
+        if (t < nt) part[(size_t)blockIdx.y * nt + t] = make_float4(AX[k], AY[k], AZ[k], PH[k]);
+    }
+}
+
+template <int TPT, int THREADS, int UNROLL, bool CAP, bool EQM, bool POT, int MINB>
+void run(const char* name, const float4* src, const float4* posh, float4* part, int n, int splits) {
+    int tblocks = (n + THREADS * TPT - 1) / (THREADS * TPT);
+    int per = ((n + splits - 1) / splits + 511) / 512 * 512;
+    int sp = (n + per - 1) / per;
+    dim3 grid(tblocks, sp);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        k_ap<TPT, THREADS, UNROLL, CAP, EQM, POT, MINB><<<grid, THREADS>>>(src, n, per, posh, n, part);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaError_t e = cudaGetLastError();
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_ap<TPT, THREADS, UNROLL, CAP, EQM, POT, MINB>, THREADS, 0);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_ap<TPT, THREADS, UNROLL, CAP, EQM, POT, MINB>);
+    printf("%-44s %8.3f ms  %6.2f TF(20/pair)  regs %3d  blocks/SM %d  grid %dx%d %s\n", name, best,
+           20.0 * (double)n * n / (best * 1e-3) / 1e12, fa.numRegs, nb, tblocks, sp, e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
+int main(int argc, char** argv) {
+    int n = argc > 1 ? atoi(argv[1]) : 262144;
+    std::vector<float4> h(n), p(n);
+    srand(1);
+    for (int i = 0; i < n; i++) {
+        float x = rand() / (float)RAND_MAX * 100, y = rand() / (float)RAND_MAX * 100, z = rand() / (float)RAND_MAX * 100;
+        h[i] = make_float4(x, y, z, 1.0f / n);
+        p[i] = make_float4(x, y, z, 0.5f);
+    }
+    float4 *src, *posh, *part;
+    cudaMalloc(&src, n * 16); cudaMalloc(&posh, n * 16); cudaMalloc(&part, (size_t)n * 16 * 64);
+    cudaMemcpy(src, h.data(), n * 16, cudaMemcpyHostToDevice);
+    cudaMemcpy(posh, p.data(), n * 16, cudaMemcpyHostToDevice);
+    //            TPT THR UNR  CAP    EQM    POT   MINB
+    run<4, 256, 8, true, false, true, 1>("shipped: tpt4 t256 u8 cap mass pot", src, posh, part, n, 28);
+    run<4, 256, 8, false, false, true, 1>("no cap (far tiles)", src, posh, part, n, 28);
+    run<4, 256, 8, true, true, true, 1>("equal mass", src, posh, part, n, 28);
+    run<4, 256, 8, false, true, true, 1>("equal mass, no cap", src, posh, part, n, 28);
+    run<4, 256, 8, false, true, false, 1>("equal mass, no cap, no potential", src, posh, part, n, 28);
+    run<2, 256, 8, true, false, true, 1>("tpt2 t256", src, posh, part, n, 14);
+    run<8, 128, 8, true, false, true, 1>("tpt8 t128", src, posh, part, n, 28);
+    run<8, 256, 4, true, false, true, 1>("tpt8 t256 u4", src, posh, part, n, 56);
+    run<4, 128, 8, true, false, true, 1>("tpt4 t128", src, posh, part, n, 14);
+    run<4, 256, 4, true, false, true, 1>("tpt4 t256 u4", src, posh, part, n, 28);
+    run<4, 256, 16, true, false, true, 1>("tpt4 t256 u16", src, posh, part, n, 28);
+    run<4, 256, 8, true, false, true, 2>("tpt4 t256 minb2", src, posh, part, n, 28);
+    run<4, 256, 8, true, false, true, 4>("tpt4 t256 minb4 (<=64 regs)", src, posh, part, n, 28);
+    run<4, 512, 8, true, false, true, 1>("tpt4 t512", src, posh, part, n, 56);
+    run<6, 128, 8, true, false, true, 1>("tpt6 t128", src, posh, part, n, 21);
+    run<3, 256, 8, true, false, true, 1>("tpt3 t256", src, posh, part, n, 21);
+    return 0;
+}

@@ -73,6 +73,7 @@ class ShardedSimulation:
 
     def upload(self, pos, vel, mass, h):
         self.sim.upload(pos, vel, mass, h)      # every rank uploads the full set (replicated state)
+        self._views = {}
 
     # -- torch views of the library's arrays (float32 words), cached per pointer
     def _view(self, name, words_per_elem):

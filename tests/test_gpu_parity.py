@@ -96,6 +96,19 @@ def test_c1_settled_h_direct(orc):
     assert 45 < got["count"].mean() < 70
 
 
+def test_direct_gravity_unequal_masses_and_far_near_tiles(orc):
+    """General-mass variant of the all-pairs kernel (the equal-mass fast path is what C1/C3 exercise), on a clumpy
+    two-body configuration so that both FAR (uncapped) and NEAR (capped + list correction) source tiles occur."""
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_collision(6000, seed=4, separation=2.2, v0=0.5)
+    rng = np.random.default_rng(3)
+    c["mass"] = (c["mass"] * rng.uniform(0.5, 2.0, len(c["mass"]))).astype(np.float32)
+    sim = run_gpu_step(c, 1 / 60, sphb200.GRAVITY_PARTICLE, max_neighbors=512)
+    ref = oracle_step(orc, c, 1 / 60, "direct", sim)
+    compare_step(orc, sim, ref, "direct")
+
+
 # ------------------------------------------------------------------ sort order / keys / grid parameters: bit-exact
 @pytest.mark.parametrize("n", [1, 2, 33, 1000, 20000])
 def test_sort_order_and_keys_bit_exact(orc, n):
