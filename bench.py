@@ -83,6 +83,8 @@ def cpu_reference_sample(c, grav, seconds_budget=20.0):
     against ALL sources.  Returns (particle_steps_per_sec, cores, sample_description, seconds_spent)."""
     from oracle import oracle as orc
     n = len(c["h"])
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it for the CPU arm)
+    orc.lib().orc_set_num_threads(len(os.sched_getaffinity(0)))
     cores = orc.lib().orc_num_threads()
     t_start = time.time()
     # -- SPH passes (neighbor search via cell list = labelled variant of the reference's BVH broadphase, then the
@@ -229,6 +231,10 @@ def run_ours(args):
 
     eng.gather_results()
     if rank != 0:
+        if world > 1:
+            import torch.distributed as td
+            td.barrier()
+            td.destroy_process_group()
         return
     # ---- roofline of the dominant kernel
     diag = sim.diagnostics()
@@ -242,8 +248,8 @@ def run_ours(args):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-    sph_ms = sum(mean.get(k, 0.0) for k in ("smoothing_bounds", "keys_sort_permute_cells", "neighbors_density_eos",
-                                            "pressure_grad", "integrate"))
+    # every pass that is neither gravity nor a collective (the sort / cell table run over all N on every rank)
+    sph_ms = sum(v for k, v in mean.items() if not k.startswith("gravity") and not k.startswith("allgather"))
     sph_bytes = (SPH_BYTES_BASE + SPH_BYTES_PER_NEIGHBOR * kbar) * n / world
     hbm_passes = {"achieved": sph_bytes / (sph_ms * 1e-3) / 1e9 if sph_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                   "frac": (sph_bytes / (sph_ms * 1e-3) / 1e9 / hbm_peak) if sph_ms > 0 else None, "ms": sph_ms,
@@ -263,8 +269,9 @@ def run_ours(args):
                 "achieved": hbm_passes["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm_passes["frac"], "traffic": None,
                 "note": "tree walk is L2-latency/FP32 mixed (no single roof, SURVEY 8d): %.2f ms of the step" % gms, "ms": sph_ms,
                 "share_of_step": sph_ms / ms_per_step}
-    if args.kernels_only:
-        cpu_v, cores, desc = None, 0, "skipped (--kernels-only profiling run)"
+    if args.kernels_only or world > 1:
+        cpu_v, cores, desc = None, 0, "skipped (%s)" % ("--kernels-only profiling run" if args.kernels_only else
+                                                        "reported at N=1 only; see --impl reference")
     else:
         cpu_v, cores, desc, _ = cpu_reference_sample(c, grav)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -274,6 +281,11 @@ def run_ours(args):
             "pass_ms": mean, "mean_neighbors": kbar, "fp32_peak_tflops_measured": fp32_peak,
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}}
     print(json.dumps(line))
+    sys.stdout.flush()
+    if world > 1:
+        import torch.distributed as td
+        td.barrier()
+        td.destroy_process_group()
 
 
 def measure_e2e(eng, c, impl, steps, barrier):

@@ -283,6 +283,17 @@ class Simulation:
         return dict(mass=out[0], momentum=out[1:4].copy(), angular_momentum=out[4:7].copy(), e_kin=out[7], e_pot=out[8],
                     e_int=out[9], mean_neighbors=out[10], max_neighbors=int(out[11]))
 
+    # -- snapshot I/O (checkpoint/resume and the golden-vector format): body-order arrays in one .npz
+    def save_snapshot(self, path):
+        d = self.download_all()
+        np.savez_compressed(path, pos=d["pos"], vel=d["vel"], mass=d["mass"], h=d["h"], n_own=d["n_own"])
+
+    def load_snapshot(self, path):
+        z = np.load(path)
+        sm = np.zeros(len(z["h"]), ParticleSmoothing)
+        sm["influenceArea"] = z["h"]; sm["supportDomain"] = 2.0 * z["h"]; sm["neighbors"] = z["n_own"]
+        self.upload(z["pos"], z["vel"], z["mass"], sm)
+
     def launch_count(self):
         v = C.c_int64(0)
         self._ck(self.L.sphb200_launch_count(self.h, C.byref(v)))

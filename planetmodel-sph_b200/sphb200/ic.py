@@ -68,6 +68,13 @@ def make_config(name, seed=1234):
     raise ValueError(name)
 
 
+def make_rotating_sphere(n, omega=0.02, seed=1234):
+    """Rigidly over-rotating sphere about z (README.md:67-71 roadmap scenario)."""
+    c = make_sphere(n, radius=scaled_radius(n), total_mass=REF_TOTAL_MASS * n / REF_COUNT, seed=seed)
+    c["vel"] = np.ascontiguousarray(np.stack([-omega * c["pos"][:, 1], omega * c["pos"][:, 0], np.zeros(n)], 1).astype(np.float32))
+    return c
+
+
 def make_collision(n_each, seed=1234, separation=3.0, v0=1.0):
     """Two-planet collision (config C5): second body has 8x the mass in 0.5x the radius (64x density)."""
     r1 = scaled_radius(n_each)

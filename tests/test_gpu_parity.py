@@ -381,3 +381,26 @@ def test_allpairs_sampled_targets_vs_oracle_64k(orc):
         ref = orc.gravity_direct(c["pos"], c["h"], c["mass"], i0=int(i), i1=int(i) + 1, accum_double=True)[0]
         assert np.linalg.norm(got[i, :3] - ref[:3]) <= RTOL * np.linalg.norm(ref[:3])
         assert got[i, 3] == pytest.approx(ref[3], rel=RTOL)
+
+
+def test_snapshot_roundtrip_resumes_bitwise(tmp_path):
+    """Checkpoint/resume: save after 3 steps, reload into a fresh handle, both continue identically."""
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_rotating_sphere(5000, seed=12)
+    a = make_sim(5000)
+    a.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    for _ in range(3):
+        a.step(0.01, sphb200.GRAVITY_TREE)
+    path = str(tmp_path / "snap.npz")
+    a.save_snapshot(path)
+    b = make_sim(5000)
+    b.load_snapshot(path)
+    a.load_snapshot(path)            # same resident order on both sides
+    for _ in range(2):
+        a.step(0.01, sphb200.GRAVITY_TREE); b.step(0.01, sphb200.GRAVITY_TREE)
+    da, db = a.download_all(), b.download_all()
+    for k in ("pos", "vel", "h", "rho", "grav"):
+        np.testing.assert_array_equal(da[k], db[k])
+    d = a.diagnostics()
+    assert abs(d["angular_momentum"][2]) > 0 and d["mass"] == pytest.approx(c["mass"].sum(), rel=1e-6)
