@@ -175,7 +175,12 @@ def run_ours(args):
     n = len(c["h"])
     impl = sphb200.GRAVITY_PARTICLE if grav == "particle" else sphb200.GRAVITY_TREE
 
-    eng = sdist.ShardedSimulation(n, device=local, rank=rank, world=world)
+    extra = {}
+    if args.leaf_max:
+        extra["leaf_max"] = args.leaf_max
+    if args.aabb_mode:
+        extra["aabb_mode"] = args.aabb_mode
+    eng = sdist.ShardedSimulation(n, device=local, rank=rank, world=world, **extra)
     eng.upload(c["pos"], c["vel"], c["mass"], c["h"])
     sim = eng.sim
 
@@ -340,6 +345,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4"])
     ap.add_argument("--gravity", default=None, choices=["tree", "particle"], help="override the workload's gravity path")
+    ap.add_argument("--leaf-max", type=int, default=0, help="bodies per tree leaf (reference: 4)")
+    ap.add_argument("--aabb-mode", type=int, default=0, help="1 = point-bounds MAC boxes (non-reference; quirk Q2 off)")
     ap.add_argument("--kernels-only", action="store_true", help="skip the e2e and CPU-baseline legs (ncu profiling runs)")
     args = ap.parse_args()
     if args.impl == "reference":
