@@ -35,10 +35,10 @@ FLOP_PER_PAIR = 20.0          # conventional N-body count per or
 SPH_BYTES_BASE, SPH_BYTES_PER_NEIGHBOR = 368.0, 12.0   # algorithmic HBM bytes / particle-step
 
 
-def workload_config(name):
+def workload_config(name, particles=None):
     from sphb200 import ic
-    c = ic.make_config(name)
-    grav = {"c1": "particle", "c2": "tree", "c3": "particle", "c4": "tree"}[name]
+    c = ic.make_config(name, particles=particles)
+    grav = {"c1": "particle", "c2": "tree", "c3": "particle", "c4": "tree", "c5": "tree"}[name]
     return c, grav
 
 
@@ -131,7 +131,7 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    c, grav = workload_config(args.workload)
+    c, grav = workload_config(args.workload, args.particles)
     vals = []
     for k in range(args.warmup + args.steps):
         v, cores, desc, _ = cpu_reference_sample(c, grav, 10.0)
@@ -148,8 +148,9 @@ def run_reference(args):
 
 
 def workload_desc(name, n, grav, gpus):
-    return {"workload": "%s: %d-particle uniform gas sphere (reference scene density), %s gravity, dt=1/60, full step" %
-            (name, n, "tiled all-pairs" if grav == "particle" else "LBVH Barnes-Hut theta=0.7"),
+    return {"workload": "%s: %d-particle %s, %s gravity, dt=1/60, full step" %
+            (name, n, "two-planet collision (64x density contrast)" if name == "c5" else "uniform gas sphere (reference scene density)",
+             "tiled all-pairs" if grav == "particle" else "LBVH Barnes-Hut theta=0.7"),
             "particles": n, "gravity": grav, "parallelism": "morton-range x%d" % gpus,
             "l2_policy": "working set (>= 190 MB of SoA + lists at 1M) exceeds the 126 MB L2; no explicit flush"}
 
@@ -169,7 +170,7 @@ def run_ours(args):
     if world > 1:
         import torch.distributed as td
         td.init_process_group("nccl", device_id=torch.device("cuda", local))
-    c, grav = workload_config(args.workload)
+    c, grav = workload_config(args.workload, args.particles)
     if args.gravity:
         grav = args.gravity
     n = len(c["h"])
@@ -346,7 +347,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4"])
+    ap.add_argument("--workload", default="c3", choices=["c1", "c2", "c3", "c4", "c5"])
+    ap.add_argument("--particles", type=int, default=None, help="scale c3/c4/c5 down (or up) to this many particles")
     ap.add_argument("--gravity", default=None, choices=["tree", "particle"], help="override the workload's gravity path")
     ap.add_argument("--leaf-max", type=int, default=0, help="bodies per tree leaf (reference: 4)")
     ap.add_argument("--aabb-mode", type=int, default=0, help="1 = point-bounds MAC boxes (non-reference; quirk Q2 off)")

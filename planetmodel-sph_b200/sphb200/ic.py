@@ -53,8 +53,13 @@ def scaled_radius(n):
     return float(REF_RADIUS * (n / REF_COUNT) ** (1.0 / 3.0))
 
 
-def make_config(name, seed=1234):
-    """Named BASELINE.json configurations."""
+def make_config(name, seed=1234, particles=None):
+    """Named BASELINE.json configurations (`particles` overrides the size of c3/c4/c5 for scaled-down runs)."""
+    if particles is not None and name in ("c3", "c4"):
+        n = int(particles)
+        return make_sphere(n, radius=scaled_radius(n), total_mass=REF_TOTAL_MASS * n / REF_COUNT, seed=seed)
+    if name == "c5":      # two-planet collision, 2 x 4M, 64x density contrast
+        return make_collision(int(particles) // 2 if particles else 4_000_000, seed=seed)
     if name == "c1":      # Jupiter v1: 3k, direct gravity
         return make_sphere(3000, seed=seed)
     if name == "c2":      # 10k, tree gravity
