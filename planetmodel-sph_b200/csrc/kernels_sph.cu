@@ -48,13 +48,6 @@ __device__ __forceinline__ float kernel_deriv_exact(float distance, float size, 
 }
 
 // ---- fast value arithmetic
-// M4 spline via the identity 4(1 - 1.5q^2 + 0.75q^3) = (2-q)^3 - 4(1-q)^3 (branch-free), norm = 1/(pi h^3)
-__device__ __forceinline__ float w_fast(float r, float hinv) {
-    float q = r * hinv;
-    float t1 = fmaxf(2.0f - q, 0.0f), t2 = fmaxf(1.0f - q, 0.0f);
-    float c = hinv * hinv * hinv * (0.25f * kInvPI);
-    return c * (t1 * t1 * t1 - 4.0f * (t2 * t2 * t2));
-}
 // (dW/dr)/r with the reference's inner branch (quirk Q1: +3q unless lead = -3):
 //   q<1 : (lead*q + 2.25 q^2)/(pi h^4)/r = (lead + 2.25 q) / (pi h^5);   1<=q<2 : -0.75 (2-q)^2 /(pi h^4) / r
 __device__ __forceinline__ float dwr_fast(float r, float rinv, float hinv, float lead) {
@@ -65,17 +58,6 @@ __device__ __forceinline__ float dwr_fast(float r, float rinv, float hinv, float
     float inner = (lead + 2.25f * q) * hinv * c4;
     float outer = -0.75f * t * t * c4 * rinv;
     return q < 1.0f ? inner : (q < 2.0f ? outer : 0.0f);
-}
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
-}
-__device__ __forceinline__ int warp_sum_i(int v) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    return v;
 }
 
 // ------------------------------------------------------------------------------------------------------------

@@ -13,7 +13,7 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     return y;
 }
 
-template <int TPT, int THREADS, int UNROLL, bool CAP, bool EQM, bool POT, int MINB>
+template <int TPT, int THREADS, int UNROLL, bool CAP, bool EQM, bool POT, int MINB, int ORDER = 0>
 __global__ void __launch_bounds__(THREADS, MINB) k_ap(const float4* __restrict__ src, int n_src, int src_per_split,
                                                       const float4* __restrict__ posh, int nt, float4* __restrict__ part) {
     constexpr int TILE = THREADS > 256 ? THREADS : 256;
@@ -52,6 +52,34 @@ __global__ void __launch_bounds__(THREADS, MINB) k_ap(const float4* __restrict__
 #pragma unroll
             for (int u = 0; u < UNROLL; u++) {
                 const float4 s = tp[u];
+                if (ORDER == 1) {
+                    float dx[TPT], dy[TPT], dz[TPT], r2[TPT], ri[TPT], g[TPT];
+#pragma unroll
+                    for (int k = 0; k < TPT; k++) dx[k] = xi[k] - s.x;
+#pragma unroll
+                    for (int k = 0; k < TPT; k++) dy[k] = yi[k] - s.y;
+#pragma unroll
+                    for (int k = 0; k < TPT; k++) dz[k] = zi[k] - s.z;
+#pragma unroll
+                    for (int k = 0; k < TPT; k++) r2[k] = dx[k] * dx[k];
+#pragma unroll
+                    for (int k = 0; k < TPT; k++) r2[k] = fmaf(dy[k], dy[k], r2[k]);
+#pragma unroll
+                    for (int k = 0; k < TPT; k++) r2[k] = fmaf(dz[k], dz[k], r2[k]);
+#pragma unroll
+                    for (int k = 0; k < TPT; k++) { if (CAP) r2[k] = fmaxf(r2[k], a2[k]); ri[k] = rsqrt_approx(r2[k]); }
+#pragma unroll
+                    for (int k = 0; k < TPT; k++) { if (EQM) { g[k] = ri[k] * ri[k]; } else { g[k] = ri[k] * ri[k]; ri[k] = s.w * ri[k]; } }
+#pragma unroll
+                    for (int k = 0; k < TPT; k++) { g[k] = g[k] * ri[k]; if (POT) ph[k] += ri[k]; }
+#pragma unroll
+                    for (int k = 0; k < TPT; k++) ax[k] = fmaf(dx[k], g[k], ax[k]);
+#pragma unroll
+                    for (int k = 0; k < TPT; k++) ay[k] = fmaf(dy[k], g[k], ay[k]);
+#pragma unroll
+                    for (int k = 0; k < TPT; k++) az[k] = fmaf(dz[k], g[k], az[k]);
+                    continue;
+                }
 #pragma unroll
                 for (int k = 0; k < TPT; k++) {
                     float dx = xi[k] - s.x, dy = yi[k] - s.y, dz = zi[k] - s.z;
@@ -83,7 +111,7 @@ __global__ void __launch_bounds__(THREADS, MINB) k_ap(const float4* __restrict__
     }
 }
 
-template <int TPT, int THREADS, int UNROLL, bool CAP, bool EQM, bool POT, int MINB>
+template <int TPT, int THREADS, int UNROLL, bool CAP, bool EQM, bool POT, int MINB, int ORDER = 0>
 void run(const char* name, const float4* src, const float4* posh, float4* part, int n, int splits) {
     int tblocks = (n + THREADS * TPT - 1) / (THREADS * TPT);
     int per = ((n + splits - 1) / splits + 511) / 512 * 512;
@@ -94,7 +122,7 @@ void run(const char* name, const float4* src, const float4* posh, float4* part, 
     float best = 1e30f;
     for (int rep = 0; rep < 4; rep++) {
         cudaEventRecord(e0);
-        k_ap<TPT, THREADS, UNROLL, CAP, EQM, POT, MINB><<<grid, THREADS>>>(src, n, per, posh, n, part);
+        k_ap<TPT, THREADS, UNROLL, CAP, EQM, POT, MINB, ORDER><<<grid, THREADS>>>(src, n, per, posh, n, part);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
@@ -102,9 +130,9 @@ void run(const char* name, const float4* src, const float4* posh, float4* part, 
     }
     cudaError_t e = cudaGetLastError();
     int nb = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_ap<TPT, THREADS, UNROLL, CAP, EQM, POT, MINB>, THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_ap<TPT, THREADS, UNROLL, CAP, EQM, POT, MINB, ORDER>, THREADS, 0);
     cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, k_ap<TPT, THREADS, UNROLL, CAP, EQM, POT, MINB>);
+    cudaFuncGetAttributes(&fa, k_ap<TPT, THREADS, UNROLL, CAP, EQM, POT, MINB, ORDER>);
     printf("%-44s %8.3f ms  %6.2f TF(20/pair)  regs %3d  blocks/SM %d  grid %dx%d %s\n", name, best,
            20.0 * (double)n * n / (best * 1e-3) / 1e12, fa.numRegs, nb, tblocks, sp, e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
@@ -139,5 +167,12 @@ int main(int argc, char** argv) {
     run<4, 512, 8, true, false, true, 1>("tpt4 t512", src, posh, part, n, 56);
     run<6, 128, 8, true, false, true, 1>("tpt6 t128", src, posh, part, n, 21);
     run<3, 256, 8, true, false, true, 1>("tpt3 t256", src, posh, part, n, 21);
+    run<4, 256, 8, false, true, true, 1, 1>("equal mass, no cap, component-major", src, posh, part, n, 28);
+    run<8, 128, 4, false, true, true, 1, 1>("eqm nocap comp-major tpt8 t128 u4", src, posh, part, n, 28);
+    run<2, 256, 8, false, true, true, 1, 1>("eqm nocap comp-major tpt2", src, posh, part, n, 14);
+    run<4, 128, 8, false, true, true, 1>("eqm nocap tpt4 t128", src, posh, part, n, 14);
+    run<2, 256, 8, false, true, true, 1>("eqm nocap tpt2 t256", src, posh, part, n, 14);
+    run<2, 128, 16, false, true, true, 1>("eqm nocap tpt2 t128 u16", src, posh, part, n, 7);
+    run<8, 128, 8, false, true, true, 1>("eqm nocap tpt8 t128", src, posh, part, n, 28);
     return 0;
 }
