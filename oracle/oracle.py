@@ -75,6 +75,8 @@ def lib():
                                        C.c_float, f32p, f32p, f32p]
         L.orc_tree_walk.argtypes = [C.c_int64, f32p, f32p, f32p, i32p, i32p, i32p, i32p, f32p, f32p, f32p, C.c_int,
                                     C.c_float, C.c_float, C.c_int64, C.c_int64, C.c_int, f32p, i32p, i32p]
+        L.orc_tree4_gravity.argtypes = [C.c_int64, f32p, f32p, f32p, f32p, C.c_float, C.c_float, C.c_float, C.c_int, f32p, i32p, i32p,
+                                        C.POINTER(C.c_int32)]
         L.orc_num_threads.restype = C.c_int
         L.orc_set_num_threads.argtypes = [C.c_int]
         _LIB = L
@@ -217,6 +219,14 @@ def tree_gravity(pos, vel, h, m, dt, theta=0.7, G=1.0, leaf_max=4, aabb_mode=0, 
     onp = np.zeros_like(npart); onp[order] = npart
     ona = np.zeros_like(napp); ona[order] = napp
     return out, onp, ona, tree, order
+
+
+def tree4_gravity(pos, vel, h, m, dt, theta=0.7, G=1.0, accum_double=False):
+    """Tree gravity on the reference-SHAPED 4-ary BVH (accuracy-envelope yardstick)."""
+    n = len(h)
+    g = np.zeros((n, 4), np.float32); npart = np.zeros(n, np.int32); napp = np.zeros(n, np.int32); nn = C.c_int32(0)
+    lib().orc_tree4_gravity(n, _f(pos), _f(vel), _f(h), _f(m), dt, theta, G, int(accum_double), g, npart, napp, C.byref(nn))
+    return g, npart, napp, nn.value
 
 
 # ---------------------------------------------------------------- full step

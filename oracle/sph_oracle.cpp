@@ -709,3 +709,126 @@ ORC_API void orc_set_num_threads(int t) {
     (void)t;
 #endif
 }
+
+// ------------------------------------------------------------------------------------------------
+// Reference-SHAPED tree: a 4-ary BVH built top-down over the centres of the particles'
+// collider boxes the way Unity.Physics' builder does it -- large ranges: split at the spatial median of the longest
+// axis, then each half again on its own longest axis (ProcessLargeRange, BoundingVolumeHierarchyBuilder.cs:331-345);
+// ranges of <= 32 points: sort along the longest axis and peel leaves of 4 (ProcessSmallRange, :294-329); leaves hold
+// <= 4 bodies; node boxes are unions of the children's collider boxes (Refit, :558-600).  It is NOT bit-faithful to the
+// vendored builder (quirk Q10 and the multi-threaded branch numbering are not reproduced: tree shape is not a parity
+// target); it exists to show that the LBVH walk and a Unity-shaped walk sit in the same accuracy envelope.
+// The moment pass and the walk are the same reference arithmetic as above (GravityFieldSystem.cs:133-215, 465-539).
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Node4 {
+    int child[4];   // internal: node ids; leaf: body ids; -1 = unused
+    int nchild = 0;
+    bool leaf = false;
+    Aabb box;
+    Moment mom;
+};
+struct Tree4 {
+    std::vector<Node4> nodes;
+    const float* cen;   // box centres (3 per body)
+    std::vector<int> idx;
+    int longest_axis(int s, int len, float& mid) const {
+        float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+        for (int k = s; k < s + len; k++)
+            for (int c = 0; c < 3; c++) { lo[c] = fminf(lo[c], cen[3 * idx[k] + c]); hi[c] = fmaxf(hi[c], cen[3 * idx[k] + c]); }
+        int ax = 0;
+        for (int c = 1; c < 3; c++) if (hi[c] - lo[c] > hi[ax] - lo[ax]) ax = c;
+        mid = 0.5f * (lo[ax] + hi[ax]);
+        return ax;
+    }
+    // spatial-median split of [s, s+len); falls back to halving by count when a side would hold < min_items
+    int split(int s, int len, int min_items) {
+        float mid; int ax = longest_axis(s, len, mid);
+        auto it = std::partition(idx.begin() + s, idx.begin() + s + len, [&](int b) { return cen[3 * b + ax] < mid; });
+        int l = (int)(it - (idx.begin() + s));
+        if (l < min_items || len - l < min_items) {
+            std::sort(idx.begin() + s, idx.begin() + s + len, [&](int a, int b) { return cen[3 * a + ax] < cen[3 * b + ax]; });
+            l = len / 2;
+        }
+        return l;
+    }
+    int make_leaf(int s, int len) {
+        Node4 nd; nd.leaf = true; nd.nchild = len;
+        for (int k = 0; k < 4; k++) nd.child[k] = k < len ? idx[s + k] : -1;
+        nodes.push_back(nd);
+        return (int)nodes.size() - 1;
+    }
+    int build(int s, int len) {
+        if (len <= 4) return make_leaf(s, len);
+        int self = (int)nodes.size();
+        nodes.emplace_back();
+        int sub_s[4], sub_l[4], ns = 0;
+        if (len <= 32) {
+            float mid; int ax = longest_axis(s, len, mid);
+            std::sort(idx.begin() + s, idx.begin() + s + len, [&](int a, int b) { return cen[3 * a + ax] < cen[3 * b + ax]; });
+            int cs = s, cl = len;
+            while (cl > 4 && ns < 3) { sub_s[ns] = cs; sub_l[ns] = 4; ns++; cs += 4; cl -= 4; }
+            if (cl > 0) { sub_s[ns] = cs; sub_l[ns] = cl; ns++; }
+        } else {
+            int l = split(s, len, 2);
+            int ll = split(s, l, 1), rl = split(s + l, len - l, 1);
+            int ss[4] = {s, s + ll, s + l, s + l + rl}, sl[4] = {ll, l - ll, rl, len - l - rl};
+            for (int k = 0; k < 4; k++) if (sl[k] > 0) { sub_s[ns] = ss[k]; sub_l[ns] = sl[k]; ns++; }
+        }
+        int ch[4] = {-1, -1, -1, -1};
+        for (int k = 0; k < ns; k++) ch[k] = build(sub_s[k], sub_l[k]);
+        Node4& nd = nodes[self];
+        nd.leaf = false; nd.nchild = ns;
+        for (int k = 0; k < 4; k++) nd.child[k] = ch[k];
+        return self;
+    }
+};
+}  // namespace
+
+ORC_API void orc_tree4_gravity(int64_t n, const float* pos, const float* vel, const float* h, const float* m, float dt,
+                               float theta, float G, int accum_double, float* grav4, int32_t* num_particles,
+                               int32_t* num_approx, int32_t* node_count) {
+    std::vector<Aabb> boxes(n);
+    std::vector<float> cen(3 * n);
+    for (int64_t i = 0; i < n; i++) {
+        boxes[i] = ParticleBox(ld3(pos, i), h[i], ld3(vel, i), dt, 0);
+        cen[3 * i] = 0.5f * (boxes[i].lo.x + boxes[i].hi.x); cen[3 * i + 1] = 0.5f * (boxes[i].lo.y + boxes[i].hi.y);
+        cen[3 * i + 2] = 0.5f * (boxes[i].lo.z + boxes[i].hi.z);
+    }
+    Tree4 T; T.cen = cen.data(); T.idx.resize(n); std::iota(T.idx.begin(), T.idx.end(), 0);
+    T.nodes.reserve(n);
+    int root = T.build(0, (int)n);
+    // Refit + moments, children before parents (ids of children are larger than their parent's: reverse order)
+    for (int k = (int)T.nodes.size() - 1; k >= 0; k--) {
+        Node4& nd = T.nodes[k];
+        nd.box = {{INFINITY, INFINITY, INFINITY}, {-INFINITY, -INFINITY, -INFINITY}};
+        nd.mom = Moment();
+        for (int c = 0; c < nd.nchild; c++) {
+            if (nd.leaf) { int b = nd.child[c]; nd.box = Union(nd.box, boxes[b]); nd.mom.Accumulate(ld3(pos, b), m[b]); }
+            else { const Node4& ch = T.nodes[nd.child[c]]; nd.box = Union(nd.box, ch.box); nd.mom.Accumulate(ch.mom.cm, ch.mom.m); }
+        }
+    }
+    if (node_count) *node_count = (int32_t)T.nodes.size();
+#pragma omp parallel
+    {
+        std::vector<int> stack; stack.reserve(256);
+#pragma omp for schedule(dynamic, 64)
+        for (int64_t t = 0; t < n; t++) {
+            F3 ri = ld3(pos, t); float a = h[t];
+            F4 g{0, 0, 0, 0}; double gd[4] = {0, 0, 0, 0}; int np = 0, na = 0;
+            auto add = [&](F4 c) { if (accum_double) { gd[0] += c.x; gd[1] += c.y; gd[2] += c.z; gd[3] += c.w; } else { g.x += c.x; g.y += c.y; g.z += c.z; g.w += c.w; } };
+            stack.clear(); stack.push_back(root);
+            do {
+                int k = stack.back(); stack.pop_back();
+                const Node4& nd = T.nodes[k];
+                if (AcceptApproximation(ri, nd.mom, nd.box, theta)) { add(nd.mom.GravityContribution(ri, G)); na++; }
+                else if (nd.leaf) { for (int c = 0; c < nd.nchild; c++) { int b = nd.child[c]; add(GravityContributionParticle(ri, ld3(pos, b), m[b], a, G)); np++; } }
+                else for (int c = 0; c < nd.nchild; c++) stack.push_back(nd.child[c]);
+            } while (!stack.empty());
+            if (accum_double) { g.x = (float)gd[0]; g.y = (float)gd[1]; g.z = (float)gd[2]; g.w = (float)gd[3]; }
+            memcpy(grav4 + 4 * t, &g, 16);
+            if (num_particles) num_particles[t] = np;
+            if (num_approx) num_approx[t] = na;
+        }
+    }
+}

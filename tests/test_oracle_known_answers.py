@@ -379,3 +379,27 @@ def test_tree_gravity_converges_to_direct_sum(orc):
     gt7, npart7, napp7, _, _ = orc.tree_gravity(c["pos"], c["vel"], c["h"], c["mass"], 0.02, theta=0.7, accum_double=True)
     err = np.linalg.norm(gt7[:, :3] - gd[:, :3], axis=1) / np.linalg.norm(gd[:, :3], axis=1)
     assert np.median(err) < 0.03 and (npart7 + napp7).mean() < 600
+
+
+def test_accuracy_envelope_lbvh_vs_reference_shaped_tree(orc):
+    """tree shape is not a parity target, but the LBVH walk and a Unity-shaped 4-ary walk (same moment /
+    MAC / walk arithmetic) must sit in the same accuracy envelope w.r.t. the direct sum and do comparable work."""
+    import sphb200.ic as ic
+    c = ic.make_sphere(6000, seed=3)
+    s = orc.State(c["pos"], c["vel"], c["mass"], c["h"])
+    for _ in range(10):                                        # let the h controller settle (~50 neighbors)
+        orc.step(s, 1 / 60, gravity="none")
+        s.pos[:] = c["pos"]; s.vel[:] = 0
+    gd = orc.gravity_direct(c["pos"], s.h, c["mass"], accum_double=True)
+    g4, np4, na4, nodes4 = orc.tree4_gravity(c["pos"], c["vel"], s.h, c["mass"], 0.02, accum_double=True)
+    gl, npl, nal, _, _ = orc.tree_gravity(c["pos"], c["vel"], s.h, c["mass"], 0.02, accum_double=True)
+
+    def err(g):
+        e = np.linalg.norm(g[:, :3] - gd[:, :3], axis=1) / np.linalg.norm(gd[:, :3], axis=1)
+        return float(np.median(e)), float(np.percentile(e, 99))
+    m4, p4 = err(g4); ml, pl = err(gl)
+    assert m4 < 0.02 and ml < 0.02 and p4 < 0.05 and pl < 0.05            # percent-level monopole accuracy, both
+    assert 0.25 < ml / m4 < 4.0 and 0.25 < pl / p4 < 4.0                  # same envelope
+    w4, wl = (np4 + na4).mean(), (npl + nal).mean()
+    assert 0.5 < wl / w4 < 2.0                                            # comparable interaction counts
+    assert nodes4 < 6000
