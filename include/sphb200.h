@@ -147,6 +147,10 @@ SPH_API int sphb200_build_neighbors(sph_handle h);
 /* GravityFieldSystem.OnUpdate (GravityFieldSystem.cs:62-74): impl = SPH_GRAVITY_*.  dt is needed because the
  * reference's MAC boxes are swept by v*dt (quirk Q2). PARTICLE mode requires build_neighbors in this step. */
 SPH_API int sphb200_gravity(sph_handle h, int impl, float dt);
+/* Optional hint, called between smoothing_update and build_neighbors: announces the gravity path of this step so that
+ * the LBVH build (which needs only the sorted particles) runs on an auxiliary stream concurrently with the neighbor
+ * pass.  The reference builds its tree in BuildPhysicsWorld, i.e. also before KernelSystem (BuildPhysicsWorld.cs:286-289). */
+SPH_API int sphb200_prepare_gravity(sph_handle h, int impl, float dt);
 /* DensityFieldSystem.OnUpdate (DensityFieldSystem.cs:38-56): publishes rho (summed inside build_neighbors). */
 SPH_API int sphb200_density(sph_handle h);
 /* PressureFieldSystem.OnUpdate (PressureFieldSystem.cs:30-70): P = K rho^2 and grad P. */

@@ -69,6 +69,9 @@ int sphb200_destroy(sph_handle c) {
     if (c->err_h) cudaFreeHost(c->err_h);
     if (c->stage_h) cudaFreeHost(c->stage_h);
     if (c->ev_created) for (int i = 0; i <= SPH_MAX_PASSES; i++) cudaEventDestroy(c->ev[i]);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return SPH_OK;
@@ -103,6 +106,9 @@ int sphb200_create(const sph_Params* params, int64_t capacity, int device, sph_h
     size_t cap = (size_t)capacity, nn = 2 * cap;
     bool ok = cudaSetDevice(device) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess;
     c->stream = c->own_stream;
     for (int k = 0; k < 2 && ok; k++) {
         ok = ok && dalloc(&c->posh[k], cap) == cudaSuccess && dalloc(&c->velm[k], cap) == cudaSuccess &&
@@ -150,7 +156,9 @@ const char* sphb200_last_error(sph_handle c) { return c ? c->err.c_str() : g_cre
 int sphb200_set_stream(sph_handle c, void* s) {
     if (!c) return SPH_ERR_INVALID_ARG;
     cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->aux_stream);
     cudaStreamSynchronize(c->stream);
+    c->tree_join_pending = false;
     c->stream = s ? (cudaStream_t)s : c->own_stream;
     return SPH_OK;
 }
@@ -223,7 +231,9 @@ int sphb200_upload(sph_handle c, int64_t n, const void* pos, int pos_stride, con
     ARG_CHECK(c, n == 0 || (pos && vel && mass && smoothing), "null component array");
     ARG_CHECK(c, pos_stride >= 12 && vel_stride >= 12 && mass_stride >= 4 && smoothing_stride >= 4, "stride too small");
     SPH_CK(c, cudaSetDevice(c->device));
+    SPH_CK(c, cudaStreamSynchronize(c->aux_stream));
     SPH_CK(c, cudaStreamSynchronize(c->stream));
+    c->tree_join_pending = c->tree_fresh = c->tree_hint = false;
     c->n = n;
     c->cur = 0;
     c->resident = true; c->lists_valid = c->pressure_valid = c->gravity_valid = c->tree_valid = c->h_updated = false;
@@ -284,14 +294,40 @@ int sphb200_smoothing_update(sph_handle c) {
     return SPH_OK;
 }
 
+// The auxiliary-stream LBVH build must have finished before the main stream overwrites anything it reads or writes.
+static int join_tree(sphb200_ctx* c) {
+    if (c->tree_join_pending) {
+        SPH_CK(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
+        c->tree_join_pending = false;
+    }
+    return SPH_OK;
+}
+
+// After a fresh sort: start the LBVH build on the auxiliary stream if the caller announced tree gravity for this step
+// (sphb200_prepare_gravity / sphb200_step), so that it overlaps the neighbor pass.
+static int maybe_fork_tree(sphb200_ctx* c) {
+    if (!c->tree_hint || c->tree_fresh) return SPH_OK;
+    SPH_CK(c, cudaEventRecord(c->ev_fork, c->stream));
+    SPH_CK(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+    int rc = sph_launch_tree_build(c, c->hint_dt, c->aux_stream);
+    if (rc) return rc;
+    SPH_CK(c, cudaEventRecord(c->ev_join, c->aux_stream));
+    c->tree_fresh = true;
+    c->tree_dt = c->hint_dt;
+    c->tree_join_pending = true;
+    c->tree_hint = false;
+    return SPH_OK;
+}
+
 static int ensure_sorted(sphb200_ctx* c) {
     if (c->sorted_valid) return SPH_OK;  // sorted for the current positions already
     int rc;
+    if ((rc = join_tree(c))) return rc;
     if (!c->h_updated) { rc = sph_launch_smoothing_bounds(c, false); if (rc) return rc; c->h_updated = true; }
     rc = sph_launch_sort_and_cells(c);
     if (rc) return rc;
     c->sorted_valid = true;
-    c->lists_valid = c->lists_fresh = c->tree_valid = false;  // slot indices changed
+    c->lists_valid = c->lists_fresh = c->tree_valid = c->tree_fresh = false;  // slot indices changed
     return SPH_OK;
 }
 
@@ -300,6 +336,7 @@ int sphb200_build_neighbors(sph_handle c) {
     if (c->n == 0) return SPH_OK;
     int rc = ensure_sorted(c);
     if (rc) return rc;
+    if ((rc = maybe_fork_tree(c))) return rc;
     rc = sph_launch_neighbors_density(c);
     if (rc) return rc;
     c->lists_valid = c->lists_fresh = true;
@@ -330,13 +367,28 @@ int sphb200_gravity(sph_handle c, int impl, float dt) {
     if (impl == SPH_GRAVITY_TREE) {
         int rc = ensure_sorted(c);
         if (rc) return rc;
-        rc = sph_launch_gravity_tree(c, dt);
+        if (c->tree_fresh && c->tree_dt == dt) {
+            if ((rc = join_tree(c))) return rc;       // built on the auxiliary stream during the neighbor pass
+        } else {
+            if ((rc = join_tree(c))) return rc;
+            if ((rc = sph_launch_tree_build(c, dt, c->stream))) return rc;
+            c->tree_fresh = true;
+            c->tree_dt = dt;
+        }
+        rc = sph_launch_tree_walk(c);
         if (rc) return rc;
         c->gravity_valid = true;
         return SPH_OK;
     }
     c->err = "unknown gravity impl";
     return SPH_ERR_INVALID_ARG;
+}
+
+int sphb200_prepare_gravity(sph_handle c, int impl, float dt) {
+    NEED_RESIDENT(c);
+    c->tree_hint = (impl == SPH_GRAVITY_TREE);
+    c->hint_dt = dt;
+    return SPH_OK;
 }
 
 int sphb200_density(sph_handle c) {
@@ -359,7 +411,9 @@ int sphb200_integrate(sph_handle c, float dt) {
     NEED_RESIDENT(c);
     if (c->n == 0) return SPH_OK;
     if (!c->pressure_valid || !c->gravity_valid) { c->err = "integrate needs pressure and gravity of this step"; return SPH_ERR_STATE; }
-    int rc = sph_launch_integrate(c, dt);
+    int rc = join_tree(c);
+    if (rc) return rc;
+    rc = sph_launch_integrate(c, dt);
     if (rc) return rc;
     // positions moved: neighbor/tree structures belong to the old positions; they stay downloadable until the next
     // sort but no longer feed any compute stage
@@ -374,8 +428,10 @@ int sphb200_step(sph_handle c, float dt, int impl) {
     pass_begin(c);
     if ((rc = sphb200_smoothing_update(c))) return rc;
     pass_mark(c, "smoothing_bounds");
+    if (impl == SPH_GRAVITY_TREE) { c->tree_hint = true; c->hint_dt = dt; }
     if ((rc = ensure_sorted(c))) return rc;
     pass_mark(c, "keys_sort_permute_cells");
+    if ((rc = maybe_fork_tree(c))) return rc;
     if ((rc = sph_launch_neighbors_density(c))) return rc;
     c->lists_valid = c->lists_fresh = true;
     pass_mark(c, "neighbors_density_eos");
@@ -504,6 +560,7 @@ int sphb200_download_sort(sph_handle c, uint32_t* order, uint32_t* keys, sph_Gri
 int sphb200_download_tree(sph_handle c, int32_t* child, int32_t* range, float* moment, float* lo, float* hi) {
     NEED_RESIDENT(c);
     if (!c->tree_valid) { c->err = "no tree: call gravity(SPH_GRAVITY_TREE) first"; return SPH_ERR_STATE; }
+    { int rcj = join_tree(c); if (rcj) return rcj; }
     int64_t nn = 2 * c->n - 1;
     if (nn <= 0) return SPH_OK;
     if (child) SPH_CK(c, cudaMemcpyAsync(child, c->child, (size_t)nn * 8, cudaMemcpyDeviceToHost, c->stream));

@@ -79,6 +79,11 @@ struct sphb200_ctx {
     bool h_updated = false;      // bounds/grid params computed for the current positions and h
     bool sorted_valid = false;   // sort + cell table match the current positions and h
     bool lists_fresh = false;    // neighbor lists/density belong to the current positions and h
+    // overlapped LBVH build (sphb200_prepare_gravity): built on aux_stream while the neighbor pass runs on `stream`
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool tree_hint = false, tree_fresh = false, tree_join_pending = false;
+    float hint_dt = 0.f, tree_dt = 0.f;
     int64_t t0 = 0, t1 = -1;
     int64_t launches = 0;
     float last_dt = 0.f;
@@ -151,7 +156,8 @@ int sph_launch_pressure(sphb200_ctx* c);
 int sph_launch_gravity_near(sphb200_ctx* c);
 int sph_launch_integrate(sphb200_ctx* c, float dt);
 int sph_launch_gravity_allpairs(sphb200_ctx* c);
-int sph_launch_gravity_tree(sphb200_ctx* c, float dt);
+int sph_launch_tree_build(sphb200_ctx* c, float dt, cudaStream_t stream);
+int sph_launch_tree_walk(sphb200_ctx* c);
 int sph_launch_diagnostics(sphb200_ctx* c, double* out12);
 int sph_launch_pack_upload(sphb200_ctx* c, int64_t n, bool has_nown);
 int sph_launch_unpack_field(sphb200_ctx* c, int field, int* elem_bytes);

@@ -65,7 +65,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_neighbors_density(
     const int shift = 3 * (10 - bits), dim = 1 << bits;
     const float fs = g->fine_scale, cw = (float)(1 << (10 - bits));  // cell width in fine units
     const float gx0 = g->min[0], gy0 = g->min[1], gz0 = g->min[2];
-    const int nst = 2 * S + 1, ncells = nst * nst * nst;
+    const int nst = 2 * S + 1;
     const int grp = lane >> 3, sl = lane & 7;
     const unsigned lt = (1u << lane) - 1u;
 

@@ -260,21 +260,28 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
 
 }  // namespace
 
-int sph_launch_gravity_tree(sphb200_ctx* c, float dt) {
+// LBVH topology + moments/boxes/packed nodes on `stream` (the handle's stream, or the auxiliary stream when the build is
+// overlapped with the neighbor pass).
+int sph_launch_tree_build(sphb200_ctx* c, float dt, cudaStream_t stream) {
+    int n = (int)c->n;
+    if (n <= 0) return SPH_OK;
+    SPH_CK(c, cudaMemsetAsync(c->flag, 0, (size_t)n * sizeof(int32_t), stream));
+    k_lbvh_topology<<<sph_div_up(n, 256), 256, 0, stream>>>(c->keys[1], n, c->child, c->range, c->parent);
+    SPH_LAUNCH_CHECK(c);
+    k_lbvh_nodes<<<sph_div_up(2 * (int64_t)n - 1, 256), 256, 0, stream>>>(c->posh[c->cur], c->velm[c->cur], n, c->child, c->range,
+                                                                         c->parent, c->p.leaf_max, c->p.aabb_mode, dt, c->flag, c->mom,
+                                                                         c->nlo, c->nhi, c->packed);
+    SPH_LAUNCH_CHECK(c);
+    c->tree_valid = true;
+    return SPH_OK;
+}
+
+int sph_launch_tree_walk(sphb200_ctx* c) {
     int n = (int)c->n;
     int t0 = (int)c->t0;
     int t1 = (c->t1 < 0 || c->t1 > c->n) ? n : (int)c->t1;
-    if (n <= 0) return SPH_OK;
-    SPH_CK(c, cudaMemsetAsync(c->flag, 0, (size_t)n * sizeof(int32_t), c->stream));
-    k_lbvh_topology<<<sph_div_up(n, 256), 256, 0, c->stream>>>(c->keys[1], n, c->child, c->range, c->parent);
-    SPH_LAUNCH_CHECK(c);
-    k_lbvh_nodes<<<sph_div_up(2 * (int64_t)n - 1, 256), 256, 0, c->stream>>>(c->posh[c->cur], c->velm[c->cur], n, c->child, c->range,
-                                                                            c->parent, c->p.leaf_max, c->p.aabb_mode, dt, c->flag,
-                                                                            c->mom, c->nlo, c->nhi, c->packed);
-    SPH_LAUNCH_CHECK(c);
-    c->tree_valid = true;
     int nt = t1 - t0;
-    if (nt <= 0) return SPH_OK;
+    if (n <= 0 || nt <= 0) return SPH_OK;
     float theta2 = c->p.theta * c->p.theta;  // fp32 product, as k_Theta*k_Theta (GravityFieldSystem.cs:246)
     k_tree_walk<<<sph_div_up(nt, TW_WARPS * 32), TW_WARPS * 32, 0, c->stream>>>(c->posh[c->cur], c->posm, c->packed, t0, t1, theta2,
                                                                                c->p.G, c->grav, c->npart, c->napprox, c->err_d);

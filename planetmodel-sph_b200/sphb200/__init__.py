@@ -55,7 +55,7 @@ assert GravityField.itemsize == 24 and ParticleInteraction.itemsize == 40
 EXPORTS = [
     "sphb200_default_params", "sphb200_create", "sphb200_destroy", "sphb200_last_error", "sphb200_set_stream",
     "sphb200_sync", "sphb200_upload", "sphb200_smoothing_update", "sphb200_build_neighbors", "sphb200_gravity",
-    "sphb200_density", "sphb200_pressure", "sphb200_integrate", "sphb200_step", "sphb200_set_target_range",
+    "sphb200_prepare_gravity", "sphb200_density", "sphb200_pressure", "sphb200_integrate", "sphb200_step", "sphb200_set_target_range",
     "sphb200_download", "sphb200_download_neighbors", "sphb200_download_interactions", "sphb200_download_sort",
     "sphb200_download_tree", "sphb200_diagnostics", "sphb200_count", "sphb200_get_params", "sphb200_device_ptr",
     "sphb200_launch_count", "sphb200_enable_timing", "sphb200_get_timings", "sphb200_fp32_peak", "sphb200_version",
@@ -92,6 +92,7 @@ def load_library():
     for fn in (L.sphb200_smoothing_update, L.sphb200_build_neighbors, L.sphb200_density, L.sphb200_pressure):
         fn.argtypes = [H]
     L.sphb200_gravity.argtypes = [H, C.c_int, C.c_float]
+    L.sphb200_prepare_gravity.argtypes = [H, C.c_int, C.c_float]
     L.sphb200_integrate.argtypes = [H, C.c_float]
     L.sphb200_step.argtypes = [H, C.c_float, C.c_int]
     L.sphb200_set_target_range.argtypes = [H, C.c_int64, C.c_int64]
@@ -204,6 +205,9 @@ class Simulation:
 
     def gravity(self, impl, dt):
         self._ck(self.L.sphb200_gravity(self.h, int(impl), float(dt)))
+
+    def prepare_gravity(self, impl, dt):
+        self._ck(self.L.sphb200_prepare_gravity(self.h, int(impl), float(dt)))
 
     def density(self):
         self._ck(self.L.sphb200_density(self.h))

@@ -109,6 +109,7 @@ class ShardedSimulation:
         self._mark("begin")
         s.set_target_range(t0, t1)
         s.smoothing_update()                    # all N (needs everyone's own-support counts: gathered last step)
+        s.prepare_gravity(impl, dt)             # tree gravity: LBVH build overlaps the neighbor pass (auxiliary stream)
         s.build_neighbors()                     # global sort + cell table (redundant), lists + density for [t0,t1)
         self._mark("smoothing_sort_neighbors_density_eos")
         allgather_slices(self._view("cvol", 1), self.rank, self.world)
