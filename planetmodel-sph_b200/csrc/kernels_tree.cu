@@ -163,98 +163,141 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
 
 constexpr int TW_WARPS = 8;
 
+struct WalkAcc {
+    float gx, gy, gz, gp;
+    int np, na;
+};
+
+// AcceptApproximation (GravityFieldSystem.cs:229-247): bmax_sq / r_sq < theta^2 with the exact op order for r_sq; the
+// quotient is taken with a fast reciprocal and re-done with the IEEE division only inside a band around theta^2.
+__device__ __forceinline__ bool mac_accept(const float4& pi, const float4& A, float b_sq, float theta2, float band, float& dx,
+                                           float& dy, float& dz, float& r_sq) {
+    dx = __fsub_rn(pi.x, A.x); dy = __fsub_rn(pi.y, A.y); dz = __fsub_rn(pi.z, A.z);
+    r_sq = dot3_rn(dx, dy, dz);
+    const float q = b_sq * rcp_approx(r_sq);
+    bool acc = q < theta2;
+    if (fabsf(q - theta2) < band) acc = __fdiv_rn(b_sq, r_sq) < theta2;   // rare: the IEEE quotient decides
+    return acc;
+}
+
+// GravitationalMoment.GravityContribution (M2P, :428-442)
+__device__ __forceinline__ void m2p(WalkAcc& w, const float4& A, float dx, float dy, float dz, float r_sq) {
+    float rinv = rsqrt_approx(r_sq);
+    float mr = A.w * rinv;
+    float g = mr * rinv * rinv;
+    w.gx = fmaf(dx, g, w.gx); w.gy = fmaf(dy, g, w.gy); w.gz = fmaf(dz, g, w.gz);
+    w.gp -= mr;
+    w.na++;
+}
+
+// Leaf bucket: bodies first .. first+count-1 summed directly with GravityContributionParticle (:332-356), a = h_i;
+// includes the target itself (quirk Q3).  `soft`: some open lane may be inside its softening radius.
+__device__ __forceinline__ void p2p_bucket(WalkAcc& w, const float4& pi, float a2, float ainv, const float4* __restrict__ posm,
+                                           int first, int cnt, bool open, bool soft) {
+    for (int s = first; s < first + cnt; s++) {
+        const float4 pj = __ldg(&posm[s]);
+        float ex = pi.x - pj.x, ey = pi.y - pj.y, ez = pi.z - pj.z;
+        float r2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+        float rinv = rsqrt_approx(fmaxf(r2, a2));
+        float mr = pj.w * rinv;
+        float g = mr * rinv * rinv, ph = -mr;
+        if (soft && r2 < a2) {
+            float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
+            float x = r * ainv, x2 = x * x, x3 = x2 * x;
+            float ma = pj.w * ainv;
+            g = ma * ainv * ainv * (8.0f - 9.0f * x + 2.0f * x3);
+            ph = -ma * (2.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
+        }
+        if (open) {
+            w.gx = fmaf(ex, g, w.gx); w.gy = fmaf(ey, g, w.gy); w.gz = fmaf(ez, g, w.gz);
+            w.gp += ph;
+            w.np++;
+        }
+    }
+}
+
+// One traversal step handles BOTH children of an opened node (4 independent node loads in flight, two MAC tests
+// interleaved); a stack entry is (left, right, mask of lanes that rejected the parent).  Every lane still sees exactly
+// the accepted nodes / opened buckets of its private walk (per-particle MAC); only the order in which a lane adds its
+// contributions differs from the depth-first order of the oracle.
 __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __restrict__ posh, const float4* __restrict__ posm,
                                                              const float4* __restrict__ packed, int t0, int t1, float theta2,
                                                              float G, float4* __restrict__ grav, int32_t* __restrict__ npart,
                                                              int32_t* __restrict__ napprox, int32_t* __restrict__ err) {
-    __shared__ int2 stack[TW_WARPS][SPH_TREE_STACK];
-    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int t = t0 + (blockIdx.x * TW_WARPS + w) * 32 + lane;
+    __shared__ int4 stack[TW_WARPS][SPH_TREE_STACK];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int t = t0 + (blockIdx.x * TW_WARPS + wid) * 32 + lane;
     const bool active = t < t1;
     const float4 pi = posh[active ? t : (t1 - 1)];
     const float a2 = pi.w * pi.w, ainv = 1.0f / pi.w;
-    // band around theta^2 inside which the fast reciprocal test is not trusted and the exact division decides
     const float band = theta2 * 8.0e-6f;
-    float gx = 0.f, gy = 0.f, gz = 0.f, gp = 0.f;
-    int np = 0, na = 0;
-    unsigned mask = __ballot_sync(FULL, active);
-    if (mask == 0) return;
-    int2* st = stack[w];
+    WalkAcc w = {0.f, 0.f, 0.f, 0.f, 0, 0};
+    const unsigned m0 = __ballot_sync(FULL, active);
+    if (m0 == 0) return;
+    int4* st = stack[wid];
     int sp = 0;
-    int k = 0;
-    while (true) {
-        const float4 A = __ldg(&packed[2 * (size_t)k]);
-        const float4 B = __ldg(&packed[2 * (size_t)k + 1]);
-        const bool mine = (mask >> lane) & 1u;
-        // AcceptApproximation (GravityFieldSystem.cs:229-247): bmax_sq / r_sq < theta^2, r_sq with the exact op order
-        const float dx = __fsub_rn(pi.x, A.x), dy = __fsub_rn(pi.y, A.y), dz = __fsub_rn(pi.z, A.z);
-        const float r_sq = dot3_rn(dx, dy, dz);
-        const float q = B.x * rcp_approx(r_sq);
-        bool acc = q < theta2;
-        if (fabsf(q - theta2) < band) acc = __fdiv_rn(B.x, r_sq) < theta2;   // rare: the IEEE quotient decides
-        acc = acc && mine;
-        if (acc) {
-            // GravitationalMoment.GravityContribution (M2P, :428-442)
-            float rinv = rsqrt_approx(r_sq);
-            float mr = A.w * rinv;
-            float g = mr * rinv * rinv;
-            gx = fmaf(dx, g, gx); gy = fmaf(dy, g, gy); gz = fmaf(dz, g, gz);
-            gp -= mr;
-            na++;
-        }
-        const unsigned rej = __ballot_sync(FULL, mine && !acc);
+    {   // root
+        const float4 A = __ldg(&packed[0]), B = __ldg(&packed[1]);
+        float dx, dy, dz, r_sq;
+        const bool acc = active && mac_accept(pi, A, B.x, theta2, band, dx, dy, dz, r_sq);
+        if (acc) m2p(w, A, dx, dy, dz, r_sq);
+        const unsigned rej = __ballot_sync(FULL, active && !acc);
         const int ia = __float_as_int(B.y), ib = __float_as_int(B.z);
-        if (rej != 0 && ib >= 0) {
-            // descend: right child now, left child later (LIFO order of GravityFieldSystem.cs:201-206)
-            if (sp >= SPH_TREE_STACK) {
-                if (lane == 0) atomicExch(&err[ERR_TREE_STACK], 1);
-                break;
-            }
-            if (lane == 0) st[sp] = make_int2(ia, (int)rej);
-            sp++;
-            k = ib;
-            mask = rej;
-            continue;
-        }
         if (rej != 0) {
-            // leaf bucket: bodies first .. first+count-1, summed directly; includes the target itself (quirk Q3)
-            const bool open = (rej >> lane) & 1u;
-            const int cnt = -ib;
-            // a body can be inside the softening radius a = h_i only if |p - cm| < a + Bmax, i.e. r_sq < 2 (a^2 + Bmax^2)
-            const bool soft = __any_sync(FULL, open && r_sq < 2.0f * (a2 + B.x));
-            for (int s = ia; s < ia + cnt; s++) {
-                const float4 pj = __ldg(&posm[s]);
-                // GravityContributionParticle (:332-356), a = h_i
-                float ex = pi.x - pj.x, ey = pi.y - pj.y, ez = pi.z - pj.z;
-                float r2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-                float rinv = rsqrt_approx(fmaxf(r2, a2));
-                float mr = pj.w * rinv;
-                float g = mr * rinv * rinv, ph = -mr;
-                if (soft && r2 < a2) {
-                    float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
-                    float x = r * ainv, x2 = x * x, x3 = x2 * x;
-                    float ma = pj.w * ainv;
-                    g = ma * ainv * ainv * (8.0f - 9.0f * x + 2.0f * x3);
-                    ph = -ma * (2.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
-                }
-                if (open) {
-                    gx = fmaf(ex, g, gx); gy = fmaf(ey, g, gy); gz = fmaf(ez, g, gz);
-                    gp += ph;
-                    np++;
-                }
+            if (ib < 0) {
+                const bool open = (rej >> lane) & 1u;
+                const bool soft = __any_sync(FULL, open && r_sq < 2.0f * (a2 + B.x));
+                p2p_bucket(w, pi, a2, ainv, posm, ia, -ib, open, soft);
+            } else {
+                if (lane == 0) st[0] = make_int4(ia, ib, (int)rej, 0);
+                sp = 1;
             }
         }
-        if (sp == 0) break;
         __syncwarp();
-        const int2 e = st[--sp];
+    }
+    while (sp > 0) {
+        const int4 e = st[--sp];
         __syncwarp();
-        k = e.x;
-        mask = (unsigned)e.y;
+        const float4 A0 = __ldg(&packed[2 * (size_t)e.x]), B0 = __ldg(&packed[2 * (size_t)e.x + 1]);
+        const float4 A1 = __ldg(&packed[2 * (size_t)e.y]), B1 = __ldg(&packed[2 * (size_t)e.y + 1]);
+        const bool mine = ((unsigned)e.z >> lane) & 1u;
+        float dx0, dy0, dz0, r0, dx1, dy1, dz1, r1;
+        const bool acc0 = mac_accept(pi, A0, B0.x, theta2, band, dx0, dy0, dz0, r0) && mine;
+        const bool acc1 = mac_accept(pi, A1, B1.x, theta2, band, dx1, dy1, dz1, r1) && mine;
+        if (acc0) m2p(w, A0, dx0, dy0, dz0, r0);
+        if (acc1) m2p(w, A1, dx1, dy1, dz1, r1);
+        const unsigned rej0 = __ballot_sync(FULL, mine && !acc0);
+        const unsigned rej1 = __ballot_sync(FULL, mine && !acc1);
+        if (rej0 != 0) {
+            const int ia = __float_as_int(B0.y), ib = __float_as_int(B0.z);
+            if (ib < 0) {
+                const bool open = (rej0 >> lane) & 1u;
+                const bool soft = __any_sync(FULL, open && r0 < 2.0f * (a2 + B0.x));
+                p2p_bucket(w, pi, a2, ainv, posm, ia, -ib, open, soft);
+            } else {
+                if (sp >= SPH_TREE_STACK) { if (lane == 0) atomicExch(&err[ERR_TREE_STACK], 1); break; }
+                if (lane == 0) st[sp] = make_int4(ia, ib, (int)rej0, 0);
+                sp++;
+            }
+        }
+        if (rej1 != 0) {
+            const int ia = __float_as_int(B1.y), ib = __float_as_int(B1.z);
+            if (ib < 0) {
+                const bool open = (rej1 >> lane) & 1u;
+                const bool soft = __any_sync(FULL, open && r1 < 2.0f * (a2 + B1.x));
+                p2p_bucket(w, pi, a2, ainv, posm, ia, -ib, open, soft);
+            } else {
+                if (sp >= SPH_TREE_STACK) { if (lane == 0) atomicExch(&err[ERR_TREE_STACK], 1); break; }
+                if (lane == 0) st[sp] = make_int4(ia, ib, (int)rej1, 0);
+                sp++;
+            }
+        }
+        __syncwarp();
     }
     if (active) {
-        grav[t] = make_float4(G * gx, G * gy, G * gz, G * gp);
-        npart[t] = np;
-        napprox[t] = na;
+        grav[t] = make_float4(G * w.gx, G * w.gy, G * w.gz, G * w.gp);
+        npart[t] = w.np;
+        napprox[t] = w.na;
     }
 }
 
