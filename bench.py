@@ -144,7 +144,7 @@ def run_reference(args):
             "dtype": "f32", "data": "synthetic", "config": workload_desc(args.workload, n, grav, args.gpus),
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_desc(name, n, grav, gpus):
@@ -289,8 +289,7 @@ def run_ours(args):
             "e2e": e2e, "gpu_launches": int(launches), "errors": errors, "roofline": roof, "hbm_passes": hbm_passes,
             "pass_ms": mean, "mean_neighbors": kbar, "fp32_peak_tflops_measured": fp32_peak,
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}}
-    print(json.dumps(line))
-    sys.stdout.flush()
+    emit(line)
     if world > 1:
         import torch.distributed as td
         td.barrier()
@@ -341,7 +340,24 @@ def measure_e2e(eng, c, impl, steps, barrier):
             "path": "sphb200_upload + sphb200_step + sphb200_download x7 per rank (host component arrays, pinned staging)"}
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    """Write the ONE JSON line to the real stdout (everything else, e.g. NCCL's banner, was diverted to stderr)."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, data)
+    else:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+
+
 def main():
+    global _REAL_STDOUT
+    # libraries (NCCL) print banners on fd 1: keep stdout for the single JSON line
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)

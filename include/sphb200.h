@@ -28,7 +28,7 @@ extern "C" {
 enum {
     SPH_OK = 0,
     SPH_ERR_INVALID_ARG = -1,
-    SPH_ERR_CAPACITY = -2,          /* n > capacity, or > 2^24-2 in ref-compat (UP/Dynamics/Simulation/Scheduler.cs:26-31,41) */
+    SPH_ERR_CAPACITY = -2,          /* n > capacity (the reference itself is capped at 2^24-2 bodies, Scheduler.cs:26-31,41; this library is not) */
     SPH_ERR_NEIGHBOR_OVERFLOW = -3, /* some particle has more than max_neighbors neighbors; lists truncated */
     SPH_ERR_CUDA = -4,
     SPH_ERR_STATE = -5,             /* stage called out of order (e.g. pressure before build_neighbors) */
