@@ -77,6 +77,13 @@ def load_library():
     if _lib is not None:
         return _lib
     if not os.path.exists(LIB_PATH):
+        # fresh checkout (the .so is git-ignored): build it in-tree when a CUDA toolchain is present
+        import shutil
+        import subprocess
+        nvcc = shutil.which("nvcc") or ("/usr/local/cuda/bin/nvcc" if os.path.exists("/usr/local/cuda/bin/nvcc") else None)
+        if nvcc:
+            subprocess.call(["make", "-C", os.path.join(os.path.dirname(_HERE), "csrc"), "-j4"], stdout=subprocess.DEVNULL)
+    if not os.path.exists(LIB_PATH):
         raise ImportError("libsphb200.so is not built (run `python __graft_entry__.py` or `make -C planetmodel-sph_b200/csrc`); "
                           "there is no CPU fallback")
     L = C.CDLL(LIB_PATH)
