@@ -6,6 +6,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <vector>
+#include <cmath>
+#include <cstdint>
 
 __device__ __forceinline__ float rsqrt_approx(float x) {
     float y;
@@ -137,6 +139,130 @@ void run(const char* name, const float4* src, const float4* posh, float4* part, 
            20.0 * (double)n * n / (best * 1e-3) / 1e12, fa.numRegs, nb, tblocks, sp, e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
+
+// ---- TMA (cp.async.bulk) variant: one elected thread streams 4 KB source tiles into a 4-stage shared-memory ring;
+// full/empty mbarriers replace the block barrier.  Sources must be padded to a multiple of 256.
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra LAB_DONE;\n"
+        "bra LAB_WAIT;\n"
+        "LAB_DONE:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(phase) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int TPT, int STAGES, bool EQM>
+__global__ void __launch_bounds__(256) k_ap_tma(const float4* __restrict__ src, int n_src_padded, int src_per_split,
+                                                const float4* __restrict__ posh, int nt, float4* __restrict__ part) {
+    constexpr int TILE = 256, THREADS = 256;
+    __shared__ __align__(128) float4 tile[STAGES][TILE];
+    __shared__ __align__(8) uint64_t full[STAGES], empty[STAGES];
+    const int tid = threadIdx.x;
+    const int tb = blockIdx.x * (THREADS * TPT);
+    float xi[TPT], yi[TPT], zi[TPT];
+    float AX[TPT], AY[TPT], AZ[TPT], PH[TPT];
+#pragma unroll
+    for (int k = 0; k < TPT; k++) {
+        int t = tb + k * THREADS + tid;
+        float4 p = posh[min(t, nt - 1)];
+        xi[k] = p.x; yi[k] = p.y; zi[k] = p.z;
+        AX[k] = AY[k] = AZ[k] = PH[k] = 0.f;
+    }
+    const int s0 = blockIdx.y * src_per_split;
+    const int s1 = min(s0 + src_per_split, n_src_padded);
+    const int ntiles = (s1 - s0) / TILE;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], THREADS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0)
+        for (int s = 0; s < STAGES && s < ntiles; s++) {
+            mbar_expect_tx(&full[s], TILE * 16);
+            tma_load_1d(tile[s], src + s0 + s * TILE, TILE * 16, &full[s]);
+        }
+    for (int it = 0; it < ntiles; it++) {
+        const int s = it % STAGES;
+        const uint32_t ph = (it / STAGES) & 1;
+        mbar_wait(&full[s], ph);
+        float ax[TPT], ay[TPT], az[TPT], pp[TPT];
+#pragma unroll
+        for (int k = 0; k < TPT; k++) ax[k] = ay[k] = az[k] = pp[k] = 0.f;
+        const float4* tp = tile[s];
+#pragma unroll 1
+        for (int j = 0; j < TILE; j += 8, tp += 8) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                const float4 q = tp[u];
+#pragma unroll
+                for (int k = 0; k < TPT; k++) {
+                    float dx = xi[k] - q.x, dy = yi[k] - q.y, dz = zi[k] - q.z;
+                    float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                    float rinv = rsqrt_approx(r2);
+                    float g;
+                    if (EQM) { g = rinv * rinv * rinv; pp[k] += rinv; }
+                    else { float mr = q.w * rinv; g = mr * (rinv * rinv); pp[k] += mr; }
+                    ax[k] = fmaf(dx, g, ax[k]); ay[k] = fmaf(dy, g, ay[k]); az[k] = fmaf(dz, g, az[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < TPT; k++) { AX[k] += ax[k]; AY[k] += ay[k]; AZ[k] += az[k]; PH[k] += pp[k]; }
+        mbar_arrive(&empty[s]);                       // this thread is done reading stage s
+        if (tid == 0 && it + STAGES < ntiles) {       // refill it once everybody is
+            mbar_wait(&empty[s], ph);
+            mbar_expect_tx(&full[s], TILE * 16);
+            tma_load_1d(tile[s], src + s0 + (it + STAGES) * TILE, TILE * 16, &full[s]);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < TPT; k++) {
+        int t = tb + k * THREADS + tid;
+        if (t < nt) part[(size_t)blockIdx.y * nt + t] = make_float4(AX[k], AY[k], AZ[k], PH[k]);
+    }
+}
+
+template <int TPT, int STAGES, bool EQM>
+void run_tma(const char* name, const float4* src, const float4* posh, float4* part, int n, int splits) {
+    int tblocks = (n + 256 * TPT - 1) / (256 * TPT);
+    int per = ((n + splits - 1) / splits + 255) / 256 * 256;
+    int sp = (n + per - 1) / per;
+    dim3 grid(tblocks, sp);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        k_ap_tma<TPT, STAGES, EQM><<<grid, 256>>>(src, n, per, posh, n, part);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_ap_tma<TPT, STAGES, EQM>);
+    printf("%-44s %8.3f ms  %6.2f TF(20/pair)  regs %3d  grid %dx%d %s\n", name, best, 20.0 * (double)n * n / (best * 1e-3) / 1e12,
+           fa.numRegs, tblocks, sp, e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
 int main(int argc, char** argv) {
     int n = argc > 1 ? atoi(argv[1]) : 262144;
     std::vector<float4> h(n), p(n);
@@ -174,5 +300,16 @@ int main(int argc, char** argv) {
     run<2, 256, 8, false, true, true, 1>("eqm nocap tpt2 t256", src, posh, part, n, 14);
     run<2, 128, 16, false, true, true, 1>("eqm nocap tpt2 t128 u16", src, posh, part, n, 7);
     run<8, 128, 8, false, true, true, 1>("eqm nocap tpt8 t128", src, posh, part, n, 28);
+    run_tma<4, 4, true>("TMA ring: eqm nocap tpt4 4 stages", src, posh, part, n, 28);
+    run_tma<4, 2, true>("TMA ring: eqm nocap tpt4 2 stages", src, posh, part, n, 28);
+    run_tma<4, 4, false>("TMA ring: mass nocap tpt4 4 stages", src, posh, part, n, 28);
+    // checksum of the last variants vs the plain kernel
+    std::vector<float4> r1(n), r2(n);
+    k_ap<4, 256, 8, false, false, true, 1><<<dim3((n + 1023) / 1024, 1), 256>>>(src, n, n, posh, n, part);
+    cudaMemcpy(r1.data(), part, n * 16, cudaMemcpyDeviceToHost);
+    k_ap_tma<4, 4, false><<<dim3((n + 1023) / 1024, 1), 256>>>(src, n, n, posh, n, part);
+    cudaMemcpy(r2.data(), part, n * 16, cudaMemcpyDeviceToHost);
+    double md = 0; for (int i = 0; i < n; i++) md = fmax(md, fabs(r1[i].x - r2[i].x) / (fabs(r1[i].x) + 1e-30));
+    printf("max rel diff plain vs TMA (x component): %.3e  %s\n", md, cudaGetErrorString(cudaGetLastError()));
     return 0;
 }
