@@ -241,23 +241,33 @@ int sphb200_upload(sph_handle c, int64_t n, const void* pos, int pos_stride, con
     // asynchronous error flags are sticky from one upload to the next (results after an overflow are tainted)
     SPH_CK(c, cudaMemsetAsync(c->err_d, 0, ERR_SLOTS * sizeof(int32_t), c->stream));
     if (n == 0) return SPH_OK;
+    // Staging layout (device): pos[3n] vel[3n] mass[n] h[n] nown[n].  Arrays with their natural stride are copied
+    // straight from the caller's memory (one DMA when it is pinned); strided arrays are packed through pinned staging.
     float* st = (float*)c->stage_h;
-    float* P = st; float* V = st + 3 * n; float* M = st + 6 * n; float* H = st + 7 * n; int32_t* NO = (int32_t*)(st + 8 * n);
+    float* sd = (float*)c->stage_d;
     bool has_nown = smoothing_stride >= (int)sizeof(sph_ParticleSmoothing);
     const char* pp = (const char*)pos; const char* vp = (const char*)vel; const char* mp = (const char*)mass; const char* sp = (const char*)smoothing;
-    if (pos_stride == 12) memcpy(P, pp, (size_t)n * 12);
-    else for (int64_t i = 0; i < n; i++) memcpy(P + 3 * i, pp + (size_t)i * pos_stride, 12);
-    if (vel_stride == 12) memcpy(V, vp, (size_t)n * 12);
-    else for (int64_t i = 0; i < n; i++) memcpy(V + 3 * i, vp + (size_t)i * vel_stride, 12);
-    if (mass_stride == 4) memcpy(M, mp, (size_t)n * 4);
-    else for (int64_t i = 0; i < n; i++) memcpy(M + i, mp + (size_t)i * mass_stride, 4);
-    if (smoothing_stride == 4) memcpy(H, sp, (size_t)n * 4);
-    else for (int64_t i = 0; i < n; i++) memcpy(H + i, sp + (size_t)i * smoothing_stride, 4);
-    if (has_nown) for (int64_t i = 0; i < n; i++) memcpy(NO + i, sp + (size_t)i * smoothing_stride + 24, 4);
+    auto put = [&](size_t off_words, const char* src, int stride, int words) -> cudaError_t {
+        size_t bytes = (size_t)n * words * 4;
+        if (stride == words * 4) return cudaMemcpyAsync(sd + off_words, src, bytes, cudaMemcpyHostToDevice, c->stream);
+        float* dst = st + off_words;
+        for (int64_t i = 0; i < n; i++) memcpy(dst + (size_t)words * i, src + (size_t)i * stride, (size_t)words * 4);
+        return cudaMemcpyAsync(sd + off_words, dst, bytes, cudaMemcpyHostToDevice, c->stream);
+    };
+    SPH_CK(c, put(0, pp, pos_stride, 3));
+    SPH_CK(c, put(3 * (size_t)n, vp, vel_stride, 3));
+    SPH_CK(c, put(6 * (size_t)n, mp, mass_stride, 1));
+    SPH_CK(c, put(7 * (size_t)n, sp, smoothing_stride, 1));
+    if (has_nown) SPH_CK(c, put(8 * (size_t)n, sp + 24, smoothing_stride, 1));
+    float m0;
+    memcpy(&m0, mp, 4);
     c->equal_mass = true;
-    c->common_mass = M[0];
-    for (int64_t i = 1; i < n && c->equal_mass; i++) c->equal_mass = (M[i] == M[0]);
-    SPH_CK(c, cudaMemcpyAsync(c->stage_d, c->stage_h, (size_t)n * 9 * 4, cudaMemcpyHostToDevice, c->stream));
+    c->common_mass = m0;
+    for (int64_t i = 1; i < n && c->equal_mass; i++) {
+        float mi;
+        memcpy(&mi, mp + (size_t)i * mass_stride, 4);
+        c->equal_mass = (mi == m0);
+    }
     int rc = sph_launch_pack_upload(c, n, has_nown);
     if (rc) return rc;
     SPH_CK(c, cudaStreamSynchronize(c->stream));
@@ -453,8 +463,10 @@ int sphb200_download(sph_handle c, int field, void* dst, int stride) {
     int rc = sph_launch_unpack_field(c, field, &eb);
     if (rc) { if (rc == SPH_ERR_INVALID_ARG) c->err = "unknown field"; return rc; }
     int64_t n = c->n;
-    SPH_CK(c, cudaMemcpyAsync(c->stage_h, c->stage_d, (size_t)n * eb, cudaMemcpyDeviceToHost, c->stream));
+    const bool direct = stride == eb && field != SPH_FIELD_SMOOTHING && field != SPH_FIELD_GRAVITY;
+    SPH_CK(c, cudaMemcpyAsync(direct ? dst : c->stage_h, c->stage_d, (size_t)n * eb, cudaMemcpyDeviceToHost, c->stream));
     rc = check_errflags(c);  // also synchronises
+    if (direct) return rc;   // natural stride: the DMA wrote the caller's array
     const char* src = (const char*)c->stage_h;
     char* d = (char*)dst;
     switch (field) {
