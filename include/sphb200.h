@@ -57,7 +57,8 @@ typedef struct sph_Params {
 } sph_Params;
 
 enum {
-    SPH_FLAG_FIX_KERNEL_DERIV_SIGN = 1 /* use -3q in KernelDeriv's inner branch (undo quirk Q1, SplineKernel.cs:135) */
+    SPH_FLAG_FIX_KERNEL_DERIV_SIGN = 1, /* use -3q in KernelDeriv's inner branch (undo quirk Q1, SplineKernel.cs:135) */
+    SPH_FLAG_KICK_DRIFT = 2             /* v += a dt first, then x += v_new dt (symplectic leapfrog; roadmap README.md:90-93) */
 };
 
 /* ---- byte-exact mirrors of the reference components */

@@ -67,6 +67,7 @@ def lib():
         L.orc_pressure_grad.argtypes = [C.c_int64, f32p, f32p, f32p, f32p, f32p, i64p, i32p, C.c_int, f32p]
         L.orc_gravity_direct.argtypes = [C.c_int64, f32p, f32p, f32p, C.c_float, C.c_int64, C.c_int64, C.c_int, f32p]
         L.orc_integrate.argtypes = [C.c_int64, f32p, f32p, f32p, f32p, f32p, C.c_float]
+        L.orc_integrate2.argtypes = [C.c_int64, f32p, f32p, f32p, f32p, f32p, C.c_float, C.c_int]
         L.orc_grid_params.argtypes = [C.c_int64, f32p, f32p, C.c_int, C.POINTER(GridParams)]
         L.orc_morton_keys.argtypes = [C.c_int64, f32p, C.POINTER(GridParams), u32p]
         L.orc_sort_order.argtypes = [C.c_int64, u32p, u32p]
@@ -156,9 +157,9 @@ def smoothing_update(h, n_own, target=50.0):
     return out
 
 
-def integrate(pos, vel, rho, gradP, grav4, dt):
+def integrate(pos, vel, rho, gradP, grav4, dt, kick_drift=False):
     pos = _f(pos).copy(); vel = _f(vel).copy()
-    lib().orc_integrate(len(rho), pos, vel, _f(rho), _f(gradP), _f(grav4), dt)
+    lib().orc_integrate2(len(rho), pos, vel, _f(rho), _f(gradP), _f(grav4), dt, int(kick_drift))
     return pos, vel
 
 
@@ -248,7 +249,7 @@ class State:
 
 
 def step(s, dt, gravity="direct", K=1000.0, G=1.0, theta=0.7, target=50.0, leaf_max=4, aabb_mode=0, max_bits=7,
-         accum_double=False, neighbor_method="auto"):
+         accum_double=False, neighbor_method="auto", kick_drift=False):
     """One reference timestep, in place. gravity in {"direct","tree","none"}."""
     # 1. ParticleSmoothingSystem: h from last step's own-support counts (quirk Q8)
     s.h = smoothing_update(s.h, s.n_own, target)
@@ -268,5 +269,5 @@ def step(s, dt, gravity="direct", K=1000.0, G=1.0, theta=0.7, target=50.0, leaf_
     s.P = eos(s.rho, K)
     s.gradP = pressure_grad(s.pos, s.h, s.mass, s.rho, s.P, s.offsets, s.nbr)
     # 5f + 9. x += v_n dt ; v += a dt
-    s.pos, s.vel = integrate(s.pos, s.vel, s.rho, s.gradP, s.grav, dt)
+    s.pos, s.vel = integrate(s.pos, s.vel, s.rho, s.gradP, s.grav, dt, kick_drift)
     return s

@@ -470,15 +470,21 @@ ORC_API void orc_gravity_direct(int64_t n, const float* pos, const float* h, con
 // Integration: x += v*dt  (UP/Dynamics/Integrator/Integrator.cs:98-101, old v), then
 //              v += (-gradP/rho - gradPhi)*dt  (A/Systems/VelocitySystem.cs:24-36)
 // ------------------------------------------------------------------------------------------------
-ORC_API void orc_integrate(int64_t n, float* pos, float* vel, const float* rho, const float* gradP,
-                           const float* grav4, float dt) {
+ORC_API void orc_integrate2(int64_t n, float* pos, float* vel, const float* rho, const float* gradP,
+                            const float* grav4, float dt, int kick_drift) {
     for (int64_t i = 0; i < n; i++)
         for (int k = 0; k < 3; k++) {
             float v = vel[3 * i + k];
-            pos[3 * i + k] = pos[3 * i + k] + v * dt;
+            if (!kick_drift) pos[3 * i + k] = pos[3 * i + k] + v * dt;
             float dvdt = -gradP[3 * i + k] / rho[i] - grav4[4 * i + k];
-            vel[3 * i + k] = v + dvdt * dt;
+            float vn = v + dvdt * dt;
+            vel[3 * i + k] = vn;
+            if (kick_drift) pos[3 * i + k] = pos[3 * i + k] + vn * dt;   // non-reference option (README.md:90-93 roadmap)
         }
+}
+ORC_API void orc_integrate(int64_t n, float* pos, float* vel, const float* rho, const float* gradP,
+                           const float* grav4, float dt) {
+    orc_integrate2(n, pos, vel, rho, gradP, grav4, dt, 0);
 }
 
 // ------------------------------------------------------------------------------------------------

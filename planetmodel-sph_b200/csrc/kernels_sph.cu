@@ -141,23 +141,32 @@ __global__ void __launch_bounds__(256) k_gravity_near(const float4* __restrict__
 
 // ------------------------------------------------------------------------------------------------------------
 // Integrate: x += v*dt (old v), v += (-gradP/rho - gradPhi)*dt ; exact op order of the reference.
+// kick_drift (SPH_FLAG_KICK_DRIFT, off by default; roadmap README.md:90-93): v first, then x += v_new*dt -- the
+// symplectic (leapfrog with staggered velocities) variant of the same one-force-evaluation step.
 // ------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_integrate(float4* __restrict__ posh, float4* __restrict__ velm,
                                                    const float* __restrict__ rho, const float4* __restrict__ gradp,
-                                                   const float4* __restrict__ grav, int t0, int t1, float dt) {
+                                                   const float4* __restrict__ grav, int t0, int t1, float dt, int kick_drift) {
     int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= t1) return;
     float4 p = posh[t], v = velm[t], gp = gradp[t], g = grav[t];
     float d = rho[t];
-    p.x = __fadd_rn(p.x, __fmul_rn(v.x, dt));
-    p.y = __fadd_rn(p.y, __fmul_rn(v.y, dt));
-    p.z = __fadd_rn(p.z, __fmul_rn(v.z, dt));
+    if (!kick_drift) {
+        p.x = __fadd_rn(p.x, __fmul_rn(v.x, dt));
+        p.y = __fadd_rn(p.y, __fmul_rn(v.y, dt));
+        p.z = __fadd_rn(p.z, __fmul_rn(v.z, dt));
+    }
     float ax = __fsub_rn(__fdiv_rn(-gp.x, d), g.x);
     float ay = __fsub_rn(__fdiv_rn(-gp.y, d), g.y);
     float az = __fsub_rn(__fdiv_rn(-gp.z, d), g.z);
     v.x = __fadd_rn(v.x, __fmul_rn(ax, dt));
     v.y = __fadd_rn(v.y, __fmul_rn(ay, dt));
     v.z = __fadd_rn(v.z, __fmul_rn(az, dt));
+    if (kick_drift) {
+        p.x = __fadd_rn(p.x, __fmul_rn(v.x, dt));
+        p.y = __fadd_rn(p.y, __fmul_rn(v.y, dt));
+        p.z = __fadd_rn(p.z, __fmul_rn(v.z, dt));
+    }
     posh[t] = p;
     velm[t] = v;
 }
@@ -342,7 +351,8 @@ int sph_launch_integrate(sphb200_ctx* c, float dt) {
     int t0, t1; target_range(c, t0, t1);
     int nt = t1 - t0;
     if (nt <= 0) return SPH_OK;
-    k_integrate<<<sph_div_up(nt, 256), 256, 0, c->stream>>>(c->posh[c->cur], c->velm[c->cur], c->rho, c->gradp, c->grav, t0, t1, dt);
+    k_integrate<<<sph_div_up(nt, 256), 256, 0, c->stream>>>(c->posh[c->cur], c->velm[c->cur], c->rho, c->gradp, c->grav, t0, t1, dt,
+                                                          (c->p.flags & SPH_FLAG_KICK_DRIFT) ? 1 : 0);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;
 }
