@@ -20,12 +20,14 @@
 // source splits -- deterministic, and ~sqrt(256) times tighter than one 10^6-term fp32 chain.
 #include "ctx.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
 constexpr int AP_THREADS = 256;
 constexpr int AP_TPT = 4;     // targets per thread (one LDS.128 feeds 4 pair evaluations)
-constexpr int AP_TILE = 256;  // sources per shared-memory tile (= inner fp32 partial-sum length)
+constexpr int AP_TILE = 256;  // sources per shared-memory tile (inner fp32 partial sums: 2 interleaved chains of 128)
+constexpr int AP_UNROLL = 4;  // source pairs per unrolled inner-loop body
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float rsqrt_approx(float x) {
@@ -63,35 +65,60 @@ __global__ void __launch_bounds__(AP_TILE) k_tile_boxes(const float4* __restrict
     }
 }
 
+// Packed FP32 (Blackwell FFMA2 / FADD2 / FMUL2, PTX *.f32x2): one instruction evaluates the same target against TWO
+// sources, halving the issue slots per pair (13.5 -> 7); the FMA pipe, not the scheduler, becomes the limit.
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+// One 256-source tile, stored as 128 source pairs: [2p] = (x0,x1,y0,y1), [2p+1] = (z0,z1,m0,m1).  The target
+// coordinates are packed (xi,xi): ptxas turns them into the broadcast-scalar operand form (R.F32).
 template <int TPT, bool CAP, bool EQM>
-__device__ __forceinline__ void tile_loop(const float4* __restrict__ tp, const float (&xi)[TPT], const float (&yi)[TPT],
-                                          const float (&zi)[TPT], const float (&a2)[TPT], float (&ax)[TPT], float (&ay)[TPT],
-                                          float (&az)[TPT], float (&ph)[TPT]) {
-#pragma unroll 1
-    for (int j = 0; j < AP_TILE; j += 8, tp += 8) {
+__device__ __forceinline__ void tile_loop(const ulonglong2* __restrict__ tp, const u64 (&xi)[TPT], const u64 (&yi)[TPT],
+                                          const u64 (&zi)[TPT], const float (&a2)[TPT], float (&AX)[TPT], float (&AY)[TPT],
+                                          float (&AZ)[TPT], float (&PH)[TPT]) {
+    u64 ax[TPT], ay[TPT], az[TPT], ph[TPT];
 #pragma unroll
-        for (int u = 0; u < 8; u++) {
-            const float4 s = tp[u];
+    for (int k = 0; k < TPT; k++) ax[k] = ay[k] = az[k] = ph[k] = pk(0.f, 0.f);
+#pragma unroll 1
+    for (int j = 0; j < AP_TILE / 2; j += AP_UNROLL, tp += 2 * AP_UNROLL) {
+#pragma unroll
+        for (int u = 0; u < AP_UNROLL; u++) {
+            const ulonglong2 A = tp[2 * u], B = tp[2 * u + 1];
 #pragma unroll
             for (int k = 0; k < TPT; k++) {
-                float dx = xi[k] - s.x, dy = yi[k] - s.y, dz = zi[k] - s.z;
-                float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                if (CAP) r2 = fmaxf(r2, a2[k]);
-                float rinv = rsqrt_approx(r2);
-                float g;
+                u64 dx = sub2(xi[k], A.x), dy = sub2(yi[k], A.y), dz = sub2(zi[k], B.x);
+                u64 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                float r2a, r2b;
+                upk(r2, r2a, r2b);
+                if (CAP) { r2a = fmaxf(r2a, a2[k]); r2b = fmaxf(r2b, a2[k]); }
+                u64 rinv = pk(rsqrt_approx(r2a), rsqrt_approx(r2b));
+                u64 g;
                 if (EQM) {
-                    g = rinv * rinv * rinv;
-                    ph[k] += rinv;
+                    g = mul2(mul2(rinv, rinv), rinv);
+                    ph[k] = add2(ph[k], rinv);
                 } else {
-                    float mr = s.w * rinv;
-                    g = mr * (rinv * rinv);
-                    ph[k] += mr;
+                    u64 mr = mul2(B.y, rinv);
+                    g = mul2(mr, mul2(rinv, rinv));
+                    ph[k] = add2(ph[k], mr);
                 }
-                ax[k] = fmaf(dx, g, ax[k]);
-                ay[k] = fmaf(dy, g, ay[k]);
-                az[k] = fmaf(dz, g, az[k]);
+                ax[k] = fma2(dx, g, ax[k]);
+                ay[k] = fma2(dy, g, ay[k]);
+                az[k] = fma2(dz, g, az[k]);
             }
         }
+    }
+#pragma unroll
+    for (int k = 0; k < TPT; k++) {   // tile partial (2 x 128 sources) into the running sum
+        float a, b;
+        upk(ax[k], a, b); AX[k] += a + b;
+        upk(ay[k], a, b); AY[k] += a + b;
+        upk(az[k], a, b); AZ[k] += a + b;
+        upk(ph[k], a, b); PH[k] += a + b;
     }
 }
 
@@ -101,20 +128,21 @@ template <int TPT, bool EQM>
 __global__ void __launch_bounds__(AP_THREADS) k_gravity_allpairs(const float4* __restrict__ src, int n_src, int src_per_split,
                                                                  const float4* __restrict__ tbox, const float4* __restrict__ posh,
                                                                  int t0, int t1, float4* __restrict__ part) {
-    __shared__ float4 tile[2][AP_TILE];
+    __shared__ __align__(16) float tile[2][AP_TILE * 4];
     __shared__ float4 tb_lo[2], tb_hi[2];
     __shared__ float ebox[6][AP_THREADS / 32];
     const int nt = t1 - t0;
     const int tid = threadIdx.x;
     const int tb = blockIdx.x * (AP_THREADS * TPT);
-    float xi[TPT], yi[TPT], zi[TPT], a2[TPT];
+    u64 xi[TPT], yi[TPT], zi[TPT];
+    float a2[TPT];
     float AX[TPT], AY[TPT], AZ[TPT], PH[TPT];
     float e[6] = {INFINITY, INFINITY, INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
     for (int k = 0; k < TPT; k++) {
         int t = tb + k * AP_THREADS + tid;
         float4 p = posh[t0 + min(t, nt - 1)];
-        xi[k] = p.x; yi[k] = p.y; zi[k] = p.z; a2[k] = p.w * p.w;
+        xi[k] = pk(p.x, p.x); yi[k] = pk(p.y, p.y); zi[k] = pk(p.z, p.z); a2[k] = p.w * p.w;
         AX[k] = AY[k] = AZ[k] = PH[k] = 0.f;
         // box of the block's targets grown by their softening radii (+0.1% against rounding)
         float a = p.w * 1.001f;
@@ -147,9 +175,10 @@ __global__ void __launch_bounds__(AP_THREADS) k_gravity_allpairs(const float4* _
     const float4 pad = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);
     float4 nxt = (s0 + tid < s1) ? src[s0 + tid] : pad;
     float4 nbx = tid < 2 ? tbox[2 * tile0 + tid] : pad;
+    const int so = (tid >> 1) * 8 + (tid & 1);   // slot of source `tid` inside its pair record
     for (int it = 0; it < ntiles; it++) {
-        float4* buf = tile[it & 1];
-        buf[tid] = nxt;
+        float* buf = tile[it & 1];
+        buf[so] = nxt.x; buf[so + 2] = nxt.y; buf[so + 4] = nxt.z; buf[so + 6] = nxt.w;
         if (tid == 0) tb_lo[it & 1] = nbx;
         if (tid == 1) tb_hi[it & 1] = nbx;
         __syncthreads();
@@ -158,13 +187,9 @@ __global__ void __launch_bounds__(AP_THREADS) k_gravity_allpairs(const float4* _
         if (tid < 2 && it + 1 < ntiles) nbx = tbox[2 * (tile0 + it + 1) + tid];
         const float4 lo = tb_lo[it & 1], hi = tb_hi[it & 1];
         const bool far = lo.x > e[3] || lo.y > e[4] || lo.z > e[5] || hi.x < e[0] || hi.y < e[1] || hi.z < e[2];
-        float ax[TPT], ay[TPT], az[TPT], ph[TPT];
-#pragma unroll
-        for (int k = 0; k < TPT; k++) ax[k] = ay[k] = az[k] = ph[k] = 0.f;
-        if (far) tile_loop<TPT, false, EQM>(buf, xi, yi, zi, a2, ax, ay, az, ph);
-        else tile_loop<TPT, true, EQM>(buf, xi, yi, zi, a2, ax, ay, az, ph);
-#pragma unroll
-        for (int k = 0; k < TPT; k++) { AX[k] += ax[k]; AY[k] += ay[k]; AZ[k] += az[k]; PH[k] += ph[k]; }
+        const ulonglong2* tp = reinterpret_cast<const ulonglong2*>(buf);
+        if (far) tile_loop<TPT, false, EQM>(tp, xi, yi, zi, a2, AX, AY, AZ, PH);
+        else tile_loop<TPT, true, EQM>(tp, xi, yi, zi, a2, AX, AY, AZ, PH);
     }
 #pragma unroll
     for (int k = 0; k < TPT; k++) {
@@ -220,7 +245,8 @@ int sph_launch_gravity_allpairs(sphb200_ctx* c) {
     int nt = t1 - t0;
     if (nt <= 0) return SPH_OK;
     int n = (int)c->n;
-    int tblocks = sph_div_up(nt, AP_THREADS * AP_TPT);
+    static int tpt = getenv("SPHB200_AP_TPT") ? atoi(getenv("SPHB200_AP_TPT")) : AP_TPT;   // tuning knob
+    int tblocks = sph_div_up(nt, AP_THREADS * tpt);
     // enough blocks for >= ~12 waves of 3 resident CTAs/SM, bounded by the partial-sum buffer (cap * gpart_splits float4)
     int want = c->sm_count * 3 * 12;
     int splits = sph_div_up(want, tblocks);
@@ -236,10 +262,11 @@ int sph_launch_gravity_allpairs(sphb200_ctx* c) {
     k_tile_boxes<<<sph_div_up(n, AP_TILE), AP_TILE, 0, c->stream>>>(c->posm, n, c->tbox);
     SPH_LAUNCH_CHECK(c);
     dim3 grid(tblocks, splits);
-    if (c->equal_mass)
-        k_gravity_allpairs<AP_TPT, true><<<grid, AP_THREADS, 0, c->stream>>>(c->posm, n, per, c->tbox, c->posh[c->cur], t0, t1, c->gpart);
-    else
-        k_gravity_allpairs<AP_TPT, false><<<grid, AP_THREADS, 0, c->stream>>>(c->posm, n, per, c->tbox, c->posh[c->cur], t0, t1, c->gpart);
+#define AP_LAUNCH(T, E) k_gravity_allpairs<T, E><<<grid, AP_THREADS, 0, c->stream>>>(c->posm, n, per, c->tbox, c->posh[c->cur], t0, t1, c->gpart)
+    if (tpt == 2) { if (c->equal_mass) AP_LAUNCH(2, true); else AP_LAUNCH(2, false); }
+    else if (tpt == 3) { if (c->equal_mass) AP_LAUNCH(3, true); else AP_LAUNCH(3, false); }
+    else { if (c->equal_mass) AP_LAUNCH(4, true); else AP_LAUNCH(4, false); }
+#undef AP_LAUNCH
     SPH_LAUNCH_CHECK(c);
     k_gravity_reduce<<<sph_div_up(nt, 256), 256, 0, c->stream>>>(c->gpart, splits, c->posh[c->cur], c->posm, t0, t1, c->p.G,
                                                                 c->equal_mass ? c->common_mass : 1.0f, c->equal_mass ? 1 : 0, c->grav,

@@ -263,6 +263,170 @@ void run_tma(const char* name, const float4* src, const float4* posh, float4* pa
            fa.numRegs, tblocks, sp, e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
+
+// ---- packed-FP32 variant (Blackwell FFMA2/FADD2/FMUL2, PTX *.f32x2): one packed instruction evaluates the SAME target
+// against TWO sources.  The tile is stored as source pairs, SoA inside the pair: A = (x0,x1,y0,y1), B = (z0,z1,m0,m1), so
+// one LDS.128 pair feeds 2 sources x TPT targets; the target coordinate is the broadcast scalar operand (R.F32).
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+
+template <int TPT, int THREADS, int UNROLL, bool CAP, bool EQM, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) k_ap2(const float4* __restrict__ src, int n_src, int src_per_split,
+                                                       const float4* __restrict__ posh, int nt, float4* __restrict__ part) {
+    constexpr int TILE = 256;
+    static_assert(THREADS == 256, "one source per thread per tile");
+    __shared__ __align__(16) float tile[2][TILE * 4];
+    const int tid = threadIdx.x;
+    const int tb = blockIdx.x * (THREADS * TPT);
+    u64 xi[TPT], yi[TPT], zi[TPT];
+    float a2[TPT];
+    float AX[TPT], AY[TPT], AZ[TPT], PH[TPT];
+#pragma unroll
+    for (int k = 0; k < TPT; k++) {
+        int t = tb + k * THREADS + tid;
+        float4 p = posh[min(t, nt - 1)];
+        xi[k] = pk(p.x, p.x); yi[k] = pk(p.y, p.y); zi[k] = pk(p.z, p.z); a2[k] = p.w * p.w;
+        AX[k] = AY[k] = AZ[k] = PH[k] = 0.f;
+    }
+    const int s0 = blockIdx.y * src_per_split;
+    const int s1 = min(s0 + src_per_split, n_src);
+    const int ntiles = (s1 - s0 + TILE - 1) / TILE;
+    const float4 pad = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.f);
+    float4 nxt = (s0 + tid < s1) ? src[s0 + tid] : pad;
+    const int so = (tid >> 1) * 8 + (tid & 1);
+    for (int it = 0; it < ntiles; it++) {
+        float* buf = tile[it & 1];
+        buf[so] = nxt.x; buf[so + 2] = nxt.y; buf[so + 4] = nxt.z; buf[so + 6] = nxt.w;
+        __syncthreads();
+        { int i = s0 + (it + 1) * TILE + tid; nxt = i < s1 ? src[i] : pad; }
+        u64 ax[TPT], ay[TPT], az[TPT], ph[TPT];
+#pragma unroll
+        for (int k = 0; k < TPT; k++) ax[k] = ay[k] = az[k] = ph[k] = pk(0.f, 0.f);
+        const ulonglong2* tp = reinterpret_cast<const ulonglong2*>(buf);
+#pragma unroll 1
+        for (int j = 0; j < TILE / 2; j += UNROLL, tp += 2 * UNROLL) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const ulonglong2 A = tp[2 * u], B = tp[2 * u + 1];   // A.x = (x0,x1) A.y = (y0,y1) B.x = (z0,z1) B.y = (m0,m1)
+#pragma unroll
+                for (int k = 0; k < TPT; k++) {
+                    u64 dx = sub2(xi[k], A.x), dy = sub2(yi[k], A.y), dz = sub2(zi[k], B.x);
+                    u64 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                    float r2a, r2b;
+                    upk(r2, r2a, r2b);
+                    if (CAP) { r2a = fmaxf(r2a, a2[k]); r2b = fmaxf(r2b, a2[k]); }
+                    u64 rinv = pk(rsqrt_approx(r2a), rsqrt_approx(r2b));
+                    u64 g;
+                    if (EQM) {
+                        g = mul2(mul2(rinv, rinv), rinv);
+                        ph[k] = add2(ph[k], rinv);
+                    } else {
+                        u64 mr = mul2(B.y, rinv);
+                        g = mul2(mr, mul2(rinv, rinv));
+                        ph[k] = add2(ph[k], mr);
+                    }
+                    ax[k] = fma2(dx, g, ax[k]);
+                    ay[k] = fma2(dy, g, ay[k]);
+                    az[k] = fma2(dz, g, az[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < TPT; k++) {
+            float a, b;
+            upk(ax[k], a, b); AX[k] += a + b;
+            upk(ay[k], a, b); AY[k] += a + b;
+            upk(az[k], a, b); AZ[k] += a + b;
+            upk(ph[k], a, b); PH[k] += a + b;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < TPT; k++) {
+        int t = tb + k * THREADS + tid;
+        if (t < nt) part[(size_t)blockIdx.y * nt + t] = make_float4(AX[k], AY[k], AZ[k], PH[k]);
+    }
+}
+
+template <int TPT, int THREADS, int UNROLL, bool CAP, bool EQM, int MINB>
+void run2(const char* name, const float4* src, const float4* posh, float4* part, int n, int splits) {
+    int tblocks = (n + THREADS * TPT - 1) / (THREADS * TPT);
+    int per = ((n + splits - 1) / splits + 511) / 512 * 512;
+    int sp = (n + per - 1) / per;
+    dim3 grid(tblocks, sp);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        k_ap2<TPT, THREADS, UNROLL, CAP, EQM, MINB><<<grid, THREADS>>>(src, n, per, posh, n, part);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaError_t e = cudaGetLastError();
+    int nb = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_ap2<TPT, THREADS, UNROLL, CAP, EQM, MINB>, THREADS, 0);
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_ap2<TPT, THREADS, UNROLL, CAP, EQM, MINB>);
+    printf("%-44s %8.3f ms  %6.2f TF(20/pair)  regs %3d  blocks/SM %d  grid %dx%d %s\n", name, best,
+           20.0 * (double)n * n / (best * 1e-3) / 1e12, fa.numRegs, nb, tblocks, sp, e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
+// FMA-pipe peak: scalar FFMA chains vs packed FFMA2 chains (both counted as 2 flop per fp32 lane-op).
+template <bool PACKED>
+__global__ void __launch_bounds__(256) k_peak(float* out, int iters, float a, float b) {
+    if (PACKED) {
+        u64 v[8], a2 = pk(a, a), b2 = pk(b, b);
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = pk((float)(threadIdx.x + k), (float)k);
+        for (int i = 0; i < iters; i++)
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = fma2(v[k], a2, b2);
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) { float x, y; upk(v[k], x, y); s += x + y; }
+        if (s == 12345.678f) out[0] = s;
+    } else {
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = (float)(threadIdx.x + k);
+        for (int i = 0; i < iters; i++)
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+#pragma unroll
+                for (int k = 0; k < 8; k++) v[k] = fmaf(v[k], a, b);
+        float s = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) s += v[k];
+        if (s == 12345.678f) out[0] = s;
+    }
+}
+template <bool PACKED>
+void run_peak(const char* name, float* out) {
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int blocks = 148 * 8, iters = 4096;
+    double best = 0;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        k_peak<PACKED><<<blocks, 256>>>(out, iters, 1.0001f, 0.5f);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        double tf = 2.0 * 64.0 * (PACKED ? 2.0 : 1.0) * iters * 256.0 * blocks / (ms * 1e-3) / 1e12;
+        if (tf > best) best = tf;
+    }
+    printf("%-44s %6.2f TFLOP/s\n", name, best);
+}
+
 int main(int argc, char** argv) {
     int n = argc > 1 ? atoi(argv[1]) : 262144;
     std::vector<float4> h(n), p(n);
@@ -300,6 +464,33 @@ int main(int argc, char** argv) {
     run<2, 256, 8, false, true, true, 1>("eqm nocap tpt2 t256", src, posh, part, n, 14);
     run<2, 128, 16, false, true, true, 1>("eqm nocap tpt2 t128 u16", src, posh, part, n, 7);
     run<8, 128, 8, false, true, true, 1>("eqm nocap tpt8 t128", src, posh, part, n, 28);
+    run_peak<false>("FMA peak: scalar FFMA chains", (float*)part);
+    run_peak<true>("FMA peak: packed FFMA2 chains", (float*)part);
+    //    TPT THR UNR CAP    EQM   MINB
+    run2<4, 256, 4, false, true, 1>("f32x2: eqm nocap tpt4 u4", src, posh, part, n, 28);
+    run2<4, 256, 2, false, true, 1>("f32x2: eqm nocap tpt4 u2", src, posh, part, n, 28);
+    run2<4, 256, 8, false, true, 1>("f32x2: eqm nocap tpt4 u8", src, posh, part, n, 28);
+    run2<2, 256, 4, false, true, 1>("f32x2: eqm nocap tpt2 u4", src, posh, part, n, 14);
+    run2<2, 256, 8, false, true, 1>("f32x2: eqm nocap tpt2 u8", src, posh, part, n, 14);
+    run2<3, 256, 4, false, true, 1>("f32x2: eqm nocap tpt3 u4", src, posh, part, n, 21);
+    run2<6, 256, 2, false, true, 1>("f32x2: eqm nocap tpt6 u2", src, posh, part, n, 42);
+    run2<8, 256, 2, false, true, 1>("f32x2: eqm nocap tpt8 u2", src, posh, part, n, 56);
+    run2<4, 256, 4, true, true, 1>("f32x2: eqm cap tpt4 u4", src, posh, part, n, 28);
+    run2<4, 256, 4, false, false, 1>("f32x2: mass nocap tpt4 u4", src, posh, part, n, 28);
+    run2<4, 256, 4, true, false, 1>("f32x2: mass cap tpt4 u4", src, posh, part, n, 28);
+    {
+        std::vector<float4> q1(n), q2(n);
+        k_ap<4, 256, 8, false, false, true, 1><<<dim3((n + 1023) / 1024, 1), 256>>>(src, n, n, posh, n, part);
+        cudaMemcpy(q1.data(), part, n * 16, cudaMemcpyDeviceToHost);
+        k_ap2<4, 256, 4, false, false, 1><<<dim3((n + 1023) / 1024, 1), 256>>>(src, n, n, posh, n, part);
+        cudaMemcpy(q2.data(), part, n * 16, cudaMemcpyDeviceToHost);
+        double md = 0, mw = 0;
+        for (int i = 0; i < n; i++) {
+            md = fmax(md, fabs(q1[i].x - q2[i].x) / (fabs(q1[i].x) + 1e-30));
+            mw = fmax(mw, fabs(q1[i].w - q2[i].w) / (fabs(q1[i].w) + 1e-30));
+        }
+        printf("max rel diff plain vs f32x2: x %.3e  phi %.3e  %s\n", md, mw, cudaGetErrorString(cudaGetLastError()));
+    }
     run_tma<4, 4, true>("TMA ring: eqm nocap tpt4 4 stages", src, posh, part, n, 28);
     run_tma<4, 2, true>("TMA ring: eqm nocap tpt4 2 stages", src, posh, part, n, 28);
     run_tma<4, 4, false>("TMA ring: mass nocap tpt4 4 stages", src, posh, part, n, 28);
