@@ -26,6 +26,8 @@ struct sphb200_ctx {
     uint32_t* orig[2] = {nullptr, nullptr};  // sorted slot -> body index
     int cur = 0;
     float4* posm = nullptr;                // x,y,z,m (gravity sources)
+    float4* posc = nullptr;                // x,y,z,C(h): neighbor-test records (sph_keep_threshold)
+    unsigned int* chunk_counter = nullptr; // work counter of k_cell_neighbors
 
     uint32_t* keys[2] = {nullptr, nullptr};
     uint32_t* idx[2] = {nullptr, nullptr};
@@ -146,6 +148,18 @@ __device__ __forceinline__ uint32_t compact10(uint32_t v) {
 // exact (non-contracted) squared distance in the reference's order: dx*dx + dy*dy + dz*dz
 __device__ __forceinline__ float dot3_rn(float x, float y, float z) {
     return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+
+// Neighbor keep threshold C(h) (kernels_neighbors.cu): the pair (i,j) is kept iff d2 < max(C(h_i), C(h_j)), where
+// C(h) = min( ((h*h)*2)*2 , t(h) ) and t(h) is the smallest float x with fsqrt_rn(x) >= 2h -- the reference's
+// "d2 < size*size*Kappa*Kappa" (SplineKernel.cs:47-53) and "Kernel(r,h) > 0 <=> r < 2h" (:62) without the sqrt.
+__device__ __forceinline__ float sph_keep_threshold(float h) {
+    const float c = __fmul_rn(h, 2.0f);
+    uint32_t u = __float_as_uint(__fmul_rn(c, c));
+    while (u > 0u && __fsqrt_rn(__uint_as_float(u - 1u)) >= c) --u;
+    while (__fsqrt_rn(__uint_as_float(u)) < c) ++u;
+    const float a = __fmul_rn(__fmul_rn(__fmul_rn(h, h), 2.0f), 2.0f);
+    return fminf(a, __uint_as_float(u));
 }
 
 // ---- kernel launchers (one translation unit each) -----------------------------------------------------------

@@ -109,7 +109,8 @@ __global__ void __launch_bounds__(256) k_permute_cells(const uint32_t* __restric
                                                        const float4* __restrict__ posh_in, const float4* __restrict__ velm_in,
                                                        const uint32_t* __restrict__ orig_in, float4* __restrict__ posh_out,
                                                        float4* __restrict__ velm_out, uint32_t* __restrict__ orig_out,
-                                                       float4* __restrict__ posm, const sph_GridParams* __restrict__ g, int n,
+                                                       float4* __restrict__ posm, float4* __restrict__ posc,
+                                                       const sph_GridParams* __restrict__ g, int n,
                                                        uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_end,
                                                        uint32_t* __restrict__ cell_hmax) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -121,6 +122,7 @@ __global__ void __launch_bounds__(256) k_permute_cells(const uint32_t* __restric
     velm_out[i] = v;
     orig_out[i] = orig_in[src];
     posm[i] = make_float4(p.x, p.y, p.z, v.w);
+    posc[i] = make_float4(p.x, p.y, p.z, sph_keep_threshold(p.w));
     int shift = 3 * (10 - g->bits);
     uint32_t ck = keys[i] >> shift;
     if (i == 0 || (keys[i - 1] >> shift) != ck) cell_start[ck] = (uint32_t)i;
@@ -160,7 +162,7 @@ int sph_launch_sort_and_cells(sphb200_ctx* c) {
     SPH_CK(c, cudaMemsetAsync(c->cell_end, 0, ncell * sizeof(uint32_t), c->stream));
     SPH_CK(c, cudaMemsetAsync(c->cell_hmax, 0, ncell * sizeof(uint32_t), c->stream));
     k_permute_cells<<<sph_div_up(n, 256), 256, 0, c->stream>>>(c->keys[1], c->idx[1], c->posh[in], c->velm[in], c->orig[in],
-                                                               c->posh[out], c->velm[out], c->orig[out], c->posm, c->grid_d, n,
+                                                               c->posh[out], c->velm[out], c->orig[out], c->posm, c->posc, c->grid_d, n,
                                                                c->cell_start, c->cell_end, c->cell_hmax);
     SPH_LAUNCH_CHECK(c);
     c->cur = out;

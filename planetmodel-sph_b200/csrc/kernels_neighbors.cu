@@ -16,12 +16,15 @@
 // Numerics contract: membership exact (non-contracted __f*_rn ops, IEEE sqrt), values fast (<= 1e-5 relative).
 #include "ctx.cuh"
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
 constexpr float kPI = 3.14159274f;  // Mathf.PI
 constexpr float kInvPI = 0.318309886f;
 constexpr unsigned FULL = 0xffffffffu;
+
+constexpr float kHugeH = 1.0e5f;   // above it W(r,h) can underflow: the literal kernel decides membership (k_neighbors_density)
 
 constexpr int K1_WARPS = 8;
 constexpr int K1_TPW = 4;     // consecutive targets per warp (L1 reuse of the neighbor cells)
@@ -59,6 +62,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_neighbors_density(
     float* __restrict__ cvol, int32_t* __restrict__ err) {
     __shared__ uint2 cellq[K1_WARPS][K1_CELLQ];
     __shared__ Surv survq[K1_WARPS][K1_SURVQ];
+    if (g->hmax < kHugeH) return;   // the cell-centric kernel below owns the normal case
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int warp = blockIdx.x * K1_WARPS + w;
     const int bits = g->bits, S = g->stencil;
@@ -215,6 +219,311 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_neighbors_density(
     }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// K1 (cell-centric): one warp per non-empty cell.  The ~11 particles of the cell are the targets (staged in shared
+// memory, <= 32 per pass); the particles of the (2S+1)^3 stencil cells are the candidates, flattened across cells so that
+// every lane owns one candidate per batch and tests it against each target in turn (LDS broadcast): 32 exact pair tests
+// per ~22 instructions, no sqrt and no division in the test.
+//
+// Exactness without the sqrt: with s = max(h_i,h_j) the reference keeps the pair iff
+//     d2 < ((s*s)*2)*2   and   ( fsqrt_rn(d2) < 2 h_i  or  fsqrt_rn(d2) < 2 h_j )      (SplineKernel.cs:47-53, :62)
+// fsqrt_rn is monotone, so "fsqrt_rn(d2) < 2h" <=> d2 < t(h), t(h) = the smallest float whose rounded root reaches 2h;
+// both bounds grow with h, hence keep <=> d2 < max(C_i, C_j) with C(h) = min(4 RN(h*h), t(h)) computed once per particle
+// by the permute kernel (sph_keep_threshold, ctx.cuh) and carried in posc.w.  Valid below h = 1e5 (kHugeH).
+//
+// Cells of the outer stencil shells (S > 1: some h exceed the typical h the cells are sized by) are culled against the
+// tight boxes of the pass's targets: the union of their own supports, and their positions grown by the cell's h_max.
+// Rows are written by ballot rank (deterministic order); density, EOS and the own-support count are then evaluated from
+// the finished rows, 32 lanes per target.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int K3_WARPS = 8;
+constexpr int K3_QCAP = 64;   // candidate-cell queue per warp
+constexpr int K3_RING = 64;   // compacted-candidate ring per warp
+
+// Row overflow (count > max_neighbors: an error state the caller is told about): the neighbor is not stored, but the
+// density and the own-support count stay complete.
+__device__ __noinline__ void k3_overflow(const float4* __restrict__ posh, const float4* __restrict__ posm, int t, int j, float d2,
+                                         bool eqm, float* orho, int* oown) {
+    const float r = __fsqrt_rn(d2);
+    const float h_t = posh[t].w;
+    const float wsym = 0.5f * (w_fast(r, 1.0f / h_t) + w_fast(r, 1.0f / posh[j].w));
+    atomicAdd(orho, eqm ? wsym : posm[j].w * wsym);
+    if (r < __fmul_rn(h_t, 2.0f)) atomicAdd(oown, 1);
+}
+
+template <bool EQM, int MINB>
+__global__ void __launch_bounds__(K3_WARPS * 32, MINB) k_cell_neighbors(
+    const float4* __restrict__ posc, const float4* __restrict__ posh, const float4* __restrict__ posm,
+    const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, const uint32_t* __restrict__ cell_hmax,
+    const sph_GridParams* __restrict__ g, int t0, int t1, int kmax, float Keos, uint32_t* __restrict__ nlist,
+    int32_t* __restrict__ ncount, int32_t* __restrict__ nown, float* __restrict__ rho, float* __restrict__ press,
+    float* __restrict__ cvol, int32_t* __restrict__ err, unsigned int* __restrict__ chunk_counter) {
+    __shared__ float4 tgt[K3_WARPS][32];
+    __shared__ uint32_t qstart[K3_WARPS][K3_QCAP];
+    __shared__ uint32_t qpre[K3_WARPS][K3_QCAP + 1];
+    __shared__ float4 ring4[K3_WARPS][K3_RING];
+    __shared__ int ringj[K3_WARPS][K3_RING];
+    __shared__ float ovf_rho[K3_WARPS][32];
+    __shared__ int ovf_own[K3_WARPS][32];
+    __shared__ int cnts[K3_WARPS][32];
+    if (!(g->hmax < kHugeH)) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const unsigned lt = (1u << lane) - 1u;
+    const int bits = g->bits, S = g->stencil, dim = 1 << bits;
+    const int nst = 2 * S + 1, nst2 = nst * nst, nst3 = nst2 * nst;
+    const int ncells = 1 << (3 * bits), nchunks = (ncells + 31) >> 5;
+    const float fs = g->fine_scale, cw = (float)(1 << (10 - bits));
+    const float g0[3] = {g->min[0], g->min[1], g->min[2]};
+    float4* tg = tgt[w];
+    uint32_t* qs_w = qstart[w];
+    uint32_t* qp_w = qpre[w];
+    float4* rb4 = ring4[w];
+    int* rbj = ringj[w];
+    int* cn_w = cnts[w];
+
+    while (true) {
+        int chunk = 0;
+        if (lane == 0) chunk = (int)atomicAdd(chunk_counter, 1u);
+        chunk = __shfl_sync(FULL, chunk, 0);
+        if (chunk >= nchunks) break;
+        const int cidx = chunk * 32 + lane;
+        int cs = 0, ce = 0;
+        if (cidx < ncells) { cs = (int)cell_start[cidx]; ce = (int)cell_end[cidx]; }
+        cs = max(cs, t0); ce = min(ce, t1);
+        unsigned nonempty = __ballot_sync(FULL, ce > cs);
+        while (nonempty) {
+            const int src = __ffs(nonempty) - 1;
+            nonempty &= nonempty - 1;
+            const int s = __shfl_sync(FULL, cs, src), e = __shfl_sync(FULL, ce, src);
+            const uint32_t ck = (uint32_t)(chunk * 32 + src);
+            const int cx = (int)compact10(ck), cy = (int)compact10(ck >> 1), cz = (int)compact10(ck >> 2);
+
+            for (int p0 = s; p0 < e; p0 += 32) {
+                const int nt = min(32, e - p0);
+                const bool tv = lane < nt;
+                const int tl = p0 + (tv ? lane : 0);
+                const float4 T = posc[tl];
+                const float hi = posh[tl].w;
+                __syncwarp();
+                tg[lane] = T;
+                ovf_rho[w][lane] = 0.f;
+                ovf_own[w][lane] = 0;
+                cn_w[lane] = 0;
+                int rh = 0, rt = 0;   // candidate ring head / tail (monotone counters)
+                // box of the targets' positions, their largest keep threshold and largest h
+                float wlo[3] = {tv ? T.x : INFINITY, tv ? T.y : INFINITY, tv ? T.z : INFINITY};
+                float whi[3] = {tv ? T.x : -INFINITY, tv ? T.y : -INFINITY, tv ? T.z : -INFINITY};
+                float cmax = tv ? T.w : 0.f, hmax_t = tv ? hi : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {
+                        wlo[k] = fminf(wlo[k], __shfl_xor_sync(FULL, wlo[k], o));
+                        whi[k] = fmaxf(whi[k], __shfl_xor_sync(FULL, whi[k], o));
+                    }
+                    cmax = fmaxf(cmax, __shfl_xor_sync(FULL, cmax, o));
+                    hmax_t = fmaxf(hmax_t, __shfl_xor_sync(FULL, hmax_t, o));
+                }
+                uint32_t* rowp = nlist + (size_t)p0 * kmax;
+                int qn = 0, qtotal = 0;
+
+                // 32 compacted candidates (ring entries rh .. rh+m-1) against every target of the pass; row fill counts live
+                // in shared memory (warp-uniform reads, lane 0 writes)
+                auto test_batch = [&](int m) {
+                    const int er = (rh + lane) & (K3_RING - 1);
+                    float4 c = rb4[er];
+                    const int j = rbj[er];
+                    if (lane >= m) c.x = INFINITY;       // idle lane: d2 = inf, never kept
+                    const int jrel = j - p0;
+                    uint32_t* rowt = rowp;
+#pragma unroll 2
+                    for (int tt = 0; tt < nt; tt++, rowt += kmax) {
+                        const float4 Tt = tg[tt];
+                        const int base = cn_w[tt];
+                        const float dx = __fsub_rn(Tt.x, c.x), dy = __fsub_rn(Tt.y, c.y), dz = __fsub_rn(Tt.z, c.z);
+                        const float d2 = dot3_rn(dx, dy, dz);
+                        const bool keep = d2 < fmaxf(Tt.w, c.w) && jrel != tt;
+                        const unsigned kb = __ballot_sync(FULL, keep);
+                        const int slot = base + __popc(kb & lt);
+                        if (keep) {
+                            if (slot < kmax) rowt[slot] = (uint32_t)j;
+                            else k3_overflow(posh, posm, p0 + tt, j, d2, EQM, &ovf_rho[w][tt], &ovf_own[w][tt]);
+                        }
+                        if (lane == 0) cn_w[tt] = base + __popc(kb);
+                    }
+                    rh += m;
+                };
+                // streams the queued cells (flattened: one candidate per lane per batch, next batch's loads in flight);
+                // a candidate enters the ring only if it can reach the box of the targets:
+                // d2(i,j) < max(C_i, C_j) for some target i needs dist^2(p_j, box) (1 - 1e-5) < max(C_max, C_j)
+                auto flush = [&]() {
+                    if (lane == 0) qp_w[qn] = (uint32_t)qtotal;
+                    __syncwarp();
+                    int q = 0;
+                    auto fetch = [&](int f0, int& j, float4& c) {
+                        const int f = f0 + lane;
+                        j = 0;
+                        if (f < qtotal) {
+                            while (qp_w[q + 1] <= (uint32_t)f) q++;
+                            j = (int)(qs_w[q] + ((uint32_t)f - qp_w[q]));
+                        }
+                        c = posc[j];
+                    };
+                    int j; float4 c;
+                    fetch(0, j, c);
+                    for (int f0 = 0; f0 < qtotal; f0 += 32) {
+                        int jn = 0; float4 cn = c;
+                        if (f0 + 32 < qtotal) fetch(f0 + 32, jn, cn);
+                        const float gx = fmaxf(fmaxf(wlo[0] - c.x, c.x - whi[0]), 0.f), gy = fmaxf(fmaxf(wlo[1] - c.y, c.y - whi[1]), 0.f),
+                                    gz = fmaxf(fmaxf(wlo[2] - c.z, c.z - whi[2]), 0.f);
+                        const bool pre = f0 + lane < qtotal && (gx * gx + gy * gy + gz * gz) * 0.99999f < fmaxf(cmax, c.w);
+                        const unsigned pb = __ballot_sync(FULL, pre);
+                        if (pre) {
+                            const int er = (rt + __popc(pb & lt)) & (K3_RING - 1);
+                            rb4[er] = c;
+                            rbj[er] = j;
+                        }
+                        rt += __popc(pb);
+                        __syncwarp();
+                        if (rt - rh >= 32) { test_batch(32); __syncwarp(); }
+                        j = jn; c = cn;
+                    }
+                    qn = 0; qtotal = 0;
+                };
+
+                // ---- stencil cells; the outer shells (S > 1) are culled against the box of the targets
+                float plo[3], phi[3], reach_t = 0.f;
+                if (S > 1) {
+#pragma unroll
+                    for (int k = 0; k < 3; k++) {   // same ops as the key kernel: monotone, so the box maps to a box
+                        plo[k] = __fmul_rn(__fsub_rn(wlo[k], g0[k]), fs);
+                        phi[k] = __fmul_rn(__fsub_rn(whi[k], g0[k]), fs);
+                    }
+                    reach_t = 2.0f * hmax_t * fs * 1.001f + 0.01f;
+                }
+                for (int base = 0; base < nst3; base += 32) {
+                    const int k = base + lane;
+                    const int oz = k / nst2, rem = k - oz * nst2, oy = rem / nst, ox = rem - oy * nst;
+                    const int nx = cx + ox - S, ny = cy + oy - S, nz = cz + oz - S;
+                    bool ok = k < nst3 && nx >= 0 && ny >= 0 && nz >= 0 && nx < dim && ny < dim && nz < dim;
+                    uint32_t a = 0, b = 0;
+                    if (ok) {
+                        const uint32_t nk = expand10((uint32_t)nx) | (expand10((uint32_t)ny) << 1) | (expand10((uint32_t)nz) << 2);
+                        a = cell_start[nk]; b = cell_end[nk];
+                        ok = b > a;
+                        if (ok && S > 1 && (abs(ox - S) > 1 || abs(oy - S) > 1 || abs(oz - S) > 1)) {
+                            const float blo[3] = {(float)nx * cw, (float)ny * cw, (float)nz * cw};
+                            float gp2 = 0.f;
+#pragma unroll
+                            for (int d = 0; d < 3; d++) {
+                                const float gp = fmaxf(fmaxf(blo[d] - phi[d], plo[d] - (blo[d] + cw)), 0.f);
+                                gp2 += gp * gp;
+                            }
+                            // conservative reach of the larger of the targets' and the cell's h: +0.1% and +0.01 fine units
+                            // cover every rounding of the scaled coordinates
+                            const float rc = fmaxf(reach_t, 2.0f * __uint_as_float(cell_hmax[nk]) * fs * 1.001f + 0.01f);
+                            ok = gp2 < rc * rc;
+                        }
+                    }
+                    const unsigned bal = __ballot_sync(FULL, ok);
+                    if (bal == 0u) continue;
+                    int incl = ok ? (int)(b - a) : 0;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int v = __shfl_up_sync(FULL, incl, o);
+                        if (lane >= o) incl += v;
+                    }
+                    if (ok) {
+                        const int pos = qn + __popc(bal & lt);
+                        qs_w[pos] = a;
+                        qp_w[pos] = (uint32_t)(qtotal + incl - (int)(b - a));
+                    }
+                    qn += __popc(bal);
+                    qtotal += __shfl_sync(FULL, incl, 31);
+                    if (qn > K3_QCAP - 32) flush();
+                }
+                if (qn > 0) flush();
+                if (rt - rh > 0) test_batch(rt - rh);
+                __syncwarp();
+
+                // counts now; density + EOS + own-support count follow in k_density (rows are complete after this kernel).
+                // Row overflow only: the partial sums of the neighbors that did not fit travel in rho / nown.
+                if (tv) {
+                    const int cnt = cn_w[lane];
+                    ncount[tl] = cnt;
+                    if (cnt > kmax) {
+                        atomicMax(&err[ERR_NEIGHBOR_OVERFLOW], cnt);
+                        rho[tl] = ovf_rho[w][lane];
+                        nown[tl] = ovf_own[w][lane];
+                    }
+                }
+            }
+        }
+    }
+}
+
+
+// K1b: density + EOS + own-support count from the finished rows, 16 lanes per target (DensityFieldSystem.cs:38-56,
+// PressureFieldSystem.cs:30-34).  Membership of i's own support: fsqrt_rn(d2) < 2 h_i with the exact d2 (SplineKernel.cs:62).
+constexpr int K1B_LPT = 16;
+
+template <bool EQM>
+__global__ void __launch_bounds__(256) k_density(const float4* __restrict__ posh, const float4* __restrict__ posm,
+                                                 const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
+                                                 const sph_GridParams* __restrict__ g, int t0, int t1, int kmax, float Keos,
+                                                 int32_t* __restrict__ nown, float* __restrict__ rho, float* __restrict__ press,
+                                                 float* __restrict__ cvol) {
+    if (!(g->hmax < kHugeH)) return;
+    const int sub = threadIdx.x & (K1B_LPT - 1);
+    const int t = t0 + (blockIdx.x * blockDim.x + threadIdx.x) / K1B_LPT;
+    const bool live = t < t1;
+    float rsum = 0.f;
+    int own = 0, cnt = 0;
+    float4 pi = make_float4(0.f, 0.f, 0.f, 1.f);
+    if (live) {
+        pi = posh[t];
+        cnt = ncount[t];
+        const float hinv_i = 1.0f / pi.w, hi2 = __fmul_rn(pi.w, 2.0f);
+        const uint32_t* row = nlist + (size_t)t * kmax;
+        const int m = min(cnt, kmax);
+        for (int k = sub; k < m; k += K1B_LPT) {
+            const uint32_t j = row[k];
+            const float4 pj = posh[j];
+            const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
+            const float r = __fsqrt_rn(dot3_rn(dx, dy, dz));
+            own += r < hi2 ? 1 : 0;
+            const float wsym = 0.5f * (w_fast(r, hinv_i) + w_fast(r, __fdividef(1.0f, pj.w)));
+            rsum = EQM ? rsum + wsym : fmaf(posm[j].w, wsym, rsum);
+        }
+    }
+#pragma unroll
+    for (int o = K1B_LPT / 2; o > 0; o >>= 1) {
+        rsum += __shfl_xor_sync(FULL, rsum, o);
+        own += __shfl_xor_sync(FULL, own, o);
+    }
+    if (live && sub == 0) {
+        if (cnt > kmax) { rsum += rho[t]; own += nown[t]; }   // overflowed row: partial sums left by k_cell_neighbors
+        // self term m_i * Kernel(0,h_i) (DensityFieldSystem.cs:45), exact: 1/(pi h^3)
+        const float mi = posm[t].w;
+        const float w0 = __fdiv_rn(1.0f, __fmul_rn(__fmul_rn(__fmul_rn(kPI, pi.w), pi.w), pi.w));
+        if (EQM) rsum *= mi;
+        const float d = __fadd_rn(__fmul_rn(mi, w0), rsum);
+        const float P = __fmul_rn(__fmul_rn(Keos, d), d);  // PressureFieldSystem.cs:31-33
+        rho[t] = d;
+        press[t] = P;
+        cvol[t] = __fmul_rn(__fdiv_rn(mi, d), P);          // m_j / rho_j * P_j (PressureFieldSystem.cs:65)
+        nown[t] = own;
+    }
+}
+
+template <bool EQM, typename... Args>
+void k3_launch(int minb, int sms, cudaStream_t st, Args... a) {
+    if (minb == 2) k_cell_neighbors<EQM, 2><<<sms * 2, K3_WARPS * 32, 0, st>>>(a...);
+    else if (minb == 3) k_cell_neighbors<EQM, 3><<<sms * 3, K3_WARPS * 32, 0, st>>>(a...);
+    else k_cell_neighbors<EQM, 4><<<sms * 4, K3_WARPS * 32, 0, st>>>(a...);
+}
+
 }  // namespace
 
 int sph_launch_neighbors_density(sphb200_ctx* c) {
@@ -223,6 +532,26 @@ int sph_launch_neighbors_density(sphb200_ctx* c) {
     if (t0 > t1) t0 = t1;
     int nt = t1 - t0;
     if (nt <= 0) return SPH_OK;
+    // cell-centric kernel (h_max < 1e5): persistent warps pull 32-cell chunks from a counter
+    SPH_CK(c, cudaMemsetAsync(c->chunk_counter, 0, sizeof(unsigned int), c->stream));
+    static int minb = getenv("SPHB200_K3_MINB") ? atoi(getenv("SPHB200_K3_MINB")) : 3;   // tuning knob
+#define K3_LAUNCH(E) k3_launch<E>(minb, c->sm_count, c->stream,                                        \
+        c->posc, c->posh[c->cur], c->posm, c->cell_start, c->cell_end, c->cell_hmax, c->grid_d, t0, t1, c->p.max_neighbors, c->p.K, \
+        c->nlist, c->ncount, c->nown, c->rho, c->press, c->cvol, c->err_d, c->chunk_counter)
+    if (c->equal_mass) K3_LAUNCH(true); else K3_LAUNCH(false);
+#undef K3_LAUNCH
+    SPH_LAUNCH_CHECK(c);
+    {
+        int tpb = 256 / K1B_LPT;
+        if (c->equal_mass)
+            k_density<true><<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->posm, c->nlist, c->ncount, c->grid_d, t0, t1,
+                                                                        c->p.max_neighbors, c->p.K, c->nown, c->rho, c->press, c->cvol);
+        else
+            k_density<false><<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->posm, c->nlist, c->ncount, c->grid_d, t0, t1,
+                                                                         c->p.max_neighbors, c->p.K, c->nown, c->rho, c->press, c->cvol);
+    }
+    SPH_LAUNCH_CHECK(c);
+    // literal-kernel variant: exits at once unless h_max >= 1e5 (decided on the device: no host sync)
     int per_block = K1_WARPS * K1_TPW;
     k_neighbors_density<<<sph_div_up(nt, per_block), K1_WARPS * 32, 0, c->stream>>>(
         c->posh[c->cur], c->posm, c->keys[1], c->cell_start, c->cell_end, c->cell_hmax, c->grid_d, t0, t1, c->p.max_neighbors,
