@@ -10,12 +10,18 @@
 // Node ids: internal 0..n-2 (root 0), leaf of sorted slot s -> n-1+s.  A node holding <= leaf_max particles plays
 // the role of a reference leaf node (never descended; bodies summed directly, including the target itself, Q3).
 //
-// Walk mapping: one warp = 32 consecutive (spatially coherent) sorted targets sharing ONE traversal stack in shared
-// memory; each stack entry carries the mask of lanes still descending that subtree, so every lane sees exactly the
-// node sequence of its private depth-first walk (per-particle MAC, same summation order as the oracle) while node
-// loads are warp-uniform broadcasts and control flow is warp-coherent.  The walk reads a packed 32-byte node
-// (centre of mass, mass, Bmax^2, children / body range): Bmax^2 depends only on the node, so it is evaluated once in
-// the build with the reference's exact op sequence instead of once per (target, node) visit.
+// Walk mapping: one warp = 32 consecutive (spatially coherent) sorted targets sharing ONE work stack of
+// (node, mask of lanes that opened every ancestor).  Each step pops up to 32 entries and turns the work sideways:
+//   1. lanes = NODES: every lane tests its node against all 32 targets (positions broadcast from shared memory) with the
+//      exact reference MAC and gets a 32-bit accept mask -- 32x32 exact decisions in ~350 instructions;
+//   2. two 32x32 bit transposes (butterfly shuffles) hand every lane = TARGET the set of batch nodes it accepts and the
+//      set of leaf buckets it must open; internal nodes that some lane rejected push both children with that lane mask;
+//   3. lanes = TARGETS: every lane sums its own M2P / P2P contributions, so no lane evaluates an interaction that
+//      belongs to another lane (the shared-walk union was 2.3x the per-lane work for P2P, 4.5x for M2P).
+// Every lane still sees exactly the accepted nodes / opened buckets of its private depth-first walk (per-particle MAC,
+// numParticles / numApprox identical to the oracle); only the order in which a lane adds its contributions differs.
+// The MAC "bmax_sq / r_sq < theta^2" is monotone in r_sq, so the build stores per node the exact threshold T with
+// accept <=> r_sq > T (found by stepping ulps around bmax_sq/theta^2 with the IEEE division): no division in the walk.
 #include "ctx.cuh"
 #include <math.h>
 
@@ -28,12 +34,6 @@ __device__ __forceinline__ float rsqrt_approx(float x) {
     asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
-__device__ __forceinline__ float rcp_approx(float x) {
-    float y;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-
 __device__ __forceinline__ int delta_fn(const uint32_t* __restrict__ keys, int n, int i, int j) {
     if (j < 0 || j >= n) return -1;
     uint32_t a = keys[i], b = keys[j];
@@ -84,10 +84,21 @@ __device__ __forceinline__ void moment_accumulate(float4& mo, float cx, float cy
     }
 }
 
-// Packed walk node: [2k] = (cm.xyz, M), [2k+1] = (Bmax^2, a, b, -) with (a,b) = (left,right) for nodes that are
-// descended and (first, -count) for leaf buckets.  Bmax^2 with the op order of AcceptApproximation (:235-243).
+// Exact MAC threshold: accept <=> RN(b_sq / r_sq) < theta2 (AcceptApproximation :246).  The quotient is non-increasing in
+// r_sq, so T = the largest float with RN(b_sq / T) >= theta2 gives accept <=> r_sq > T.  b_sq == 0: 0/r_sq = 0 accepts for
+// every r_sq > 0 and 0/0 = NaN rejects => T = 0.
+__device__ __forceinline__ float mac_threshold(float b_sq, float theta2) {
+    if (!(b_sq > 0.0f)) return 0.0f;
+    uint32_t u = __float_as_uint(__fdiv_rn(b_sq, theta2));
+    while (u > 0u && !(__fdiv_rn(b_sq, __uint_as_float(u)) >= theta2)) --u;
+    while (__fdiv_rn(b_sq, __uint_as_float(u + 1u)) >= theta2) ++u;
+    return __uint_as_float(u);
+}
+
+// Packed walk node: [2k] = (cm.xyz, T) test record, [2k+1] = (M, a, b, Bmax^2) with (a,b) = (left,right) for nodes that
+// are descended and (first, -count) for leaf buckets.  Bmax^2 with the op order of AcceptApproximation (:235-243).
 __device__ __forceinline__ void pack_node(float4* __restrict__ packed, int k, float4 mo, const float lo[3], const float hi[3],
-                                          int2 ch, int2 rg, int leaf_max) {
+                                          int2 ch, int2 rg, int leaf_max, float theta2) {
     float bx = fmaxf(__fsub_rn(hi[0], mo.x), __fsub_rn(mo.x, lo[0]));
     float by = fmaxf(__fsub_rn(hi[1], mo.y), __fsub_rn(mo.y, lo[1]));
     float bz = fmaxf(__fsub_rn(hi[2], mo.z), __fsub_rn(mo.z, lo[2]));
@@ -95,8 +106,8 @@ __device__ __forceinline__ void pack_node(float4* __restrict__ packed, int k, fl
     int cnt = rg.y - rg.x + 1;
     int a = cnt <= leaf_max ? rg.x : ch.x;
     int b = cnt <= leaf_max ? -cnt : ch.y;
-    packed[2 * (size_t)k] = mo;
-    packed[2 * (size_t)k + 1] = make_float4(b_sq, __int_as_float(a), __int_as_float(b), 0.f);
+    packed[2 * (size_t)k] = make_float4(mo.x, mo.y, mo.z, mac_threshold(b_sq, theta2));
+    packed[2 * (size_t)k + 1] = make_float4(mo.w, __int_as_float(a), __int_as_float(b), b_sq);
 }
 
 // Moments + MAC boxes.  Small nodes (<= leaf_max bodies) are evaluated directly from their particle range (reference
@@ -104,7 +115,7 @@ __device__ __forceinline__ void pack_node(float4* __restrict__ packed, int k, fl
 __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ posh, const float4* __restrict__ velm, int n,
                                                     const int2* __restrict__ child, const int2* __restrict__ range,
                                                     const int32_t* __restrict__ parent, int leaf_max, int aabb_mode, float dt,
-                                                    int32_t* __restrict__ flag, float4* mom, float4* nlo, float4* nhi,
+                                                    float theta2, int32_t* __restrict__ flag, float4* mom, float4* nlo, float4* nhi,
                                                     float4* __restrict__ packed) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= 2 * n - 1) return;
@@ -135,7 +146,7 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
     mom[k] = mo;
     nlo[k] = make_float4(lo[0], lo[1], lo[2], __int_as_float(rg.x));
     nhi[k] = make_float4(hi[0], hi[1], hi[2], __int_as_float(rg.y));
-    pack_node(packed, k, mo, lo, hi, child[k], rg, leaf_max);
+    pack_node(packed, k, mo, lo, hi, child[k], rg, leaf_max, theta2);
     int cur = k;
     while (true) {
         int p = parent[cur];
@@ -156,140 +167,135 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
         mom[p] = acc;
         nlo[p] = make_float4(plo[0], plo[1], plo[2], __int_as_float(prg.x));
         nhi[p] = make_float4(phi[0], phi[1], phi[2], __int_as_float(prg.y));
-        pack_node(packed, p, acc, plo, phi, ch, prg, leaf_max);
+        pack_node(packed, p, acc, plo, phi, ch, prg, leaf_max, theta2);
         cur = p;
     }
 }
 
-constexpr int TW_WARPS = 8;
+constexpr int TW_WARPS = 4;
+constexpr int TW_STACK = 1024;   // per-warp work stack entries (node, lane mask)
 
 struct WalkAcc {
     float gx, gy, gz, gp;
     int np, na;
 };
 
-// AcceptApproximation (GravityFieldSystem.cs:229-247): bmax_sq / r_sq < theta^2 with the exact op order for r_sq; the
-// quotient is taken with a fast reciprocal and re-done with the IEEE division only inside a band around theta^2.
-__device__ __forceinline__ bool mac_accept(const float4& pi, const float4& A, float b_sq, float theta2, float band, float& dx,
-                                           float& dy, float& dz, float& r_sq) {
-    dx = __fsub_rn(pi.x, A.x); dy = __fsub_rn(pi.y, A.y); dz = __fsub_rn(pi.z, A.z);
-    r_sq = dot3_rn(dx, dy, dz);
-    const float q = b_sq * rcp_approx(r_sq);
-    bool acc = q < theta2;
-    if (fabsf(q - theta2) < band) acc = __fdiv_rn(b_sq, r_sq) < theta2;   // rare: the IEEE quotient decides
-    return acc;
-}
-
-// GravitationalMoment.GravityContribution (M2P, :428-442)
-__device__ __forceinline__ void m2p(WalkAcc& w, const float4& A, float dx, float dy, float dz, float r_sq) {
-    float rinv = rsqrt_approx(r_sq);
-    float mr = A.w * rinv;
-    float g = mr * rinv * rinv;
-    w.gx = fmaf(dx, g, w.gx); w.gy = fmaf(dy, g, w.gy); w.gz = fmaf(dz, g, w.gz);
-    w.gp -= mr;
-    w.na++;
-}
-
-// Leaf bucket: bodies first .. first+count-1 summed directly with GravityContributionParticle (:332-356), a = h_i;
-// includes the target itself (quirk Q3).  `soft`: some open lane may be inside its softening radius.
-__device__ __forceinline__ void p2p_bucket(WalkAcc& w, const float4& pi, float a2, float ainv, const float4* __restrict__ posm,
-                                           int first, int cnt, bool open, bool soft) {
-    for (int s = first; s < first + cnt; s++) {
-        const float4 pj = __ldg(&posm[s]);
-        float ex = pi.x - pj.x, ey = pi.y - pj.y, ez = pi.z - pj.z;
-        float r2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-        float rinv = rsqrt_approx(fmaxf(r2, a2));
-        float mr = pj.w * rinv;
-        float g = mr * rinv * rinv, ph = -mr;
-        if (soft && r2 < a2) {
-            float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
-            float x = r * ainv, x2 = x * x, x3 = x2 * x;
-            float ma = pj.w * ainv;
-            g = ma * ainv * ainv * (8.0f - 9.0f * x + 2.0f * x3);
-            ph = -ma * (2.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
-        }
-        if (open) {
-            w.gx = fmaf(ex, g, w.gx); w.gy = fmaf(ey, g, w.gy); w.gz = fmaf(ez, g, w.gz);
-            w.gp += ph;
-            w.np++;
-        }
+// 32x32 bit-matrix transpose across the warp: in: lane i holds row i, out: lane j holds column j
+__device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const unsigned m = o == 16 ? 0x0000FFFFu : o == 8 ? 0x00FF00FFu : o == 4 ? 0x0F0F0F0Fu : o == 2 ? 0x33333333u : 0x55555555u;
+        const unsigned y = __shfl_xor_sync(FULL, x, o);
+        x = (lane & o) ? ((x & ~m) | ((y >> o) & m)) : ((x & m) | ((y << o) & ~m));
     }
+    return x;
 }
 
-// One traversal step handles BOTH children of an opened node (4 independent node loads in flight, two MAC tests
-// interleaved); a stack entry is (left, right, mask of lanes that rejected the parent).  Every lane still sees exactly
-// the accepted nodes / opened buckets of its private walk (per-particle MAC); only the order in which a lane adds its
-// contributions differs from the depth-first order of the oracle.
 __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __restrict__ posh, const float4* __restrict__ posm,
-                                                             const float4* __restrict__ packed, int t0, int t1, float theta2,
-                                                             float G, float4* __restrict__ grav, int32_t* __restrict__ npart,
+                                                             const float4* __restrict__ packed, int t0, int t1, float G,
+                                                             float4* __restrict__ grav, int32_t* __restrict__ npart,
                                                              int32_t* __restrict__ napprox, int32_t* __restrict__ err) {
-    __shared__ int4 stack[TW_WARPS][SPH_TREE_STACK];
+    __shared__ int2 stack[TW_WARPS][TW_STACK];
+    __shared__ float4 tgt[TW_WARPS][32];     // target positions (lanes = nodes phase)
+    __shared__ float4 bcm[TW_WARPS][32];     // batch nodes: (cm, M)            (lanes = targets phase)
+    __shared__ int2 bkt[TW_WARPS][32];       // batch nodes: (first, count) of leaf buckets
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int t = t0 + (blockIdx.x * TW_WARPS + wid) * 32 + lane;
     const bool active = t < t1;
     const float4 pi = posh[active ? t : (t1 - 1)];
     const float a2 = pi.w * pi.w, ainv = 1.0f / pi.w;
-    const float band = theta2 * 8.0e-6f;
     WalkAcc w = {0.f, 0.f, 0.f, 0.f, 0, 0};
     const unsigned m0 = __ballot_sync(FULL, active);
     if (m0 == 0) return;
-    int4* st = stack[wid];
-    int sp = 0;
-    {   // root
-        const float4 A = __ldg(&packed[0]), B = __ldg(&packed[1]);
-        float dx, dy, dz, r_sq;
-        const bool acc = active && mac_accept(pi, A, B.x, theta2, band, dx, dy, dz, r_sq);
-        if (acc) m2p(w, A, dx, dy, dz, r_sq);
-        const unsigned rej = __ballot_sync(FULL, active && !acc);
-        const int ia = __float_as_int(B.y), ib = __float_as_int(B.z);
-        if (rej != 0) {
-            if (ib < 0) {
-                const bool open = (rej >> lane) & 1u;
-                const bool soft = __any_sync(FULL, open && r_sq < 2.0f * (a2 + B.x));
-                p2p_bucket(w, pi, a2, ainv, posm, ia, -ib, open, soft);
-            } else {
-                if (lane == 0) st[0] = make_int4(ia, ib, (int)rej, 0);
-                sp = 1;
-            }
-        }
-        __syncwarp();
-    }
+    int2* st = stack[wid];
+    float4* tg = tgt[wid];
+    float4* bc = bcm[wid];
+    int2* bk = bkt[wid];
+    tg[lane] = pi;
+    if (lane == 0) st[0] = make_int2(0, (int)m0);
+    int sp = 1;
+    __syncwarp();
     while (sp > 0) {
-        const int4 e = st[--sp];
+        // ---- 1. lanes = nodes
+        const int nb = min(sp, 32);
+        const bool have = lane < nb;
+        int2 e = make_int2(0, 0);
+        if (have) e = st[sp - 1 - lane];
+        sp -= nb;
+        const float4 N = __ldg(&packed[2 * (size_t)e.x]);
+        const float4 X = __ldg(&packed[2 * (size_t)e.x + 1]);
+        unsigned amask = 0u;
+#pragma unroll 8
+        for (int tt = 0; tt < 32; tt++) {
+            const float4 T = tg[tt];
+            const float dx = __fsub_rn(T.x, N.x), dy = __fsub_rn(T.y, N.y), dz = __fsub_rn(T.z, N.z);
+            if (dot3_rn(dx, dy, dz) > N.w) amask |= 1u << tt;   // AcceptApproximation, exact
+        }
+        const unsigned mask = (unsigned)e.y;
+        const unsigned acc = amask & mask, rej = mask & ~amask;
+        const int ia = __float_as_int(X.y), ib = __float_as_int(X.z);
+        const bool bucket = ib < 0;
         __syncwarp();
-        const float4 A0 = __ldg(&packed[2 * (size_t)e.x]), B0 = __ldg(&packed[2 * (size_t)e.x + 1]);
-        const float4 A1 = __ldg(&packed[2 * (size_t)e.y]), B1 = __ldg(&packed[2 * (size_t)e.y + 1]);
-        const bool mine = ((unsigned)e.z >> lane) & 1u;
-        float dx0, dy0, dz0, r0, dx1, dy1, dz1, r1;
-        const bool acc0 = mac_accept(pi, A0, B0.x, theta2, band, dx0, dy0, dz0, r0) && mine;
-        const bool acc1 = mac_accept(pi, A1, B1.x, theta2, band, dx1, dy1, dz1, r1) && mine;
-        if (acc0) m2p(w, A0, dx0, dy0, dz0, r0);
-        if (acc1) m2p(w, A1, dx1, dy1, dz1, r1);
-        const unsigned rej0 = __ballot_sync(FULL, mine && !acc0);
-        const unsigned rej1 = __ballot_sync(FULL, mine && !acc1);
-        if (rej0 != 0) {
-            const int ia = __float_as_int(B0.y), ib = __float_as_int(B0.z);
-            if (ib < 0) {
-                const bool open = (rej0 >> lane) & 1u;
-                const bool soft = __any_sync(FULL, open && r0 < 2.0f * (a2 + B0.x));
-                p2p_bucket(w, pi, a2, ainv, posm, ia, -ib, open, soft);
-            } else {
-                if (sp >= SPH_TREE_STACK) { if (lane == 0) atomicExch(&err[ERR_TREE_STACK], 1); break; }
-                if (lane == 0) st[sp] = make_int4(ia, ib, (int)rej0, 0);
-                sp++;
+        bc[lane] = make_float4(N.x, N.y, N.z, X.x);
+        bk[lane] = make_int2(ia, -ib);
+        // internal nodes some lane rejected: both children inherit that lane mask
+        const bool open = have && !bucket && rej != 0u;
+        const unsigned ob = __ballot_sync(FULL, open);
+        if (sp + 2 * __popc(ob) > TW_STACK) { if (lane == 0) atomicExch(&err[ERR_TREE_STACK], 1); break; }
+        if (open) {
+            const int pos = sp + 2 * __popc(ob & ((1u << lane) - 1u));
+            st[pos] = make_int2(ia, (int)rej);
+            st[pos + 1] = make_int2(ib, (int)rej);
+        }
+        sp += 2 * __popc(ob);
+        // ---- 2. sideways: which batch nodes does target `lane` accept, which buckets does it open
+        unsigned nmask = transpose32(acc, lane);
+        unsigned bmask = transpose32(bucket ? rej : 0u, lane);
+        __syncwarp();
+        // ---- 3. lanes = targets: M2P (GravitationalMoment.GravityContribution, :428-442)
+        w.na += __popc(nmask);
+        while (__any_sync(FULL, nmask != 0u)) {
+            if (nmask != 0u) {
+                const int b = __ffs(nmask) - 1;
+                nmask &= nmask - 1u;
+                const float4 A = bc[b];
+                const float dx = pi.x - A.x, dy = pi.y - A.y, dz = pi.z - A.z;
+                const float r_sq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                const float rinv = rsqrt_approx(r_sq);
+                const float mr = A.w * rinv;
+                const float g = mr * rinv * rinv;
+                w.gx = fmaf(dx, g, w.gx); w.gy = fmaf(dy, g, w.gy); w.gz = fmaf(dz, g, w.gz);
+                w.gp -= mr;
             }
         }
-        if (rej1 != 0) {
-            const int ia = __float_as_int(B1.y), ib = __float_as_int(B1.z);
-            if (ib < 0) {
-                const bool open = (rej1 >> lane) & 1u;
-                const bool soft = __any_sync(FULL, open && r1 < 2.0f * (a2 + B1.x));
-                p2p_bucket(w, pi, a2, ainv, posm, ia, -ib, open, soft);
-            } else {
-                if (sp >= SPH_TREE_STACK) { if (lane == 0) atomicExch(&err[ERR_TREE_STACK], 1); break; }
-                if (lane == 0) st[sp] = make_int4(ia, ib, (int)rej1, 0);
-                sp++;
+        // P2P over the opened buckets (GravityContributionParticle :332-356, a = h_i; includes the target itself, Q3):
+        // one body per lane per iteration, each lane walking its own bucket list
+        int first = 0, rem = 0;
+        while (__any_sync(FULL, (bmask | (unsigned)rem) != 0u)) {
+            if (rem == 0 && bmask != 0u) {
+                const int b = __ffs(bmask) - 1;
+                bmask &= bmask - 1u;
+                const int2 fc = bk[b];
+                first = fc.x; rem = fc.y;
+            }
+            if (rem > 0) {
+                const float4 pj = __ldg(&posm[first]);
+                first++; rem--;
+                const float ex = pi.x - pj.x, ey = pi.y - pj.y, ez = pi.z - pj.z;
+                const float r2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+                const float rinv = rsqrt_approx(fmaxf(r2, a2));
+                const float mr = pj.w * rinv;
+                float g = mr * rinv * rinv, ph = -mr;
+                if (r2 < a2) {
+                    const float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
+                    const float x = r * ainv, x2 = x * x, x3 = x2 * x;
+                    const float ma = pj.w * ainv;
+                    g = ma * ainv * ainv * (8.0f - 9.0f * x + 2.0f * x3);
+                    ph = -ma * (2.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
+                }
+                w.gx = fmaf(ex, g, w.gx); w.gy = fmaf(ey, g, w.gy); w.gz = fmaf(ez, g, w.gz);
+                w.gp += ph;
+                w.np++;
             }
         }
         __syncwarp();
@@ -312,7 +318,8 @@ int sph_launch_tree_build(sphb200_ctx* c, float dt, cudaStream_t stream) {
     k_lbvh_topology<<<sph_div_up(n, 256), 256, 0, stream>>>(c->keys[1], n, c->child, c->range, c->parent);
     SPH_LAUNCH_CHECK(c);
     k_lbvh_nodes<<<sph_div_up(2 * (int64_t)n - 1, 256), 256, 0, stream>>>(c->posh[c->cur], c->velm[c->cur], n, c->child, c->range,
-                                                                         c->parent, c->p.leaf_max, c->p.aabb_mode, dt, c->flag, c->mom,
+                                                                         c->parent, c->p.leaf_max, c->p.aabb_mode, dt,
+                                                                         c->p.theta * c->p.theta /* fp32 product, as k_Theta*k_Theta (GravityFieldSystem.cs:246) */, c->flag, c->mom,
                                                                          c->nlo, c->nhi, c->packed);
     SPH_LAUNCH_CHECK(c);
     c->tree_valid = true;
@@ -325,8 +332,7 @@ int sph_launch_tree_walk(sphb200_ctx* c) {
     int t1 = (c->t1 < 0 || c->t1 > c->n) ? n : (int)c->t1;
     int nt = t1 - t0;
     if (n <= 0 || nt <= 0) return SPH_OK;
-    float theta2 = c->p.theta * c->p.theta;  // fp32 product, as k_Theta*k_Theta (GravityFieldSystem.cs:246)
-    k_tree_walk<<<sph_div_up(nt, TW_WARPS * 32), TW_WARPS * 32, 0, c->stream>>>(c->posh[c->cur], c->posm, c->packed, t0, t1, theta2,
+    k_tree_walk<<<sph_div_up(nt, TW_WARPS * 32), TW_WARPS * 32, 0, c->stream>>>(c->posh[c->cur], c->posm, c->packed, t0, t1,
                                                                                c->p.G, c->grav, c->npart, c->napprox, c->err_d);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;
