@@ -173,12 +173,19 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
 }
 
 constexpr int TW_WARPS = 4;
-constexpr int TW_STACK = 1024;   // per-warp work stack entries (node, lane mask)
+constexpr int TW_STACK = 512;    // per-warp work stack entries (node, lane mask); batches shrink when it is nearly full
+constexpr int TW_SHARE = 10;     // an item wanted by >= this many lanes is evaluated warp-wide (uniform loads)
 
 struct WalkAcc {
     float gx, gy, gz, gp;
     int np, na;
 };
+
+typedef unsigned long long u64;
+__device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(a), "f"(b)); return r; }
+__device__ __forceinline__ void upk2(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
 // 32x32 bit-matrix transpose across the warp: in: lane i holds row i, out: lane j holds column j
 __device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
@@ -196,7 +203,8 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
                                                              float4* __restrict__ grav, int32_t* __restrict__ npart,
                                                              int32_t* __restrict__ napprox, int32_t* __restrict__ err) {
     __shared__ int2 stack[TW_WARPS][TW_STACK];
-    __shared__ float4 tgt[TW_WARPS][32];     // target positions (lanes = nodes phase)
+    __shared__ ulonglong2 tgxy[TW_WARPS][16];  // target positions as pairs: (x0,x1), (y0,y1)   (lanes = nodes phase)
+    __shared__ u64 tgzz[TW_WARPS][16];         //                           (z0,z1)
     __shared__ float4 bcm[TW_WARPS][32];     // batch nodes: (cm, M)            (lanes = targets phase)
     __shared__ int2 bkt[TW_WARPS][32];       // batch nodes: (first, count) of leaf buckets
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -208,28 +216,45 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
     const unsigned m0 = __ballot_sync(FULL, active);
     if (m0 == 0) return;
     int2* st = stack[wid];
-    float4* tg = tgt[wid];
+    ulonglong2* tgp = tgxy[wid];
+    u64* tgz = tgzz[wid];
     float4* bc = bcm[wid];
     int2* bk = bkt[wid];
-    tg[lane] = pi;
+    {
+        float* fx = reinterpret_cast<float*>(tgp);
+        float* fz = reinterpret_cast<float*>(tgz);
+        fx[(lane >> 1) * 4 + (lane & 1)] = pi.x;
+        fx[(lane >> 1) * 4 + 2 + (lane & 1)] = pi.y;
+        fz[lane] = pi.z;
+    }
     if (lane == 0) st[0] = make_int2(0, (int)m0);
     int sp = 1;
     __syncwarp();
     while (sp > 0) {
         // ---- 1. lanes = nodes
-        const int nb = min(sp, 32);
+        const int nb = min(min(sp, 32), TW_STACK - sp);   // a batch of nb nodes grows the stack by at most nb
+        if (nb <= 0) { if (lane == 0) atomicExch(&err[ERR_TREE_STACK], 1); break; }
         const bool have = lane < nb;
         int2 e = make_int2(0, 0);
         if (have) e = st[sp - 1 - lane];
         sp -= nb;
         const float4 N = __ldg(&packed[2 * (size_t)e.x]);
         const float4 X = __ldg(&packed[2 * (size_t)e.x + 1]);
+        // exact MAC, 2 targets per packed subtract / multiply (FADD2 / FMUL2 are IEEE round-to-nearest per half): the
+        // reference's (dx*dx + dy*dy) + dz*dz bit for bit
         unsigned amask = 0u;
-#pragma unroll 8
-        for (int tt = 0; tt < 32; tt++) {
-            const float4 T = tg[tt];
-            const float dx = __fsub_rn(T.x, N.x), dy = __fsub_rn(T.y, N.y), dz = __fsub_rn(T.z, N.z);
-            if (dot3_rn(dx, dy, dz) > N.w) amask |= 1u << tt;   // AcceptApproximation, exact
+        const u64 nx = pk2(N.x, N.x), ny = pk2(N.y, N.y), nz = pk2(N.z, N.z);
+#pragma unroll
+        for (int tp = 0; tp < 16; tp++) {
+            const ulonglong2 P = tgp[tp];          // (x0,x1), (y0,y1)
+            const u64 Z = tgz[tp];                 // (z0,z1)
+            const u64 dx = sub2(P.x, nx), dy = sub2(P.y, ny), dz = sub2(Z, nz);
+            // the sums stay scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would round once
+            float xa, xb, ya, yb, za, zb;
+            upk2(mul2(dx, dx), xa, xb); upk2(mul2(dy, dy), ya, yb); upk2(mul2(dz, dz), za, zb);
+            const float ra = __fadd_rn(__fadd_rn(xa, ya), za), rb = __fadd_rn(__fadd_rn(xb, yb), zb);
+            amask |= (ra > N.w ? 1u : 0u) << (2 * tp);   // AcceptApproximation, exact
+            amask |= (rb > N.w ? 1u : 0u) << (2 * tp + 1);
         }
         const unsigned mask = (unsigned)e.y;
         const unsigned acc = amask & mask, rej = mask & ~amask;
@@ -241,7 +266,6 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
         // internal nodes some lane rejected: both children inherit that lane mask
         const bool open = have && !bucket && rej != 0u;
         const unsigned ob = __ballot_sync(FULL, open);
-        if (sp + 2 * __popc(ob) > TW_STACK) { if (lane == 0) atomicExch(&err[ERR_TREE_STACK], 1); break; }
         if (open) {
             const int pos = sp + 2 * __popc(ob & ((1u << lane) - 1u));
             st[pos] = make_int2(ia, (int)rej);
@@ -251,10 +275,63 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
         // ---- 2. sideways: which batch nodes does target `lane` accept, which buckets does it open
         unsigned nmask = transpose32(acc, lane);
         unsigned bmask = transpose32(bucket ? rej : 0u, lane);
-        __syncwarp();
-        // ---- 3. lanes = targets: M2P (GravitationalMoment.GravityContribution, :428-442)
         w.na += __popc(nmask);
-        while (__any_sync(FULL, nmask != 0u)) {
+        // items wanted by many lanes are evaluated once for the warp (uniform loads, predicated lanes); the rest lane by lane
+        unsigned sh_a = __ballot_sync(FULL, __popc(acc) >= TW_SHARE);
+        unsigned sh_b = __ballot_sync(FULL, bucket && __popc(rej) >= TW_SHARE);
+        const unsigned nshared = nmask & sh_a, bshared = bmask & sh_b;
+        nmask &= ~sh_a;
+        bmask &= ~sh_b;
+        __syncwarp();
+        // ---- 3a. shared M2P (GravitationalMoment.GravityContribution, :428-442)
+        while (sh_a != 0u) {
+            const int b = __ffs(sh_a) - 1;
+            sh_a &= sh_a - 1u;
+            const float4 A = bc[b];
+            const float dx = pi.x - A.x, dy = pi.y - A.y, dz = pi.z - A.z;
+            const float r_sq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            const float rinv = rsqrt_approx(r_sq);
+            const float mr = A.w * rinv;
+            const float g = mr * rinv * rinv;
+            if ((nshared >> b) & 1u) {   // (a lane sitting exactly on the node's centre rejects it: r_sq = 0 must not leak a NaN)
+                w.gx = fmaf(dx, g, w.gx); w.gy = fmaf(dy, g, w.gy); w.gz = fmaf(dz, g, w.gz);
+                w.gp -= mr;
+            }
+        }
+        // ---- 3b. shared P2P (GravityContributionParticle :332-356, a = h_i; includes the target itself, Q3)
+        while (sh_b != 0u) {
+            const int b = __ffs(sh_b) - 1;
+            sh_b &= sh_b - 1u;
+            const int2 fc = bk[b];
+            const bool mine = (bshared >> b) & 1u;
+            for (int s0 = 0; s0 < fc.y; s0 += 4) {
+                float4 pq[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) pq[u] = __ldg(&posm[fc.x + min(s0 + u, fc.y - 1)]);
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const float4 pj = pq[u];
+                    const bool on = mine && s0 + u < fc.y;
+                    const float ex = pi.x - pj.x, ey = pi.y - pj.y, ez = pi.z - pj.z;
+                    const float r2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+                    const float rinv = rsqrt_approx(fmaxf(r2, a2));
+                    const float mr = on ? pj.w * rinv : 0.f;
+                    float g = mr * rinv * rinv, ph = -mr;
+                    if (on && r2 < a2) {
+                        const float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
+                        const float x = r * ainv, x2 = x * x, x3 = x2 * x;
+                        const float ma = pj.w * ainv;
+                        g = ma * ainv * ainv * (8.0f - 9.0f * x + 2.0f * x3);
+                        ph = -ma * (2.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
+                    }
+                    w.gx = fmaf(ex, g, w.gx); w.gy = fmaf(ey, g, w.gy); w.gz = fmaf(ez, g, w.gz);
+                    w.gp += ph;
+                    w.np += on ? 1 : 0;
+                }
+            }
+        }
+        // ---- 3c. lane-private M2P: every lane sums the nodes only few lanes accept
+        for (int it = __reduce_max_sync(FULL, __popc(nmask)); it > 0; it--) {
             if (nmask != 0u) {
                 const int b = __ffs(nmask) - 1;
                 nmask &= nmask - 1u;
@@ -268,8 +345,7 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
                 w.gp -= mr;
             }
         }
-        // P2P over the opened buckets (GravityContributionParticle :332-356, a = h_i; includes the target itself, Q3):
-        // one body per lane per iteration, each lane walking its own bucket list
+        // ---- 3d. lane-private P2P: one body per lane per iteration, each lane walking its own bucket list
         int first = 0, rem = 0;
         while (__any_sync(FULL, (bmask | (unsigned)rem) != 0u)) {
             if (rem == 0 && bmask != 0u) {

@@ -164,6 +164,30 @@ def test_c2_tree_code_parity_same_lbvh(orc):
     assert np.median(err) < 0.03
 
 
+
+def test_tree_mac_decisions_exact_300k(orc):
+    """~6e8 per-particle MAC decisions (300k particles x ~2000 node tests): numParticles / numApprox must equal the
+    oracle's for every particle.  A one-ulp difference in r_sq (e.g. an FMA contraction of dx*dx + dy*dy + dz*dz) flips
+    a few dozen decisions at this size."""
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_config("c3", particles=300_000)
+    radius = np.abs(c["pos"]).max()
+    c["h"][:] = 0.5 * (50.0 / 300_000) ** (1.0 / 3.0) * radius     # ~50 neighbors inside 2h: the settled regime (Q2 boxes scale with h)
+    c["vel"] = np.random.default_rng(2).normal(0, 0.5, c["pos"].shape).astype(np.float32)
+    dt = 1.0 / 60.0
+    sim = make_sim(len(c["h"]))
+    sim.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    sim.build_neighbors()
+    sim.gravity(sphb200.GRAVITY_TREE, dt)
+    p = sim.effective_params()
+    _, npart, napp, _, _ = orc.tree_gravity(c["pos"], c["vel"], c["h"], c["mass"], dt, p.theta, p.G, p.leaf_max,
+                                            p.aabb_mode, p.max_grid_bits)
+    got = sim.download(sphb200.FIELD_GRAVITY)
+    np.testing.assert_array_equal(got["numParticles"], npart)
+    np.testing.assert_array_equal(got["numApprox"], napp)
+
+
 def test_c2_multistep_drift_matches_oracle(orc):
     """P2: 20 steps of the C2 regime; trajectories are compared through aggregates and their drift."""
     import sphb200
