@@ -174,7 +174,8 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
 
 constexpr int TW_WARPS = 4;
 constexpr int TW_STACK = 512;    // per-warp work stack entries (node, lane mask); batches shrink when it is nearly full
-constexpr int TW_SHARE = 10;     // an item wanted by >= this many lanes is evaluated warp-wide (uniform loads)
+constexpr int TW_SHARE_A = 12;   // a node accepted by >= this many lanes gets its M2P evaluated warp-wide (uniform load) ...
+constexpr int TW_SHARE_B = 6;    // ... a bucket opened by >= this many lanes its P2P; the rest is summed lane by lane
 
 struct WalkAcc {
     float gx, gy, gz, gp;
@@ -277,8 +278,8 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
         unsigned bmask = transpose32(bucket ? rej : 0u, lane);
         w.na += __popc(nmask);
         // items wanted by many lanes are evaluated once for the warp (uniform loads, predicated lanes); the rest lane by lane
-        unsigned sh_a = __ballot_sync(FULL, __popc(acc) >= TW_SHARE);
-        unsigned sh_b = __ballot_sync(FULL, bucket && __popc(rej) >= TW_SHARE);
+        unsigned sh_a = __ballot_sync(FULL, __popc(acc) >= TW_SHARE_A);
+        unsigned sh_b = __ballot_sync(FULL, bucket && __popc(rej) >= TW_SHARE_B);
         const unsigned nshared = nmask & sh_a, bshared = bmask & sh_b;
         nmask &= ~sh_a;
         bmask &= ~sh_b;
@@ -310,14 +311,14 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
                 for (int u = 0; u < 4; u++) pq[u] = __ldg(&posm[fc.x + min(s0 + u, fc.y - 1)]);
 #pragma unroll
                 for (int u = 0; u < 4; u++) {
+                    if (s0 + u >= fc.y) break;   // warp-uniform
                     const float4 pj = pq[u];
-                    const bool on = mine && s0 + u < fc.y;
                     const float ex = pi.x - pj.x, ey = pi.y - pj.y, ez = pi.z - pj.z;
                     const float r2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
                     const float rinv = rsqrt_approx(fmaxf(r2, a2));
-                    const float mr = on ? pj.w * rinv : 0.f;
+                    const float mr = mine ? pj.w * rinv : 0.f;
                     float g = mr * rinv * rinv, ph = -mr;
-                    if (on && r2 < a2) {
+                    if (mine && r2 < a2) {
                         const float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
                         const float x = r * ainv, x2 = x * x, x3 = x2 * x;
                         const float ma = pj.w * ainv;
@@ -326,9 +327,9 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
                     }
                     w.gx = fmaf(ex, g, w.gx); w.gy = fmaf(ey, g, w.gy); w.gz = fmaf(ez, g, w.gz);
                     w.gp += ph;
-                    w.np += on ? 1 : 0;
                 }
             }
+            w.np += mine ? fc.y : 0;
         }
         // ---- 3c. lane-private M2P: every lane sums the nodes only few lanes accept
         for (int it = __reduce_max_sync(FULL, __popc(nmask)); it > 0; it--) {
