@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
     __shared__ u64 tgzz[TW_WARPS][16];         //                           (z0,z1)
     __shared__ float4 bcm[TW_WARPS][32];     // batch nodes: (cm, M)            (lanes = targets phase)
     __shared__ int2 bkt[TW_WARPS][32];       // batch nodes: (first, count) of leaf buckets
+    __shared__ int2 sbody[TW_WARPS][128];    // flattened bodies of the shared buckets: (slot, lane mask)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int t = t0 + (blockIdx.x * TW_WARPS + wid) * 32 + lane;
     const bool active = t < t1;
@@ -221,6 +222,7 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
     u64* tgz = tgzz[wid];
     float4* bc = bcm[wid];
     int2* bk = bkt[wid];
+    int2* sb = sbody[wid];
     {
         float* fx = reinterpret_cast<float*>(tgp);
         float* fz = reinterpret_cast<float*>(tgz);
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
         unsigned amask = 0u;
         const u64 nx = pk2(N.x, N.x), ny = pk2(N.y, N.y), nz = pk2(N.z, N.z);
 #pragma unroll
-        for (int tp = 0; tp < 16; tp++) {
+        for (int tp = 15; tp >= 0; tp--) {         // descending: every result is shifted in at bit 0
             const ulonglong2 P = tgp[tp];          // (x0,x1), (y0,y1)
             const u64 Z = tgz[tp];                 // (z0,z1)
             const u64 dx = sub2(P.x, nx), dy = sub2(P.y, ny), dz = sub2(Z, nz);
@@ -254,8 +256,9 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
             float xa, xb, ya, yb, za, zb;
             upk2(mul2(dx, dx), xa, xb); upk2(mul2(dy, dy), ya, yb); upk2(mul2(dz, dz), za, zb);
             const float ra = __fadd_rn(__fadd_rn(xa, ya), za), rb = __fadd_rn(__fadd_rn(xb, yb), zb);
-            amask |= (ra > N.w ? 1u : 0u) << (2 * tp);   // AcceptApproximation, exact
-            amask |= (rb > N.w ? 1u : 0u) << (2 * tp + 1);
+            // AcceptApproximation, exact: r_sq > T <=> T - r_sq < 0 (a difference of distinct floats never rounds to zero)
+            amask = __funnelshift_l(__float_as_uint(__fsub_rn(N.w, rb)), amask, 1);
+            amask = __funnelshift_l(__float_as_uint(__fsub_rn(N.w, ra)), amask, 1);
         }
         const unsigned mask = (unsigned)e.y;
         const unsigned acc = amask & mask, rej = mask & ~amask;
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
         // items wanted by many lanes are evaluated once for the warp (uniform loads, predicated lanes); the rest lane by lane
         unsigned sh_a = __ballot_sync(FULL, __popc(acc) >= TW_SHARE_A);
         unsigned sh_b = __ballot_sync(FULL, bucket && __popc(rej) >= TW_SHARE_B);
-        const unsigned nshared = nmask & sh_a, bshared = bmask & sh_b;
+        const unsigned nshared = nmask & sh_a;
         nmask &= ~sh_a;
         bmask &= ~sh_b;
         __syncwarp();
@@ -299,37 +302,55 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
                 w.gp -= mr;
             }
         }
-        // ---- 3b. shared P2P (GravityContributionParticle :332-356, a = h_i; includes the target itself, Q3)
-        while (sh_b != 0u) {
-            const int b = __ffs(sh_b) - 1;
-            sh_b &= sh_b - 1u;
-            const int2 fc = bk[b];
-            const bool mine = (bshared >> b) & 1u;
-            for (int s0 = 0; s0 < fc.y; s0 += 4) {
-                float4 pq[4];
+        // ---- 3b. shared P2P (GravityContributionParticle :332-356, a = h_i; includes the target itself, Q3): the bodies of
+        // the shared buckets are flattened into one list (4 per bucket per round; one round when leaf_max <= 4)
+        {
+            int brem = (have && bucket && __popc(rej) >= TW_SHARE_B) ? -ib : 0, bfirst = ia;
+            while (__any_sync(FULL, brem > 0)) {
+                const int c4 = min(brem, 4);
+                int incl = c4;
 #pragma unroll
-                for (int u = 0; u < 4; u++) pq[u] = __ldg(&posm[fc.x + min(s0 + u, fc.y - 1)]);
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (s0 + u >= fc.y) break;   // warp-uniform
-                    const float4 pj = pq[u];
-                    const float ex = pi.x - pj.x, ey = pi.y - pj.y, ez = pi.z - pj.z;
-                    const float r2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-                    const float rinv = rsqrt_approx(fmaxf(r2, a2));
-                    const float mr = mine ? pj.w * rinv : 0.f;
-                    float g = mr * rinv * rinv, ph = -mr;
-                    if (mine && r2 < a2) {
-                        const float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
-                        const float x = r * ainv, x2 = x * x, x3 = x2 * x;
-                        const float ma = pj.w * ainv;
-                        g = ma * ainv * ainv * (8.0f - 9.0f * x + 2.0f * x3);
-                        ph = -ma * (2.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
-                    }
-                    w.gx = fmaf(ex, g, w.gx); w.gy = fmaf(ey, g, w.gy); w.gz = fmaf(ez, g, w.gz);
-                    w.gp += ph;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int v = __shfl_up_sync(FULL, incl, o);
+                    if (lane >= o) incl += v;
                 }
+                const int total = __shfl_sync(FULL, incl, 31);
+#pragma unroll
+                for (int u = 0; u < 4; u++)
+                    if (u < c4) sb[incl - c4 + u] = make_int2(bfirst + u, (int)rej);
+                bfirst += c4; brem -= c4;
+                __syncwarp();
+                for (int k = 0; k < total; k += 4) {
+                    int2 en[4];
+                    float4 pq[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) en[u] = sb[min(k + u, total - 1)];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) pq[u] = __ldg(&posm[en[u].x]);
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        if (k + u >= total) break;   // warp-uniform
+                        const float4 pj = pq[u];
+                        const bool mine = ((unsigned)en[u].y >> lane) & 1u;
+                        const float ex = pi.x - pj.x, ey = pi.y - pj.y, ez = pi.z - pj.z;
+                        const float r2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
+                        const float rinv = rsqrt_approx(fmaxf(r2, a2));
+                        const float mr = mine ? pj.w * rinv : 0.f;
+                        float g = mr * rinv * rinv, ph = -mr;
+                        if (mine && r2 < a2) {
+                            const float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
+                            const float x = r * ainv, x2 = x * x, x3 = x2 * x;
+                            const float ma = pj.w * ainv;
+                            g = ma * ainv * ainv * (8.0f - 9.0f * x + 2.0f * x3);
+                            ph = -ma * (2.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
+                        }
+                        w.gx = fmaf(ex, g, w.gx); w.gy = fmaf(ey, g, w.gy); w.gz = fmaf(ez, g, w.gz);
+                        w.gp += ph;
+                        w.np += mine ? 1 : 0;
+                    }
+                }
+                __syncwarp();
             }
-            w.np += mine ? fc.y : 0;
         }
         // ---- 3c. lane-private M2P: every lane sums the nodes only few lanes accept
         for (int it = __reduce_max_sync(FULL, __popc(nmask)); it > 0; it--) {
