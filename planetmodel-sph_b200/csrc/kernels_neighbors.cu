@@ -241,17 +241,6 @@ constexpr int K3_WARPS = 8;
 constexpr int K3_QCAP = 64;   // candidate-cell queue per warp
 constexpr int K3_RING = 64;   // compacted-candidate ring per warp
 
-// Row overflow (count > max_neighbors: an error state the caller is told about): the neighbor is not stored, but the
-// density and the own-support count stay complete.
-__device__ __noinline__ void k3_overflow(const float4* __restrict__ posh, const float4* __restrict__ posm, int t, int j, float d2,
-                                         bool eqm, float* orho, int* oown) {
-    const float r = __fsqrt_rn(d2);
-    const float h_t = posh[t].w;
-    const float wsym = 0.5f * (w_fast(r, 1.0f / h_t) + w_fast(r, 1.0f / posh[j].w));
-    atomicAdd(orho, eqm ? wsym : posm[j].w * wsym);
-    if (r < __fmul_rn(h_t, 2.0f)) atomicAdd(oown, 1);
-}
-
 template <bool EQM, int MINB>
 __global__ void __launch_bounds__(K3_WARPS * 32, MINB) k_cell_neighbors(
     const float4* __restrict__ posc, const float4* __restrict__ posh, const float4* __restrict__ posm,
@@ -264,8 +253,6 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB) k_cell_neighbors(
     __shared__ uint32_t qpre[K3_WARPS][K3_QCAP + 1];
     __shared__ float4 ring4[K3_WARPS][K3_RING];
     __shared__ int ringj[K3_WARPS][K3_RING];
-    __shared__ float ovf_rho[K3_WARPS][32];
-    __shared__ int ovf_own[K3_WARPS][32];
     __shared__ int cnts[K3_WARPS][32];
     if (!(g->hmax < kHugeH)) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -307,8 +294,6 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB) k_cell_neighbors(
                 const float hi = posh[tl].w;
                 __syncwarp();
                 tg[lane] = T;
-                ovf_rho[w][lane] = 0.f;
-                ovf_own[w][lane] = 0;
                 cn_w[lane] = 0;
                 int rh = 0, rt = 0;   // candidate ring head / tail (monotone counters)
                 // box of the targets' positions, their largest keep threshold and largest h
@@ -346,10 +331,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB) k_cell_neighbors(
                         const bool keep = d2 < fmaxf(Tt.w, c.w) && jrel != tt;
                         const unsigned kb = __ballot_sync(FULL, keep);
                         const int slot = base + __popc(kb & lt);
-                        if (keep) {
-                            if (slot < kmax) rowt[slot] = (uint32_t)j;
-                            else k3_overflow(posh, posm, p0 + tt, j, d2, EQM, &ovf_rho[w][tt], &ovf_own[w][tt]);
-                        }
+                        if (keep && slot < kmax) rowt[slot] = (uint32_t)j;   // beyond max_neighbors: counted, not stored
                         if (lane == 0) cn_w[tt] = base + __popc(kb);
                     }
                     rh += m;
@@ -360,15 +342,18 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB) k_cell_neighbors(
                 auto flush = [&]() {
                     if (lane == 0) qp_w[qn] = (uint32_t)qtotal;
                     __syncwarp();
-                    int q = 0;
+                    int q0 = 0;   // queue entry holding flattened position f0 of the batch being fetched
                     auto fetch = [&](int f0, int& j, float4& c) {
+                        // entries q0+1 .. q0+32 that start within positions f0+1 .. f0+32 (lengths are >= 1, so there are
+                        // at most 32): bit (pos-1) per start; lane L sits in entry q0 + #starts at positions <= L
+                        const int qi = q0 + 1 + lane;
+                        const int pos = qi < qn ? (int)qp_w[qi] - f0 : 64;
+                        const unsigned starts = __reduce_or_sync(FULL, pos <= 32 ? 1u << (pos - 1) : 0u);
+                        const int q = q0 + __popc(starts & lt);
                         const int f = f0 + lane;
-                        j = 0;
-                        if (f < qtotal) {
-                            while (qp_w[q + 1] <= (uint32_t)f) q++;
-                            j = (int)(qs_w[q] + ((uint32_t)f - qp_w[q]));
-                        }
+                        j = f < qtotal ? (int)(qs_w[q] + ((uint32_t)f - qp_w[q])) : 0;
                         c = posc[j];
+                        q0 += __popc(starts);
                     };
                     int j; float4 c;
                     fetch(0, j, c);
@@ -447,16 +432,11 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB) k_cell_neighbors(
                 if (rt - rh > 0) test_batch(rt - rh);
                 __syncwarp();
 
-                // counts now; density + EOS + own-support count follow in k_density (rows are complete after this kernel).
-                // Row overflow only: the partial sums of the neighbors that did not fit travel in rho / nown.
+                // counts now; density + EOS + own-support count follow in k_density (rows are complete after this kernel)
                 if (tv) {
                     const int cnt = cn_w[lane];
                     ncount[tl] = cnt;
-                    if (cnt > kmax) {
-                        atomicMax(&err[ERR_NEIGHBOR_OVERFLOW], cnt);
-                        rho[tl] = ovf_rho[w][lane];
-                        nown[tl] = ovf_own[w][lane];
-                    }
+                    if (cnt > kmax) atomicMax(&err[ERR_NEIGHBOR_OVERFLOW], cnt);
                 }
             }
         }
@@ -470,6 +450,8 @@ constexpr int K1B_LPT = 16;
 
 template <bool EQM>
 __global__ void __launch_bounds__(256) k_density(const float4* __restrict__ posh, const float4* __restrict__ posm,
+                                                 const float4* __restrict__ posc, const uint32_t* __restrict__ keys,
+                                                 const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
                                                  const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
                                                  const sph_GridParams* __restrict__ g, int t0, int t1, int kmax, float Keos,
                                                  int32_t* __restrict__ nown, float* __restrict__ rho, float* __restrict__ press,
@@ -479,22 +461,44 @@ __global__ void __launch_bounds__(256) k_density(const float4* __restrict__ posh
     const int t = t0 + (blockIdx.x * blockDim.x + threadIdx.x) / K1B_LPT;
     const bool live = t < t1;
     float rsum = 0.f;
-    int own = 0, cnt = 0;
+    int own = 0;
     float4 pi = make_float4(0.f, 0.f, 0.f, 1.f);
     if (live) {
         pi = posh[t];
-        cnt = ncount[t];
+        const int cnt = ncount[t];
         const float hinv_i = 1.0f / pi.w, hi2 = __fmul_rn(pi.w, 2.0f);
-        const uint32_t* row = nlist + (size_t)t * kmax;
-        const int m = min(cnt, kmax);
-        for (int k = sub; k < m; k += K1B_LPT) {
-            const uint32_t j = row[k];
-            const float4 pj = posh[j];
+        auto add = [&](uint32_t j, const float4 pj) {
             const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
             const float r = __fsqrt_rn(dot3_rn(dx, dy, dz));
             own += r < hi2 ? 1 : 0;
             const float wsym = 0.5f * (w_fast(r, hinv_i) + w_fast(r, __fdividef(1.0f, pj.w)));
             rsum = EQM ? rsum + wsym : fmaf(posm[j].w, wsym, rsum);
+        };
+        if (cnt <= kmax) {
+            const uint32_t* row = nlist + (size_t)t * kmax;
+            for (int k = sub; k < cnt; k += K1B_LPT) {
+                const uint32_t j = row[k];
+                add(j, posh[j]);
+            }
+        } else {
+            // Row overflow (an error state the caller is told about): the list is truncated, but the density and the
+            // own-support count stay complete -- rescan the stencil with the same keep rule as k_cell_neighbors.
+            const int bits = g->bits, S = g->stencil, dim = 1 << bits;
+            const uint32_t ck = keys[t] >> (3 * (10 - bits));
+            const int cx = (int)compact10(ck), cy = (int)compact10(ck >> 1), cz = (int)compact10(ck >> 2);
+            const float c_t = posc[t].w;
+            for (int oz = -S; oz <= S; oz++)
+                for (int oy = -S; oy <= S; oy++)
+                    for (int ox = -S; ox <= S; ox++) {
+                        const int nx = cx + ox, ny = cy + oy, nz = cz + oz;
+                        if (nx < 0 || ny < 0 || nz < 0 || nx >= dim || ny >= dim || nz >= dim) continue;
+                        const uint32_t nk = expand10((uint32_t)nx) | (expand10((uint32_t)ny) << 1) | (expand10((uint32_t)nz) << 2);
+                        for (uint32_t j = cell_start[nk] + sub; j < cell_end[nk]; j += K1B_LPT) {
+                            const float4 cj = posc[j];
+                            const float dx = __fsub_rn(pi.x, cj.x), dy = __fsub_rn(pi.y, cj.y), dz = __fsub_rn(pi.z, cj.z);
+                            if (dot3_rn(dx, dy, dz) < fmaxf(c_t, cj.w) && j != (uint32_t)t) add(j, posh[j]);
+                        }
+                    }
         }
     }
 #pragma unroll
@@ -503,7 +507,6 @@ __global__ void __launch_bounds__(256) k_density(const float4* __restrict__ posh
         own += __shfl_xor_sync(FULL, own, o);
     }
     if (live && sub == 0) {
-        if (cnt > kmax) { rsum += rho[t]; own += nown[t]; }   // overflowed row: partial sums left by k_cell_neighbors
         // self term m_i * Kernel(0,h_i) (DensityFieldSystem.cs:45), exact: 1/(pi h^3)
         const float mi = posm[t].w;
         const float w0 = __fdiv_rn(1.0f, __fmul_rn(__fmul_rn(__fmul_rn(kPI, pi.w), pi.w), pi.w));
@@ -544,10 +547,12 @@ int sph_launch_neighbors_density(sphb200_ctx* c) {
     {
         int tpb = 256 / K1B_LPT;
         if (c->equal_mass)
-            k_density<true><<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->posm, c->nlist, c->ncount, c->grid_d, t0, t1,
+            k_density<true><<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->posm, c->posc, c->keys[1], c->cell_start,
+                                                                        c->cell_end, c->nlist, c->ncount, c->grid_d, t0, t1,
                                                                         c->p.max_neighbors, c->p.K, c->nown, c->rho, c->press, c->cvol);
         else
-            k_density<false><<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->posm, c->nlist, c->ncount, c->grid_d, t0, t1,
+            k_density<false><<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->posm, c->posc, c->keys[1], c->cell_start,
+                                                                         c->cell_end, c->nlist, c->ncount, c->grid_d, t0, t1,
                                                                          c->p.max_neighbors, c->p.K, c->nown, c->rho, c->press, c->cvol);
     }
     SPH_LAUNCH_CHECK(c);
