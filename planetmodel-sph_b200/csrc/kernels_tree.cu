@@ -200,7 +200,7 @@ __device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
 }
 
 __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __restrict__ posh, const float4* __restrict__ posm,
-                                                             const float4* __restrict__ packed, int t0, int t1, float G,
+                                                             const float4* __restrict__ packed, int n, int t0, int t1, float G,
                                                              float4* __restrict__ grav, int32_t* __restrict__ npart,
                                                              int32_t* __restrict__ napprox, int32_t* __restrict__ err) {
     __shared__ int2 stack[TW_WARPS][TW_STACK];
@@ -210,9 +210,13 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
     __shared__ int2 bkt[TW_WARPS][32];       // batch nodes: (first, count) of leaf buckets
     __shared__ int2 sbody[TW_WARPS][128];    // flattened bodies of the shared buckets: (slot, lane mask)
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int t = t0 + (blockIdx.x * TW_WARPS + wid) * 32 + lane;
-    const bool active = t < t1;
-    const float4 pi = posh[active ? t : (t1 - 1)];
+    // Warps are aligned to absolute multiples of 32 sorted slots and every slot < n walks, whether or not it lies in this
+    // rank's target range [t0,t1): the order in which a lane adds its contributions depends on its 31 companions, so a
+    // sharded run stays bit-identical to the single-GPU run only if the groups are the same.
+    const int t = (t0 & ~31) + (blockIdx.x * TW_WARPS + wid) * 32 + lane;
+    if (t - lane >= t1) return;   // whole group beyond the range
+    const bool active = t < n;
+    const float4 pi = posh[active ? t : (n - 1)];
     const float a2 = pi.w * pi.w, ainv = 1.0f / pi.w;
     WalkAcc w = {0.f, 0.f, 0.f, 0.f, 0, 0};
     const unsigned m0 = __ballot_sync(FULL, active);
@@ -398,7 +402,7 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
         }
         __syncwarp();
     }
-    if (active) {
+    if (t >= t0 && t < t1) {
         grav[t] = make_float4(G * w.gx, G * w.gy, G * w.gz, G * w.gp);
         npart[t] = w.np;
         napprox[t] = w.na;
@@ -430,7 +434,7 @@ int sph_launch_tree_walk(sphb200_ctx* c) {
     int t1 = (c->t1 < 0 || c->t1 > c->n) ? n : (int)c->t1;
     int nt = t1 - t0;
     if (n <= 0 || nt <= 0) return SPH_OK;
-    k_tree_walk<<<sph_div_up(nt, TW_WARPS * 32), TW_WARPS * 32, 0, c->stream>>>(c->posh[c->cur], c->posm, c->packed, t0, t1,
+    k_tree_walk<<<sph_div_up(t1 - (t0 & ~31), TW_WARPS * 32), TW_WARPS * 32, 0, c->stream>>>(c->posh[c->cur], c->posm, c->packed, n, t0, t1,
                                                                                c->p.G, c->grav, c->npart, c->napprox, c->err_d);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;
