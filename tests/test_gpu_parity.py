@@ -188,6 +188,55 @@ def test_tree_mac_decisions_exact_300k(orc):
     np.testing.assert_array_equal(got["numApprox"], napp)
 
 
+
+@pytest.mark.parametrize("leaf_max,aabb_mode", [(1, 0), (4, 1), (8, 0), (16, 0)])
+def test_tree_walk_variants_leaf_size_and_point_boxes(orc, leaf_max, aabb_mode):
+    """Bucket sizes other than the reference's 4 (the shared-body list takes several rounds above 4) and point-bounds MAC
+    boxes (b_sq = 0 single-particle nodes: threshold 0, a target sitting on the node centre must reject it)."""
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_sphere(6000, seed=11)
+    c["vel"] = np.random.default_rng(3).normal(0, 0.5, c["pos"].shape).astype(np.float32)
+    dt = 0.02
+    sim = run_gpu_step(c, dt, sphb200.GRAVITY_TREE, leaf_max=leaf_max, aabb_mode=aabb_mode)
+    ref = oracle_step(orc, c, dt, "tree", sim)
+    compare_step(orc, sim, ref, "tree")
+
+
+def test_dense_clump_cells_with_more_than_32_targets(orc):
+    """A clump far denser than the cells are sized for: cells hold > 32 particles (several target passes per cell, long
+    candidate queues); neighbor sets must still be exact."""
+    import sphb200
+    rng = np.random.default_rng(21)
+    n = 4000
+    pos = rng.uniform(-20, 20, (n, 3)).astype(np.float32)
+    pos[:300] = rng.normal(0, 0.15, (300, 3)).astype(np.float32)          # 300 particles inside a fraction of one cell
+    h = np.full(n, 1.0, np.float32)
+    c = dict(pos=pos, vel=np.zeros((n, 3), np.float32), mass=np.full(n, 0.01, np.float32), h=h)
+    sim = run_gpu_step(c, 0.01, sphb200.GRAVITY_TREE, max_neighbors=512)
+    ref = oracle_step(orc, c, 0.01, "tree", sim)
+    got = compare_step(orc, sim, ref, "tree")
+    assert got["count"].max() >= 299
+
+
+def test_step_is_deterministic_run_to_run():
+    """Same inputs, two handles: every output bit-identical (ballot-rank rows, fixed-order sums, no float atomics)."""
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_sphere(20000, seed=4)
+    outs = []
+    for _ in range(2):
+        sim = make_sim(20000)
+        sim.upload(c["pos"], c["vel"], c["mass"], c["h"])
+        for _ in range(3):
+            sim.step(0.02, sphb200.GRAVITY_TREE)
+        outs.append(sim.download_all())
+        off, nbr = sim.download_neighbors()
+        outs[-1]["nbr"] = nbr
+    for k in outs[0]:
+        np.testing.assert_array_equal(outs[0][k], outs[1][k], err_msg=k)
+
+
 def test_c2_multistep_drift_matches_oracle(orc):
     """P2: 20 steps of the C2 regime; trajectories are compared through aggregates and their drift."""
     import sphb200
