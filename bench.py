@@ -315,8 +315,8 @@ def measure_e2e(eng, c, impl, steps, barrier):
     outs = {f: torch.empty(n * w, dtype=torch.float32).pin_memory() for f, w in
             ((sphb200.FIELD_TRANSLATION, 3), (sphb200.FIELD_VELOCITY, 3), (sphb200.FIELD_DENSITY, 1), (sphb200.FIELD_PRESSURE, 1),
              (sphb200.FIELD_PRESSURE_GRAD, 3), (sphb200.FIELD_GRAVITY, 6))}
-    h2d = n * (12 + 12 + 4 + 4 + 4)
-    d2h = n * (12 + 12 + 8 + 4 + 4 + 12 + 24)
+    h2d = n * (12 + 12 + 4 + 28)                  # Translation, PhysicsVelocity.linear, ParticleMass, ParticleSmoothing records
+    d2h = n * (12 + 12 + 4 + 4 + 12 + 24 + 28)    # ... + density, pressure, pressure gradient, GravityField, ParticleSmoothing
 
     def one():
         eng.upload(host["pos"].numpy().reshape(n, 3), host["vel"].numpy().reshape(n, 3), host["mass"].numpy(), sm)
@@ -337,7 +337,7 @@ def measure_e2e(eng, c, impl, steps, barrier):
     dt = time.perf_counter() - t0
     return {"value": n * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d * eng.world, "d2h_bytes_per_step": d2h * eng.world,
             "steps": steps, "ms_per_step": 1e3 * dt / steps,
-            "path": "sphb200_upload + sphb200_step + sphb200_download x7 per rank (host component arrays, pinned staging)"}
+            "path": "sphb200_upload + sphb200_step + sphb200_download x7 per rank (pinned host component arrays with their natural strides: one DMA each)"}
 
 
 _REAL_STDOUT = None

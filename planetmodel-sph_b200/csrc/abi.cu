@@ -115,7 +115,7 @@ int sphb200_create(const sph_Params* params, int64_t capacity, int device, sph_h
              dalloc(&c->orig[k], cap) == cudaSuccess && dalloc(&c->keys[k], cap) == cudaSuccess && dalloc(&c->idx[k], cap) == cudaSuccess;
     }
     c->cub_bytes = sph_sort_temp_bytes(capacity);
-    c->stage_bytes = std::max<size_t>(cap * 9 * 4, (cap + 1) * 8);
+    c->stage_bytes = std::max<size_t>(cap * 14 * 4, (cap + 1) * 8);   // upload: pos3 vel3 mass1 + raw smoothing records (7)
     ok = ok && dalloc(&c->posm, cap) == cudaSuccess && dalloc(&c->posc, cap) == cudaSuccess && dalloc(&c->chunk_counter, 1) == cudaSuccess && cudaMalloc(&c->cub_tmp, std::max<size_t>(c->cub_bytes, 16)) == cudaSuccess &&
          dalloc(&c->cell_start, c->ncell_max) == cudaSuccess && dalloc(&c->cell_end, c->ncell_max) == cudaSuccess && dalloc(&c->cell_hmax, c->ncell_max) == cudaSuccess &&
          dalloc(&c->nlist, cap * (size_t)p.max_neighbors) == cudaSuccess && dalloc(&c->ncount, cap) == cudaSuccess &&
@@ -257,8 +257,15 @@ int sphb200_upload(sph_handle c, int64_t n, const void* pos, int pos_stride, con
     SPH_CK(c, put(0, pp, pos_stride, 3));
     SPH_CK(c, put(3 * (size_t)n, vp, vel_stride, 3));
     SPH_CK(c, put(6 * (size_t)n, mp, mass_stride, 1));
-    SPH_CK(c, put(7 * (size_t)n, sp, smoothing_stride, 1));
-    if (has_nown) SPH_CK(c, put(8 * (size_t)n, sp + 24, smoothing_stride, 1));
+    int nown_mode = has_nown ? 1 : 0;
+    if (smoothing_stride == (int)sizeof(sph_ParticleSmoothing)) {
+        // the component array as it is: one DMA, h and the neighbor count are picked out on the device
+        SPH_CK(c, cudaMemcpyAsync(sd + 7 * (size_t)n, sp, (size_t)n * sizeof(sph_ParticleSmoothing), cudaMemcpyHostToDevice, c->stream));
+        nown_mode = 2;
+    } else {
+        SPH_CK(c, put(7 * (size_t)n, sp, smoothing_stride, 1));
+        if (has_nown) SPH_CK(c, put(8 * (size_t)n, sp + 24, smoothing_stride, 1));
+    }
     float m0;
     memcpy(&m0, mp, 4);
     c->equal_mass = true;
@@ -268,7 +275,7 @@ int sphb200_upload(sph_handle c, int64_t n, const void* pos, int pos_stride, con
         memcpy(&mi, mp + (size_t)i * mass_stride, 4);
         c->equal_mass = (mi == m0);
     }
-    int rc = sph_launch_pack_upload(c, n, has_nown);
+    int rc = sph_launch_pack_upload(c, n, nown_mode);
     if (rc) return rc;
     SPH_CK(c, cudaStreamSynchronize(c->stream));
     return SPH_OK;
@@ -460,10 +467,13 @@ int sphb200_download(sph_handle c, int field, void* dst, int stride) {
     ARG_CHECK(c, dst || c->n == 0, "null dst");
     if (c->n == 0) return SPH_OK;
     int eb = 0;
-    int rc = sph_launch_unpack_field(c, field, &eb);
+    if (field < 0 || field >= SPH_FIELD_COUNT_) { c->err = "unknown field"; return SPH_ERR_INVALID_ARG; }
+    // a sph_ParticleSmoothing array with its natural stride is assembled on the device and written by one DMA
+    const bool sm_record = field == SPH_FIELD_SMOOTHING && stride == (int)sizeof(sph_ParticleSmoothing);
+    int rc = sph_launch_unpack_field(c, sm_record ? (int)SPH_FIELD_COUNT_ : field, &eb);
     if (rc) { if (rc == SPH_ERR_INVALID_ARG) c->err = "unknown field"; return rc; }
     int64_t n = c->n;
-    const bool direct = stride == eb && field != SPH_FIELD_SMOOTHING && field != SPH_FIELD_GRAVITY;
+    const bool direct = stride == eb && (field != SPH_FIELD_SMOOTHING || sm_record);
     SPH_CK(c, cudaMemcpyAsync(direct ? dst : c->stage_h, c->stage_d, (size_t)n * eb, cudaMemcpyDeviceToHost, c->stream));
     rc = check_errflags(c);  // also synchronises
     if (direct) return rc;   // natural stride: the DMA wrote the caller's array

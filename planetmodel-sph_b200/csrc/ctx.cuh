@@ -173,7 +173,7 @@ int sph_launch_gravity_allpairs(sphb200_ctx* c);
 int sph_launch_tree_build(sphb200_ctx* c, float dt, cudaStream_t stream);
 int sph_launch_tree_walk(sphb200_ctx* c);
 int sph_launch_diagnostics(sphb200_ctx* c, double* out12);
-int sph_launch_pack_upload(sphb200_ctx* c, int64_t n, bool has_nown);
+int sph_launch_pack_upload(sphb200_ctx* c, int64_t n, int has_nown);
 int sph_launch_unpack_field(sphb200_ctx* c, int field, int* elem_bytes);
 int sph_launch_neighbor_rows_sorted(sphb200_ctx* c, int32_t* rows_d);
 int sph_launch_interactions(sphb200_ctx* c, int64_t total, const int64_t* offsets_d, const int32_t* nbr_d, sph_ParticleInteraction* out_d);

@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(256) k_integrate(float4* __restrict__ posh, fl
 // Upload / download packing
 // ------------------------------------------------------------------------------------------------------------
 // staging (device): pos[3n] vel[3n] mass[n] h[n] nown[n]
+// has_nown: 0 = h only (st[7n..8n)), 1 = h[n] then nown[n], 2 = raw sph_ParticleSmoothing records (7 words each) at st[7n..14n)
 __global__ void __launch_bounds__(256) k_pack_upload(const float* __restrict__ st, int n, int has_nown, float4* __restrict__ posh,
                                                      float4* __restrict__ velm, uint32_t* __restrict__ orig,
                                                      int32_t* __restrict__ nown) {
@@ -185,10 +186,11 @@ __global__ void __launch_bounds__(256) k_pack_upload(const float* __restrict__ s
     const float* mass = st + 6 * (size_t)n;
     const float* h = st + 7 * (size_t)n;
     const int32_t* no = (const int32_t*)(st + 8 * (size_t)n);
-    posh[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], h[i]);
+    const float hi = has_nown == 2 ? h[7 * (size_t)i] : h[i];
+    posh[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], hi);
     velm[i] = make_float4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], mass[i]);
     orig[i] = (uint32_t)i;
-    nown[i] = has_nown ? no[i] : 0;
+    nown[i] = has_nown == 2 ? ((const int32_t*)h)[7 * (size_t)i + 6] : has_nown ? no[i] : 0;
 }
 
 __global__ void __launch_bounds__(256) k_unpack_field(int field, int n, const uint32_t* __restrict__ orig,
@@ -206,6 +208,13 @@ __global__ void __launch_bounds__(256) k_unpack_field(int field, int n, const ui
         case SPH_FIELD_VELOCITY: { float4 v = velm[i]; out[3 * b] = v.x; out[3 * b + 1] = v.y; out[3 * b + 2] = v.z; break; }
         case SPH_FIELD_MASS: out[b] = velm[i].w; break;
         case SPH_FIELD_SMOOTHING: out[2 * b] = posh[i].w; ((int32_t*)out)[2 * b + 1] = nown[i]; break;
+        case SPH_FIELD_COUNT_: {   // the full sph_ParticleSmoothing record (ParticleSmoothing.cs:16-31), 7 words
+            const float h = posh[i].w;
+            float* o = out + 7 * b;
+            o[0] = h; o[1] = 2.0f * h; o[2] = 0.f; o[3] = 0.f; o[4] = 0.f; o[5] = 2.0f * h;
+            ((int32_t*)o)[6] = nown[i];
+            break;
+        }
         case SPH_FIELD_DENSITY: out[b] = rho[i]; break;
         case SPH_FIELD_PRESSURE: out[b] = press[i]; break;
         case SPH_FIELD_PRESSURE_GRAD: { float4 q = gradp[i]; out[3 * b] = q.x; out[3 * b + 1] = q.y; out[3 * b + 2] = q.z; break; }
@@ -357,16 +366,16 @@ int sph_launch_integrate(sphb200_ctx* c, float dt) {
     return SPH_OK;
 }
 
-int sph_launch_pack_upload(sphb200_ctx* c, int64_t n, bool has_nown) {
-    k_pack_upload<<<sph_div_up(n, 256), 256, 0, c->stream>>>((const float*)c->stage_d, (int)n, has_nown ? 1 : 0, c->posh[0],
+int sph_launch_pack_upload(sphb200_ctx* c, int64_t n, int has_nown) {
+    k_pack_upload<<<sph_div_up(n, 256), 256, 0, c->stream>>>((const float*)c->stage_d, (int)n, has_nown, c->posh[0],
                                                             c->velm[0], c->orig[0], c->nown);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;
 }
 
 int sph_launch_unpack_field(sphb200_ctx* c, int field, int* elem_bytes) {
-    static const int words[SPH_FIELD_COUNT_] = {3, 3, 1, 2, 1, 1, 3, 6, 1};
-    if (field < 0 || field >= SPH_FIELD_COUNT_) return SPH_ERR_INVALID_ARG;
+    static const int words[SPH_FIELD_COUNT_ + 1] = {3, 3, 1, 2, 1, 1, 3, 6, 1, 7};   // [SPH_FIELD_COUNT_] = full smoothing record
+    if (field < 0 || field > SPH_FIELD_COUNT_) return SPH_ERR_INVALID_ARG;
     *elem_bytes = words[field] * 4;
     int n = (int)c->n;
     k_unpack_field<<<sph_div_up(n, 256), 256, 0, c->stream>>>(field, n, c->orig[c->cur], c->posh[c->cur], c->velm[c->cur], c->rho,
