@@ -240,26 +240,27 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_neighbors_density(
 constexpr int K3_WARPS = 8;
 constexpr int K3_QCAP = 64;   // candidate-cell queue per warp
 constexpr int K3_RING = 64;   // compacted-candidate ring per warp
+constexpr int K3_MAXT = 32;   // targets per pass (cells are sized for ~11); consecutive sorted slots: a compact sub-box of the cell
 
 template <bool EQM, int MINB>
 __global__ void __launch_bounds__(K3_WARPS * 32, MINB) k_cell_neighbors(
     const float4* __restrict__ posc, const float4* __restrict__ posh, const float4* __restrict__ posm,
-    const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, const uint32_t* __restrict__ cell_hmax,
-    const sph_GridParams* __restrict__ g, int t0, int t1, int kmax, float Keos, uint32_t* __restrict__ nlist,
-    int32_t* __restrict__ ncount, int32_t* __restrict__ nown, float* __restrict__ rho, float* __restrict__ press,
+    const uint32_t* __restrict__ keys, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
+    const uint32_t* __restrict__ cell_hmax, const sph_GridParams* __restrict__ g, int t0, int t1, int kmax, float Keos,
+    uint32_t* __restrict__ nlist, int32_t* __restrict__ ncount, int32_t* __restrict__ nown, float* __restrict__ rho, float* __restrict__ press,
     float* __restrict__ cvol, int32_t* __restrict__ err, unsigned int* __restrict__ chunk_counter) {
-    __shared__ float4 tgt[K3_WARPS][32];
+    __shared__ float4 tgt[K3_WARPS][K3_MAXT];
     __shared__ uint32_t qstart[K3_WARPS][K3_QCAP];
     __shared__ uint32_t qpre[K3_WARPS][K3_QCAP + 1];
     __shared__ float4 ring4[K3_WARPS][K3_RING];
     __shared__ int ringj[K3_WARPS][K3_RING];
-    __shared__ int cnts[K3_WARPS][32];
+    __shared__ int cnts[K3_WARPS][K3_MAXT];
     if (!(g->hmax < kHugeH)) return;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const unsigned lt = (1u << lane) - 1u;
     const int bits = g->bits, S = g->stencil, dim = 1 << bits;
     const int nst = 2 * S + 1, nst2 = nst * nst, nst3 = nst2 * nst;
-    const int ncells = 1 << (3 * bits), nchunks = (ncells + 31) >> 5;
+    const int inv1 = ((1 << 20) + nst - 1) / nst, inv2 = ((1 << 20) + nst2 - 1) / nst2;
     const float fs = g->fine_scale, cw = (float)(1 << (10 - bits));
     const float g0[3] = {g->min[0], g->min[1], g->min[2]};
     float4* tg = tgt[w];
@@ -269,37 +270,50 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB) k_cell_neighbors(
     int* rbj = ringj[w];
     int* cn_w = cnts[w];
 
+    // Scheduling: the work items are the passes -- runs of <= 32 consecutive targets of one cell -- and a pass is owned by
+    // the 32-slot block of the sorted array that holds its first target.  Warps pull 32-slot blocks from a counter and find
+    // the pass heads in them from the sorted keys, so the unit of work is ~32 targets whatever the cell occupancy (cells
+    // are sized by the typical h: in a region with much smaller h they hold ~100 particles), and empty cells cost nothing.
+    const int shift = 3 * (10 - bits);
+    const int ngrab = (t1 - t0 + 31) >> 5;
     while (true) {
-        int chunk = 0;
-        if (lane == 0) chunk = (int)atomicAdd(chunk_counter, 1u);
-        chunk = __shfl_sync(FULL, chunk, 0);
-        if (chunk >= nchunks) break;
-        const int cidx = chunk * 32 + lane;
-        int cs = 0, ce = 0;
-        if (cidx < ncells) { cs = (int)cell_start[cidx]; ce = (int)cell_end[cidx]; }
-        cs = max(cs, t0); ce = min(ce, t1);
-        unsigned nonempty = __ballot_sync(FULL, ce > cs);
-        while (nonempty) {
-            const int src = __ffs(nonempty) - 1;
-            nonempty &= nonempty - 1;
-            const int s = __shfl_sync(FULL, cs, src), e = __shfl_sync(FULL, ce, src);
-            const uint32_t ck = (uint32_t)(chunk * 32 + src);
+        int grab = 0;
+        if (lane == 0) grab = (int)atomicAdd(chunk_counter, 1u);
+        grab = __shfl_sync(FULL, grab, 0);
+        if (grab >= ngrab) break;
+        const int slot = t0 + grab * 32 + lane;
+        bool head = false;
+        int my_e = 0;
+        uint32_t my_ck = 0u;
+        if (slot < t1) {
+            my_ck = keys[slot] >> shift;
+            const int cs = max((int)cell_start[my_ck], t0);
+            my_e = min((int)cell_end[my_ck], t1);
+            head = ((slot - cs) % K3_MAXT) == 0;
+        }
+        unsigned heads = __ballot_sync(FULL, head);
+        while (heads) {
+            const int src = __ffs(heads) - 1;
+            heads &= heads - 1u;
+            const int p0 = t0 + grab * 32 + src, e = __shfl_sync(FULL, my_e, src);
+            const uint32_t ck = __shfl_sync(FULL, my_ck, src);
             const int cx = (int)compact10(ck), cy = (int)compact10(ck >> 1), cz = (int)compact10(ck >> 2);
-
-            for (int p0 = s; p0 < e; p0 += 32) {
-                const int nt = min(32, e - p0);
-                const bool tv = lane < nt;
-                const int tl = p0 + (tv ? lane : 0);
-                const float4 T = posc[tl];
-                const float hi = posh[tl].w;
+            {
+                const int nt = min(K3_MAXT, e - p0);   // targets of this pass (a cell far denser than its size: several passes)
                 __syncwarp();
-                tg[lane] = T;
-                cn_w[lane] = 0;
                 int rh = 0, rt = 0;   // candidate ring head / tail (monotone counters)
-                // box of the targets' positions, their largest keep threshold and largest h
-                float wlo[3] = {tv ? T.x : INFINITY, tv ? T.y : INFINITY, tv ? T.z : INFINITY};
-                float whi[3] = {tv ? T.x : -INFINITY, tv ? T.y : -INFINITY, tv ? T.z : -INFINITY};
-                float cmax = tv ? T.w : 0.f, hmax_t = tv ? hi : 0.f;
+                // stage the targets; box of their positions, their largest keep threshold and largest h
+                float wlo[3] = {INFINITY, INFINITY, INFINITY}, whi[3] = {-INFINITY, -INFINITY, -INFINITY};
+                float cmax = 0.f, hmax_t = 0.f;
+                for (int i = lane; i < nt; i += 32) {
+                    const float4 T = posc[p0 + i];
+                    tg[i] = T;
+                    cn_w[i] = 0;
+                    wlo[0] = fminf(wlo[0], T.x); wlo[1] = fminf(wlo[1], T.y); wlo[2] = fminf(wlo[2], T.z);
+                    whi[0] = fmaxf(whi[0], T.x); whi[1] = fmaxf(whi[1], T.y); whi[2] = fmaxf(whi[2], T.z);
+                    cmax = fmaxf(cmax, T.w);
+                    hmax_t = fmaxf(hmax_t, posh[p0 + i].w);
+                }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
@@ -389,7 +403,8 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB) k_cell_neighbors(
                 }
                 for (int base = 0; base < nst3; base += 32) {
                     const int k = base + lane;
-                    const int oz = k / nst2, rem = k - oz * nst2, oy = rem / nst, ox = rem - oy * nst;
+                    // k < 729, divisors <= 81: (k * ceil(2^20/d)) >> 20 == k / d
+                    const int oz = (k * inv2) >> 20, rem = k - oz * nst2, oy = (rem * inv1) >> 20, ox = rem - oy * nst;
                     const int nx = cx + ox - S, ny = cy + oy - S, nz = cz + oz - S;
                     bool ok = k < nst3 && nx >= 0 && ny >= 0 && nz >= 0 && nx < dim && ny < dim && nz < dim;
                     uint32_t a = 0, b = 0;
@@ -433,9 +448,9 @@ __global__ void __launch_bounds__(K3_WARPS * 32, MINB) k_cell_neighbors(
                 __syncwarp();
 
                 // counts now; density + EOS + own-support count follow in k_density (rows are complete after this kernel)
-                if (tv) {
-                    const int cnt = cn_w[lane];
-                    ncount[tl] = cnt;
+                for (int i = lane; i < nt; i += 32) {
+                    const int cnt = cn_w[i];
+                    ncount[p0 + i] = cnt;
                     if (cnt > kmax) atomicMax(&err[ERR_NEIGHBOR_OVERFLOW], cnt);
                 }
             }
@@ -539,7 +554,7 @@ int sph_launch_neighbors_density(sphb200_ctx* c) {
     SPH_CK(c, cudaMemsetAsync(c->chunk_counter, 0, sizeof(unsigned int), c->stream));
     static int minb = getenv("SPHB200_K3_MINB") ? atoi(getenv("SPHB200_K3_MINB")) : 3;   // tuning knob
 #define K3_LAUNCH(E) k3_launch<E>(minb, c->sm_count, c->stream,                                        \
-        c->posc, c->posh[c->cur], c->posm, c->cell_start, c->cell_end, c->cell_hmax, c->grid_d, t0, t1, c->p.max_neighbors, c->p.K, \
+        c->posc, c->posh[c->cur], c->posm, c->keys[1], c->cell_start, c->cell_end, c->cell_hmax, c->grid_d, t0, t1, c->p.max_neighbors, c->p.K, \
         c->nlist, c->ncount, c->nown, c->rho, c->press, c->cvol, c->err_d, c->chunk_counter)
     if (c->equal_mass) K3_LAUNCH(true); else K3_LAUNCH(false);
 #undef K3_LAUNCH
