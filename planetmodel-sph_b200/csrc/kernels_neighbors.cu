@@ -491,7 +491,14 @@ __global__ void __launch_bounds__(256) k_density(const float4* __restrict__ posh
         };
         if (cnt <= kmax) {
             const uint32_t* row = nlist + (size_t)t * kmax;
-            for (int k = sub; k < cnt; k += K1B_LPT) {
+            int k = sub;
+            for (; k + K1B_LPT < cnt; k += 2 * K1B_LPT) {   // two gathers in flight
+                const uint32_t j0 = row[k], j1 = row[k + K1B_LPT];
+                const float4 q0 = posh[j0], q1 = posh[j1];
+                add(j0, q0);
+                add(j1, q1);
+            }
+            if (k < cnt) {
                 const uint32_t j = row[k];
                 add(j, posh[j]);
             }
