@@ -15,17 +15,16 @@
 //     the capped self term is removed in k_gravity_reduce;
 //   * when every particle has the same mass (the reference spawner, ParticleAuthoring.cs:208) the mass multiply
 //     leaves the loop (EQM variant) and is applied once in the reduce.
-// Issue slots per pair (SASS): 13.4 far/equal-mass ... 15.4 near/general; measured rates in profiles/README.md.
+// Issue slots per pair (SASS): 7.7 far/equal-mass (packed FP32, below); measured rates in profiles/README.md.
 // Summation: per-tile fp32 partials (256 sources) added into a running sum, then a fixed-order reduction over the
 // source splits -- deterministic, and ~sqrt(256) times tighter than one 10^6-term fp32 chain.
 #include "ctx.cuh"
 #include <math.h>
-#include <stdlib.h>
 
 namespace {
 
 constexpr int AP_THREADS = 256;
-constexpr int AP_TPT = 4;     // targets per thread (one LDS.128 feeds 4 pair evaluations)
+constexpr int AP_TPT = 4;     // targets per thread (2, 3, 4 and 6 measure within 3 %: profiles/r01_tune_allpairs.txt)
 constexpr int AP_TILE = 256;  // sources per shared-memory tile (inner fp32 partial sums: 2 interleaved chains of 128)
 constexpr int AP_UNROLL = 4;  // source pairs per unrolled inner-loop body
 constexpr unsigned FULL = 0xffffffffu;
@@ -245,8 +244,7 @@ int sph_launch_gravity_allpairs(sphb200_ctx* c) {
     int nt = t1 - t0;
     if (nt <= 0) return SPH_OK;
     int n = (int)c->n;
-    static int tpt = getenv("SPHB200_AP_TPT") ? atoi(getenv("SPHB200_AP_TPT")) : AP_TPT;   // tuning knob
-    int tblocks = sph_div_up(nt, AP_THREADS * tpt);
+    int tblocks = sph_div_up(nt, AP_THREADS * AP_TPT);
     // enough blocks for >= ~12 waves of 3 resident CTAs/SM, bounded by the partial-sum buffer (cap * gpart_splits float4)
     int want = c->sm_count * 3 * 12;
     int splits = sph_div_up(want, tblocks);
@@ -262,11 +260,10 @@ int sph_launch_gravity_allpairs(sphb200_ctx* c) {
     k_tile_boxes<<<sph_div_up(n, AP_TILE), AP_TILE, 0, c->stream>>>(c->posm, n, c->tbox);
     SPH_LAUNCH_CHECK(c);
     dim3 grid(tblocks, splits);
-#define AP_LAUNCH(T, E) k_gravity_allpairs<T, E><<<grid, AP_THREADS, 0, c->stream>>>(c->posm, n, per, c->tbox, c->posh[c->cur], t0, t1, c->gpart)
-    if (tpt == 2) { if (c->equal_mass) AP_LAUNCH(2, true); else AP_LAUNCH(2, false); }
-    else if (tpt == 3) { if (c->equal_mass) AP_LAUNCH(3, true); else AP_LAUNCH(3, false); }
-    else { if (c->equal_mass) AP_LAUNCH(4, true); else AP_LAUNCH(4, false); }
-#undef AP_LAUNCH
+    if (c->equal_mass)
+        k_gravity_allpairs<AP_TPT, true><<<grid, AP_THREADS, 0, c->stream>>>(c->posm, n, per, c->tbox, c->posh[c->cur], t0, t1, c->gpart);
+    else
+        k_gravity_allpairs<AP_TPT, false><<<grid, AP_THREADS, 0, c->stream>>>(c->posm, n, per, c->tbox, c->posh[c->cur], t0, t1, c->gpart);
     SPH_LAUNCH_CHECK(c);
     k_gravity_reduce<<<sph_div_up(nt, 256), 256, 0, c->stream>>>(c->gpart, splits, c->posh[c->cur], c->posm, t0, t1, c->p.G,
                                                                 c->equal_mass ? c->common_mass : 1.0f, c->equal_mass ? 1 : 0, c->grav,

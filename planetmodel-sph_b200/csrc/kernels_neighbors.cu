@@ -16,7 +16,6 @@
 // Numerics contract: membership exact (non-contracted __f*_rn ops, IEEE sqrt), values fast (<= 1e-5 relative).
 #include "ctx.cuh"
 #include <math.h>
-#include <stdlib.h>
 
 namespace {
 
@@ -238,12 +237,13 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_neighbors_density(
 // the finished rows, 32 lanes per target.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int K3_WARPS = 8;
+constexpr int K3_MINB = 3;    // resident blocks per SM (80 registers; 2 and 4 measured slower)
 constexpr int K3_QCAP = 64;   // candidate-cell queue per warp
 constexpr int K3_RING = 64;   // compacted-candidate ring per warp
 constexpr int K3_MAXT = 32;   // targets per pass (cells are sized for ~11); consecutive sorted slots: a compact sub-box of the cell
 
-template <bool EQM, int MINB>
-__global__ void __launch_bounds__(K3_WARPS * 32, MINB) k_cell_neighbors(
+template <bool EQM>
+__global__ void __launch_bounds__(K3_WARPS * 32, K3_MINB) k_cell_neighbors(
     const float4* __restrict__ posc, const float4* __restrict__ posh, const float4* __restrict__ posm,
     const uint32_t* __restrict__ keys, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
     const uint32_t* __restrict__ cell_hmax, const sph_GridParams* __restrict__ g, int t0, int t1, int kmax, float Keos,
@@ -542,13 +542,6 @@ __global__ void __launch_bounds__(256) k_density(const float4* __restrict__ posh
     }
 }
 
-template <bool EQM, typename... Args>
-void k3_launch(int minb, int sms, cudaStream_t st, Args... a) {
-    if (minb == 2) k_cell_neighbors<EQM, 2><<<sms * 2, K3_WARPS * 32, 0, st>>>(a...);
-    else if (minb == 3) k_cell_neighbors<EQM, 3><<<sms * 3, K3_WARPS * 32, 0, st>>>(a...);
-    else k_cell_neighbors<EQM, 4><<<sms * 4, K3_WARPS * 32, 0, st>>>(a...);
-}
-
 }  // namespace
 
 int sph_launch_neighbors_density(sphb200_ctx* c) {
@@ -559,8 +552,7 @@ int sph_launch_neighbors_density(sphb200_ctx* c) {
     if (nt <= 0) return SPH_OK;
     // cell-centric kernel (h_max < 1e5): persistent warps pull 32-cell chunks from a counter
     SPH_CK(c, cudaMemsetAsync(c->chunk_counter, 0, sizeof(unsigned int), c->stream));
-    static int minb = getenv("SPHB200_K3_MINB") ? atoi(getenv("SPHB200_K3_MINB")) : 3;   // tuning knob
-#define K3_LAUNCH(E) k3_launch<E>(minb, c->sm_count, c->stream,                                        \
+#define K3_LAUNCH(E) k_cell_neighbors<E><<<c->sm_count * K3_MINB, K3_WARPS * 32, 0, c->stream>>>(                                        \
         c->posc, c->posh[c->cur], c->posm, c->keys[1], c->cell_start, c->cell_end, c->cell_hmax, c->grid_d, t0, t1, c->p.max_neighbors, c->p.K, \
         c->nlist, c->ncount, c->nown, c->rho, c->press, c->cvol, c->err_d, c->chunk_counter)
     if (c->equal_mass) K3_LAUNCH(true); else K3_LAUNCH(false);

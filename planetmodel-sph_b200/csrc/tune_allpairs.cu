@@ -378,6 +378,134 @@ void run2(const char* name, const float4* src, const float4* posh, float4* part,
            20.0 * (double)n * n / (best * 1e-3) / 1e12, fa.numRegs, nb, tblocks, sp, e == cudaSuccess ? "" : cudaGetErrorString(e));
 }
 
+
+// ---- expansion variant (far tiles only): coordinates relative to the target block's centre c, sources carry
+// s_j = |x_j - c|^2 (the mass slot is free for equal masses): r^2 = s_j + (s_i - 2 x_i'.x_j') = 3 FFMA2 + 1 FADD2 and the
+// acceleration is accumulated as sum(g x_j') - x_i' sum(g): 11 FMA-pipe lane-ops per pair instead of 12.
+template <int TPT, int UNROLL>
+__global__ void __launch_bounds__(256, 1) k_ap2x(const float4* __restrict__ src, int n_src, int src_per_split,
+                                                 const float4* __restrict__ posh, int nt, float4* __restrict__ part) {
+    constexpr int TILE = 256, THREADS = 256;
+    __shared__ __align__(16) float tile[2][TILE * 4];
+    __shared__ float cbox[6][THREADS / 32];
+    const int tid = threadIdx.x;
+    const int tb = blockIdx.x * (THREADS * TPT);
+    float px[TPT], py[TPT], pz[TPT];
+    float lo[3] = {1e30f, 1e30f, 1e30f}, hi[3] = {-1e30f, -1e30f, -1e30f};
+#pragma unroll
+    for (int k = 0; k < TPT; k++) {
+        int t = tb + k * THREADS + tid;
+        float4 p = posh[min(t, nt - 1)];
+        px[k] = p.x; py[k] = p.y; pz[k] = p.z;
+        lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+        hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(0xffffffffu, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(0xffffffffu, hi[k], o));
+        }
+    if ((tid & 31) == 0) for (int k = 0; k < 3; k++) { cbox[k][tid >> 5] = lo[k]; cbox[3 + k][tid >> 5] = hi[k]; }
+    __syncthreads();
+    float c[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float a = cbox[k][0], b = cbox[3 + k][0];
+        for (int j = 1; j < THREADS / 32; j++) { a = fminf(a, cbox[k][j]); b = fmaxf(b, cbox[3 + k][j]); }
+        c[k] = 0.5f * (a + b);
+    }
+    u64 mx[TPT], my[TPT], mz[TPT], si[TPT];   // -2 x_i' (packed twice), s_i
+    float qx[TPT], qy[TPT], qz[TPT];
+    float AX[TPT], AY[TPT], AZ[TPT], PH[TPT];
+#pragma unroll
+    for (int k = 0; k < TPT; k++) {
+        qx[k] = px[k] - c[0]; qy[k] = py[k] - c[1]; qz[k] = pz[k] - c[2];
+        mx[k] = pk(-2.f * qx[k], -2.f * qx[k]); my[k] = pk(-2.f * qy[k], -2.f * qy[k]); mz[k] = pk(-2.f * qz[k], -2.f * qz[k]);
+        float s = qx[k] * qx[k] + qy[k] * qy[k] + qz[k] * qz[k];
+        si[k] = pk(s, s);
+        AX[k] = AY[k] = AZ[k] = PH[k] = 0.f;
+    }
+    const int s0 = blockIdx.y * src_per_split;
+    const int s1 = min(s0 + src_per_split, n_src);
+    const int ntiles = (s1 - s0 + TILE - 1) / TILE;
+    const float4 pad = make_float4(1.0e15f, 1.0e15f, 1.0e15f, 0.f);
+    float4 nxt = (s0 + tid < s1) ? src[s0 + tid] : pad;
+    const int so = (tid >> 1) * 8 + (tid & 1);
+    for (int it = 0; it < ntiles; it++) {
+        float* buf = tile[it & 1];
+        {
+            float x = nxt.x - c[0], y = nxt.y - c[1], z = nxt.z - c[2];
+            buf[so] = x; buf[so + 2] = y; buf[so + 4] = z; buf[so + 6] = x * x + y * y + z * z;
+        }
+        __syncthreads();
+        { int i = s0 + (it + 1) * TILE + tid; nxt = i < s1 ? src[i] : pad; }
+        u64 ax[TPT], ay[TPT], az[TPT], sg[TPT], ph[TPT];
+#pragma unroll
+        for (int k = 0; k < TPT; k++) ax[k] = ay[k] = az[k] = sg[k] = ph[k] = pk(0.f, 0.f);
+        const ulonglong2* tp = reinterpret_cast<const ulonglong2*>(buf);
+#pragma unroll 1
+        for (int j = 0; j < TILE / 2; j += UNROLL, tp += 2 * UNROLL) {
+#pragma unroll
+            for (int u = 0; u < UNROLL; u++) {
+                const ulonglong2 A = tp[2 * u], B = tp[2 * u + 1];   // A = (x0,x1),(y0,y1)  B = (z0,z1),(s0,s1)
+#pragma unroll
+                for (int k = 0; k < TPT; k++) {
+                    u64 r2 = add2(fma2(mx[k], A.x, fma2(my[k], A.y, fma2(mz[k], B.x, B.y))), si[k]);
+                    float r2a, r2b;
+                    upk(r2, r2a, r2b);
+                    u64 rinv = pk(rsqrt_approx(r2a), rsqrt_approx(r2b));
+                    u64 g = mul2(mul2(rinv, rinv), rinv);
+                    ph[k] = add2(ph[k], rinv);
+                    sg[k] = add2(sg[k], g);
+                    ax[k] = fma2(A.x, g, ax[k]);
+                    ay[k] = fma2(A.y, g, ay[k]);
+                    az[k] = fma2(B.x, g, az[k]);
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < TPT; k++) {   // d = x_i - x_j = x_i' - x_j': sum(g d) = x_i' sum(g) - sum(g x_j')
+            float a, b, ga, gb;
+            upk(sg[k], ga, gb); const float gs = ga + gb;
+            upk(ax[k], a, b); AX[k] += fmaf(qx[k], gs, -(a + b));
+            upk(ay[k], a, b); AY[k] += fmaf(qy[k], gs, -(a + b));
+            upk(az[k], a, b); AZ[k] += fmaf(qz[k], gs, -(a + b));
+            upk(ph[k], a, b); PH[k] += a + b;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < TPT; k++) {
+        int t = tb + k * THREADS + tid;
+        if (t < nt) part[(size_t)blockIdx.y * nt + t] = make_float4(AX[k], AY[k], AZ[k], PH[k]);
+    }
+}
+
+template <int TPT, int UNROLL>
+void run2x(const char* name, const float4* src, const float4* posh, float4* part, int n, int splits) {
+    int tblocks = (n + 256 * TPT - 1) / (256 * TPT);
+    int per = ((n + splits - 1) / splits + 511) / 512 * 512;
+    int sp = (n + per - 1) / per;
+    dim3 grid(tblocks, sp);
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        cudaEventRecord(e0);
+        k_ap2x<TPT, UNROLL><<<grid, 256>>>(src, n, per, posh, n, part);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms; cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaError_t e = cudaGetLastError();
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, k_ap2x<TPT, UNROLL>);
+    printf("%-44s %8.3f ms  %6.2f TF(20/pair)  regs %3d  grid %dx%d %s\n", name, best, 20.0 * (double)n * n / (best * 1e-3) / 1e12,
+           fa.numRegs, tblocks, sp, e == cudaSuccess ? "" : cudaGetErrorString(e));
+}
+
 // FMA-pipe peak: scalar FFMA chains vs packed FFMA2 chains (both counted as 2 flop per fp32 lane-op).
 template <bool PACKED>
 __global__ void __launch_bounds__(256) k_peak(float* out, int iters, float a, float b) {
@@ -491,6 +619,10 @@ int main(int argc, char** argv) {
         }
         printf("max rel diff plain vs f32x2: x %.3e  phi %.3e  %s\n", md, mw, cudaGetErrorString(cudaGetLastError()));
     }
+    run2x<4, 4>("f32x2 expansion (far tiles): eqm tpt4 u4", src, posh, part, n, 28);
+    run2x<4, 2>("f32x2 expansion (far tiles): eqm tpt4 u2", src, posh, part, n, 28);
+    run2x<2, 4>("f32x2 expansion (far tiles): eqm tpt2 u4", src, posh, part, n, 14);
+    run2x<3, 4>("f32x2 expansion (far tiles): eqm tpt3 u4", src, posh, part, n, 21);
     run_tma<4, 4, true>("TMA ring: eqm nocap tpt4 4 stages", src, posh, part, n, 28);
     run_tma<4, 2, true>("TMA ring: eqm nocap tpt4 2 stages", src, posh, part, n, 28);
     run_tma<4, 4, false>("TMA ring: mass nocap tpt4 4 stages", src, posh, part, n, 28);
