@@ -110,8 +110,8 @@ __device__ __forceinline__ void pack_node(float4* __restrict__ packed, int k, fl
     packed[2 * (size_t)k + 1] = make_float4(mo.w, __int_as_float(a), __int_as_float(b), b_sq);
 }
 
-// Moments + MAC boxes.  Small nodes (<= leaf_max bodies) are evaluated directly from their particle range (reference
-// leaf rule); larger nodes are finished bottom-up by the second thread to arrive (fixed left-then-right order).
+// Moments + MAC boxes.  Buckets (maximal nodes with <= leaf_max bodies) are evaluated directly from their particle range
+// (reference leaf rule; the nodes inside a bucket are unreachable and skipped); larger nodes are finished bottom-up by the second thread to arrive (fixed left-then-right order).
 __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ posh, const float4* __restrict__ velm, int n,
                                                     const int2* __restrict__ child, const int2* __restrict__ range,
                                                     const int32_t* __restrict__ parent, int leaf_max, int aabb_mode, float dt,
@@ -121,6 +121,13 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
     if (k >= 2 * n - 1) return;
     int2 rg = range[k];
     if (rg.y - rg.x + 1 > leaf_max) return;
+    {   // a small node whose parent is small too lies strictly inside a bucket: the walk never reaches it
+        const int p = parent[k];
+        if (p >= 0) {
+            const int2 prg = range[p];
+            if (prg.y - prg.x + 1 <= leaf_max) return;
+        }
+    }
     float4 mo = make_float4(0.f, 0.f, 0.f, 0.f);
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
     const float margin = 0.1f * 0.5f;  // CollisionTolerance * 0.5 (Broadphase.cs:200, CollisionWorld.cs:32)

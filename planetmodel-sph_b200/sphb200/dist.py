@@ -114,10 +114,16 @@ class ShardedSimulation:
         self._mark("smoothing_sort_neighbors_density_eos")
         allgather_slices(self._view("cvol", 1), self.rank, self.world)
         self._mark("allgather_cvol")
+        if impl == GRAVITY_TREE:
+            # the pressure gradient does not depend on gravity: running it first gives the LBVH build on the auxiliary
+            # stream (all N on every rank, the critical path once the neighbor pass is 1/world) more time to finish
+            s.pressure()
+            self._mark("pressure_grad")
         s.gravity(impl, dt)                     # sources: all N (posm / LBVH are global), targets [t0,t1)
         self._mark({GRAVITY_TREE: "gravity_tree", GRAVITY_PARTICLE: "gravity_allpairs"}.get(impl, "gravity_none"))
-        s.pressure()
-        self._mark("pressure_grad")
+        if impl != GRAVITY_TREE:
+            s.pressure()
+            self._mark("pressure_grad")
         s.integrate(dt)
         self._mark("integrate")
         allgather_slices(self._view("posh", 4), self.rank, self.world)
