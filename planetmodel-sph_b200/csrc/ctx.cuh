@@ -154,6 +154,7 @@ __device__ __forceinline__ float dot3_rn(float x, float y, float z) {
 // C(h) = min( ((h*h)*2)*2 , t(h) ) and t(h) is the smallest float x with fsqrt_rn(x) >= 2h -- the reference's
 // "d2 < size*size*Kappa*Kappa" (SplineKernel.cs:47-53) and "Kernel(r,h) > 0 <=> r < 2h" (:62) without the sqrt.
 __device__ __forceinline__ float sph_keep_threshold(float h) {
+    if (!(h > 0.0f)) return 0.0f;   // h <= 0 or NaN (invalid input): no neighbors, and the ulp search below must not run
     const float c = __fmul_rn(h, 2.0f);
     uint32_t u = __float_as_uint(__fmul_rn(c, c));
     while (u > 0u && __fsqrt_rn(__uint_as_float(u - 1u)) >= c) --u;

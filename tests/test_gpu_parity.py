@@ -237,6 +237,26 @@ def test_step_is_deterministic_run_to_run():
         np.testing.assert_array_equal(outs[0][k], outs[1][k], err_msg=k)
 
 
+
+def test_huge_smoothing_lengths_take_the_literal_kernel_path(orc):
+    """h >= 1e5: W(r,h) can underflow, so 'r < 2h' no longer decides the keep rule; the library switches (on the device) to
+    the kernel that evaluates the reference's literal Kernel(r,h) > 0.  Fake units far from the reference scene."""
+    import sphb200
+    rng = np.random.default_rng(31)
+    n = 1500
+    pos = rng.uniform(-2.0e6, 2.0e6, (n, 3)).astype(np.float32)
+    h = rng.uniform(1.5e5, 3.0e5, n).astype(np.float32)
+    c = dict(pos=pos, vel=np.zeros((n, 3), np.float32), mass=np.full(n, 1.0e12, np.float32), h=h)
+    sim = run_gpu_step(c, 0.01, sphb200.GRAVITY_NONE, max_neighbors=512)
+    ref = oracle_step(orc, c, 0.01, "none", sim)
+    got = sim.download_all()
+    off, nbr = sim.download_neighbors()
+    np.testing.assert_array_equal(off, ref.offsets)
+    np.testing.assert_array_equal(nbr, ref.nbr)
+    np.testing.assert_array_equal(got["n_own"], ref.n_own)
+    np.testing.assert_allclose(got["rho"], ref.rho, rtol=RTOL)
+
+
 def test_c2_multistep_drift_matches_oracle(orc):
     """P2: 20 steps of the C2 regime; trajectories are compared through aggregates and their drift."""
     import sphb200
