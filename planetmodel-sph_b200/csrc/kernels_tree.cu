@@ -195,6 +195,19 @@ __device__ __forceinline__ void upk2(u64 v, float& a, float& b) { asm("mov.b64 {
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
+__device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+
+
+// softened pair law inside a = h_i (GravityFieldSystem.cs:340-347, Dyer & Ip)
+__device__ __forceinline__ void p2p_soft(WalkAcc& w, float ex, float ey, float ez, float r2, float m, float ainv) {
+    const float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
+    const float x = r * ainv, x2 = x * x, x3 = x2 * x;
+    const float ma = m * ainv;
+    const float g = ma * ainv * ainv * (8.0f - 9.0f * x + 2.0f * x3);
+    w.gx = fmaf(ex, g, w.gx); w.gy = fmaf(ey, g, w.gy); w.gz = fmaf(ez, g, w.gz);
+    w.gp -= ma * (2.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
+}
+
 // 32x32 bit-matrix transpose across the warp: in: lane i holds row i, out: lane j holds column j
 __device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
 #pragma unroll
@@ -215,7 +228,8 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
     __shared__ u64 tgzz[TW_WARPS][16];         //                           (z0,z1)
     __shared__ float4 bcm[TW_WARPS][32];     // batch nodes: (cm, M)            (lanes = targets phase)
     __shared__ int2 bkt[TW_WARPS][32];       // batch nodes: (first, count) of leaf buckets
-    __shared__ int2 sbody[TW_WARPS][128];    // flattened bodies of the shared buckets: (slot, lane mask)
+    __shared__ __align__(16) float sbodyf[TW_WARPS][128 * 4];   // flattened bodies of the shared buckets, as pairs: (x0,x1,y0,y1),(z0,z1,m0,m1)
+    __shared__ __align__(8) unsigned sbodym[TW_WARPS][128 + 2];  // ... and the lane mask of each body
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // Warps are aligned to absolute multiples of 32 sorted slots and every slot < n walks, whether or not it lies in this
     // rank's target range [t0,t1): the order in which a lane adds its contributions depends on its 31 companions, so a
@@ -226,6 +240,8 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
     const float4 pi = posh[active ? t : (n - 1)];
     const float a2 = pi.w * pi.w, ainv = 1.0f / pi.w;
     WalkAcc w = {0.f, 0.f, 0.f, 0.f, 0, 0};
+    u64 gx2 = pk2(0.f, 0.f), gy2 = gx2, gz2 = gx2, gp2 = gx2;   // packed partial sums of the shared P2P loop
+    const u64 pix = pk2(pi.x, pi.x), piy = pk2(pi.y, pi.y), piz = pk2(pi.z, pi.z);
     const unsigned m0 = __ballot_sync(FULL, active);
     if (m0 == 0) return;
     int2* st = stack[wid];
@@ -233,7 +249,8 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
     u64* tgz = tgzz[wid];
     float4* bc = bcm[wid];
     int2* bk = bkt[wid];
-    int2* sb = sbody[wid];
+    float* sbf = sbodyf[wid];
+    unsigned* sbm = sbodym[wid];
     {
         float* fx = reinterpret_cast<float*>(tgp);
         float* fz = reinterpret_cast<float*>(tgz);
@@ -314,7 +331,8 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
             }
         }
         // ---- 3b. shared P2P (GravityContributionParticle :332-356, a = h_i; includes the target itself, Q3): the bodies of
-        // the shared buckets are flattened into one list (4 per bucket per round; one round when leaf_max <= 4)
+        // the shared buckets are flattened (4 per bucket per round; one round when leaf_max <= 4) into a shared-memory list of
+        // body PAIRS, SoA inside the pair like the all-pairs tiles, and summed with packed FP32: one instruction, two bodies
         {
             int brem = (have && bucket && __popc(rej) >= TW_SHARE_B) ? -ib : 0, bfirst = ia;
             while (__any_sync(FULL, brem > 0)) {
@@ -328,36 +346,43 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
                 const int total = __shfl_sync(FULL, incl, 31);
 #pragma unroll
                 for (int u = 0; u < 4; u++)
-                    if (u < c4) sb[incl - c4 + u] = make_int2(bfirst + u, (int)rej);
+                    if (u < c4) {
+                        const int pos = incl - c4 + u;
+                        const float4 pj = __ldg(&posm[bfirst + u]);
+                        float* rec = sbf + (pos >> 1) * 8 + (pos & 1);
+                        rec[0] = pj.x; rec[2] = pj.y; rec[4] = pj.z; rec[6] = pj.w;
+                        sbm[pos] = rej;
+                    }
+                if (lane == 0 && (total & 1)) {   // odd count: the last pair's second body is a far-away zero-mass dummy
+                    float* rec = sbf + (total >> 1) * 8 + 1;
+                    rec[0] = 1.0e18f; rec[2] = 1.0e18f; rec[4] = 1.0e18f; rec[6] = 0.f;
+                    sbm[total] = 0u;
+                }
                 bfirst += c4; brem -= c4;
                 __syncwarp();
-                for (int k = 0; k < total; k += 4) {
-                    int2 en[4];
-                    float4 pq[4];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) en[u] = sb[min(k + u, total - 1)];
-#pragma unroll
-                    for (int u = 0; u < 4; u++) pq[u] = __ldg(&posm[en[u].x]);
-#pragma unroll
-                    for (int u = 0; u < 4; u++) {
-                        if (k + u >= total) break;   // warp-uniform
-                        const float4 pj = pq[u];
-                        const bool mine = ((unsigned)en[u].y >> lane) & 1u;
-                        const float ex = pi.x - pj.x, ey = pi.y - pj.y, ez = pi.z - pj.z;
-                        const float r2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-                        const float rinv = rsqrt_approx(fmaxf(r2, a2));
-                        const float mr = mine ? pj.w * rinv : 0.f;
-                        float g = mr * rinv * rinv, ph = -mr;
-                        if (mine && r2 < a2) {
-                            const float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
-                            const float x = r * ainv, x2 = x * x, x3 = x2 * x;
-                            const float ma = pj.w * ainv;
-                            g = ma * ainv * ainv * (8.0f - 9.0f * x + 2.0f * x3);
-                            ph = -ma * (2.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
-                        }
-                        w.gx = fmaf(ex, g, w.gx); w.gy = fmaf(ey, g, w.gy); w.gz = fmaf(ez, g, w.gz);
-                        w.gp += ph;
-                        w.np += mine ? 1 : 0;
+                const ulonglong2* recs = reinterpret_cast<const ulonglong2*>(sbf);
+#pragma unroll 2
+                for (int k = 0; k < total; k += 2) {
+                    const ulonglong2 A = recs[k], B = recs[k + 1];   // (x0,x1),(y0,y1) | (z0,z1),(m0,m1)
+                    const uint2 mk = *reinterpret_cast<const uint2*>(sbm + k);
+                    const bool m0 = (mk.x >> lane) & 1u, m1 = (mk.y >> lane) & 1u;
+                    const u64 ex = sub2(pix, A.x), ey = sub2(piy, A.y), ez = sub2(piz, B.x);
+                    const u64 r2 = fma2(ez, ez, fma2(ey, ey, mul2(ex, ex)));
+                    float ra, rb, ma, mb;
+                    upk2(r2, ra, rb);
+                    upk2(B.y, ma, mb);
+                    const bool s0 = m0 && ra < a2, s1 = m1 && rb < a2;   // inside the softening radius: scalar law below
+                    const u64 rinv = pk2(rsqrt_approx(fmaxf(ra, a2)), rsqrt_approx(fmaxf(rb, a2)));
+                    const u64 mr = mul2(pk2(m0 && !s0 ? ma : 0.f, m1 && !s1 ? mb : 0.f), rinv);
+                    const u64 g = mul2(mr, mul2(rinv, rinv));
+                    gx2 = fma2(ex, g, gx2); gy2 = fma2(ey, g, gy2); gz2 = fma2(ez, g, gz2);
+                    gp2 = sub2(gp2, mr);
+                    w.np += (m0 ? 1 : 0) + (m1 ? 1 : 0);
+                    if (s0 || s1) {
+                        float exa, exb, eya, eyb, eza, ezb;
+                        upk2(ex, exa, exb); upk2(ey, eya, eyb); upk2(ez, eza, ezb);
+                        if (s0) p2p_soft(w, exa, eya, eza, ra, ma, ainv);
+                        if (s1) p2p_soft(w, exb, eyb, ezb, rb, mb, ainv);
                     }
                 }
                 __syncwarp();
@@ -410,6 +435,11 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
         __syncwarp();
     }
     if (t >= t0 && t < t1) {
+        float a, b;
+        upk2(gx2, a, b); w.gx += a + b;
+        upk2(gy2, a, b); w.gy += a + b;
+        upk2(gz2, a, b); w.gz += a + b;
+        upk2(gp2, a, b); w.gp += a + b;
         grav[t] = make_float4(G * w.gx, G * w.gy, G * w.gz, G * w.gp);
         npart[t] = w.np;
         napprox[t] = w.na;
