@@ -267,8 +267,8 @@ def run_ours(args):
         roof = {"bound": "fp32", "kernel": "k_gravity_allpairs", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": ach / fp32_peak if ach else None,
                 # DRAM bytes per launch of this kernel at C3 / 1 GPU from the committed ncu --set full capture
-                # (profiles/r01_allpairs_full.txt: 65.7 MB read + 111.1 MB written); not re-measured in this run
-                "traffic": 176.8e6 if (world == 1 and n == (1 << 20)) else None,
+                # (profiles/r01_allpairs_full.txt: 69.2 MB read + 109.9 MB written); not re-measured in this run
+                "traffic": 179.1e6 if (world == 1 and n == (1 << 20)) else None,
                 "note": "FP32 FMA-pipe bound (not a contraction: no tensor roof applies); peak = FMA microbenchmark measured "
                         "in this run; flops = 20 per ordered pair (SURVEY 8d)", "ms": gms, "share_of_step": gms / ms_per_step}
     else:
