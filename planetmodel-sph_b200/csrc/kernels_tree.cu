@@ -16,8 +16,10 @@
 //      exact reference MAC and gets a 32-bit accept mask -- 32x32 exact decisions in ~350 instructions;
 //   2. two 32x32 bit transposes (butterfly shuffles) hand every lane = TARGET the set of batch nodes it accepts and the
 //      set of leaf buckets it must open; internal nodes that some lane rejected push both children with that lane mask;
-//   3. lanes = TARGETS: every lane sums its own M2P / P2P contributions, so no lane evaluates an interaction that
-//      belongs to another lane (the shared-walk union was 2.3x the per-lane work for P2P, 4.5x for M2P).
+//   3. the opened buckets' bodies are flattened into a shared-memory list and summed warp-wide (uniform loads, lanes that
+//      did not open a bucket contribute zero mass): measured faster than lane-private P2P, whose per-batch imbalance left
+//      25 % of the lanes busy; lanes = TARGETS for M2P: every lane sums only the nodes it accepts itself (the shared-walk
+//      union was 4.5x the per-lane M2P work).  Both loops use packed FP32 (two bodies / nodes per instruction).
 // Every lane still sees exactly the accepted nodes / opened buckets of its private depth-first walk (per-particle MAC,
 // numParticles / numApprox identical to the oracle); only the order in which a lane adds its contributions differs.
 // The MAC "bmax_sq / r_sq < theta^2" is monotone in r_sq, so the build stores per node the exact threshold T with
@@ -181,8 +183,6 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
 
 constexpr int TW_WARPS = 4;
 constexpr int TW_STACK = 512;    // per-warp work stack entries (node, lane mask); batches shrink when it is nearly full
-constexpr int TW_SHARE_A = 12;   // a node accepted by >= this many lanes gets its M2P evaluated warp-wide (uniform load) ...
-constexpr int TW_SHARE_B = 6;    // ... a bucket opened by >= this many lanes its P2P; the rest is summed lane by lane
 
 struct WalkAcc {
     float gx, gy, gz, gp;
@@ -227,7 +227,6 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
     __shared__ ulonglong2 tgxy[TW_WARPS][16];  // target positions as pairs: (x0,x1), (y0,y1)   (lanes = nodes phase)
     __shared__ u64 tgzz[TW_WARPS][16];         //                           (z0,z1)
     __shared__ float4 bcm[TW_WARPS][32];     // batch nodes: (cm, M)            (lanes = targets phase)
-    __shared__ int2 bkt[TW_WARPS][32];       // batch nodes: (first, count) of leaf buckets
     __shared__ __align__(16) float sbodyf[TW_WARPS][128 * 4];   // flattened bodies of the shared buckets, as pairs: (x0,x1,y0,y1),(z0,z1,m0,m1)
     __shared__ __align__(8) unsigned sbodym[TW_WARPS][128 + 2];  // ... and the lane mask of each body
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -240,7 +239,7 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
     const float4 pi = posh[active ? t : (n - 1)];
     const float a2 = pi.w * pi.w, ainv = 1.0f / pi.w;
     WalkAcc w = {0.f, 0.f, 0.f, 0.f, 0, 0};
-    u64 gx2 = pk2(0.f, 0.f), gy2 = gx2, gz2 = gx2, gp2 = gx2;   // packed partial sums of the shared P2P loop
+    u64 gx2 = pk2(0.f, 0.f), gy2 = gx2, gz2 = gx2, gp2 = gx2;   // packed partial sums (P2P and M2P loops)
     const u64 pix = pk2(pi.x, pi.x), piy = pk2(pi.y, pi.y), piz = pk2(pi.z, pi.z);
     const unsigned m0 = __ballot_sync(FULL, active);
     if (m0 == 0) return;
@@ -248,7 +247,6 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
     ulonglong2* tgp = tgxy[wid];
     u64* tgz = tgzz[wid];
     float4* bc = bcm[wid];
-    int2* bk = bkt[wid];
     float* sbf = sbodyf[wid];
     unsigned* sbm = sbodym[wid];
     {
@@ -294,7 +292,6 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
         const bool bucket = ib < 0;
         __syncwarp();
         bc[lane] = make_float4(N.x, N.y, N.z, X.x);
-        bk[lane] = make_int2(ia, -ib);
         // internal nodes some lane rejected: both children inherit that lane mask
         const bool open = have && !bucket && rej != 0u;
         const unsigned ob = __ballot_sync(FULL, open);
@@ -304,37 +301,15 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
             st[pos + 1] = make_int2(ib, (int)rej);
         }
         sp += 2 * __popc(ob);
-        // ---- 2. sideways: which batch nodes does target `lane` accept, which buckets does it open
+        // ---- 2. sideways: which batch nodes does target `lane` accept
         unsigned nmask = transpose32(acc, lane);
-        unsigned bmask = transpose32(bucket ? rej : 0u, lane);
         w.na += __popc(nmask);
-        // items wanted by many lanes are evaluated once for the warp (uniform loads, predicated lanes); the rest lane by lane
-        unsigned sh_a = __ballot_sync(FULL, __popc(acc) >= TW_SHARE_A);
-        unsigned sh_b = __ballot_sync(FULL, bucket && __popc(rej) >= TW_SHARE_B);
-        const unsigned nshared = nmask & sh_a;
-        nmask &= ~sh_a;
-        bmask &= ~sh_b;
         __syncwarp();
-        // ---- 3a. shared M2P (GravitationalMoment.GravityContribution, :428-442)
-        while (sh_a != 0u) {
-            const int b = __ffs(sh_a) - 1;
-            sh_a &= sh_a - 1u;
-            const float4 A = bc[b];
-            const float dx = pi.x - A.x, dy = pi.y - A.y, dz = pi.z - A.z;
-            const float r_sq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-            const float rinv = rsqrt_approx(r_sq);
-            const float mr = A.w * rinv;
-            const float g = mr * rinv * rinv;
-            if ((nshared >> b) & 1u) {   // (a lane sitting exactly on the node's centre rejects it: r_sq = 0 must not leak a NaN)
-                w.gx = fmaf(dx, g, w.gx); w.gy = fmaf(dy, g, w.gy); w.gz = fmaf(dz, g, w.gz);
-                w.gp -= mr;
-            }
-        }
-        // ---- 3b. shared P2P (GravityContributionParticle :332-356, a = h_i; includes the target itself, Q3): the bodies of
-        // the shared buckets are flattened (4 per bucket per round; one round when leaf_max <= 4) into a shared-memory list of
+        // ---- 3a. P2P, warp-wide (GravityContributionParticle :332-356, a = h_i; includes the target itself, Q3): the bodies of
+        // the opened buckets are flattened (4 per bucket per round; one round when leaf_max <= 4) into a shared-memory list of
         // body PAIRS, SoA inside the pair like the all-pairs tiles, and summed with packed FP32: one instruction, two bodies
         {
-            int brem = (have && bucket && __popc(rej) >= TW_SHARE_B) ? -ib : 0, bfirst = ia;
+            int brem = (have && bucket && rej != 0u) ? -ib : 0, bfirst = ia;
             while (__any_sync(FULL, brem > 0)) {
                 const int c4 = min(brem, 4);
                 int incl = c4;
@@ -388,48 +363,25 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
                 __syncwarp();
             }
         }
-        // ---- 3c. lane-private M2P: every lane sums the nodes only few lanes accept
-        for (int it = __reduce_max_sync(FULL, __popc(nmask)); it > 0; it--) {
+        // ---- 3b. M2P, lane-private (GravitationalMoment.GravityContribution, :428-442): every lane sums the nodes it accepts,
+        // two per iteration with packed FP32 (an odd last one is paired with a zero-mass copy of itself; r_sq > T >= 0)
+        for (int it = __reduce_max_sync(FULL, (__popc(nmask) + 1) >> 1); it > 0; it--) {
             if (nmask != 0u) {
-                const int b = __ffs(nmask) - 1;
+                const int b0 = __ffs(nmask) - 1;
                 nmask &= nmask - 1u;
-                const float4 A = bc[b];
-                const float dx = pi.x - A.x, dy = pi.y - A.y, dz = pi.z - A.z;
-                const float r_sq = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                const float rinv = rsqrt_approx(r_sq);
-                const float mr = A.w * rinv;
-                const float g = mr * rinv * rinv;
-                w.gx = fmaf(dx, g, w.gx); w.gy = fmaf(dy, g, w.gy); w.gz = fmaf(dz, g, w.gz);
-                w.gp -= mr;
-            }
-        }
-        // ---- 3d. lane-private P2P: one body per lane per iteration, each lane walking its own bucket list
-        int first = 0, rem = 0;
-        while (__any_sync(FULL, (bmask | (unsigned)rem) != 0u)) {
-            if (rem == 0 && bmask != 0u) {
-                const int b = __ffs(bmask) - 1;
-                bmask &= bmask - 1u;
-                const int2 fc = bk[b];
-                first = fc.x; rem = fc.y;
-            }
-            if (rem > 0) {
-                const float4 pj = __ldg(&posm[first]);
-                first++; rem--;
-                const float ex = pi.x - pj.x, ey = pi.y - pj.y, ez = pi.z - pj.z;
-                const float r2 = fmaf(ez, ez, fmaf(ey, ey, ex * ex));
-                const float rinv = rsqrt_approx(fmaxf(r2, a2));
-                const float mr = pj.w * rinv;
-                float g = mr * rinv * rinv, ph = -mr;
-                if (r2 < a2) {
-                    const float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
-                    const float x = r * ainv, x2 = x * x, x3 = x2 * x;
-                    const float ma = pj.w * ainv;
-                    g = ma * ainv * ainv * (8.0f - 9.0f * x + 2.0f * x3);
-                    ph = -ma * (2.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
-                }
-                w.gx = fmaf(ex, g, w.gx); w.gy = fmaf(ey, g, w.gy); w.gz = fmaf(ez, g, w.gz);
-                w.gp += ph;
-                w.np++;
+                const bool two = nmask != 0u;
+                const int b1 = two ? __ffs(nmask) - 1 : b0;
+                nmask &= nmask - 1u;
+                const float4 A0 = bc[b0], A1 = bc[b1];
+                const u64 dx = sub2(pix, pk2(A0.x, A1.x)), dy = sub2(piy, pk2(A0.y, A1.y)), dz = sub2(piz, pk2(A0.z, A1.z));
+                const u64 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+                float ra, rb;
+                upk2(r2, ra, rb);
+                const u64 rinv = pk2(rsqrt_approx(ra), rsqrt_approx(rb));
+                const u64 mr = mul2(pk2(A0.w, two ? A1.w : 0.f), rinv);
+                const u64 g = mul2(mr, mul2(rinv, rinv));
+                gx2 = fma2(dx, g, gx2); gy2 = fma2(dy, g, gy2); gz2 = fma2(dz, g, gz2);
+                gp2 = sub2(gp2, mr);
             }
         }
         __syncwarp();
