@@ -1,18 +1,25 @@
-// kernels_neighbors.cu -- K1: neighbor lists + density + EOS in one pass (warp-cooperative gather).
+// kernels_neighbors.cu -- K1: neighbor lists, density and EOS.
 //
 // Replaces: the Unity.Physics broadphase pair stream + KernelSystem.FilterPairs / CalculateInteractionJob
 // (UP/Collision/World/Broadphase.cs:275-351, A/Systems/KernelSystem.cs:234-335, 583-633), SplineKernel
 // (A/Util/SplineKernel.cs:47-89) and DensityFieldSystem + the EOS (A/Systems/DensityFieldSystem.cs:38-56,
 // A/Systems/PressureFieldSystem.cs:30-34).
 //
-// One warp per target particle, three phases, each with all 32 lanes busy:
-//   1. CELLS   lanes enumerate the (2S+1)^3 stencil cells around the target's cell, read (start, end, hmax) from the
-//              cell table and cull every cell whose box is farther than 2*max(h_i, hmax_cell) from the target -- the
-//              variable-h rule "r < 2 max(h_i,h_j)" without paying for the global h_max in every cell.
-//   2. TEST    surviving cells are contiguous slot ranges of the Morton-sorted SoA; four 8-lane groups stream them
-//              with coalesced float4 loads and apply the reference's exact fp32 predicate + keep rule.
-//   3. SUM     survivors are queued in shared memory and evaluated 32 at a time (kernel values, density sum,
-//              own-support count); list rows are written coalesced.
+// Three kernels, all launched every step (which one does the work is decided on the device from the grid's h_max, so
+// the host never synchronises):
+//   k_cell_neighbors    h_max <  1e5 (every real run): cell-centric list build, one warp per pass of <= 32 targets of one
+//                       cell, sqrt-free exact keep thresholds -- described at its definition below;
+//   k_density           h_max <  1e5: density + EOS + own-support count from the finished rows, 16 lanes per target;
+//   k_neighbors_density h_max >= 1e5 (W(r,h) can underflow, the threshold form is not valid): the warp-per-target kernel
+//                       that evaluates the reference's literal Kernel(r,h) > 0 keep rule, lists + density + EOS in one
+//                       pass.  One warp per target particle, three phases:
+//     1. CELLS   lanes enumerate the (2S+1)^3 stencil cells around the target's cell, read (start, end, hmax) from the
+//                cell table and cull every cell whose box is farther than 2*max(h_i, hmax_cell) from the target -- the
+//                variable-h rule "r < 2 max(h_i,h_j)" without paying for the global h_max in every cell.
+//     2. TEST    surviving cells are contiguous slot ranges of the Morton-sorted SoA; four 8-lane groups stream them
+//                with coalesced float4 loads and apply the reference's exact fp32 predicate + keep rule.
+//     3. SUM     survivors are queued in shared memory and evaluated 32 at a time (kernel values, density sum,
+//                own-support count); list rows are written coalesced.
 // Numerics contract: membership exact (non-contracted __f*_rn ops, IEEE sqrt), values fast (<= 1e-5 relative).
 #include "ctx.cuh"
 #include <math.h>
@@ -220,10 +227,12 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_neighbors_density(
 
 
 // ------------------------------------------------------------------------------------------------------------
-// K1 (cell-centric): one warp per non-empty cell.  The ~11 particles of the cell are the targets (staged in shared
-// memory, <= 32 per pass); the particles of the (2S+1)^3 stencil cells are the candidates, flattened across cells so that
-// every lane owns one candidate per batch and tests it against each target in turn (LDS broadcast): 32 exact pair tests
-// per ~22 instructions, no sqrt and no division in the test.
+// K1 (cell-centric): one warp per PASS = up to 32 consecutive targets of one cell (a cell holds ~11 particles when h is
+// uniform, ~100 where h is much smaller than the typical h the cells are sized by).  The targets are staged in shared
+// memory; the particles of the (2S+1)^3 stencil cells are the candidates: their cell ranges are flattened so that every
+// lane fetches one candidate per batch, candidates that cannot reach the box of the pass's targets are dropped and the
+// rest compacted into a shared-memory ring; every lane then owns one compacted candidate and tests it against each target
+// in turn (LDS broadcast): 32 exact pair tests per ~30 instructions, no sqrt and no division in the test.
 //
 // Exactness without the sqrt: with s = max(h_i,h_j) the reference keeps the pair iff
 //     d2 < ((s*s)*2)*2   and   ( fsqrt_rn(d2) < 2 h_i  or  fsqrt_rn(d2) < 2 h_j )      (SplineKernel.cs:47-53, :62)
@@ -232,9 +241,9 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_neighbors_density(
 // by the permute kernel (sph_keep_threshold, ctx.cuh) and carried in posc.w.  Valid below h = 1e5 (kHugeH).
 //
 // Cells of the outer stencil shells (S > 1: some h exceed the typical h the cells are sized by) are culled against the
-// tight boxes of the pass's targets: the union of their own supports, and their positions grown by the cell's h_max.
-// Rows are written by ballot rank (deterministic order); density, EOS and the own-support count are then evaluated from
-// the finished rows, 32 lanes per target.
+// box of the pass's targets grown by the larger of the targets' and the cell's h_max.
+// Rows are written by ballot rank: the order of a row depends only on the cell enumeration order, never on which warp or
+// which rank built it (sharded runs stay bit-identical); density, EOS and the own-support count follow in k_density.
 // ------------------------------------------------------------------------------------------------------------
 constexpr int K3_WARPS = 8;
 constexpr int K3_MINB = 3;    // resident blocks per SM (80 registers; 2 and 4 measured slower)
