@@ -88,3 +88,42 @@ def make_collision(n_each, seed=1234, separation=3.0, v0=1.0):
     b = make_sphere(n_each, radius=0.5 * r1, total_mass=8 * REF_TOTAL_MASS * n_each / REF_COUNT, seed=seed + 1,
                     center=(0.5 * separation * r1, 0, 0), velocity=(-v0, 0, 0))
     return {k: np.ascontiguousarray(np.concatenate([a[k], b[k]])) for k in a}
+
+
+def polytrope_radius(K=1000.0, G=1.0):
+    """Equilibrium radius of the n = 1 polytrope that the reference's EOS P = K rho^2 (PressureFieldSystem.cs:31-33)
+    supports against self-gravity: R = pi sqrt(K / (2 pi G)), independent of the mass (39.63 for K = 1000, G = 1)."""
+    return float(np.pi * np.sqrt(K / (2.0 * np.pi * G)))
+
+
+def make_polytrope(n, total_mass=REF_TOTAL_MASS, K=1000.0, G=1.0, neighbors=50.0, seed=1234, center=(0.0, 0.0, 0.0),
+                   velocity=(0.0, 0.0, 0.0), omega=0.0):
+    """Non-uniform density initial condition (README.md:85-89 roadmap: "nonuniform density", "automatic particle size",
+    "initial group velocity / angular momentum"): equal-mass particles drawn from the hydrostatic n = 1 polytrope
+    rho(r) = rho_c sin(xi)/xi, xi = pi r / R, R = polytrope_radius(K, G) -- the equilibrium of the reference's own EOS, so
+    the sphere starts near rest instead of ringing like the uniform ball.  Radii by inverse transform of the enclosed mass
+    m(r)/M = (sin(xi) - xi cos(xi)) / pi, directions isotropic.  h is set from the local density so that ~`neighbors`
+    particles lie inside 2h (the controller's target, ParticleSmoothingSystem.cs:18).  `omega` adds rigid rotation about z."""
+    rng = np.random.Generator(np.random.Philox(seed))
+    R = polytrope_radius(K, G)
+    # inverse transform on a fine table of the (monotone) enclosed-mass fraction
+    xi_t = np.linspace(0.0, np.pi, 20001)
+    m_t = (np.sin(xi_t) - xi_t * np.cos(xi_t)) / np.pi
+    xi = np.interp(rng.uniform(0.0, 1.0, n), m_t, xi_t)
+    r = xi * (R / np.pi)
+    mu = rng.uniform(-1.0, 1.0, n)
+    ph = rng.uniform(0.0, 2.0 * np.pi, n)
+    st = np.sqrt(1.0 - mu * mu)
+    pos = np.stack([r * st * np.cos(ph), r * st * np.sin(ph), r * mu], 1)
+    rho_c = total_mass * np.pi / (4.0 * R ** 3)                     # M = 4 R^3 rho_c / pi
+    with np.errstate(invalid="ignore", divide="ignore"):
+        rho = rho_c * np.where(xi > 1e-6, np.sin(xi) / xi, 1.0)
+    rho = np.maximum(rho, rho_c * 1e-3)                             # the surface density -> 0: cap the smoothing length
+    m = total_mass / n
+    h = 0.5 * (3.0 * neighbors * m / (4.0 * np.pi * rho)) ** (1.0 / 3.0)
+    vel = np.tile(np.asarray(velocity, np.float64), (n, 1))
+    if omega:
+        vel = vel + np.stack([-omega * pos[:, 1], omega * pos[:, 0], np.zeros(n)], 1)
+    pos = pos + np.asarray(center, np.float64)
+    return dict(pos=np.ascontiguousarray(pos, np.float32), vel=np.ascontiguousarray(vel, np.float32),
+                mass=np.full(n, np.float32(m), np.float32), h=np.ascontiguousarray(h, np.float32))
