@@ -61,7 +61,7 @@ int sphb200_destroy(sph_handle c) {
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     for (int k = 0; k < 2; k++) { cudaFree(c->posh[k]); cudaFree(c->velm[k]); cudaFree(c->orig[k]); cudaFree(c->keys[k]); cudaFree(c->idx[k]); }
-    cudaFree(c->posm); cudaFree(c->posc); cudaFree(c->chunk_counter); cudaFree(c->cub_tmp); cudaFree(c->cell_start); cudaFree(c->cell_end); cudaFree(c->cell_hmax); cudaFree(c->nlist);
+    cudaFree(c->posm); cudaFree(c->posc); cudaFree(c->chunk_counter); cudaFree(c->sort_hist); cudaFree(c->cell_start); cudaFree(c->cell_end); cudaFree(c->cell_hmax); cudaFree(c->nlist);
     cudaFree(c->ncount); cudaFree(c->nown); cudaFree(c->rho); cudaFree(c->press); cudaFree(c->cvol); cudaFree(c->gradp);
     cudaFree(c->grav); cudaFree(c->npart); cudaFree(c->napprox); cudaFree(c->gpart); cudaFree(c->tbox); cudaFree(c->child); cudaFree(c->range);
     cudaFree(c->parent); cudaFree(c->flag); cudaFree(c->mom); cudaFree(c->nlo); cudaFree(c->nhi); cudaFree(c->packed); cudaFree(c->bounds);
@@ -114,9 +114,8 @@ int sphb200_create(const sph_Params* params, int64_t capacity, int device, sph_h
         ok = ok && dalloc(&c->posh[k], cap) == cudaSuccess && dalloc(&c->velm[k], cap) == cudaSuccess &&
              dalloc(&c->orig[k], cap) == cudaSuccess && dalloc(&c->keys[k], cap) == cudaSuccess && dalloc(&c->idx[k], cap) == cudaSuccess;
     }
-    c->cub_bytes = sph_sort_temp_bytes(capacity);
     c->stage_bytes = std::max<size_t>(cap * 14 * 4, (cap + 1) * 8);   // upload: pos3 vel3 mass1 + raw smoothing records (7)
-    ok = ok && dalloc(&c->posm, cap) == cudaSuccess && dalloc(&c->posc, cap) == cudaSuccess && dalloc(&c->chunk_counter, 1) == cudaSuccess && cudaMalloc(&c->cub_tmp, std::max<size_t>(c->cub_bytes, 16)) == cudaSuccess &&
+    ok = ok && dalloc(&c->posm, cap) == cudaSuccess && dalloc(&c->posc, cap) == cudaSuccess && dalloc(&c->chunk_counter, 1) == cudaSuccess && dalloc(&c->sort_hist, sph_sort_hist_words(capacity)) == cudaSuccess &&
          dalloc(&c->cell_start, c->ncell_max) == cudaSuccess && dalloc(&c->cell_end, c->ncell_max) == cudaSuccess && dalloc(&c->cell_hmax, c->ncell_max) == cudaSuccess &&
          dalloc(&c->nlist, cap * (size_t)p.max_neighbors) == cudaSuccess && dalloc(&c->ncount, cap) == cudaSuccess &&
          dalloc(&c->nown, cap) == cudaSuccess && dalloc(&c->rho, cap) == cudaSuccess && dalloc(&c->press, cap) == cudaSuccess &&

@@ -31,8 +31,7 @@ struct sphb200_ctx {
 
     uint32_t* keys[2] = {nullptr, nullptr};
     uint32_t* idx[2] = {nullptr, nullptr};
-    void* cub_tmp = nullptr;
-    size_t cub_bytes = 0;
+    uint32_t* sort_hist = nullptr;   // radix sort: digit counts [256][tiles] + totals [256]
     uint32_t* cell_start = nullptr;
     uint32_t* cell_end = nullptr;
     uint32_t* cell_hmax = nullptr;  // max h per cell (fp32 bit pattern)
@@ -179,4 +178,7 @@ int sph_launch_unpack_field(sphb200_ctx* c, int field, int* elem_bytes);
 int sph_launch_neighbor_rows_sorted(sphb200_ctx* c, int32_t* rows_d);
 int sph_launch_interactions(sphb200_ctx* c, int64_t total, const int64_t* offsets_d, const int32_t* nbr_d, sph_ParticleInteraction* out_d);
 int sph_fp32_peak(sphb200_ctx* c, double* tflops);
-size_t sph_sort_temp_bytes(int64_t cap);
+size_t sph_sort_hist_words(int64_t cap);
+int sph_launch_radix_sort(sphb200_ctx* c, int n, cudaStream_t stream);
+int sph_launch_digit_pass(sphb200_ctx* c, const uint32_t* keys_in, const uint32_t* vals_in, const uint8_t* bucket, int n, int shift,
+                          uint32_t* keys_out, uint32_t* vals_out, uint32_t* total_out, cudaStream_t stream);

@@ -6,7 +6,6 @@
 // sorts (A/Systems/KernelSystem.cs:411-464, 539-568, 638-663).  Key arithmetic is specified by
 // oracle/sph_oracle.cpp (orc_grid_params / orc_morton_keys) and must match it bit-for-bit.
 #include "ctx.cuh"
-#include <cub/device/device_radix_sort.cuh>
 #include <math.h>
 
 namespace {
@@ -91,7 +90,7 @@ __global__ void k_grid_setup(uint32_t* bounds, sph_GridParams* g, int max_bits, 
 }
 
 __global__ void __launch_bounds__(256) k_keys(const float4* __restrict__ posh, const sph_GridParams* __restrict__ g, int n,
-                                              uint32_t* __restrict__ keys, uint32_t* __restrict__ idx) {
+                                              uint32_t* __restrict__ keys) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 p = posh[i];
@@ -101,7 +100,6 @@ __global__ void __launch_bounds__(256) k_keys(const float4* __restrict__ posh, c
     int qz = (int)__fmul_rn(__fsub_rn(p.z, g->min[2]), fs);
     qx = min(max(qx, 0), 1023); qy = min(max(qy, 0), 1023); qz = min(max(qz, 0), 1023);
     keys[i] = expand10((uint32_t)qx) | (expand10((uint32_t)qy) << 1) | (expand10((uint32_t)qz) << 2);
-    idx[i] = (uint32_t)i;
 }
 
 // Gather the resident SoA into sorted order and emit the cell table from the sorted keys.
@@ -132,13 +130,6 @@ __global__ void __launch_bounds__(256) k_permute_cells(const uint32_t* __restric
 
 }  // namespace
 
-size_t sph_sort_temp_bytes(int64_t cap) {
-    size_t bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, (const uint32_t*)nullptr, (uint32_t*)nullptr, (const uint32_t*)nullptr,
-                                    (uint32_t*)nullptr, (int)cap, 0, 30);
-    return bytes;
-}
-
 int sph_launch_smoothing_bounds(sphb200_ctx* c, bool update_h) {
     int n = (int)c->n;
     int blocks = min(sph_div_up(n, 256), c->sm_count * 8);
@@ -152,11 +143,9 @@ int sph_launch_smoothing_bounds(sphb200_ctx* c, bool update_h) {
 int sph_launch_sort_and_cells(sphb200_ctx* c) {
     int n = (int)c->n;
     int in = c->cur, out = c->cur ^ 1;
-    k_keys<<<sph_div_up(n, 256), 256, 0, c->stream>>>(c->posh[in], c->grid_d, n, c->keys[0], c->idx[0]);
+    k_keys<<<sph_div_up(n, 256), 256, 0, c->stream>>>(c->posh[in], c->grid_d, n, c->keys[1]);
     SPH_LAUNCH_CHECK(c);
-    size_t bytes = c->cub_bytes;
-    SPH_CK(c, cub::DeviceRadixSort::SortPairs(c->cub_tmp, bytes, c->keys[0], c->keys[1], c->idx[0], c->idx[1], n, 0, 30, c->stream));
-    // (CUB's radix-sort kernels are library launches and are NOT counted in c->launches)
+    { int rc = sph_launch_radix_sort(c, n, c->stream); if (rc) return rc; }   // (keys[1], iota) -> (keys[1], idx[1]), stable
     size_t ncell = c->ncell_max;
     SPH_CK(c, cudaMemsetAsync(c->cell_start, 0, ncell * sizeof(uint32_t), c->stream));
     SPH_CK(c, cudaMemsetAsync(c->cell_end, 0, ncell * sizeof(uint32_t), c->stream));

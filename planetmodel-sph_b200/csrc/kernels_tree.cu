@@ -182,7 +182,10 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
 }
 
 constexpr int TW_WARPS = 4;
-constexpr int TW_STACK = 512;    // per-warp work stack entries (node, lane mask); batches shrink when it is nearly full
+constexpr int TW_STACK = 512;    // per-warp work stack entries (node, lane mask)
+constexpr int TW_HEADROOM = 72;  // > the deepest possible LBVH (30 key bits + 32 tie-break bits): once the stack is this close to
+                                 // full the walk degrades to one node per step -- plain depth-first, which grows the stack by
+                                 // at most one entry per tree level -- instead of failing (clustered / duplicate-key inputs)
 
 struct WalkAcc {
     float gx, gy, gz, gp;
@@ -261,8 +264,9 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
     __syncwarp();
     while (sp > 0) {
         // ---- 1. lanes = nodes
-        const int nb = min(min(sp, 32), TW_STACK - sp);   // a batch of nb nodes grows the stack by at most nb
-        if (nb <= 0) { if (lane == 0) atomicExch(&err[ERR_TREE_STACK], 1); break; }
+        // a batch of nb nodes grows the stack by at most nb; wide batches keep TW_HEADROOM entries free
+        const int nb = max(min(min(sp, 32), TW_STACK - TW_HEADROOM - sp), 1);
+        if (sp >= TW_STACK) { if (lane == 0) atomicExch(&err[ERR_TREE_STACK], 1); break; }   // unreachable for trees of depth < TW_HEADROOM
         const bool have = lane < nb;
         int2 e = make_int2(0, 0);
         if (have) e = st[sp - 1 - lane];
