@@ -32,7 +32,8 @@ enum {
     SPH_ERR_NEIGHBOR_OVERFLOW = -3, /* some particle has more than max_neighbors neighbors; lists truncated */
     SPH_ERR_CUDA = -4,
     SPH_ERR_STATE = -5,             /* stage called out of order (e.g. pressure before build_neighbors) */
-    SPH_ERR_TREE_STACK = -6         /* traversal stack overflow in the LBVH walk */
+    SPH_ERR_TREE_STACK = -6,        /* traversal stack / top-tree list overflow in the LBVH gravity */
+    SPH_ERR_NCCL = -7               /* multi-GPU group: libnccl missing or a collective failed */
 };
 
 /* ---- gravity implementation (GravityFieldSystem.cs:19-25 `GravityImpl`) */
@@ -200,6 +201,57 @@ SPH_API int sphb200_get_timings(sph_handle h, const char** names, float* ms, int
 /* FP32 FMA-pipe microbenchmark (roofline denominator for all-pairs gravity): returns TFLOP/s. */
 SPH_API int sphb200_fp32_peak(sph_handle h, double* tflops);
 SPH_API const char* sphb200_version(void);
+
+/* ---- multi-GPU groups: Morton-range domain decomposition with NVLink halo exchange -------------------------------------
+ * The reference has one process and shared-memory job threads only (UP/Collision/World/Broadphase.cs:163) and is capped at
+ * 2^24-2 bodies (UP/Dynamics/Simulation/Scheduler.cs:24-41); a group is how this library scales N.
+ * Every rank (one per GPU) keeps the particles of one contiguous Morton-key range plus a halo; per step the ranks exchange
+ * migrating particles, halo particles, (m/rho)P of the halo, and all-gather the gravity sources (and the packed LBVH
+ * nodes for tree gravity) over NCCL.  Results are bit-identical to a single handle for tree gravity.
+ * Body-order slices: with chunk = ceil(n/world), rank r uploads and downloads bodies [r*chunk, min((r+1)*chunk, n)):
+ * host<->device traffic per GPU is 1/world of the state; the particles travel between GPUs over NVLink. */
+typedef struct sphb200_group* sph_group;
+
+typedef struct sph_GroupInfo {
+    int32_t world, nlocal, rank0;
+    int32_t transport;            /* 0 = NCCL, 1 = in-process peer copies, 2 = none (world 1) */
+    int64_t n_total, steps;
+    int64_t migrated_last_step;   /* particles that changed rank in the last step (this process's ranks, incoming) */
+    int64_t halo_last_step;       /* halo particles received in the last step (this process's ranks) */
+    int64_t cap_own, cap_halo;    /* per-rank capacities: own slots, halo slots on either side */
+    int64_t launches;             /* kernels launched by this process's ranks since create */
+    int64_t n_own[32], n_halo[32];/* per local rank */
+} sph_GroupInfo;
+
+/* One process drives `ndev` GPUs (what a C# host does: INTEGRATION.md).  devices == NULL: 0..ndev-1.  NCCL communicators come
+ * from ncclCommInitAll; if a device is listed twice (several ranks on one GPU: tests) or SPHB200_GROUP_TRANSPORT=local, the
+ * ranks exchange by in-process peer copies instead.  capacity = particles of the whole group.
+ * Replaces: World creation (OnCreate of the six systems), as sphb200_create. */
+SPH_API int sphb200_group_create(const sph_Params* params, int64_t capacity, int ndev, const int* devices, sph_group* out);
+/* One process per GPU (torchrun, MPI): rank 0 calls sphb200_group_unique_id, the host distributes the 128 bytes, every
+ * process calls sphb200_group_create_rank with its rank and device. */
+SPH_API int sphb200_group_unique_id(void* id128);
+SPH_API int sphb200_group_create_rank(const sph_Params* params, int64_t capacity, const void* id128, int world, int rank,
+                                      int device, sph_group* out);
+SPH_API int sphb200_group_destroy(sph_group g);
+SPH_API const char* sphb200_group_last_error(sph_group g);
+/* Bodies this process uploads / downloads: [*body0, *body0 + *count). */
+SPH_API int sphb200_group_body_range(sph_group g, int64_t n_total, int64_t* body0, int64_t* count);
+/* As sphb200_upload; the arrays hold this process's bodies only (element 0 = body *body0). n_total = bodies of the group. */
+SPH_API int sphb200_group_upload(sph_group g, int64_t n_total, const void* pos, int pos_stride, const void* vel, int vel_stride,
+                                 const void* mass, int mass_stride, const void* smoothing, int smoothing_stride);
+/* One FixedStepSimulationSystemGroup tick on all ranks (as sphb200_step). */
+SPH_API int sphb200_group_step(sph_group g, float dt, int gravity_impl);
+/* As sphb200_download, for this process's bodies (element 0 = body *body0). */
+SPH_API int sphb200_group_download(sph_group g, int field, void* dst, int stride);
+SPH_API int sphb200_group_sync(sph_group g);
+/* As sphb200_diagnostics, reduced over the group. */
+SPH_API int sphb200_group_diagnostics(sph_group g, double* out12);
+SPH_API int sphb200_group_info(sph_group g, sph_GroupInfo* out);
+SPH_API int sphb200_group_enable_timing(sph_group g, int enable);
+SPH_API int sphb200_group_get_timings(sph_group g, const char** names, float* ms, int cap);
+/* Context of local rank `local_rank` (owned by the group) for inspection through the sphb200_* getters. */
+SPH_API int sphb200_group_rank_handle(sph_group g, int local_rank, sph_handle* out);
 
 #ifdef __cplusplus
 }

@@ -77,33 +77,42 @@ int sphb200_destroy(sph_handle c) {
     return SPH_OK;
 }
 
-int sphb200_create(const sph_Params* params, int64_t capacity, int device, sph_handle* out) {
-    if (!out) return SPH_ERR_INVALID_ARG;
+}  // extern "C"
+
+// Largest grid for n particles: ~2 cells per particle at most, <= 2^8 cells per axis.  A function of the particle count
+// (not of the handle's capacity) so that a group rank and a single handle lay the same grid over the same particles.
+int sph_grid_bits_for(const sph_Params& p, int64_t n) {
+    if (p.max_grid_bits > 0) return p.max_grid_bits;
+    int bits = (int)floor(log2(2.0 * (double)std::max<int64_t>(n, 1)) / 3.0);
+    return std::min(std::max(bits, 1), 8);
+}
+
+int sph_validate_params(const sph_Params& p, int64_t capacity, std::string& err) {
+    if (capacity <= 0 || capacity > 0x7fffff00LL / 2) { err = "capacity out of range"; return SPH_ERR_CAPACITY; }
+    if (p.max_neighbors <= 0 || p.max_neighbors % 32 != 0 || p.max_neighbors > 1024) { err = "max_neighbors must be a multiple of 32 in [32,1024]"; return SPH_ERR_INVALID_ARG; }
+    if (p.leaf_max < 1 || p.leaf_max > 64) { err = "leaf_max must be in [1,64]"; return SPH_ERR_INVALID_ARG; }
+    if (p.max_grid_bits < 0 || p.max_grid_bits > 8) { err = "max_grid_bits must be in [0,8]"; return SPH_ERR_INVALID_ARG; }
+    return SPH_OK;
+}
+
+// Allocate a context: `slots` resident particle slots, neighbor rows / staging for `rows` of them, an LBVH over `tree`
+// (global) slots, a cell table for up to `total` particles.  A single handle uses one capacity for all four.
+int sph_ctx_create(const sph_Params& p, int device, int64_t slots, int64_t rows, int64_t tree, int64_t total, bool pingpong,
+                   sphb200_ctx** out, std::string& err) {
     *out = nullptr;
-    sph_Params p;
-    if (params) p = *params; else sphb200_default_params(&p);
-    if (capacity <= 0 || capacity > 0x7fffff00LL / 2) { g_create_err = "capacity out of range"; return SPH_ERR_CAPACITY; }
-    if (p.max_neighbors <= 0 || p.max_neighbors % 32 != 0 || p.max_neighbors > 1024) { g_create_err = "max_neighbors must be a multiple of 32 in [32,1024]"; return SPH_ERR_INVALID_ARG; }
-    if (p.leaf_max < 1 || p.leaf_max > 64) { g_create_err = "leaf_max must be in [1,64]"; return SPH_ERR_INVALID_ARG; }
-    if (p.max_grid_bits < 0 || p.max_grid_bits > 8) { g_create_err = "max_grid_bits must be in [0,8]"; return SPH_ERR_INVALID_ARG; }
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
-    if (e != cudaSuccess || ndev == 0) { g_create_err = std::string("no CUDA device (no CPU fallback exists): ") + cudaGetErrorString(e); return SPH_ERR_CUDA; }
-    if (device < 0 || device >= ndev) { g_create_err = "bad device index"; return SPH_ERR_INVALID_ARG; }
+    if (e != cudaSuccess || ndev == 0) { err = std::string("no CUDA device (no CPU fallback exists): ") + cudaGetErrorString(e); return SPH_ERR_CUDA; }
+    if (device < 0 || device >= ndev) { err = "bad device index"; return SPH_ERR_INVALID_ARG; }
     cudaDeviceProp prop;
-    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) { g_create_err = "device is not sm_100-class (library is built for sm_100a only)"; return SPH_ERR_CUDA; }
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10) { err = "device is not sm_100-class (library is built for sm_100a only)"; return SPH_ERR_CUDA; }
     sphb200_ctx* c = new (std::nothrow) sphb200_ctx();
     if (!c) return SPH_ERR_CUDA;
-    c->p = p; c->device = device; c->cap = capacity; c->sm_count = prop.multiProcessorCount;
-    int bits = p.max_grid_bits;
-    if (bits == 0) {  // ~2 cells per particle at most
-        bits = (int)floor(log2(2.0 * (double)capacity) / 3.0);
-        bits = std::min(std::max(bits, 1), 8);
-    }
-    c->grid_bits_max = bits;
-    c->ncell_max = (size_t)1 << (3 * bits);
+    c->p = p; c->device = device; c->cap = slots; c->cap_rows = rows; c->sm_count = prop.multiProcessorCount;
+    c->grid_bits_max = sph_grid_bits_for(p, total);
+    c->ncell_max = (size_t)1 << (3 * c->grid_bits_max);
     c->gpart_splits = 8;
-    size_t cap = (size_t)capacity, nn = 2 * cap;
+    size_t cap = (size_t)slots, nr = (size_t)rows, nn = 2 * (size_t)tree;
     bool ok = cudaSetDevice(device) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -111,25 +120,26 @@ int sphb200_create(const sph_Params* params, int64_t capacity, int device, sph_h
     ok = ok && cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess;
     c->stream = c->own_stream;
     for (int k = 0; k < 2 && ok; k++) {
-        ok = ok && dalloc(&c->posh[k], cap) == cudaSuccess && dalloc(&c->velm[k], cap) == cudaSuccess &&
-             dalloc(&c->orig[k], cap) == cudaSuccess && dalloc(&c->keys[k], cap) == cudaSuccess && dalloc(&c->idx[k], cap) == cudaSuccess;
+        if (k == 0 || pingpong)
+            ok = ok && dalloc(&c->posh[k], cap) == cudaSuccess && dalloc(&c->velm[k], cap) == cudaSuccess && dalloc(&c->orig[k], cap) == cudaSuccess;
+        ok = ok && dalloc(&c->keys[k], cap) == cudaSuccess && dalloc(&c->idx[k], cap) == cudaSuccess;
     }
-    c->stage_bytes = std::max<size_t>(cap * 14 * 4, (cap + 1) * 8);   // upload: pos3 vel3 mass1 + raw smoothing records (7)
-    ok = ok && dalloc(&c->posm, cap) == cudaSuccess && dalloc(&c->posc, cap) == cudaSuccess && dalloc(&c->chunk_counter, 1) == cudaSuccess && dalloc(&c->sort_hist, sph_sort_hist_words(capacity)) == cudaSuccess &&
+    c->stage_bytes = std::max<size_t>(nr * 14 * 4, (nr + 1) * 8);   // upload: pos3 vel3 mass1 + raw smoothing records (7)
+    ok = ok && dalloc(&c->posm, cap) == cudaSuccess && dalloc(&c->posc, cap) == cudaSuccess && dalloc(&c->chunk_counter, 1) == cudaSuccess && dalloc(&c->sort_hist, sph_sort_hist_words(slots)) == cudaSuccess &&
          dalloc(&c->cell_start, c->ncell_max) == cudaSuccess && dalloc(&c->cell_end, c->ncell_max) == cudaSuccess && dalloc(&c->cell_hmax, c->ncell_max) == cudaSuccess &&
-         dalloc(&c->nlist, cap * (size_t)p.max_neighbors) == cudaSuccess && dalloc(&c->ncount, cap) == cudaSuccess &&
+         dalloc(&c->nlist, nr * (size_t)p.max_neighbors) == cudaSuccess && dalloc(&c->ncount, cap) == cudaSuccess &&
          dalloc(&c->nown, cap) == cudaSuccess && dalloc(&c->rho, cap) == cudaSuccess && dalloc(&c->press, cap) == cudaSuccess &&
          dalloc(&c->cvol, cap) == cudaSuccess && dalloc(&c->gradp, cap) == cudaSuccess && dalloc(&c->grav, cap) == cudaSuccess &&
          dalloc(&c->npart, cap) == cudaSuccess && dalloc(&c->napprox, cap) == cudaSuccess &&
-         dalloc(&c->gpart, cap * (size_t)c->gpart_splits) == cudaSuccess && dalloc(&c->tbox, 2 * (cap / 256 + 2)) == cudaSuccess && dalloc(&c->child, nn) == cudaSuccess &&
+         dalloc(&c->gpart, nr * (size_t)c->gpart_splits) == cudaSuccess && dalloc(&c->tbox, 2 * ((size_t)tree / 256 + 2)) == cudaSuccess && dalloc(&c->child, nn) == cudaSuccess &&
          dalloc(&c->range, nn) == cudaSuccess && dalloc(&c->parent, nn) == cudaSuccess && dalloc(&c->flag, nn) == cudaSuccess &&
          dalloc(&c->mom, nn) == cudaSuccess && dalloc(&c->nlo, nn) == cudaSuccess && dalloc(&c->nhi, nn) == cudaSuccess && dalloc(&c->packed, 2 * nn) == cudaSuccess &&
          dalloc(&c->bounds, 16) == cudaSuccess && dalloc(&c->grid_d, 1) == cudaSuccess && dalloc(&c->err_d, ERR_SLOTS) == cudaSuccess &&
-         dalloc(&c->rr_table, SPH_RR_TABLE) == cudaSuccess && dalloc(&c->diag_d, 16) == cudaSuccess &&
-         cudaMalloc(&c->stage_d, c->stage_bytes) == cudaSuccess && cudaMallocHost((void**)&c->err_h, ERR_SLOTS * sizeof(int32_t)) == cudaSuccess &&
+         dalloc(&c->rr_table, SPH_RR_TABLE) == cudaSuccess && dalloc(&c->diag_d, 32) == cudaSuccess &&
+         cudaMalloc(&c->stage_d, c->stage_bytes) == cudaSuccess && cudaMallocHost((void**)&c->err_h, 2 * ERR_SLOTS * sizeof(int32_t)) == cudaSuccess &&
          cudaMallocHost(&c->stage_h, c->stage_bytes) == cudaSuccess;
     if (!ok) {
-        g_create_err = std::string("allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+        err = std::string("allocation failed: ") + cudaGetErrorString(cudaGetLastError());
         sphb200_destroy(c);
         return SPH_ERR_CUDA;
     }
@@ -144,10 +154,23 @@ int sphb200_create(const sph_Params* params, int64_t capacity, int device, sph_h
     ok = cudaMemcpy(c->rr_table, rr.data(), SPH_RR_TABLE * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemcpy(c->bounds, b0, sizeof(b0), cudaMemcpyHostToDevice) == cudaSuccess &&
          cudaMemset(c->err_d, 0, ERR_SLOTS * sizeof(int32_t)) == cudaSuccess &&
-         cudaMemset(c->nown, 0, cap * sizeof(int32_t)) == cudaSuccess;
-    if (!ok) { g_create_err = "initialisation failed"; sphb200_destroy(c); return SPH_ERR_CUDA; }
+         cudaMemset(c->nown, 0, cap * sizeof(int32_t)) == cudaSuccess && cudaMemset(c->ncount, 0, cap * sizeof(int32_t)) == cudaSuccess &&
+         cudaMemset(c->npart, 0, cap * sizeof(int32_t)) == cudaSuccess && cudaMemset(c->napprox, 0, cap * sizeof(int32_t)) == cudaSuccess;
+    if (!ok) { err = "initialisation failed"; sphb200_destroy(c); return SPH_ERR_CUDA; }
     *out = c;
     return SPH_OK;
+}
+
+extern "C" {
+
+int sphb200_create(const sph_Params* params, int64_t capacity, int device, sph_handle* out) {
+    if (!out) return SPH_ERR_INVALID_ARG;
+    *out = nullptr;
+    sph_Params p;
+    if (params) p = *params; else sphb200_default_params(&p);
+    int rc = sph_validate_params(p, capacity, g_create_err);
+    if (rc) return rc;
+    return sph_ctx_create(p, device, capacity, capacity, capacity, capacity, true, out, g_create_err);
 }
 
 const char* sphb200_last_error(sph_handle c) { return c ? c->err.c_str() : g_create_err.c_str(); }
@@ -222,23 +245,27 @@ int sphb200_set_target_range(sph_handle c, int64_t t0, int64_t t1) {
 }
 
 // ---- upload ---------------------------------------------------------------------------------------------------------
-int sphb200_upload(sph_handle c, int64_t n, const void* pos, int pos_stride, const void* vel, int vel_stride, const void* mass,
-                   int mass_stride, const void* smoothing, int smoothing_stride) {
-    if (!c) return SPH_ERR_INVALID_ARG;
+}  // extern "C"
+
+// Stage the component arrays of `n` bodies (body indices orig0 .. orig0+n-1) and pack them into the resident SoA at slot 0.
+// Asynchronous on the context's stream; the mass range lands in bounds[12..13] (ordered uints) for sph_upload_finish.
+int sph_upload_core(sphb200_ctx* c, int64_t n, uint32_t orig0, const void* pos, int pos_stride, const void* vel, int vel_stride,
+                    const void* mass, int mass_stride, const void* smoothing, int smoothing_stride) {
     ARG_CHECK(c, n >= 0, "n < 0");
-    if (n > c->cap) { c->err = "n exceeds capacity"; return SPH_ERR_CAPACITY; }
     ARG_CHECK(c, n == 0 || (pos && vel && mass && smoothing), "null component array");
     ARG_CHECK(c, pos_stride >= 12 && vel_stride >= 12 && mass_stride >= 4 && smoothing_stride >= 4, "stride too small");
+    ARG_CHECK(c, (size_t)n * 14 * 4 <= c->stage_bytes || n == 0, "upload larger than the staging buffer");
     SPH_CK(c, cudaSetDevice(c->device));
     SPH_CK(c, cudaStreamSynchronize(c->aux_stream));
     SPH_CK(c, cudaStreamSynchronize(c->stream));
     c->tree_join_pending = c->tree_fresh = c->tree_hint = false;
-    c->n = n;
     c->cur = 0;
     c->resident = true; c->lists_valid = c->pressure_valid = c->gravity_valid = c->tree_valid = c->h_updated = false;
     c->sorted_valid = c->lists_fresh = false;
     // asynchronous error flags are sticky from one upload to the next (results after an overflow are tainted)
     SPH_CK(c, cudaMemsetAsync(c->err_d, 0, ERR_SLOTS * sizeof(int32_t), c->stream));
+    const uint32_t mm0[2] = {0xffffffffu, 0u};
+    SPH_CK(c, cudaMemcpyAsync(c->bounds + 12, mm0, sizeof(mm0), cudaMemcpyHostToDevice, c->stream));
     if (n == 0) return SPH_OK;
     // Staging layout (device): pos[3n] vel[3n] mass[n] h[n] nown[n].  Arrays with their natural stride are copied
     // straight from the caller's memory (one DMA when it is pinned); strided arrays are packed through pinned staging.
@@ -265,19 +292,35 @@ int sphb200_upload(sph_handle c, int64_t n, const void* pos, int pos_stride, con
         SPH_CK(c, put(7 * (size_t)n, sp, smoothing_stride, 1));
         if (has_nown) SPH_CK(c, put(8 * (size_t)n, sp + 24, smoothing_stride, 1));
     }
-    float m0;
-    memcpy(&m0, mp, 4);
-    c->equal_mass = true;
-    c->common_mass = m0;
-    for (int64_t i = 1; i < n && c->equal_mass; i++) {
-        float mi;
-        memcpy(&mi, mp + (size_t)i * mass_stride, 4);
-        c->equal_mass = (mi == m0);
-    }
-    int rc = sph_launch_pack_upload(c, n, nown_mode);
-    if (rc) return rc;
+    return sph_launch_pack_upload(c, n, nown_mode, orig0);   // also reduces the mass range into bounds[12..13]
+}
+
+// Blocks; equal masses (the reference spawner, ParticleAuthoring.cs:208) select the kernels that hoist the mass multiply.
+int sph_upload_finish(sphb200_ctx* c) {
+    SPH_CK(c, cudaMemcpyAsync(c->err_h + 4, c->bounds + 12, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     SPH_CK(c, cudaStreamSynchronize(c->stream));
+    const uint32_t lo = (uint32_t)c->err_h[4], hi = (uint32_t)c->err_h[5];
+    c->equal_mass = lo == hi;
+    const uint32_t bits = (lo & 0x80000000u) ? (lo & 0x7fffffffu) : ~lo;   // ord2f on the host
+    memcpy(&c->common_mass, &bits, 4);
     return SPH_OK;
+}
+
+extern "C" {
+
+int sphb200_upload(sph_handle c, int64_t n, const void* pos, int pos_stride, const void* vel, int vel_stride, const void* mass,
+                   int mass_stride, const void* smoothing, int smoothing_stride) {
+    if (!c) return SPH_ERR_INVALID_ARG;
+    if (n > c->cap) { c->err = "n exceeds capacity"; return SPH_ERR_CAPACITY; }
+    int rc = sph_upload_core(c, n, 0u, pos, pos_stride, vel, vel_stride, mass, mass_stride, smoothing, smoothing_stride);
+    if (rc) return rc;
+    c->n = n;
+    // single handle: the resident slots are the global slots
+    c->skeys = c->tkeys = c->keys[1];
+    c->gsrc = c->posm; c->gsrc_n = n;
+    c->tree_n = n; c->tree_g0 = 0; c->tree_g1 = n; c->tree_off = 0; c->row_base = 0;
+    c->grid_bits_max = sph_grid_bits_for(c->p, n);   // a function of n, not of the capacity (same grid as any other handle / group)
+    return sph_upload_finish(c);
 }
 
 // ---- stages ----------------------------------------------------------------------------------------------------------

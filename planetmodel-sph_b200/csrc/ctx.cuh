@@ -8,16 +8,24 @@
 
 #define SPH_MAX_PASSES 24
 #define SPH_RR_TABLE 4096          // radius-ratio table entries (own-support count 1..4095)
-#define SPH_TREE_STACK 160         // per-warp traversal stack entries
-#define SPH_BODY_CAP 16777214      // 2^24-2, UP/Dynamics/Simulation/Scheduler.cs:26-31,41 (quirk Q12)
+#define SPH_MAX_RANKS 32           // ranks of one group (halo masks are 32-bit)
+#define SPH_TOP_LEAF 64            // >= the largest leaf_max: boundary particles published per rank side
+#define SPH_TOP_CAP 512            // per-rank capacity of the top-tree lists (nodes that straddle a rank boundary)
 
-enum { ERR_NEIGHBOR_OVERFLOW = 0, ERR_TREE_STACK = 1, ERR_SLOTS = 4 };
+enum { ERR_NEIGHBOR_OVERFLOW = 0, ERR_TREE_STACK = 1, ERR_TOP_TREE = 2, ERR_SLOTS = 4 };
+
+// Top-tree records of the distributed LBVH build (kernels_tree.cu / kernels_group.cu).  A node whose particle range crosses
+// a rank boundary cannot be finished by one rank: its owner emits its topology, the owners of its finished children emit
+// their moments, and every rank then completes the few straddling nodes redundantly (bit-identical on all ranks).
+struct TopNode { int id, a, b, lo, hi, pad0, pad1, pad2; };        // a/b = children (internal) ; lo..hi = particle range
+struct FrontNode { int id, pad0, pad1, pad2; float4 mom, lo, hi; };   // a finished node whose parent is a top node
 
 struct sphb200_ctx {
     sph_Params p{};
     int device = 0;
     int sm_count = 148;
-    int64_t cap = 0, n = 0;
+    int64_t cap = 0, n = 0;      // resident slots: capacity, in use
+    int64_t cap_rows = 0;        // slots that can be targets (neighbor rows, all-pairs partial sums, staging)
     cudaStream_t own_stream = nullptr, stream = nullptr;
 
     // resident SoA state, sorted (Morton) order after build_neighbors; ping-pong through the permute
@@ -31,6 +39,7 @@ struct sphb200_ctx {
 
     uint32_t* keys[2] = {nullptr, nullptr};
     uint32_t* idx[2] = {nullptr, nullptr};
+    uint32_t* skeys = nullptr;               // sorted keys of the resident slots (single handle: keys[1]; group rank: extended set)
     uint32_t* sort_hist = nullptr;   // radix sort: digit counts [256][tiles] + totals [256]
     uint32_t* cell_start = nullptr;
     uint32_t* cell_end = nullptr;
@@ -38,7 +47,8 @@ struct sphb200_ctx {
     int grid_bits_max = 0;
     size_t ncell_max = 0;
 
-    uint32_t* nlist = nullptr;   // [cap][max_neighbors] sorted-slot indices
+    uint32_t* nlist = nullptr;   // [rows][max_neighbors] sorted-slot indices; row of slot t = t - row_base
+    int64_t row_base = 0;        // group ranks keep rows for their own slots only
     int32_t* ncount = nullptr;   // symmetric neighbor count
     int32_t* nown = nullptr;     // own-support count (KernelThis.w > 0)
     float* rho = nullptr;
@@ -53,6 +63,16 @@ struct sphb200_ctx {
     float common_mass = 0.f;
     float4* gpart = nullptr;     // all-pairs partial sums [splits][n]
     int gpart_splits = 0;
+    float4* gsrc = nullptr;      // gravity sources (x,y,z,m) in GLOBAL sorted order: posm for a single handle, the all-gathered
+    int64_t gsrc_n = 0;          // array for a group rank
+    // LBVH addressing: the tree spans tree_n global slots; this context builds the nodes of slots [tree_g0, tree_g1) and its
+    // resident slot of global slot s is s + tree_off
+    uint32_t* tkeys = nullptr;
+    int64_t tree_n = 0, tree_g0 = 0, tree_g1 = 0, tree_off = 0;
+    TopNode* top_nodes = nullptr;     // [world][SPH_TOP_CAP] (own segment filled by the build, the rest all-gathered)
+    FrontNode* front_nodes = nullptr; // [world][SPH_TOP_CAP]
+    int32_t* top_counts = nullptr;    // [world][4]: top nodes, frontier nodes
+    int top_rank = 0;                 // own segment
 
     // LBVH (2n-1 nodes)
     int2* child = nullptr;
@@ -162,9 +182,18 @@ __device__ __forceinline__ float sph_keep_threshold(float h) {
     return fminf(a, __uint_as_float(u));
 }
 
+int sph_grid_bits_for(const sph_Params& p, int64_t n);
+int sph_validate_params(const sph_Params& p, int64_t capacity, std::string& err);
+int sph_ctx_create(const sph_Params& p, int device, int64_t slots, int64_t rows, int64_t tree, int64_t total, bool pingpong,
+                   sphb200_ctx** out, std::string& err);
+
 // ---- kernel launchers (one translation unit each) -----------------------------------------------------------
 int sph_launch_smoothing_bounds(sphb200_ctx* c, bool update_h);
 int sph_launch_sort_and_cells(sphb200_ctx* c);
+int sph_launch_bounds_range(sphb200_ctx* c, float4* posh, const int32_t* nown, int n, bool update_h);
+int sph_launch_grid_setup(sphb200_ctx* c, int64_t n_total);
+int sph_launch_keys(sphb200_ctx* c, const float4* posh, int n, uint32_t* keys);
+int sph_launch_rowscan(sphb200_ctx* c, uint32_t* rows_d, int nblocks, int rows, uint32_t* totals, cudaStream_t stream);
 int sph_launch_neighbors_density(sphb200_ctx* c);
 int sph_launch_pressure(sphb200_ctx* c);
 int sph_launch_gravity_near(sphb200_ctx* c);
@@ -172,8 +201,13 @@ int sph_launch_integrate(sphb200_ctx* c, float dt);
 int sph_launch_gravity_allpairs(sphb200_ctx* c);
 int sph_launch_tree_build(sphb200_ctx* c, float dt, cudaStream_t stream);
 int sph_launch_tree_walk(sphb200_ctx* c);
+int sph_launch_top_tree(sphb200_ctx* c, int world, const float4* bnd, const int64_t* g0_d, float dt);
 int sph_launch_diagnostics(sphb200_ctx* c, double* out12);
-int sph_launch_pack_upload(sphb200_ctx* c, int64_t n, int has_nown);
+int sph_launch_diagnostics_range(sphb200_ctx* c, int off, int n);
+int sph_launch_pack_upload(sphb200_ctx* c, int64_t n, int has_nown, uint32_t orig0);
+int sph_upload_core(sphb200_ctx* c, int64_t n, uint32_t orig0, const void* pos, int pos_stride, const void* vel, int vel_stride,
+                    const void* mass, int mass_stride, const void* smoothing, int smoothing_stride);
+int sph_upload_finish(sphb200_ctx* c);
 int sph_launch_unpack_field(sphb200_ctx* c, int field, int* elem_bytes);
 int sph_launch_neighbor_rows_sorted(sphb200_ctx* c, int32_t* rows_d);
 int sph_launch_interactions(sphb200_ctx* c, int64_t total, const int64_t* offsets_d, const int32_t* nbr_d, sph_ParticleInteraction* out_d);

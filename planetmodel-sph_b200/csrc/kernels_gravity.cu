@@ -243,12 +243,13 @@ int sph_launch_gravity_allpairs(sphb200_ctx* c) {
     int t1 = (c->t1 < 0 || c->t1 > c->n) ? (int)c->n : (int)c->t1;
     int nt = t1 - t0;
     if (nt <= 0) return SPH_OK;
-    int n = (int)c->n;
+    int n = (int)c->gsrc_n;          // sources: every particle of the (global) sorted order
+    const float4* src = c->gsrc;
     int tblocks = sph_div_up(nt, AP_THREADS * AP_TPT);
     // enough blocks for >= ~12 waves of 3 resident CTAs/SM, bounded by the partial-sum buffer (cap * gpart_splits float4)
     int want = c->sm_count * 3 * 12;
     int splits = sph_div_up(want, tblocks);
-    int64_t mem_splits = (int64_t)c->cap * c->gpart_splits / nt;
+    int64_t mem_splits = (int64_t)c->cap_rows * c->gpart_splits / nt;
     if (splits > mem_splits) splits = (int)mem_splits;
     int max_by_src = sph_div_up(n, AP_TILE);
     if (splits > max_by_src) splits = max_by_src;
@@ -257,13 +258,13 @@ int sph_launch_gravity_allpairs(sphb200_ctx* c) {
     int per = sph_div_up(n, splits);
     per = sph_div_up(per, AP_TILE) * AP_TILE;
     splits = sph_div_up(n, per);
-    k_tile_boxes<<<sph_div_up(n, AP_TILE), AP_TILE, 0, c->stream>>>(c->posm, n, c->tbox);
+    k_tile_boxes<<<sph_div_up(n, AP_TILE), AP_TILE, 0, c->stream>>>(src, n, c->tbox);
     SPH_LAUNCH_CHECK(c);
     dim3 grid(tblocks, splits);
     if (c->equal_mass)
-        k_gravity_allpairs<AP_TPT, true><<<grid, AP_THREADS, 0, c->stream>>>(c->posm, n, per, c->tbox, c->posh[c->cur], t0, t1, c->gpart);
+        k_gravity_allpairs<AP_TPT, true><<<grid, AP_THREADS, 0, c->stream>>>(src, n, per, c->tbox, c->posh[c->cur], t0, t1, c->gpart);
     else
-        k_gravity_allpairs<AP_TPT, false><<<grid, AP_THREADS, 0, c->stream>>>(c->posm, n, per, c->tbox, c->posh[c->cur], t0, t1, c->gpart);
+        k_gravity_allpairs<AP_TPT, false><<<grid, AP_THREADS, 0, c->stream>>>(src, n, per, c->tbox, c->posh[c->cur], t0, t1, c->gpart);
     SPH_LAUNCH_CHECK(c);
     k_gravity_reduce<<<sph_div_up(nt, 256), 256, 0, c->stream>>>(c->gpart, splits, c->posh[c->cur], c->posm, t0, t1, c->p.G,
                                                                 c->equal_mass ? c->common_mass : 1.0f, c->equal_mass ? 1 : 0, c->grav,

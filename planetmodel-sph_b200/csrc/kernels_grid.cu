@@ -130,12 +130,28 @@ __global__ void __launch_bounds__(256) k_permute_cells(const uint32_t* __restric
 
 }  // namespace
 
-int sph_launch_smoothing_bounds(sphb200_ctx* c, bool update_h) {
-    int n = (int)c->n;
+// smoothing-length update + bounds accumulation over `n` resident particles starting at posh / nown
+int sph_launch_bounds_range(sphb200_ctx* c, float4* posh, const int32_t* nown, int n, bool update_h) {
+    if (n <= 0) return SPH_OK;
     int blocks = min(sph_div_up(n, 256), c->sm_count * 8);
-    k_smoothing_bounds<<<blocks, 256, 0, c->stream>>>(c->posh[c->cur], c->nown, c->rr_table, n, update_h ? 1 : 0, c->bounds);
+    k_smoothing_bounds<<<blocks, 256, 0, c->stream>>>(posh, nown, c->rr_table, n, update_h ? 1 : 0, c->bounds);
     SPH_LAUNCH_CHECK(c);
-    k_grid_setup<<<1, 1, 0, c->stream>>>(c->bounds, c->grid_d, c->grid_bits_max, n);
+    return SPH_OK;
+}
+// bounds (of all n_total particles: a group all-reduces them first) -> grid parameters; re-arms the accumulator
+int sph_launch_grid_setup(sphb200_ctx* c, int64_t n_total) {
+    k_grid_setup<<<1, 1, 0, c->stream>>>(c->bounds, c->grid_d, c->grid_bits_max, (int)n_total);
+    SPH_LAUNCH_CHECK(c);
+    return SPH_OK;
+}
+int sph_launch_smoothing_bounds(sphb200_ctx* c, bool update_h) {
+    int rc = sph_launch_bounds_range(c, c->posh[c->cur], c->nown, (int)c->n, update_h);
+    if (rc) return rc;
+    return sph_launch_grid_setup(c, c->n);
+}
+int sph_launch_keys(sphb200_ctx* c, const float4* posh, int n, uint32_t* keys) {
+    if (n <= 0) return SPH_OK;
+    k_keys<<<sph_div_up(n, 256), 256, 0, c->stream>>>(posh, c->grid_d, n, keys);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;
 }
@@ -146,7 +162,7 @@ int sph_launch_sort_and_cells(sphb200_ctx* c) {
     k_keys<<<sph_div_up(n, 256), 256, 0, c->stream>>>(c->posh[in], c->grid_d, n, c->keys[1]);
     SPH_LAUNCH_CHECK(c);
     { int rc = sph_launch_radix_sort(c, n, c->stream); if (rc) return rc; }   // (keys[1], iota) -> (keys[1], idx[1]), stable
-    size_t ncell = c->ncell_max;
+    size_t ncell = (size_t)1 << (3 * c->grid_bits_max);   // cells of the largest grid this particle count can get
     SPH_CK(c, cudaMemsetAsync(c->cell_start, 0, ncell * sizeof(uint32_t), c->stream));
     SPH_CK(c, cudaMemsetAsync(c->cell_end, 0, ncell * sizeof(uint32_t), c->stream));
     SPH_CK(c, cudaMemsetAsync(c->cell_hmax, 0, ncell * sizeof(uint32_t), c->stream));

@@ -63,7 +63,7 @@ struct Surv { uint32_t j; float r; float hj; };  // r carries "inside i's own su
 __global__ void __launch_bounds__(K1_WARPS * 32) k_neighbors_density(
     const float4* __restrict__ posh, const float4* __restrict__ posm, const uint32_t* __restrict__ keys,
     const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end, const uint32_t* __restrict__ cell_hmax,
-    const sph_GridParams* __restrict__ g, int t0, int t1, int kmax, float Keos, uint32_t* __restrict__ nlist,
+    const sph_GridParams* __restrict__ g, int t0, int t1, int rowbase, int kmax, float Keos, uint32_t* __restrict__ nlist,
     int32_t* __restrict__ ncount, int32_t* __restrict__ nown, float* __restrict__ rho, float* __restrict__ press,
     float* __restrict__ cvol, int32_t* __restrict__ err) {
     __shared__ uint2 cellq[K1_WARPS][K1_CELLQ];
@@ -89,7 +89,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_neighbors_density(
                     sz = __fmul_rn(__fsub_rn(pi.z, gz0), fs);
         const uint32_t ck = keys[t] >> shift;
         const int cx = (int)compact10(ck), cy = (int)compact10(ck >> 1), cz = (int)compact10(ck >> 2);
-        uint32_t* row = nlist + (size_t)t * kmax;
+        uint32_t* row = nlist + (size_t)(t - rowbase) * kmax;
         float rho_l = 0.f;
         int own_l = 0, count = 0;
         int qn = 0;            // relevant cells queued
@@ -255,7 +255,7 @@ template <bool EQM>
 __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINB) k_cell_neighbors(
     const float4* __restrict__ posc, const float4* __restrict__ posh, const float4* __restrict__ posm,
     const uint32_t* __restrict__ keys, const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
-    const uint32_t* __restrict__ cell_hmax, const sph_GridParams* __restrict__ g, int t0, int t1, int kmax, float Keos,
+    const uint32_t* __restrict__ cell_hmax, const sph_GridParams* __restrict__ g, int t0, int t1, int rowbase, int kmax, float Keos,
     uint32_t* __restrict__ nlist, int32_t* __restrict__ ncount, int32_t* __restrict__ nown, float* __restrict__ rho, float* __restrict__ press,
     float* __restrict__ cvol, int32_t* __restrict__ err, unsigned int* __restrict__ chunk_counter) {
     __shared__ float4 tgt[K3_WARPS][K3_MAXT];
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINB) k_cell_neighbors(
                     cmax = fmaxf(cmax, __shfl_xor_sync(FULL, cmax, o));
                     hmax_t = fmaxf(hmax_t, __shfl_xor_sync(FULL, hmax_t, o));
                 }
-                uint32_t* rowp = nlist + (size_t)p0 * kmax;
+                uint32_t* rowp = nlist + (size_t)(p0 - rowbase) * kmax;
                 int qn = 0, qtotal = 0;
 
                 // 32 compacted candidates (ring entries rh .. rh+m-1) against every target of the pass; row fill counts live
@@ -477,7 +477,7 @@ __global__ void __launch_bounds__(256) k_density(const float4* __restrict__ posh
                                                  const float4* __restrict__ posc, const uint32_t* __restrict__ keys,
                                                  const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
                                                  const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
-                                                 const sph_GridParams* __restrict__ g, int t0, int t1, int kmax, float Keos,
+                                                 const sph_GridParams* __restrict__ g, int t0, int t1, int rowbase, int kmax, float Keos,
                                                  int32_t* __restrict__ nown, float* __restrict__ rho, float* __restrict__ press,
                                                  float* __restrict__ cvol) {
     if (!(g->hmax < kHugeH)) return;
@@ -499,7 +499,7 @@ __global__ void __launch_bounds__(256) k_density(const float4* __restrict__ posh
             rsum = EQM ? rsum + wsym : fmaf(posm[j].w, wsym, rsum);
         };
         if (cnt <= kmax) {
-            const uint32_t* row = nlist + (size_t)t * kmax;
+            const uint32_t* row = nlist + (size_t)(t - rowbase) * kmax;
             int k = sub;
             for (; k + K1B_LPT < cnt; k += 2 * K1B_LPT) {   // two gathers in flight
                 const uint32_t j0 = row[k], j1 = row[k + K1B_LPT];
@@ -562,7 +562,7 @@ int sph_launch_neighbors_density(sphb200_ctx* c) {
     // cell-centric kernel (h_max < 1e5): persistent warps pull 32-cell chunks from a counter
     SPH_CK(c, cudaMemsetAsync(c->chunk_counter, 0, sizeof(unsigned int), c->stream));
 #define K3_LAUNCH(E) k_cell_neighbors<E><<<c->sm_count * K3_MINB, K3_WARPS * 32, 0, c->stream>>>(                                        \
-        c->posc, c->posh[c->cur], c->posm, c->keys[1], c->cell_start, c->cell_end, c->cell_hmax, c->grid_d, t0, t1, c->p.max_neighbors, c->p.K, \
+        c->posc, c->posh[c->cur], c->posm, c->skeys, c->cell_start, c->cell_end, c->cell_hmax, c->grid_d, t0, t1, (int)c->row_base, c->p.max_neighbors, c->p.K, \
         c->nlist, c->ncount, c->nown, c->rho, c->press, c->cvol, c->err_d, c->chunk_counter)
     if (c->equal_mass) K3_LAUNCH(true); else K3_LAUNCH(false);
 #undef K3_LAUNCH
@@ -570,19 +570,19 @@ int sph_launch_neighbors_density(sphb200_ctx* c) {
     {
         int tpb = 256 / K1B_LPT;
         if (c->equal_mass)
-            k_density<true><<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->posm, c->posc, c->keys[1], c->cell_start,
+            k_density<true><<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->posm, c->posc, c->skeys, c->cell_start,
                                                                         c->cell_end, c->nlist, c->ncount, c->grid_d, t0, t1,
-                                                                        c->p.max_neighbors, c->p.K, c->nown, c->rho, c->press, c->cvol);
+                                                                        (int)c->row_base, c->p.max_neighbors, c->p.K, c->nown, c->rho, c->press, c->cvol);
         else
-            k_density<false><<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->posm, c->posc, c->keys[1], c->cell_start,
+            k_density<false><<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->posm, c->posc, c->skeys, c->cell_start,
                                                                          c->cell_end, c->nlist, c->ncount, c->grid_d, t0, t1,
-                                                                         c->p.max_neighbors, c->p.K, c->nown, c->rho, c->press, c->cvol);
+                                                                         (int)c->row_base, c->p.max_neighbors, c->p.K, c->nown, c->rho, c->press, c->cvol);
     }
     SPH_LAUNCH_CHECK(c);
     // literal-kernel variant: exits at once unless h_max >= 1e5 (decided on the device: no host sync)
     int per_block = K1_WARPS * K1_TPW;
     k_neighbors_density<<<sph_div_up(nt, per_block), K1_WARPS * 32, 0, c->stream>>>(
-        c->posh[c->cur], c->posm, c->keys[1], c->cell_start, c->cell_end, c->cell_hmax, c->grid_d, t0, t1, c->p.max_neighbors,
+        c->posh[c->cur], c->posm, c->skeys, c->cell_start, c->cell_end, c->cell_hmax, c->grid_d, t0, t1, (int)c->row_base, c->p.max_neighbors,
         c->p.K, c->nlist, c->ncount, c->nown, c->rho, c->press, c->cvol, c->err_d);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;

@@ -153,6 +153,13 @@ __global__ void __launch_bounds__(SORT_THREADS) k_digit_scatter(const uint32_t* 
 
 size_t sph_sort_hist_words(int64_t cap) { return (size_t)256 * (size_t)sph_div_up(cap, SORT_TILE) + 256; }
 
+// exclusive scan of `rows` rows of `nblocks` counters each (row-major), totals[row] = row sum
+int sph_launch_rowscan(sphb200_ctx* c, uint32_t* rows_d, int nblocks, int rows, uint32_t* totals, cudaStream_t stream) {
+    k_digit_rowscan<<<rows, 256, 0, stream>>>(rows_d, nblocks, totals);
+    SPH_LAUNCH_CHECK(c);
+    return SPH_OK;
+}
+
 // One stable counting pass.  bucket != nullptr: partition by bucket id (keys may be nullptr); total_out (256 words, device)
 // receives the bucket sizes.
 int sph_launch_digit_pass(sphb200_ctx* c, const uint32_t* keys_in, const uint32_t* vals_in, const uint8_t* bucket, int n, int shift,

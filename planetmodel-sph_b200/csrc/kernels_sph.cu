@@ -67,7 +67,7 @@ constexpr int K2_LPT = 16;
 
 __global__ void __launch_bounds__(256) k_pressure_grad(const float4* __restrict__ posh, const float* __restrict__ cvol,
                                                        const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
-                                                       int t0, int t1, int kmax, float lead, float4* __restrict__ gradp) {
+                                                       int t0, int t1, int rowbase, int kmax, float lead, float4* __restrict__ gradp) {
     const int sub = threadIdx.x & (K2_LPT - 1);
     const int t = t0 + (blockIdx.x * blockDim.x + threadIdx.x) / K2_LPT;
     const bool live = t < t1;
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256) k_pressure_grad(const float4* __restrict_
         const float4 pi = posh[t];
         const float hinv_i = 1.0f / pi.w;
         const int cnt = min(ncount[t], kmax);
-        const uint32_t* row = nlist + (size_t)t * kmax;
+        const uint32_t* row = nlist + (size_t)(t - rowbase) * kmax;
         for (int k = sub; k < cnt; k += K2_LPT) {
             uint32_t j = row[k];
             float4 pj = posh[j];
@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(256) k_pressure_grad(const float4* __restrict_
 // (GravityFieldSystem.cs:340-347).  Every such pair is in i's list because r < h_i < 2 max(h_i,h_j).
 __global__ void __launch_bounds__(256) k_gravity_near(const float4* __restrict__ posh, const float4* __restrict__ posm,
                                                       const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
-                                                      int t0, int t1, int kmax, float G, float4* __restrict__ grav) {
+                                                      int t0, int t1, int rowbase, int kmax, float G, float4* __restrict__ grav) {
     const int sub = threadIdx.x & (K2_LPT - 1);
     const int t = t0 + (blockIdx.x * blockDim.x + threadIdx.x) / K2_LPT;
     const bool live = t < t1;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k_gravity_near(const float4* __restrict__
         const float hinv_i = 1.0f / pi.w;
         const float a2 = pi.w * pi.w;
         const int cnt = min(ncount[t], kmax);
-        const uint32_t* row = nlist + (size_t)t * kmax;
+        const uint32_t* row = nlist + (size_t)(t - rowbase) * kmax;
         for (int k = sub; k < cnt; k += K2_LPT) {
             uint32_t j = row[k];
             float4 pj = posm[j];
@@ -176,10 +176,16 @@ __global__ void __launch_bounds__(256) k_integrate(float4* __restrict__ posh, fl
 // ------------------------------------------------------------------------------------------------------------
 // staging (device): pos[3n] vel[3n] mass[n] h[n] nown[n]
 // has_nown: 0 = h only (st[7n..8n)), 1 = h[n] then nown[n], 2 = raw sph_ParticleSmoothing records (7 words each) at st[7n..14n)
-__global__ void __launch_bounds__(256) k_pack_upload(const float* __restrict__ st, int n, int has_nown, float4* __restrict__ posh,
+// Also reduces the range of the masses into mm[0..1] (ordered uints): equal masses select the hoisted-mass kernels.
+__global__ void __launch_bounds__(256) k_pack_upload(const float* __restrict__ st, int n, int has_nown, uint32_t orig0, float4* __restrict__ posh,
                                                      float4* __restrict__ velm, uint32_t* __restrict__ orig,
-                                                     int32_t* __restrict__ nown) {
+                                                     int32_t* __restrict__ nown, uint32_t* __restrict__ mm) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    {
+        const uint32_t mo = i < n ? f2ord(st[6 * (size_t)n + i]) : 0u;
+        const uint32_t lo = __reduce_min_sync(FULL, i < n ? mo : 0xffffffffu), hi = __reduce_max_sync(FULL, mo);
+        if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(&mm[0], lo); atomicMax(&mm[1], hi); }
+    }
     if (i >= n) return;
     const float* pos = st;
     const float* vel = st + 3 * (size_t)n;
@@ -189,7 +195,7 @@ __global__ void __launch_bounds__(256) k_pack_upload(const float* __restrict__ s
     const float hi = has_nown == 2 ? h[7 * (size_t)i] : h[i];
     posh[i] = make_float4(pos[3 * i], pos[3 * i + 1], pos[3 * i + 2], hi);
     velm[i] = make_float4(vel[3 * i], vel[3 * i + 1], vel[3 * i + 2], mass[i]);
-    orig[i] = (uint32_t)i;
+    orig[i] = orig0 + (uint32_t)i;
     nown[i] = has_nown == 2 ? ((const int32_t*)h)[7 * (size_t)i + 6] : has_nown ? no[i] : 0;
 }
 
@@ -231,14 +237,14 @@ __global__ void __launch_bounds__(256) k_unpack_field(int field, int n, const ui
 // One warp per sorted slot: map the list row to body indices, bitonic-sort ascending, write at offsets[body].
 __global__ void __launch_bounds__(128) k_neighbor_rows(const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
                                                        const uint32_t* __restrict__ orig, const int64_t* __restrict__ offsets,
-                                                       int n, int kmax, int p2, int32_t* __restrict__ nbr) {
+                                                       int n, int rowbase, int kmax, int p2, int32_t* __restrict__ nbr) {
     extern __shared__ uint32_t sm[];
     int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     int t = blockIdx.x * 4 + w;
     if (t >= n) return;
     uint32_t* a = sm + (size_t)w * p2;
     int cnt = min(ncount[t], kmax);
-    for (int k = lane; k < p2; k += 32) a[k] = k < cnt ? orig[nlist[(size_t)t * kmax + k]] : 0xffffffffu;
+    for (int k = lane; k < p2; k += 32) a[k] = k < cnt ? orig[nlist[(size_t)(t - rowbase) * kmax + k]] : 0xffffffffu;
     __syncwarp();
     for (int size = 2; size <= p2; size <<= 1)
         for (int stride = size >> 1; stride > 0; stride >>= 1) {
@@ -340,7 +346,7 @@ int sph_launch_pressure(sphb200_ctx* c) {
     float lead = (c->p.flags & SPH_FLAG_FIX_KERNEL_DERIV_SIGN) ? -3.0f : 3.0f;
     int tpb = 256 / K2_LPT;
     k_pressure_grad<<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->cvol, c->nlist, c->ncount, t0, t1,
-                                                                c->p.max_neighbors, lead, c->gradp);
+                                                                (int)c->row_base, c->p.max_neighbors, lead, c->gradp);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;
 }
@@ -351,7 +357,7 @@ int sph_launch_gravity_near(sphb200_ctx* c) {
     if (nt <= 0) return SPH_OK;
     int tpb = 256 / K2_LPT;
     k_gravity_near<<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->posm, c->nlist, c->ncount, t0, t1,
-                                                               c->p.max_neighbors, c->p.G, c->grav);
+                                                               (int)c->row_base, c->p.max_neighbors, c->p.G, c->grav);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;
 }
@@ -366,9 +372,9 @@ int sph_launch_integrate(sphb200_ctx* c, float dt) {
     return SPH_OK;
 }
 
-int sph_launch_pack_upload(sphb200_ctx* c, int64_t n, int has_nown) {
-    k_pack_upload<<<sph_div_up(n, 256), 256, 0, c->stream>>>((const float*)c->stage_d, (int)n, has_nown, c->posh[0],
-                                                            c->velm[0], c->orig[0], c->nown);
+int sph_launch_pack_upload(sphb200_ctx* c, int64_t n, int has_nown, uint32_t orig0) {
+    k_pack_upload<<<sph_div_up(n, 256), 256, 0, c->stream>>>((const float*)c->stage_d, (int)n, has_nown, orig0, c->posh[0],
+                                                            c->velm[0], c->orig[0], c->nown, c->bounds + 12);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;
 }
@@ -393,7 +399,7 @@ int sph_launch_neighbor_rows_sorted(sphb200_ctx* c, int32_t* rows_d) {
     while (p2 < kmax) p2 <<= 1;
     const int64_t* offsets_d = (const int64_t*)c->stage_d;
     k_neighbor_rows<<<sph_div_up(n, 4), 128, 4 * p2 * sizeof(uint32_t), c->stream>>>(c->nlist, c->ncount, c->orig[c->cur], offsets_d, n,
-                                                                                    kmax, p2, rows_d);
+                                                                                    (int)c->row_base, kmax, p2, rows_d);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;
 }
@@ -411,13 +417,22 @@ int sph_launch_interactions(sphb200_ctx* c, int64_t total, const int64_t* offset
     return SPH_OK;
 }
 
-int sph_launch_diagnostics(sphb200_ctx* c, double* out12) {
-    int n = (int)c->n;
+// sums over resident slots [off, off+n) into diag_d[0..10], max neighbor count into the int at diag_d[12]
+int sph_launch_diagnostics_range(sphb200_ctx* c, int off, int n) {
     SPH_CK(c, cudaMemsetAsync(c->diag_d, 0, 16 * sizeof(double), c->stream));
+    if (n <= 0) return SPH_OK;
     int* maxc = (int*)(c->diag_d + 12);
     int blocks = min(sph_div_up(n, 256), c->sm_count * 4);
-    k_diagnostics<<<blocks, 256, 0, c->stream>>>(c->posh[c->cur], c->velm[c->cur], c->rho, c->grav, c->ncount, n, c->p.K, c->diag_d, maxc);
+    k_diagnostics<<<blocks, 256, 0, c->stream>>>(c->posh[c->cur] + off, c->velm[c->cur] + off, c->rho + off, c->grav + off, c->ncount + off, n,
+                                                 c->p.K, c->diag_d, maxc);
     SPH_LAUNCH_CHECK(c);
+    return SPH_OK;
+}
+
+int sph_launch_diagnostics(sphb200_ctx* c, double* out12) {
+    int n = (int)c->n;
+    int rc = sph_launch_diagnostics_range(c, 0, n);
+    if (rc) return rc;
     double tmp[16];
     SPH_CK(c, cudaMemcpyAsync(tmp, c->diag_d, 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     SPH_CK(c, cudaStreamSynchronize(c->stream));

@@ -43,10 +43,14 @@ __device__ __forceinline__ int delta_fn(const uint32_t* __restrict__ keys, int n
 }
 
 // Karras (2012) binary radix tree over (key, slot) -- integer-only, identical to orc_lbvh_topology.
-__global__ void __launch_bounds__(256) k_lbvh_topology(const uint32_t* __restrict__ keys, int n, int2* __restrict__ child,
-                                                       int2* __restrict__ range, int32_t* __restrict__ parent) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+// This launch builds the nodes of slots [i0, i1) (a group rank: its own Morton range; keys[] is the global key array).  An
+// internal node whose particle range leaves [i0, i1) is a TOP node: its topology is also appended to `top` so that every rank
+// can finish it once the ranks have exchanged their frontier moments (k_top_tree, kernels_group.cu).
+__global__ void __launch_bounds__(256) k_lbvh_topology(const uint32_t* __restrict__ keys, int n, int i0, int i1, int2* __restrict__ child,
+                                                       int2* __restrict__ range, int32_t* __restrict__ parent,
+                                                       TopNode* __restrict__ top, int32_t* __restrict__ top_count, int32_t* __restrict__ err) {
+    int i = i0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= i1) return;
     child[n - 1 + i] = make_int2(-1, -1);
     range[n - 1 + i] = make_int2(i, i);
     if (i == 0) parent[0] = -1;
@@ -73,6 +77,11 @@ __global__ void __launch_bounds__(256) k_lbvh_topology(const uint32_t* __restric
     range[i] = make_int2(lo, hi);
     parent[lc] = i;
     parent[rc] = i;
+    if (lo < i0 || hi >= i1) {
+        const int k = atomicAdd(&top_count[0], 1);
+        if (k < SPH_TOP_CAP) top[k] = TopNode{i, lc, rc, lo, hi, 0, 0, 0};
+        else atomicExch(&err[ERR_TOP_TREE], 1);
+    }
 }
 
 // GravitationalMoment.Accumulate (GravityFieldSystem.cs:398-411), exact op order
@@ -112,15 +121,44 @@ __device__ __forceinline__ void pack_node(float4* __restrict__ packed, int k, fl
     packed[2 * (size_t)k + 1] = make_float4(mo.w, __int_as_float(a), __int_as_float(b), b_sq);
 }
 
+// One body of a bucket: GravitationalMoment.Accumulate (GravityFieldSystem.cs:398-411) and the union of the collider AABBs
+// (quirk Q2) -- or of the positions, aabb_mode 1.
+__device__ __forceinline__ void sph_bucket_add(float4& mo, float lo[3], float hi[3], const float4 p, const float4 v, int aabb_mode, float dt) {
+    const float margin = 0.1f * 0.5f;  // CollisionTolerance * 0.5 (Broadphase.cs:200, CollisionWorld.cs:32)
+    moment_accumulate(mo, p.x, p.y, p.z, v.w);
+    float x[3] = {p.x, p.y, p.z}, vel[3] = {v.x, v.y, v.z};
+    for (int c = 0; c < 3; c++) {
+        float bl, bh;
+        if (aabb_mode == 1) { bl = x[c]; bh = x[c]; }
+        else {
+            // sphere AABB radius 2h (Physics_SphereCollider.cs:129-137), swept by v*dt (Motion.cs:142-146), +-margin
+            float rad = __fmul_rn(p.w, 2.0f);
+            bl = __fsub_rn(x[c], rad); bh = __fadd_rn(x[c], rad);
+            float lin = __fmul_rn(vel[c], dt);
+            bh = __fadd_rn(fmaxf(bh, __fadd_rn(bh, lin)), 0.0f);
+            bl = __fsub_rn(fminf(bl, __fadd_rn(bl, lin)), 0.0f);
+            bl = __fsub_rn(bl, margin); bh = __fadd_rn(bh, margin);
+        }
+        lo[c] = fminf(lo[c], bl); hi[c] = fmaxf(hi[c], bh);
+    }
+}
+
 // Moments + MAC boxes.  Buckets (maximal nodes with <= leaf_max bodies) are evaluated directly from their particle range
 // (reference leaf rule; the nodes inside a bucket are unreachable and skipped); larger nodes are finished bottom-up by the second thread to arrive (fixed left-then-right order).
-__global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ posh, const float4* __restrict__ velm, int n,
-                                                    const int2* __restrict__ child, const int2* __restrict__ range,
+// nodes of this launch: the internal nodes g0 .. g1-1 and the leaves of slots g0 .. g1-1 (node ids n-1+slot); the particle
+// of global slot s is resident at posh[s + off].  Single handle: g0 = 0, g1 = n, off = 0.  A group rank finishes only the nodes
+// whose particle range lies inside [g0, g1); every finished node whose parent is unknown here (built by another rank) or
+// straddles a rank boundary is appended to `front`.
+__global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ posh, const float4* __restrict__ velm, int n, int g0, int g1,
+                                                    int off, const int2* __restrict__ child, const int2* __restrict__ range,
                                                     const int32_t* __restrict__ parent, int leaf_max, int aabb_mode, float dt,
                                                     float theta2, int32_t* __restrict__ flag, float4* mom, float4* nlo, float4* nhi,
-                                                    float4* __restrict__ packed) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= 2 * n - 1) return;
+                                                    float4* __restrict__ packed, FrontNode* __restrict__ front,
+                                                    int32_t* __restrict__ top_count, int32_t* __restrict__ err) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, nown = g1 - g0;
+    if (u >= 2 * nown) return;
+    const int k = u < nown ? g0 + u : n - 1 + g0 + (u - nown);
+    if (u < nown && k >= n - 1) return;   // n slots have n-1 internal nodes
     int2 rg = range[k];
     if (rg.y - rg.x + 1 > leaf_max) return;
     {   // a small node whose parent is small too lies strictly inside a bucket: the walk never reaches it
@@ -130,37 +168,30 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
             if (prg.y - prg.x + 1 <= leaf_max) return;
         }
     }
+    if (rg.x < g0 || rg.y >= g1) return;  // bucket across a rank boundary: a top node (k_lbvh_topology listed it), finished by
+                                          // k_top_tree from the ranks' boundary particles
     float4 mo = make_float4(0.f, 0.f, 0.f, 0.f);
     float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
-    const float margin = 0.1f * 0.5f;  // CollisionTolerance * 0.5 (Broadphase.cs:200, CollisionWorld.cs:32)
-    for (int s = rg.x; s <= rg.y; s++) {
-        float4 p = posh[s], v = velm[s];
-        moment_accumulate(mo, p.x, p.y, p.z, v.w);
-        float x[3] = {p.x, p.y, p.z}, vel[3] = {v.x, v.y, v.z};
-        for (int c = 0; c < 3; c++) {
-            float bl, bh;
-            if (aabb_mode == 1) { bl = x[c]; bh = x[c]; }
-            else {
-                // sphere AABB radius 2h (Physics_SphereCollider.cs:129-137), swept by v*dt (Motion.cs:142-146), +-margin
-                float rad = __fmul_rn(p.w, 2.0f);
-                bl = __fsub_rn(x[c], rad); bh = __fadd_rn(x[c], rad);
-                float lin = __fmul_rn(vel[c], dt);
-                bh = __fadd_rn(fmaxf(bh, __fadd_rn(bh, lin)), 0.0f);
-                bl = __fsub_rn(fminf(bl, __fadd_rn(bl, lin)), 0.0f);
-                bl = __fsub_rn(bl, margin); bh = __fadd_rn(bh, margin);
-            }
-            lo[c] = fminf(lo[c], bl); hi[c] = fmaxf(hi[c], bh);
-        }
-    }
+    for (int s = rg.x; s <= rg.y; s++) sph_bucket_add(mo, lo, hi, posh[s + off], velm[s + off], aabb_mode, dt);
     mom[k] = mo;
     nlo[k] = make_float4(lo[0], lo[1], lo[2], __int_as_float(rg.x));
     nhi[k] = make_float4(hi[0], hi[1], hi[2], __int_as_float(rg.y));
     pack_node(packed, k, mo, lo, hi, child[k], rg, leaf_max, theta2);
     int cur = k;
+    float4 cmo = mo, clo = make_float4(lo[0], lo[1], lo[2], 0.f), chi = make_float4(hi[0], hi[1], hi[2], 0.f);
     while (true) {
         int p = parent[cur];
-        if (p < 0) break;
-        int2 prg = range[p];
+        int2 prg = p >= 0 ? range[p] : make_int2(0, 0);
+        if (p < 0 || prg.x < g0 || prg.y >= g1) {
+            // the root -- or, on a group rank, a parent that is built elsewhere / straddles the rank boundary: `cur` is a
+            // frontier node of the top tree
+            if (cur != 0) {
+                const int q = atomicAdd(&top_count[1], 1);
+                if (q < SPH_TOP_CAP) front[q] = FrontNode{cur, 0, 0, 0, cmo, clo, chi};
+                else atomicExch(&err[ERR_TOP_TREE], 1);
+            }
+            break;
+        }
         if (prg.y - prg.x + 1 <= leaf_max) break;  // parent is a small node, evaluated by its own thread
         __threadfence();
         if (atomicAdd(&flag[p], 1) == 0) break;    // first arrival: sibling not ready yet
@@ -178,6 +209,7 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
         nhi[p] = make_float4(phi[0], phi[1], phi[2], __int_as_float(prg.y));
         pack_node(packed, p, acc, plo, phi, ch, prg, leaf_max, theta2);
         cur = p;
+        cmo = acc; clo = make_float4(plo[0], plo[1], plo[2], 0.f); chi = make_float4(phi[0], phi[1], phi[2], 0.f);
     }
 }
 
@@ -222,8 +254,10 @@ __device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
     return x;
 }
 
+// Slots are GLOBAL sorted slots: posm / packed span all n particles (a group rank holds the all-gathered arrays), the targets
+// are slots [t0, t1) and the resident arrays (posh, grav, ...) hold slot t at t + off.
 __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __restrict__ posh, const float4* __restrict__ posm,
-                                                             const float4* __restrict__ packed, int n, int t0, int t1, float G,
+                                                             const float4* __restrict__ packed, int n, int t0, int t1, int off, float G,
                                                              float4* __restrict__ grav, int32_t* __restrict__ npart,
                                                              int32_t* __restrict__ napprox, int32_t* __restrict__ err) {
     __shared__ int2 stack[TW_WARPS][TW_STACK];
@@ -235,11 +269,14 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // Warps are aligned to absolute multiples of 32 sorted slots and every slot < n walks, whether or not it lies in this
     // rank's target range [t0,t1): the order in which a lane adds its contributions depends on its 31 companions, so a
-    // sharded run stays bit-identical to the single-GPU run only if the groups are the same.
+    // sharded run stays bit-identical to the single-GPU run only if the groups are the same.  Companions outside the range
+    // take their position from the global source array (their softening length is irrelevant: the results are dropped).
     const int t = (t0 & ~31) + (blockIdx.x * TW_WARPS + wid) * 32 + lane;
     if (t - lane >= t1) return;   // whole group beyond the range
     const bool active = t < n;
-    const float4 pi = posh[active ? t : (n - 1)];
+    const bool mine = t >= t0 && t < t1;
+    float4 pi = __ldg(&posm[active ? t : (n - 1)]);
+    pi.w = mine ? posh[t + off].w : 1.0f;
     const float a2 = pi.w * pi.w, ainv = 1.0f / pi.w;
     WalkAcc w = {0.f, 0.f, 0.f, 0.f, 0, 0};
     u64 gx2 = pk2(0.f, 0.f), gy2 = gx2, gz2 = gx2, gp2 = gx2;   // packed partial sums (P2P and M2P loops)
@@ -390,44 +427,189 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
         }
         __syncwarp();
     }
-    if (t >= t0 && t < t1) {
+    if (mine) {
         float a, b;
         upk2(gx2, a, b); w.gx += a + b;
         upk2(gy2, a, b); w.gy += a + b;
         upk2(gz2, a, b); w.gz += a + b;
         upk2(gp2, a, b); w.gp += a + b;
-        grav[t] = make_float4(G * w.gx, G * w.gy, G * w.gz, G * w.gp);
-        npart[t] = w.np;
-        napprox[t] = w.na;
+        grav[t + off] = make_float4(G * w.gx, G * w.gy, G * w.gz, G * w.gp);
+        npart[t + off] = w.np;
+        napprox[t + off] = w.na;
     }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Top tree of the distributed build (group ranks only).  Inputs, all-gathered from every rank: the topology of the nodes
+// that straddle a rank boundary (`top`), the moments/boxes of the finished nodes hanging below them (`front`) and the
+// first / last TOP_LEAF particles of every rank (`bnd`, for buckets that straddle a boundary).  One block finishes the
+// straddling nodes bottom-up, sweep by sweep, with the reference's arithmetic in the reference's order -- every rank
+// computes the same bits.  Writes mom / nlo / nhi / packed of the top nodes.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int TOP_MAX = 4096;    // straddling nodes of the whole group (<= (world-1) * tree depth)
+
+struct TopArgs {
+    const TopNode* top; const FrontNode* front; const int32_t* counts;   // [world][SPH_TOP_CAP], [world][SPH_TOP_CAP], [world][4]
+    const float4* bnd;            // [world][2][SPH_TOP_LEAF][2]: (posh, velm) of the first / last particles (last: right-aligned)
+    const int64_t* g0;            // [world+1] global slot ranges of the ranks (device)
+    int world, leaf_max, aabb_mode; float dt, theta2;
+    float4 *mom, *nlo, *nhi, *packed; int32_t* err;
+};
+
+__global__ void __launch_bounds__(1024) k_top_tree(TopArgs A) {
+    __shared__ int tid_[TOP_MAX];              // node id of top node t
+    __shared__ short trank[TOP_MAX];           // where its record lives
+    __shared__ short tslot[TOP_MAX];
+    __shared__ unsigned char done[TOP_MAX];
+    __shared__ int nbase[SPH_MAX_RANKS + 1];
+    const int tx = threadIdx.x;
+    if (tx == 0) {
+        int acc = 0;
+        for (int r = 0; r < A.world; r++) { nbase[r] = acc; acc += min(A.counts[4 * r], SPH_TOP_CAP); }
+        nbase[A.world] = acc;
+    }
+    __syncthreads();
+    const int T = min(nbase[A.world], TOP_MAX);
+    if (nbase[A.world] > TOP_MAX && tx == 0) atomicExch(&A.err[ERR_TOP_TREE], 1);
+    for (int t = tx; t < T; t += blockDim.x) {
+        int r = 0;
+        while (nbase[r + 1] <= t) r++;
+        trank[t] = (short)r; tslot[t] = (short)(t - nbase[r]);
+        tid_[t] = A.top[r * SPH_TOP_CAP + (t - nbase[r])].id;
+        done[t] = 0;
+    }
+    // frontier moments of every rank into the node arrays
+    for (int r = 0; r < A.world; r++) {
+        const int nf = min(A.counts[4 * r + 1], SPH_TOP_CAP);
+        for (int k = tx; k < nf; k += blockDim.x) {
+            const FrontNode f = A.front[r * SPH_TOP_CAP + k];
+            A.mom[f.id] = f.mom; A.nlo[f.id] = f.lo; A.nhi[f.id] = f.hi;
+        }
+    }
+    __syncthreads();
+    // children of my nodes: index in the top list, or -1 (a frontier node: ready)
+    constexpr int PER = TOP_MAX / 1024;
+    int ca[PER], cb[PER];
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+        const int t = tx + u * 1024;
+        ca[u] = cb[u] = -1;
+        if (t < T) {
+            const TopNode nd = A.top[trank[t] * SPH_TOP_CAP + tslot[t]];
+            if (nd.hi - nd.lo + 1 > A.leaf_max)
+                for (int q = 0; q < T; q++) {
+                    const int id = tid_[q];
+                    if (id == nd.a) ca[u] = q;
+                    if (id == nd.b) cb[u] = q;
+                }
+        }
+    }
+    for (int sweep = 0; sweep < 4 * TOP_MAX; sweep++) {
+        int progress = 0;
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const int t = tx + u * 1024;
+            if (t >= T || done[t]) continue;
+            const TopNode nd = A.top[trank[t] * SPH_TOP_CAP + tslot[t]];
+            const int2 rg = make_int2(nd.lo, nd.hi);
+            float4 mo = make_float4(0.f, 0.f, 0.f, 0.f);
+            float lo[3] = {INFINITY, INFINITY, INFINITY}, hi[3] = {-INFINITY, -INFINITY, -INFINITY};
+            if (nd.hi - nd.lo + 1 <= A.leaf_max) {
+                // bucket across a boundary: its bodies are among the first / last particles of their ranks
+                int r = 0;
+                for (int s = nd.lo; s <= nd.hi; s++) {
+                    while (A.g0[r + 1] <= s) r++;
+                    const int i = s - (int)A.g0[r];
+                    const int j = s - ((int)A.g0[r + 1] - SPH_TOP_LEAF);
+                    const float4* rec = A.bnd + ((size_t)(r * 2 + (i < SPH_TOP_LEAF ? 0 : 1)) * SPH_TOP_LEAF + (i < SPH_TOP_LEAF ? i : j)) * 2;
+                    sph_bucket_add(mo, lo, hi, rec[0], rec[1], A.aabb_mode, A.dt);
+                }
+            } else {
+                if ((ca[u] >= 0 && done[ca[u]] != 1) || (cb[u] >= 0 && done[cb[u]] != 1)) continue;
+                const float4 ml = __ldcg(&A.mom[nd.a]), mr = __ldcg(&A.mom[nd.b]);
+                const float4 ll = __ldcg(&A.nlo[nd.a]), lr = __ldcg(&A.nlo[nd.b]);
+                const float4 hl = __ldcg(&A.nhi[nd.a]), hr = __ldcg(&A.nhi[nd.b]);
+                moment_accumulate(mo, ml.x, ml.y, ml.z, ml.w);  // GravityFieldSystem.cs:513-521, children in Data order
+                moment_accumulate(mo, mr.x, mr.y, mr.z, mr.w);
+                lo[0] = fminf(ll.x, lr.x); lo[1] = fminf(ll.y, lr.y); lo[2] = fminf(ll.z, lr.z);
+                hi[0] = fmaxf(hl.x, hr.x); hi[1] = fmaxf(hl.y, hr.y); hi[2] = fmaxf(hl.z, hr.z);
+            }
+            A.mom[nd.id] = mo;
+            A.nlo[nd.id] = make_float4(lo[0], lo[1], lo[2], __int_as_float(rg.x));
+            A.nhi[nd.id] = make_float4(hi[0], hi[1], hi[2], __int_as_float(rg.y));
+            pack_node(A.packed, nd.id, mo, lo, hi, make_int2(nd.a, nd.b), rg, A.leaf_max, A.theta2);
+            __threadfence_block();
+            done[t] = 2;      // visible as "done" only after the barrier below (value 2 -> 1)
+            progress = 1;
+        }
+        const int any = __syncthreads_or(progress);
+#pragma unroll
+        for (int u = 0; u < PER; u++) {
+            const int t = tx + u * 1024;
+            if (t < T && done[t] == 2) done[t] = 1;
+        }
+        __syncthreads();
+        if (!any) break;
+    }
+    // every top node must have been finished (otherwise a child record was missing: list overflow)
+    int left = 0;
+#pragma unroll
+    for (int u = 0; u < PER; u++) {
+        const int t = tx + u * 1024;
+        if (t < T && !done[t]) left = 1;
+    }
+    if (left) atomicExch(&A.err[ERR_TOP_TREE], 1);
 }
 
 }  // namespace
 
 // LBVH topology + moments/boxes/packed nodes on `stream` (the handle's stream, or the auxiliary stream when the build is
 // overlapped with the neighbor pass).
+// The tree spans c->tree_n global slots (keys c->tkeys); this context builds the nodes of slots [tree_g0, tree_g1).
 int sph_launch_tree_build(sphb200_ctx* c, float dt, cudaStream_t stream) {
-    int n = (int)c->n;
-    if (n <= 0) return SPH_OK;
-    SPH_CK(c, cudaMemsetAsync(c->flag, 0, (size_t)n * sizeof(int32_t), stream));
-    k_lbvh_topology<<<sph_div_up(n, 256), 256, 0, stream>>>(c->keys[1], n, c->child, c->range, c->parent);
+    const int n = (int)c->tree_n, g0 = (int)c->tree_g0, g1 = (int)c->tree_g1, own = g1 - g0;
+    if (n <= 0 || own <= 0) return SPH_OK;
+    const bool part = own < n;   // group rank: unknown parents must read as -1 (root / built elsewhere)
+    TopNode* top = c->top_nodes ? c->top_nodes + (size_t)c->top_rank * SPH_TOP_CAP : nullptr;
+    FrontNode* front = c->front_nodes ? c->front_nodes + (size_t)c->top_rank * SPH_TOP_CAP : nullptr;
+    int32_t* tcount = c->top_counts ? c->top_counts + 4 * c->top_rank : nullptr;
+    SPH_CK(c, cudaMemsetAsync(c->flag + g0, 0, (size_t)own * sizeof(int32_t), stream));
+    if (part) {
+        SPH_CK(c, cudaMemsetAsync(c->parent + g0, 0xff, (size_t)own * sizeof(int32_t), stream));
+        SPH_CK(c, cudaMemsetAsync(c->parent + (n - 1 + g0), 0xff, (size_t)own * sizeof(int32_t), stream));
+        SPH_CK(c, cudaMemsetAsync(tcount, 0, 4 * sizeof(int32_t), stream));
+    }
+    k_lbvh_topology<<<sph_div_up(own, 256), 256, 0, stream>>>(c->tkeys, n, g0, g1, c->child, c->range, c->parent, top, tcount, c->err_d);
     SPH_LAUNCH_CHECK(c);
-    k_lbvh_nodes<<<sph_div_up(2 * (int64_t)n - 1, 256), 256, 0, stream>>>(c->posh[c->cur], c->velm[c->cur], n, c->child, c->range,
-                                                                         c->parent, c->p.leaf_max, c->p.aabb_mode, dt,
-                                                                         c->p.theta * c->p.theta /* fp32 product, as k_Theta*k_Theta (GravityFieldSystem.cs:246) */, c->flag, c->mom,
-                                                                         c->nlo, c->nhi, c->packed);
+    k_lbvh_nodes<<<sph_div_up(2 * (int64_t)own, 256), 256, 0, stream>>>(c->posh[c->cur], c->velm[c->cur], n, g0, g1, (int)c->tree_off,
+                                                                       c->child, c->range, c->parent, c->p.leaf_max, c->p.aabb_mode, dt,
+                                                                       c->p.theta * c->p.theta /* fp32 product, as k_Theta*k_Theta (GravityFieldSystem.cs:246) */,
+                                                                       c->flag, c->mom, c->nlo, c->nhi, c->packed, front, tcount, c->err_d);
     SPH_LAUNCH_CHECK(c);
     c->tree_valid = true;
     return SPH_OK;
 }
 
+// Finish the nodes that straddle rank boundaries (after the all-gather of top lists, frontier moments, boundary particles).
+int sph_launch_top_tree(sphb200_ctx* c, int world, const float4* bnd, const int64_t* g0_d, float dt) {
+    TopArgs A;
+    A.top = c->top_nodes; A.front = c->front_nodes; A.counts = c->top_counts; A.bnd = bnd; A.g0 = g0_d;
+    A.world = world; A.leaf_max = c->p.leaf_max; A.aabb_mode = c->p.aabb_mode; A.dt = dt; A.theta2 = c->p.theta * c->p.theta;
+    A.mom = c->mom; A.nlo = c->nlo; A.nhi = c->nhi; A.packed = c->packed; A.err = c->err_d;
+    k_top_tree<<<1, 1024, 0, c->stream>>>(A);
+    SPH_LAUNCH_CHECK(c);
+    return SPH_OK;
+}
+
 int sph_launch_tree_walk(sphb200_ctx* c) {
-    int n = (int)c->n;
+    // resident target slots [t0, t1) -> global slots [t0 - off, t1 - off)
+    int n = (int)c->tree_n, off = (int)c->tree_off;
     int t0 = (int)c->t0;
-    int t1 = (c->t1 < 0 || c->t1 > c->n) ? n : (int)c->t1;
+    int t1 = (c->t1 < 0 || c->t1 > c->n) ? (int)c->n : (int)c->t1;
     int nt = t1 - t0;
     if (n <= 0 || nt <= 0) return SPH_OK;
-    k_tree_walk<<<sph_div_up(t1 - (t0 & ~31), TW_WARPS * 32), TW_WARPS * 32, 0, c->stream>>>(c->posh[c->cur], c->posm, c->packed, n, t0, t1,
+    t0 -= off; t1 -= off;
+    k_tree_walk<<<sph_div_up(t1 - (t0 & ~31), TW_WARPS * 32), TW_WARPS * 32, 0, c->stream>>>(c->posh[c->cur], c->gsrc, c->packed, n, t0, t1, off,
                                                                                c->p.G, c->grav, c->npart, c->napprox, c->err_d);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;

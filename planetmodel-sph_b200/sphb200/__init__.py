@@ -22,6 +22,7 @@ SPH_ERR_NEIGHBOR_OVERFLOW = -3
 SPH_ERR_CUDA = -4
 SPH_ERR_STATE = -5
 SPH_ERR_TREE_STACK = -6
+SPH_ERR_NCCL = -7
 
 GRAVITY_TREE, GRAVITY_PARTICLE, GRAVITY_NONE = 0, 1, 2
 FLAG_FIX_KERNEL_DERIV_SIGN = 1
@@ -60,7 +61,18 @@ EXPORTS = [
     "sphb200_download", "sphb200_download_neighbors", "sphb200_download_interactions", "sphb200_download_sort",
     "sphb200_download_tree", "sphb200_diagnostics", "sphb200_count", "sphb200_get_params", "sphb200_device_ptr",
     "sphb200_launch_count", "sphb200_enable_timing", "sphb200_get_timings", "sphb200_fp32_peak", "sphb200_version",
+    "sphb200_group_create", "sphb200_group_unique_id", "sphb200_group_create_rank", "sphb200_group_destroy",
+    "sphb200_group_last_error", "sphb200_group_body_range", "sphb200_group_upload", "sphb200_group_step",
+    "sphb200_group_download", "sphb200_group_sync", "sphb200_group_diagnostics", "sphb200_group_info",
+    "sphb200_group_enable_timing", "sphb200_group_get_timings", "sphb200_group_rank_handle",
 ]
+
+
+class GroupInfo(C.Structure):
+    _fields_ = [("world", C.c_int32), ("nlocal", C.c_int32), ("rank0", C.c_int32), ("transport", C.c_int32),
+                ("n_total", C.c_int64), ("steps", C.c_int64), ("migrated_last_step", C.c_int64), ("halo_last_step", C.c_int64),
+                ("cap_own", C.c_int64), ("cap_halo", C.c_int64), ("launches", C.c_int64),
+                ("n_own", C.c_int64 * 32), ("n_halo", C.c_int64 * 32)]
 
 
 class SphError(RuntimeError):
@@ -118,6 +130,22 @@ def load_library():
     L.sphb200_get_timings.argtypes = [H, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     L.sphb200_fp32_peak.argtypes = [H, C.POINTER(C.c_double)]
     L.sphb200_version.restype = C.c_char_p
+    L.sphb200_group_create.argtypes = [C.POINTER(Params), C.c_int64, C.c_int, C.POINTER(C.c_int), C.POINTER(H)]
+    L.sphb200_group_unique_id.argtypes = [C.c_void_p]
+    L.sphb200_group_create_rank.argtypes = [C.POINTER(Params), C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(H)]
+    L.sphb200_group_destroy.argtypes = [H]
+    L.sphb200_group_last_error.argtypes = [H]
+    L.sphb200_group_last_error.restype = C.c_char_p
+    L.sphb200_group_body_range.argtypes = [H, C.c_int64, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+    L.sphb200_group_upload.argtypes = [H, C.c_int64, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    L.sphb200_group_step.argtypes = [H, C.c_float, C.c_int]
+    L.sphb200_group_download.argtypes = [H, C.c_int, C.c_void_p, C.c_int]
+    L.sphb200_group_sync.argtypes = [H]
+    L.sphb200_group_diagnostics.argtypes = [H, C.c_void_p]
+    L.sphb200_group_info.argtypes = [H, C.POINTER(GroupInfo)]
+    L.sphb200_group_enable_timing.argtypes = [H, C.c_int]
+    L.sphb200_group_get_timings.argtypes = [H, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
+    L.sphb200_group_rank_handle.argtypes = [H, C.c_int, C.POINTER(H)]
     _lib = L
     return L
 
