@@ -6,7 +6,8 @@ gravity + integrate) on synthetic gas spheres, per BASELINE.json.
 
 Workloads (BASELINE.json configs): c3 = 1 048 576-particle sphere, tiled all-pairs gravity (default; the 1-GPU headline);
 c4 = 16 000 000-particle sphere, LBVH tree gravity; c1/c2 = the reference's own 3k / 10k scenes.
-One rank per GPU (torchrun for N > 1): targets are split by Morton range, positions are all-gathered over NCCL.
+One rank per GPU (torchrun for N > 1): Morton-range domain decomposition behind the C ABI (sphb200_group_*), halo exchange
+and gravity-source all-gather over NCCL/NVLink inside the library.
 
 Prints ONE JSON line (rank 0).  `value` = particles * K / max-over-ranks device time with the state resident in HBM;
 `e2e` = the same through the C ABI with HOST component arrays uploaded and downloaded every step;
@@ -33,6 +34,7 @@ UNIT = "particle-steps/s"
 DT = 1.0 / 60.0
 FLOP_PER_PAIR = 20.0          # conventional N-body count per ordered pair
 SPH_BYTES_BASE, SPH_BYTES_PER_NEIGHBOR = 368.0, 12.0   # algorithmic HBM bytes / particle-step
+NCU_TRAFFIC_ALLPAIRS_C3 = 179.1e6   # profiles/r01_allpairs_full.txt: 69.2 MB read + 109.9 MB written per launch at C3
 
 
 def workload_config(name, particles=None):
@@ -152,7 +154,7 @@ def workload_desc(name, n, grav, gpus):
     return {"workload": "%s: %d-particle %s, %s gravity, dt=1/60, full step" %
             (name, n, "two-planet collision (64x density contrast)" if name == "c5" else "uniform gas sphere (reference scene density)",
              "tiled all-pairs" if grav == "particle" else "LBVH Barnes-Hut theta=0.7"),
-            "particles": n, "gravity": grav, "parallelism": "morton-range x%d" % gpus,
+            "particles": n, "gravity": grav, "parallelism": "morton-range decomposition x%d" % gpus,
             "l2_policy": "working set (>= 190 MB of SoA + lists at 1M) exceeds the 126 MB L2; no explicit flush"}
 
 
@@ -187,10 +189,39 @@ def run_ours(args):
         td.destroy_process_group()
 
 
+class Engine:
+    """N = 1: one handle (sphb200_*).  N > 1: one rank of a Morton-range-decomposed group (sphb200_group_*), one process per
+    GPU, NCCL over NVLink inside the library.  Either way every process holds only its body slice of the host state."""
+
+    def __init__(self, c, world, rank, local, **params):
+        import sphb200
+        from sphb200 import group as sgroup
+        self.world, self.rank = world, rank
+        self.n = len(c["h"])
+        if world == 1:
+            self.sim = sphb200.Simulation(self.n, device=local, **params)
+            self.b0, self.cnt = 0, self.n
+        else:
+            self.sim = sgroup.Group.from_env(self.n, device=local, **params)
+            self.b0, self.cnt = self.sim.body_range(self.n)
+        self.slice = {k: np.ascontiguousarray(v[self.b0:self.b0 + self.cnt]) for k, v in c.items()}
+
+    def upload(self, pos, vel, mass, sm):
+        if self.world == 1:
+            self.sim.upload(pos, vel, mass, sm)
+        else:
+            self.sim.upload(self.n, pos, vel, mass, sm)
+
+    def step(self, dt, impl):
+        self.sim.step(dt, impl)
+
+    def close(self):
+        self.sim.close()
+
+
 def measure_workload(args, workload, world, rank, local, headline):
     import torch
     import sphb200
-    from sphb200 import dist as sdist
     c, grav = workload_config(workload, args.particles)
     if args.gravity:
         grav = args.gravity
@@ -202,8 +233,9 @@ def measure_workload(args, workload, world, rank, local, headline):
         extra["leaf_max"] = args.leaf_max
     if args.aabb_mode:
         extra["aabb_mode"] = args.aabb_mode
-    eng = sdist.ShardedSimulation(n, device=local, rank=rank, world=world, **extra)
-    eng.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    eng = Engine(c, world, rank, local, **extra)
+    sl = eng.slice
+    eng.upload(sl["pos"], sl["vel"], sl["mass"], sl["h"])
     sim = eng.sim
 
     def barrier():
@@ -216,20 +248,22 @@ def measure_workload(args, workload, world, rank, local, headline):
     # ---- warm-up (also settles h towards ~50 own-support neighbors)
     for _ in range(args.warmup):
         eng.step(DT, impl)
+    sim.sync()
     barrier()
-    eng.enable_timing(True)
+    sim.enable_timing(True)
     launches0 = sim.launch_count()
     sampler = ClockSampler(local)
     sampler.start()
-    stream = eng.stream if eng.stream is not None else torch.cuda.current_stream()
+    stream = torch.cuda.ExternalStream(sim.stream_ptr(), device=torch.device("cuda", local))   # the library's own stream
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     pass_ms = {}
     e0.record(stream)
     for _ in range(args.steps):
         eng.step(DT, impl)
-        for nm, ms in eng.timings():            # reads the CUDA events of the step just issued (all ranks alike)
+        for nm, ms in sim.timings():            # reads the CUDA events of the step just issued (all ranks alike)
             pass_ms.setdefault(nm, []).append(ms)
     e1.record(stream)
+    e1.synchronize()
     barrier()
     sampler.stop_flag = True
     ms_total = e0.elapsed_time(e1)
@@ -239,32 +273,43 @@ def measure_workload(args, workload, world, rank, local, headline):
         t = torch.tensor([ms_total], device="cuda")
         td.all_reduce(t, op=td.ReduceOp.MAX)
         ms_total = float(t.item())
+        t = torch.tensor([float(launches)], device="cuda")
+        td.all_reduce(t)
+        launches = int(t.item())
     ms_per_step = ms_total / args.steps
     value = n * args.steps / (ms_total * 1e-3)
-    eng.enable_timing(False)
+    sim.enable_timing(False)
     errors = None
     try:
         sim.sync()                      # surfaces sticky asynchronous errors (neighbor-list overflow, tree stack)
     except sphb200.SphError as ex:
         errors = str(ex)
+    info = sim.info() if world > 1 else None
     if rank == 0:
-        print("[bench] %d steps, %.3f ms/step, passes %s" % (args.steps, ms_per_step,
-              {k: round(float(np.mean(v)), 3) for k, v in pass_ms.items()}), file=sys.stderr)
+        print("[bench] %s: %d steps, %.3f ms/step, passes %s%s" % (workload, args.steps, ms_per_step,
+              {k: round(float(np.mean(v)), 3) for k, v in pass_ms.items()},
+              "" if info is None else ", rank 0 owns %s + halo %s, %d migrated last step" % (info["n_own"], info["n_halo"], info["migrated_last_step"])),
+              file=sys.stderr)
 
-    # ---- e2e: host component arrays in, host component arrays out, every step (N = 1 path of the C ABI)
+    # ---- e2e: host component arrays in, host component arrays out, every step
     e2e = None
     if not args.kernels_only:
-        e2e = measure_e2e(eng, c, impl, max(1, min(args.steps, 3)), barrier)
+        e2e = measure_e2e(eng, impl, max(1, min(args.steps, 3)), barrier)
 
-    eng.gather_results()
+    diag = sim.diagnostics()            # collective in a group
     if rank != 0:
-        sim.close()
+        eng.close()
         return None
     # ---- roofline of the dominant kernel
-    diag = sim.diagnostics()
     kbar = diag["mean_neighbors"]
     mean = {k: float(np.mean(v)) for k, v in pass_ms.items()}
-    fp32_peak = sim.fp32_peak_tflops()
+    fp32_peak = None
+    if world == 1:
+        fp32_peak = sim.fp32_peak_tflops()
+    else:
+        probe = sphb200.Simulation(1024, device=local)
+        fp32_peak = probe.fp32_peak_tflops()
+        probe.close()
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -272,8 +317,8 @@ def measure_workload(args, workload, world, rank, local, headline):
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     hbm_src = "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
-    # every pass that is neither gravity nor a collective (the sort / cell table run over all N on every rank)
-    sph_ms = sum(v for k, v in mean.items() if not k.startswith("gravity") and not k.startswith("allgather"))
+    # every pass that is not gravity: bounds, keys/migration/sort, halo exchange + cell table, neighbors + density, pressure, integrate
+    sph_ms = sum(v for k, v in mean.items() if not k.startswith("gravity"))
     sph_bytes = (SPH_BYTES_BASE + SPH_BYTES_PER_NEIGHBOR * kbar) * n / world
     hbm_passes = {"achieved": sph_bytes / (sph_ms * 1e-3) / 1e9 if sph_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                   "frac": (sph_bytes / (sph_ms * 1e-3) / 1e9 / hbm_peak) if sph_ms > 0 else None, "ms": sph_ms,
@@ -284,15 +329,15 @@ def measure_workload(args, workload, world, rank, local, headline):
         ach = flops / (gms * 1e-3) / 1e12 if gms > 0 else None
         roof = {"bound": "fp32", "kernel": "k_gravity_allpairs", "achieved": ach, "peak": fp32_peak, "unit": "TFLOP/s",
                 "frac": ach / fp32_peak if ach else None,
-                # DRAM bytes per launch of this kernel at C3 / 1 GPU from the committed ncu --set full capture
-                # (profiles/r01_allpairs_full.txt: 69.2 MB read + 109.9 MB written); not re-measured in this run
-                "traffic": 179.1e6 if (world == 1 and n == (1 << 20)) else None,
+                # DRAM bytes per launch of this kernel at C3 / 1 GPU: dram__bytes_read.sum + dram__bytes_write.sum of the committed
+                # ncu --set full capture (profiles/); ncu cannot run inside a timed bench, so it is not re-measured here
+                "traffic": NCU_TRAFFIC_ALLPAIRS_C3 if (world == 1 and n == (1 << 20)) else None,
                 "note": "FP32 FMA-pipe bound (not a contraction: no tensor roof applies); peak = FMA microbenchmark measured "
-                        "in this run; flops = 20 per ordered pair (SURVEY 8d)", "ms": gms, "share_of_step": gms / ms_per_step}
+                        "in this run; flops = 20 per ordered pair (SURVEY 8d); the pass also holds the source all-gather at N > 1",
+                "ms": gms, "share_of_step": gms / ms_per_step}
     else:
         gms = mean.get("gravity_tree", 0.0)
-        inter = float(diag.get("mean_neighbors", 0))
-        roof = {"bound": "hbm", "kernel": "sph passes (keys/sort/permute/neighbors+density/pressure/integrate)",
+        roof = {"bound": "hbm", "kernel": "sph passes (keys/sort/cells/neighbors+density/pressure/integrate)",
                 "achieved": hbm_passes["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm_passes["frac"], "traffic": None,
                 "note": "tree walk is L2-latency/FP32 mixed (no single roof, SURVEY 8d): %.2f ms of the step" % gms, "ms": sph_ms,
                 "share_of_step": sph_ms / ms_per_step}
@@ -307,39 +352,42 @@ def measure_workload(args, workload, world, rank, local, headline):
             "e2e": e2e, "gpu_launches": int(launches), "errors": errors, "roofline": roof, "hbm_passes": hbm_passes,
             "pass_ms": mean, "mean_neighbors": kbar, "fp32_peak_tflops_measured": fp32_peak,
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}}
-    sim.close()
+    if info is not None:
+        line["decomposition"] = {"rank0_own": info["n_own"], "rank0_halo": info["n_halo"], "migrated_last_step": info["migrated_last_step"],
+                                 "transport": info["transport"]}
+    eng.close()
     return line
 
 
-def measure_e2e(eng, c, impl, steps, barrier):
+def measure_e2e(eng, impl, steps, barrier):
     """Drop-in usage: ECS owns the components on the host; every step uploads them (pinned) and reads all results back.
-    With N > 1 ranks every rank uploads the (replicated) host state and downloads the gathered results; the time is the
-    wall clock between two barriers."""
+    In a group every process moves only its body slice (1/N of the state) over PCIe; the particles travel between the
+    GPUs over NVLink inside the step.  Wall clock between two barriers."""
     import torch
     import sphb200
     sim = eng.sim
-    n = len(c["h"])
+    n, cnt = eng.n, eng.cnt
+    sl = eng.slice
     host = {
-        "pos": torch.from_numpy(c["pos"].copy().reshape(-1)).pin_memory(),
-        "vel": torch.from_numpy(c["vel"].copy().reshape(-1)).pin_memory(),
-        "mass": torch.from_numpy(c["mass"].copy()).pin_memory(),
-        "sm": torch.from_numpy(np.zeros(n * 7, np.float32)).pin_memory(),
+        "pos": torch.from_numpy(sl["pos"].copy().reshape(-1)).pin_memory(),
+        "vel": torch.from_numpy(sl["vel"].copy().reshape(-1)).pin_memory(),
+        "mass": torch.from_numpy(sl["mass"].copy()).pin_memory(),
+        "sm": torch.from_numpy(np.zeros(cnt * 7, np.float32)).pin_memory(),
     }
     sm = host["sm"].numpy().view(sphb200.ParticleSmoothing)
-    sm["influenceArea"] = c["h"]
-    outs = {f: torch.empty(n * w, dtype=torch.float32).pin_memory() for f, w in
+    sm["influenceArea"] = sl["h"]
+    outs = {f: torch.empty(cnt * w, dtype=torch.float32).pin_memory() for f, w in
             ((sphb200.FIELD_TRANSLATION, 3), (sphb200.FIELD_VELOCITY, 3), (sphb200.FIELD_DENSITY, 1), (sphb200.FIELD_PRESSURE, 1),
              (sphb200.FIELD_PRESSURE_GRAD, 3), (sphb200.FIELD_GRAVITY, 6))}
     h2d = n * (12 + 12 + 4 + 28)                  # Translation, PhysicsVelocity.linear, ParticleMass, ParticleSmoothing records
     d2h = n * (12 + 12 + 4 + 4 + 12 + 24 + 28)    # ... + density, pressure, pressure gradient, GravityField, ParticleSmoothing
 
     def one():
-        eng.upload(host["pos"].numpy().reshape(n, 3), host["vel"].numpy().reshape(n, 3), host["mass"].numpy(), sm)
+        eng.upload(host["pos"].numpy().reshape(cnt, 3), host["vel"].numpy().reshape(cnt, 3), host["mass"].numpy(), sm)
         eng.step(DT, impl)
-        eng.gather_results()
         for f, buf in outs.items():
-            w = buf.numel() // n
-            sim.download(f, buf.numpy().reshape(n, w) if w > 1 else buf.numpy(), allow_overflow=True)
+            w = buf.numel() // max(cnt, 1)
+            sim.download(f, buf.numpy().reshape(cnt, w) if w > 1 else buf.numpy(), allow_overflow=True)
         sim.download(sphb200.FIELD_SMOOTHING, sm, allow_overflow=True)
         # feed the results back as next step's host state (what the ECS write-back does)
         host["pos"].copy_(outs[sphb200.FIELD_TRANSLATION]); host["vel"].copy_(outs[sphb200.FIELD_VELOCITY])
@@ -350,9 +398,10 @@ def measure_e2e(eng, c, impl, steps, barrier):
         one()
     barrier()
     dt = time.perf_counter() - t0
-    return {"value": n * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d * eng.world, "d2h_bytes_per_step": d2h * eng.world,
+    return {"value": n * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "steps": steps, "ms_per_step": 1e3 * dt / steps,
-            "path": "sphb200_upload + sphb200_step + sphb200_download x7 per rank (pinned host component arrays with their natural strides: one DMA each)"}
+            "path": "sphb200%s_upload + _step + _download x7 per process; every process moves its body slice (1/%d of the bytes) "
+                    "between pinned host component arrays and its GPU, one DMA per component array" % ("_group" if eng.world > 1 else "", eng.world)}
 
 
 _REAL_STDOUT = None

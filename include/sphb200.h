@@ -125,6 +125,8 @@ SPH_API int sphb200_destroy(sph_handle h);
 SPH_API const char* sphb200_last_error(sph_handle h);
 /* Run on an externally owned cudaStream_t (e.g. torch's current stream); NULL = the handle's own stream. */
 SPH_API int sphb200_set_stream(sph_handle h, void* cuda_stream);
+/* The cudaStream_t the handle currently runs on (for CUDA-event timing by the caller). */
+SPH_API int sphb200_get_stream(sph_handle h, void** cuda_stream);
 /* Blocks until the handle's stream is idle; returns sticky asynchronous errors of the steps issued since the last
  * neighbor build (SPH_ERR_NEIGHBOR_OVERFLOW, SPH_ERR_TREE_STACK). */
 SPH_API int sphb200_sync(sph_handle h);
@@ -250,6 +252,8 @@ SPH_API int sphb200_group_diagnostics(sph_group g, double* out12);
 SPH_API int sphb200_group_info(sph_group g, sph_GroupInfo* out);
 SPH_API int sphb200_group_enable_timing(sph_group g, int enable);
 SPH_API int sphb200_group_get_timings(sph_group g, const char** names, float* ms, int cap);
+/* cudaStream_t of local rank `local_rank` (for CUDA-event timing by the caller). */
+SPH_API int sphb200_group_stream(sph_group g, int local_rank, void** cuda_stream);
 /* Context of local rank `local_rank` (owned by the group) for inspection through the sphb200_* getters. */
 SPH_API int sphb200_group_rank_handle(sph_group g, int local_rank, sph_handle* out);
 

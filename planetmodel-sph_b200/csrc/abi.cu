@@ -185,6 +185,12 @@ int sphb200_set_stream(sph_handle c, void* s) {
     return SPH_OK;
 }
 
+int sphb200_get_stream(sph_handle c, void** s) {
+    if (!c || !s) return SPH_ERR_INVALID_ARG;
+    *s = (void*)c->stream;
+    return SPH_OK;
+}
+
 static int check_errflags(sphb200_ctx* c);
 
 int sphb200_sync(sph_handle c) {

@@ -534,7 +534,9 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
         G_RC(g, R, sph_launch_keys(c, c->posh[0] + R.own0, (int)R.n_own, c->keys[1]));
         G_RC(g, R, grk_bin_hist(c, c->keys[1], c->ncount + R.own0, c->npart + R.own0, c->napprox + R.own0, (int)R.n_own, R.hist));
     }
+    pass_mark(g, "keys_hist");
     { auto b = ptrs(g, [](GroupRank& R) { return R.hist; }); if ((rc = g_allreduce(g, b.data(), 2 * (size_t)SPH_NBINS, GR_U32, GR_SUM))) return rc; }
+    pass_mark(g, "allreduce_hist");
     FOR_RANKS(g, R) {
         G_CUDA(g, cudaSetDevice(R.device));
         sphb200_ctx* c = R.c;
@@ -551,6 +553,7 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
         G_CUDA(g, cudaMemcpyAsync(R.split_h, R.split_d, 2 * (size_t)(W + 1) * sizeof(int64_t), cudaMemcpyDeviceToHost, R.c->stream));
         G_CUDA(g, cudaMemcpyAsync(R.grid_h, R.c->grid_d, sizeof(sph_GridParams), cudaMemcpyDeviceToHost, R.c->stream));
     }
+    pass_mark(g, "splitters_partition");
     if ((rc = sync_all(g))) return rc;                                   // ---- host sync 1: migration counts
     const uint32_t* M = g->r[0].cnt_h;
     const int64_t* sp = g->r[0].split_h;
@@ -576,6 +579,7 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
         auto d = ptrs(g, [](GroupRank& R) { return R.mig_recv; });
         if ((rc = g_alltoallv(g, s.data(), d.data(), roff, M, 48))) return rc;
     }
+    pass_mark(g, "migrate");
     // 3. local stable sort of the received set
     for (int l = 0; l < g->nlocal; l++) {
         GroupRank& R = g->r[l];
@@ -584,11 +588,12 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
         R.n_own = roff[l][W];
         G_RC(g, R, grk_mig_keys(c, R.mig_recv, (int)R.n_own, c->keys[1]));
         G_RC(g, R, sph_launch_radix_sort(c, (int)R.n_own, c->stream));
+        if (l == 0) pass_mark(g, "sort");
         // 4. halo lists
         G_RC(g, R, grk_halo_lists(c, c->keys[1], (int)R.n_own, R.split_d, W, R.rank, R.hmask, R.hcnt, R.htot, R.hlist));
         G_CUDA(g, cudaMemcpyAsync(R.cnt_d + (size_t)R.rank * W, R.htot, W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
     }
-    pass_mark(g, "keys_migrate_sort");
+    pass_mark(g, "halo_lists");
     { auto b = ptrs(g, [](GroupRank& R) { return R.cnt_d; }); if ((rc = g_allgather(g, b.data(), W * sizeof(uint32_t)))) return rc; }
     FOR_RANKS(g, R) {
         G_CUDA(g, cudaSetDevice(R.device));
@@ -880,6 +885,12 @@ int sphb200_group_get_timings(sph_group g, const char** names, float* ms, int ca
         if (ms) ms[k] = t;
     }
     return k;
+}
+
+int sphb200_group_stream(sph_group g, int local_rank, void** s) {
+    if (!g || !s || local_rank < 0 || local_rank >= g->nlocal) return SPH_ERR_INVALID_ARG;
+    *s = (void*)g->r[local_rank].c->stream;
+    return SPH_OK;
 }
 
 // the context of local rank l (stage-level inspection in tests: device_ptr, download_sort, ...); owned by the group

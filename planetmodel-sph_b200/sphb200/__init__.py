@@ -64,7 +64,8 @@ EXPORTS = [
     "sphb200_group_create", "sphb200_group_unique_id", "sphb200_group_create_rank", "sphb200_group_destroy",
     "sphb200_group_last_error", "sphb200_group_body_range", "sphb200_group_upload", "sphb200_group_step",
     "sphb200_group_download", "sphb200_group_sync", "sphb200_group_diagnostics", "sphb200_group_info",
-    "sphb200_group_enable_timing", "sphb200_group_get_timings", "sphb200_group_rank_handle",
+    "sphb200_group_enable_timing", "sphb200_group_get_timings", "sphb200_group_rank_handle", "sphb200_group_stream",
+    "sphb200_get_stream",
 ]
 
 
@@ -146,6 +147,8 @@ def load_library():
     L.sphb200_group_enable_timing.argtypes = [H, C.c_int]
     L.sphb200_group_get_timings.argtypes = [H, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     L.sphb200_group_rank_handle.argtypes = [H, C.c_int, C.POINTER(H)]
+    L.sphb200_group_stream.argtypes = [H, C.c_int, C.POINTER(C.c_void_p)]
+    L.sphb200_get_stream.argtypes = [H, C.POINTER(C.c_void_p)]
     _lib = L
     return L
 
@@ -206,6 +209,11 @@ class Simulation:
 
     def sync(self):
         self._ck(self.L.sphb200_sync(self.h))
+
+    def stream_ptr(self):
+        p = C.c_void_p()
+        self._ck(self.L.sphb200_get_stream(self.h, C.byref(p)))
+        return p.value or 0
 
     def effective_params(self):
         p = Params()

@@ -127,6 +127,11 @@ class Group:
     def sync(self):
         self._ck(self.L.sphb200_group_sync(self.h))
 
+    def stream_ptr(self, local_rank=0):
+        p = C.c_void_p()
+        self._ck(self.L.sphb200_group_stream(self.h, int(local_rank), C.byref(p)))
+        return p.value or 0
+
     _SHAPES = {FIELD_TRANSLATION: ("f4", 3), FIELD_VELOCITY: ("f4", 3), FIELD_MASS: ("f4", 1), FIELD_DENSITY: ("f4", 1),
                FIELD_PRESSURE: ("f4", 1), FIELD_PRESSURE_GRAD: ("f4", 3), FIELD_NEIGHBOR_COUNT: ("i4", 1)}
 
