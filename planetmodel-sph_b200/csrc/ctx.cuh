@@ -172,14 +172,20 @@ __device__ __forceinline__ float dot3_rn(float x, float y, float z) {
 // Neighbor keep threshold C(h) (kernels_neighbors.cu): the pair (i,j) is kept iff d2 < max(C(h_i), C(h_j)), where
 // C(h) = min( ((h*h)*2)*2 , t(h) ) and t(h) is the smallest float x with fsqrt_rn(x) >= 2h -- the reference's
 // "d2 < size*size*Kappa*Kappa" (SplineKernel.cs:47-53) and "Kernel(r,h) > 0 <=> r < 2h" (:62) without the sqrt.
-__device__ __forceinline__ float sph_keep_threshold(float h) {
-    if (!(h > 0.0f)) return 0.0f;   // h <= 0 or NaN (invalid input): no neighbors, and the ulp search below must not run
+// t(h): the smallest float x with fsqrt_rn(x) >= 2h, i.e. fsqrt_rn(d2) < 2h <=> d2 < t(h) -- "inside the support of h"
+// (Kernel(r,h) > 0 <=> r < 2h, SplineKernel.cs:62) decided on the squared distance.
+__device__ __forceinline__ float sph_own_threshold(float h) {
+    if (!(h > 0.0f)) return 0.0f;   // h <= 0 or NaN (invalid input): empty support, and the ulp search below must not run
     const float c = __fmul_rn(h, 2.0f);
     uint32_t u = __float_as_uint(__fmul_rn(c, c));
     while (u > 0u && __fsqrt_rn(__uint_as_float(u - 1u)) >= c) --u;
     while (__fsqrt_rn(__uint_as_float(u)) < c) ++u;
+    return __uint_as_float(u);
+}
+__device__ __forceinline__ float sph_keep_threshold(float h) {
+    if (!(h > 0.0f)) return 0.0f;
     const float a = __fmul_rn(__fmul_rn(__fmul_rn(h, h), 2.0f), 2.0f);
-    return fminf(a, __uint_as_float(u));
+    return fminf(a, sph_own_threshold(h));
 }
 
 int sph_grid_bits_for(const sph_Params& p, int64_t n);

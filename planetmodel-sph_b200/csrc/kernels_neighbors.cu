@@ -22,6 +22,7 @@
 //                own-support count); list rows are written coalesced.
 // Numerics contract: membership exact (non-contracted __f*_rn ops, IEEE sqrt), values fast (<= 1e-5 relative).
 #include "ctx.cuh"
+#include "rowstream.cuh"
 #include <math.h>
 
 namespace {
@@ -468,80 +469,105 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINB) k_cell_neighbors(
 }
 
 
-// K1b: density + EOS + own-support count from the finished rows, 16 lanes per target (DensityFieldSystem.cs:38-56,
-// PressureFieldSystem.cs:30-34).  Membership of i's own support: fsqrt_rn(d2) < 2 h_i with the exact d2 (SplineKernel.cs:62).
-constexpr int K1B_LPT = 16;
+// K1b: density + EOS + own-support count from the finished rows (DensityFieldSystem.cs:38-56, PressureFieldSystem.cs:30-34).
+// One warp per 32 consecutive targets, rows consumed as a flat stream of octets with canonical summation order (rowstream.cuh).
+// Own-support membership: fsqrt_rn(d2) < 2 h_i with the exact d2 (SplineKernel.cs:62) <=> d2 < t(h_i), t(h) = the smallest
+// float whose rounded root reaches 2h (sph_own_threshold): no IEEE sqrt per pair.
+// (pi h^3) W(q) = 0.25 (2-q)+^3 - (1-q)+^3  (SplineKernel.cs:55-89, branch-free)
+__device__ __forceinline__ float w_shape(float q) {
+    const float t1 = fmaxf(2.0f - q, 0.0f), t2 = fmaxf(1.0f - q, 0.0f);
+    return fmaf(0.25f * t1, t1 * t1, -(t2 * t2) * t2);
+}
 
 template <bool EQM>
-__global__ void __launch_bounds__(256) k_density(const float4* __restrict__ posh, const float4* __restrict__ posm,
-                                                 const float4* __restrict__ posc, const uint32_t* __restrict__ keys,
-                                                 const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
-                                                 const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
-                                                 const sph_GridParams* __restrict__ g, int t0, int t1, int rowbase, int kmax, float Keos,
-                                                 int32_t* __restrict__ nown, float* __restrict__ rho, float* __restrict__ press,
-                                                 float* __restrict__ cvol) {
+__global__ void __launch_bounds__(RS_WARPS * 32, 4) k_density(const float4* __restrict__ posh, const float4* __restrict__ posm,
+                                                              const float4* __restrict__ posc, const uint32_t* __restrict__ keys,
+                                                              const uint32_t* __restrict__ cell_start, const uint32_t* __restrict__ cell_end,
+                                                              const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
+                                                              const sph_GridParams* __restrict__ g, int t0, int t1, int rowbase, int kmax, float Keos,
+                                                              int32_t* __restrict__ nown, float* __restrict__ rho, float* __restrict__ press,
+                                                              float* __restrict__ cvol) {
+    __shared__ RowStreamSmem<1> smem[RS_WARPS];   // tg[0]: x, y, z, 1/h   tg[1]: t(h), 1/(pi h^3), -, -
     if (!(g->hmax < kHugeH)) return;
-    const int sub = threadIdx.x & (K1B_LPT - 1);
-    const int t = t0 + (blockIdx.x * blockDim.x + threadIdx.x) / K1B_LPT;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int base = t0 + (blockIdx.x * RS_WARPS + w) * 32;
+    if (base >= t1) return;
+    RowStreamSmem<1>& S = smem[w];
+    const int t = base + lane;
     const bool live = t < t1;
-    float rsum = 0.f;
-    int own = 0;
     float4 pi = make_float4(0.f, 0.f, 0.f, 1.f);
-    if (live) {
-        pi = posh[t];
-        const int cnt = ncount[t];
-        const float hinv_i = 1.0f / pi.w, hi2 = __fmul_rn(pi.w, 2.0f);
-        auto add = [&](uint32_t j, const float4 pj) {
-            const float dx = __fsub_rn(pi.x, pj.x), dy = __fsub_rn(pi.y, pj.y), dz = __fsub_rn(pi.z, pj.z);
-            const float r = __fsqrt_rn(dot3_rn(dx, dy, dz));
-            own += r < hi2 ? 1 : 0;
-            const float wsym = 0.5f * (w_fast(r, hinv_i) + w_fast(r, __fdividef(1.0f, pj.w)));
-            rsum = EQM ? rsum + wsym : fmaf(posm[j].w, wsym, rsum);
-        };
-        if (cnt <= kmax) {
-            const uint32_t* row = nlist + (size_t)(t - rowbase) * kmax;
-            int k = sub;
-            for (; k + K1B_LPT < cnt; k += 2 * K1B_LPT) {   // two gathers in flight
-                const uint32_t j0 = row[k], j1 = row[k + K1B_LPT];
-                const float4 q0 = posh[j0], q1 = posh[j1];
-                add(j0, q0);
-                add(j1, q1);
-            }
-            if (k < cnt) {
-                const uint32_t j = row[k];
-                add(j, posh[j]);
-            }
-        } else {
-            // Row overflow (an error state the caller is told about): the list is truncated, but the density and the
-            // own-support count stay complete -- rescan the stencil with the same keep rule as k_cell_neighbors.
-            const int bits = g->bits, S = g->stencil, dim = 1 << bits;
-            const uint32_t ck = keys[t] >> (3 * (10 - bits));
-            const int cx = (int)compact10(ck), cy = (int)compact10(ck >> 1), cz = (int)compact10(ck >> 2);
-            const float c_t = posc[t].w;
-            for (int oz = -S; oz <= S; oz++)
-                for (int oy = -S; oy <= S; oy++)
-                    for (int ox = -S; ox <= S; ox++) {
-                        const int nx = cx + ox, ny = cy + oy, nz = cz + oz;
-                        if (nx < 0 || ny < 0 || nz < 0 || nx >= dim || ny >= dim || nz >= dim) continue;
-                        const uint32_t nk = expand10((uint32_t)nx) | (expand10((uint32_t)ny) << 1) | (expand10((uint32_t)nz) << 2);
-                        for (uint32_t j = cell_start[nk] + sub; j < cell_end[nk]; j += K1B_LPT) {
-                            const float4 cj = posc[j];
-                            const float dx = __fsub_rn(pi.x, cj.x), dy = __fsub_rn(pi.y, cj.y), dz = __fsub_rn(pi.z, cj.z);
-                            if (dot3_rn(dx, dy, dz) < fmaxf(c_t, cj.w) && j != (uint32_t)t) add(j, posh[j]);
+    int cnt = 0;
+    if (live) { pi = posh[t]; cnt = ncount[t]; }
+    const bool ovf = cnt > kmax;   // truncated row (an error state the caller is told about): re-scanned from the stencil below
+    const float hinv_i = 1.0f / pi.w;
+    S.tg[0][lane] = make_float4(pi.x, pi.y, pi.z, hinv_i);
+    S.tg[1][lane] = make_float4(sph_own_threshold(pi.w), hinv_i * hinv_i * hinv_i * kInvPI, 0.f, 0.f);
+    float acc[1];
+    int own;
+    row_stream<1, true>(S, nlist + (size_t)(base - rowbase) * kmax, (uint32_t)base, kmax, ovf ? 0 : cnt,
+        [&](const float4 A, const float4 B, uint32_t j, float (&v)[1], bool& in_i) {
+            const float4 pj = posh[j];
+            const float dx = __fsub_rn(A.x, pj.x), dy = __fsub_rn(A.y, pj.y), dz = __fsub_rn(A.z, pj.z);
+            const float d2 = dot3_rn(dx, dy, dz);
+            in_i = d2 < B.x;
+            const float r = d2 * rs_rsqrt(fmaxf(d2, 1.0e-37f));
+            const float hinv_j = rs_rcp(pj.w);
+            const float cw_j = hinv_j * hinv_j * hinv_j * kInvPI;
+            float wsum = fmaf(B.y, w_shape(r * A.w), cw_j * w_shape(r * hinv_j));
+            if (!EQM) wsum *= __ldg(&posm[j].w);
+            v[0] = wsum;
+        }, acc, own);
+    float rsum = acc[0];
+
+    // Row overflow: the list is truncated, but the density and the own-support count stay complete -- the whole warp
+    // re-scans the stencil of such a target with the keep rule of k_cell_neighbors (lane-strided partial sums, butterfly).
+    unsigned ovm = __ballot_sync(FULL, ovf);
+    while (ovm) {
+        const int src = __ffs(ovm) - 1;
+        ovm &= ovm - 1u;
+        const int tq = base + src;
+        const float4 A = S.tg[0][src];
+        const float4 C = S.tg[1][src];
+        const int bits = g->bits, S = g->stencil, dim = 1 << bits;
+        const uint32_t ck = keys[tq] >> (3 * (10 - bits));
+        const int cx = (int)compact10(ck), cy = (int)compact10(ck >> 1), cz = (int)compact10(ck >> 2);
+        const float c_t = posc[tq].w;
+        float s = 0.f;
+        int no = 0;
+        for (int oz = -S; oz <= S; oz++)
+            for (int oy = -S; oy <= S; oy++)
+                for (int ox = -S; ox <= S; ox++) {
+                    const int nx = cx + ox, ny = cy + oy, nz = cz + oz;
+                    if (nx < 0 || ny < 0 || nz < 0 || nx >= dim || ny >= dim || nz >= dim) continue;
+                    const uint32_t nk = expand10((uint32_t)nx) | (expand10((uint32_t)ny) << 1) | (expand10((uint32_t)nz) << 2);
+                    for (uint32_t j = cell_start[nk] + lane; j < cell_end[nk]; j += 32) {
+                        const float4 cj = posc[j];
+                        const float dx = __fsub_rn(A.x, cj.x), dy = __fsub_rn(A.y, cj.y), dz = __fsub_rn(A.z, cj.z);
+                        const float d2 = dot3_rn(dx, dy, dz);
+                        if (d2 < fmaxf(c_t, cj.w) && j != (uint32_t)tq) {
+                            const float hj = posh[j].w;
+                            const float mj = EQM ? 1.0f : posm[j].w;
+                            no += d2 < C.x ? 1 : 0;
+                            const float r = d2 * rs_rsqrt(fmaxf(d2, 1.0e-37f));
+                            const float hinv_j = rs_rcp(hj);
+                            const float wsum = fmaf(C.y, w_shape(r * A.w), hinv_j * hinv_j * hinv_j * kInvPI * w_shape(r * hinv_j));
+                            s += EQM ? wsum : mj * wsum;
                         }
                     }
-        }
-    }
+                }
 #pragma unroll
-    for (int o = K1B_LPT / 2; o > 0; o >>= 1) {
-        rsum += __shfl_xor_sync(FULL, rsum, o);
-        own += __shfl_xor_sync(FULL, own, o);
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(FULL, s, o);
+            no += __shfl_xor_sync(FULL, no, o);
+        }
+        if (lane == src) { rsum = s; own = no; }
     }
-    if (live && sub == 0) {
-        // self term m_i * Kernel(0,h_i) (DensityFieldSystem.cs:45), exact: 1/(pi h^3)
+
+    if (live) {
+        // self term m_i * Kernel(0,h_i) (DensityFieldSystem.cs:45), exact: 1/(pi h^3); rsum holds sum (W_i + W_j), halved here
         const float mi = posm[t].w;
         const float w0 = __fdiv_rn(1.0f, __fmul_rn(__fmul_rn(__fmul_rn(kPI, pi.w), pi.w), pi.w));
-        if (EQM) rsum *= mi;
+        rsum *= EQM ? 0.5f * mi : 0.5f;
         const float d = __fadd_rn(__fmul_rn(mi, w0), rsum);
         const float P = __fmul_rn(__fmul_rn(Keos, d), d);  // PressureFieldSystem.cs:31-33
         rho[t] = d;
@@ -568,7 +594,7 @@ int sph_launch_neighbors_density(sphb200_ctx* c) {
 #undef K3_LAUNCH
     SPH_LAUNCH_CHECK(c);
     {
-        int tpb = 256 / K1B_LPT;
+        int tpb = RS_WARPS * 32;   // targets per block: 32 per warp
         if (c->equal_mass)
             k_density<true><<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->posm, c->posc, c->skeys, c->cell_start,
                                                                         c->cell_end, c->nlist, c->ncount, c->grid_d, t0, t1,

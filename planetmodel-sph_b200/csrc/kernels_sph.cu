@@ -10,6 +10,7 @@
 // reference's fp32 op sequence exactly (non-contracted __f*_rn intrinsics, IEEE sqrt); *values* (W, grad W, sums) use
 // fast arithmetic (reciprocal multiplies, rsqrt, FMA, warp-tree sums) and are held to <= 1e-5 relative by the tests.
 #include "ctx.cuh"
+#include "rowstream.cuh"
 #include <math.h>
 
 namespace {
@@ -47,59 +48,64 @@ __device__ __forceinline__ float kernel_deriv_exact(float distance, float size, 
     return __fdiv_rn(num, __fmul_rn(4.0f, pi_h_4th));
 }
 
-// ---- fast value arithmetic
-// (dW/dr)/r with the reference's inner branch (quirk Q1: +3q unless lead = -3):
-//   q<1 : (lead*q + 2.25 q^2)/(pi h^4)/r = (lead + 2.25 q) / (pi h^5);   1<=q<2 : -0.75 (2-q)^2 /(pi h^4) / r
-__device__ __forceinline__ float dwr_fast(float r, float rinv, float hinv, float lead) {
-    float q = r * hinv;
-    float h2 = hinv * hinv;
-    float c4 = h2 * h2 * kInvPI;
-    float t = 2.0f - q;
-    float inner = (lead + 2.25f * q) * hinv * c4;
-    float outer = -0.75f * t * t * c4 * rinv;
-    return q < 1.0f ? inner : (q < 2.0f ? outer : 0.0f);
+// ------------------------------------------------------------------------------------------------------------
+// K2: pressure gradient over the materialised lists (PressureFieldSystem.cs:44-70): one warp per 32 consecutive targets,
+// rows consumed as a flat stream of octets with canonical summation order (rowstream.cuh).  grad W_sym is recomputed from the
+// positions (no stored kernels); the two gathers per pair (posh[j], (m/rho)P of j) are independent and in flight together.
+// (dW/dr)/r with the reference's inner branch (quirk Q1: +3q unless lead = -3), c4 = 1/(pi h^4):
+//   q < 1 : (lead + 2.25 q) / h * c4 ;   1 <= q < 2 : -0.75 (2-q)^2 / r * c4 ;  0 beyond -- branch-free via t = max(2-q, 0).
+// Rows beyond max_neighbors (an error state the caller is told about) contribute their stored part only.
+// ------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dwr_shape(float q, float hinv, float rinv, float lead) {
+    const float t = fmaxf(2.0f - q, 0.0f);
+    const float outer = (-0.75f * t) * (t * rinv);
+    const float inner = fmaf(2.25f, q, lead) * hinv;
+    return q < 1.0f ? inner : outer;
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// K2: pressure gradient over the materialised lists (16 lanes per target).
-// ------------------------------------------------------------------------------------------------------------
-constexpr int K2_LPT = 16;
+constexpr int K2_WARPS = 4;   // 7.6 KB of stream state per warp
 
-__global__ void __launch_bounds__(256) k_pressure_grad(const float4* __restrict__ posh, const float* __restrict__ cvol,
-                                                       const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
-                                                       int t0, int t1, int rowbase, int kmax, float lead, float4* __restrict__ gradp) {
-    const int sub = threadIdx.x & (K2_LPT - 1);
-    const int t = t0 + (blockIdx.x * blockDim.x + threadIdx.x) / K2_LPT;
+__global__ void __launch_bounds__(K2_WARPS * 32, 6) k_pressure_grad(const float4* __restrict__ posh, const float* __restrict__ cvol,
+                                                                    const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
+                                                                    int t0, int t1, int rowbase, int kmax, float lead, float4* __restrict__ gradp) {
+    __shared__ RowStreamSmem<3> smem[K2_WARPS];   // tg[0]: x, y, z, 1/h   tg[1]: 1/(pi h^4), -, -, -
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int base = t0 + (blockIdx.x * K2_WARPS + w) * 32;
+    if (base >= t1) return;
+    RowStreamSmem<3>& S = smem[w];
+    const int t = base + lane;
     const bool live = t < t1;
-    float ax = 0.f, ay = 0.f, az = 0.f;
-    if (live) {
-        const float4 pi = posh[t];
-        const float hinv_i = 1.0f / pi.w;
-        const int cnt = min(ncount[t], kmax);
-        const uint32_t* row = nlist + (size_t)(t - rowbase) * kmax;
-        for (int k = sub; k < cnt; k += K2_LPT) {
-            uint32_t j = row[k];
-            float4 pj = posh[j];
-            float cj = cvol[j];
-            float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
-            float r2 = dx * dx + dy * dy + dz * dz;
-            float rinv = r2 > 0.f ? rsqrtf(r2) : 0.f;   // coincident distinct particles: gradient 0 (reference: NaN, quirk Q9)
-            float r = r2 * rinv;
-            float hinv_j = __fdividef(1.0f, pj.w);
-            float s = 0.5f * (dwr_fast(r, rinv, hinv_i, lead) + dwr_fast(r, rinv, hinv_j, lead)) * cj;
-            ax = fmaf(dx, s, ax); ay = fmaf(dy, s, ay); az = fmaf(dz, s, az);
-        }
-    }
-#pragma unroll
-    for (int o = K2_LPT / 2; o > 0; o >>= 1) {
-        ax += __shfl_xor_sync(FULL, ax, o); ay += __shfl_xor_sync(FULL, ay, o); az += __shfl_xor_sync(FULL, az, o);
-    }
-    if (live && sub == 0) gradp[t] = make_float4(ax, ay, az, 0.f);
+    float4 pi = make_float4(0.f, 0.f, 0.f, 1.f);
+    int cnt = 0;
+    if (live) { pi = posh[t]; cnt = min(ncount[t], kmax); }
+    const float hinv_i = 1.0f / pi.w, h2 = hinv_i * hinv_i;
+    S.tg[0][lane] = make_float4(pi.x, pi.y, pi.z, hinv_i);
+    S.tg[1][lane] = make_float4(h2 * h2 * kInvPI, 0.f, 0.f, 0.f);
+    float acc[3];
+    int unused;
+    row_stream<3, false>(S, nlist + (size_t)(base - rowbase) * kmax, (uint32_t)base, kmax, cnt,
+        [&](const float4 A, const float4 B, uint32_t j, float (&v)[3], bool& flag) {
+            const float4 pj = posh[j];
+            const float cj = cvol[j];
+            const float dx = A.x - pj.x, dy = A.y - pj.y, dz = A.z - pj.z;
+            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+            // coincident distinct particles: d = 0, finite factor => gradient contribution 0 (reference: NaN, quirk Q9)
+            const float rinv = rs_rsqrt(fmaxf(r2, 1.0e-37f));
+            const float r = r2 * rinv;
+            const float hinv_j = rs_rcp(pj.w), g2 = hinv_j * hinv_j;
+            const float c4_j = g2 * g2 * kInvPI;
+            const float s = fmaf(B.x, dwr_shape(r * A.w, A.w, rinv, lead), c4_j * dwr_shape(r * hinv_j, hinv_j, rinv, lead)) * cj;
+            v[0] = dx * s; v[1] = dy * s; v[2] = dz * s;
+            flag = false;
+        }, acc, unused);
+    if (live) gradp[t] = make_float4(0.5f * acc[0], 0.5f * acc[1], 0.5f * acc[2], 0.f);
 }
 
 // Near-pair correction of the all-pairs gravity kernel (kernels_gravity.cu): for neighbors with r < a = h_i add
 // "Dyer & Ip softened law minus the capped Newtonian value the all-pairs kernel already summed"
 // (GravityFieldSystem.cs:340-347).  Every such pair is in i's list because r < h_i < 2 max(h_i,h_j).
+constexpr int K2_LPT = 16;
+
 __global__ void __launch_bounds__(256) k_gravity_near(const float4* __restrict__ posh, const float4* __restrict__ posm,
                                                       const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
                                                       int t0, int t1, int rowbase, int kmax, float G, float4* __restrict__ grav) {
@@ -344,8 +350,8 @@ int sph_launch_pressure(sphb200_ctx* c) {
     int nt = t1 - t0;
     if (nt <= 0) return SPH_OK;
     float lead = (c->p.flags & SPH_FLAG_FIX_KERNEL_DERIV_SIGN) ? -3.0f : 3.0f;
-    int tpb = 256 / K2_LPT;
-    k_pressure_grad<<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->cvol, c->nlist, c->ncount, t0, t1,
+    int tpb = K2_WARPS * 32;   // targets per block: 32 per warp
+    k_pressure_grad<<<sph_div_up(nt, tpb), K2_WARPS * 32, 0, c->stream>>>(c->posh[c->cur], c->cvol, c->nlist, c->ncount, t0, t1,
                                                                 (int)c->row_base, c->p.max_neighbors, lead, c->gradp);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;
