@@ -115,7 +115,12 @@ int sph_ctx_create(const sph_Params& p, int device, int64_t slots, int64_t rows,
     size_t cap = (size_t)slots, nr = (size_t)rows, nn = 2 * (size_t)tree;
     bool ok = cudaSetDevice(device) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
-    ok = ok && cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking) == cudaSuccess;
+    {   // the auxiliary stream (LBVH build / gravity-source exchange behind the neighbor pass) gets the highest priority: its
+        // blocks are placed first whenever an SM frees resources
+        int lo = 0, hi = 0;
+        ok = ok && cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess;
+        ok = ok && cudaStreamCreateWithPriority(&c->aux_stream, cudaStreamNonBlocking, hi) == cudaSuccess;
+    }
     ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess;
     c->stream = c->own_stream;

@@ -43,6 +43,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommInitAll)(ncclComm_t*, int, const int*) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommSplit)(ncclComm_t, int, int, ncclComm_t*, void*) = nullptr;   // optional (NCCL >= 2.18)
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -67,13 +68,16 @@ NcclApi* nccl_api() {
     NSYM(CommDestroy, "ncclCommDestroy") NSYM(AllReduce, "ncclAllReduce") NSYM(AllGather, "ncclAllGather") NSYM(Send, "ncclSend")
     NSYM(Recv, "ncclRecv") NSYM(GroupStart, "ncclGroupStart") NSYM(GroupEnd, "ncclGroupEnd") NSYM(GetErrorString, "ncclGetErrorString")
 #undef NSYM
+    *(void**)(&api.CommSplit) = dlsym(api.lib, "ncclCommSplit");
     return &api;
 }
 
 struct GroupRank {
     sphb200_ctx* c = nullptr;
     int rank = 0, device = 0;
-    ncclComm_t comm = nullptr;
+    ncclComm_t comm = nullptr;       // the communicator the collectives currently use (comm_main or comm_aux)
+    ncclComm_t comm_main = nullptr, comm_aux = nullptr;   // comm_aux: a split of comm_main for the auxiliary stream (null: no overlap)
+    cudaStream_t main_stream = nullptr;
     // device buffers
     uint4 *mig_send = nullptr, *mig_recv = nullptr;   // 6 x 16 B per own slot: migration records (48 B) / result records (96 B)
     uint8_t* dest = nullptr;
@@ -82,6 +86,8 @@ struct GroupRank {
     uint4 *halo_send = nullptr, *halo_recv = nullptr;
     float* cv_send = nullptr;
     uint32_t* hist = nullptr;
+    unsigned long long* bpart = nullptr;   // run sums of the histograms (k_bin_partials)
+    uint32_t* bmask = nullptr;             // owners around every bin (k_bin_owner_mask)
     int64_t* split_d = nullptr;      // g0[0..world], sbin[0..world]
     uint32_t* cnt_d = nullptr;       // [world][world] count matrices (migration, halo, download)
     float4* posm_g = nullptr;
@@ -286,6 +292,41 @@ int sync_all(sphb200_group* g) {
     return SPH_OK;
 }
 
+// Auxiliary lane: between aux_begin and aux_end everything a rank issues (kernels of its context, collectives) goes to its
+// auxiliary stream / communicator and runs concurrently with what is issued on the main stream afterwards, until aux_join.
+bool aux_available(sphb200_group* g) {
+    if (g->world == 1) return false;
+    if (g->local) return getenv("SPHB200_GROUP_NO_OVERLAP") == nullptr;
+    for (auto& R : g->r) if (!R.comm_aux) return false;
+    return true;
+}
+int aux_begin(sphb200_group* g) {
+    FOR_RANKS(g, R) {
+        G_CUDA(g, cudaSetDevice(R.device));
+        sphb200_ctx* c = R.c;
+        G_CUDA(g, cudaEventRecord(c->ev_fork, c->stream));
+        G_CUDA(g, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        R.main_stream = c->stream;
+        c->stream = c->aux_stream;
+        if (!g->local) R.comm = R.comm_aux;
+    }
+    return SPH_OK;
+}
+int aux_end(sphb200_group* g) {
+    FOR_RANKS(g, R) {
+        G_CUDA(g, cudaSetDevice(R.device));
+        sphb200_ctx* c = R.c;
+        G_CUDA(g, cudaEventRecord(c->ev_join, c->stream));
+        c->stream = R.main_stream;
+        R.comm = R.comm_main;
+    }
+    return SPH_OK;
+}
+int aux_join(sphb200_group* g) {
+    FOR_RANKS(g, R) { G_CUDA(g, cudaSetDevice(R.device)); G_CUDA(g, cudaStreamWaitEvent(R.c->stream, R.c->ev_join, 0)); }
+    return SPH_OK;
+}
+
 template <typename T>
 std::vector<void*> ptrs(sphb200_group* g, T f) {
     std::vector<void*> v;
@@ -317,7 +358,7 @@ template <typename T> cudaError_t dal(T** p, size_t count) { return cudaMalloc((
 void free_rank(GroupRank& R) {
     if (R.c) cudaSetDevice(R.device);
     cudaFree(R.mig_send); cudaFree(R.mig_recv); cudaFree(R.dest); cudaFree(R.perm); cudaFree(R.tot256); cudaFree(R.hmask); cudaFree(R.hlist);
-    cudaFree(R.hcnt); cudaFree(R.htot); cudaFree(R.halo_send); cudaFree(R.halo_recv); cudaFree(R.cv_send); cudaFree(R.hist);
+    cudaFree(R.hcnt); cudaFree(R.htot); cudaFree(R.halo_send); cudaFree(R.halo_recv); cudaFree(R.cv_send); cudaFree(R.hist); cudaFree(R.bpart); cudaFree(R.bmask);
     cudaFree(R.split_d); cudaFree(R.cnt_d); cudaFree(R.posm_g); cudaFree(R.keys_g); cudaFree(R.bnd); cudaFree(R.red_scratch);
     if (R.c) { cudaFree(R.c->top_nodes); cudaFree(R.c->front_nodes); cudaFree(R.c->top_counts); R.c->top_nodes = nullptr; R.c->front_nodes = nullptr; R.c->top_counts = nullptr; }
     if (R.cnt_h) cudaFreeHost(R.cnt_h);
@@ -325,7 +366,8 @@ void free_rank(GroupRank& R) {
     if (R.grid_h) cudaFreeHost(R.grid_h);
     if (R.diag_h) cudaFreeHost(R.diag_h);
     if (R.ev) cudaEventDestroy(R.ev);
-    if (R.comm && nccl_api()->lib) nccl_api()->CommDestroy(R.comm);
+    if (R.comm_aux && nccl_api()->lib) nccl_api()->CommDestroy(R.comm_aux);
+    if (R.comm_main && nccl_api()->lib) nccl_api()->CommDestroy(R.comm_main);
     if (R.c) sphb200_destroy(R.c);
     R = GroupRank();
 }
@@ -342,7 +384,7 @@ int alloc_rank(sphb200_group* g, GroupRank& R) {
          dal(&R.perm, own) == cudaSuccess && dal(&R.tot256, 256) == cudaSuccess && dal(&R.hmask, own) == cudaSuccess &&
          dal(&R.hlist, halo) == cudaSuccess && dal(&R.hcnt, grk_halo_cnt_words(g->cap_own)) == cudaSuccess && dal(&R.htot, 256) == cudaSuccess &&
          dal(&R.halo_send, 2 * halo) == cudaSuccess && dal(&R.halo_recv, 2 * halo) == cudaSuccess && dal(&R.cv_send, halo) == cudaSuccess &&
-         dal(&R.hist, 2 * (size_t)SPH_NBINS) == cudaSuccess && dal(&R.split_d, 2 * (size_t)(W + 1)) == cudaSuccess &&
+         dal(&R.hist, 2 * (size_t)SPH_NBINS) == cudaSuccess && dal(&R.bpart, 2 * (size_t)SPH_NBINS / 1024) == cudaSuccess && dal(&R.bmask, (size_t)SPH_NBINS) == cudaSuccess && dal(&R.split_d, 2 * (size_t)(W + 1)) == cudaSuccess &&
          dal(&R.cnt_d, (size_t)W * W) == cudaSuccess && dal(&R.posm_g, N) == cudaSuccess && dal(&R.keys_g, N) == cudaSuccess &&
          dal(&R.bnd, (size_t)W * 2 * SPH_TOP_LEAF * 2) == cudaSuccess &&
          (!g->local || cudaMalloc(&R.red_scratch, R.red_bytes) == cudaSuccess) &&
@@ -419,7 +461,13 @@ int sphb200_group_create(const sph_Params* params, int64_t capacity, int ndev, c
         std::vector<ncclComm_t> comms(ndev);
         ncclResult_t r = N->CommInitAll(comms.data(), ndev, devs.data());
         if (r != ncclSuccess) { g_group_err = std::string("ncclCommInitAll: ") + N->GetErrorString(r); sphb200_group_destroy(g); return SPH_ERR_NCCL; }
-        for (int l = 0; l < ndev; l++) g->r[l].comm = comms[l];
+        for (int l = 0; l < ndev; l++) g->r[l].comm = g->r[l].comm_main = comms[l];
+        if (N->CommSplit && !getenv("SPHB200_GROUP_NO_OVERLAP")) {
+            bool okk = N->GroupStart() == ncclSuccess;
+            for (int l = 0; l < ndev && okk; l++) { cudaSetDevice(devs[l]); okk = N->CommSplit(comms[l], 0, l, &g->r[l].comm_aux, nullptr) == ncclSuccess; }
+            okk = (N->GroupEnd() == ncclSuccess) && okk;
+            if (!okk) for (int l = 0; l < ndev; l++) g->r[l].comm_aux = nullptr;
+        }
     }
     *out = g;
     return SPH_OK;
@@ -439,6 +487,11 @@ int sphb200_group_create_rank(const sph_Params* params, int64_t capacity, const 
         cudaSetDevice(device);
         ncclResult_t r = N->CommInitRank(&g->r[0].comm, world, id, rank);
         if (r != ncclSuccess) { g_group_err = std::string("ncclCommInitRank: ") + N->GetErrorString(r); sphb200_group_destroy(g); return SPH_ERR_NCCL; }
+        g->r[0].comm_main = g->r[0].comm;
+        // a second communicator over the same ranks for the auxiliary stream (collective call: every rank makes it or none --
+        // the environment switch must be set for all ranks alike)
+        if (N->CommSplit && !getenv("SPHB200_GROUP_NO_OVERLAP") && N->CommSplit(g->r[0].comm, 0, rank, &g->r[0].comm_aux, nullptr) != ncclSuccess)
+            g->r[0].comm_aux = nullptr;
     }
     *out = g;
     return SPH_OK;
@@ -540,7 +593,7 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
     FOR_RANKS(g, R) {
         G_CUDA(g, cudaSetDevice(R.device));
         sphb200_ctx* c = R.c;
-        G_RC(g, R, grk_splitters(c, R.hist, W, R.split_d));
+        G_RC(g, R, grk_splitters(c, R.hist, W, R.split_d, R.bpart, R.bmask));
         G_RC(g, R, grk_dest(c, c->keys[1], (int)R.n_own, R.split_d, W, R.dest));
         G_CUDA(g, cudaMemsetAsync(R.tot256, 0, 256 * sizeof(uint32_t), c->stream));
         G_RC(g, R, sph_launch_digit_pass(c, nullptr, nullptr, R.dest, (int)R.n_own, 0, nullptr, R.perm, R.tot256, c->stream));
@@ -590,7 +643,7 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
         G_RC(g, R, sph_launch_radix_sort(c, (int)R.n_own, c->stream));
         if (l == 0) pass_mark(g, "sort");
         // 4. halo lists
-        G_RC(g, R, grk_halo_lists(c, c->keys[1], (int)R.n_own, R.split_d, W, R.rank, R.hmask, R.hcnt, R.htot, R.hlist));
+        G_RC(g, R, grk_halo_lists(c, c->keys[1], (int)R.n_own, R.split_d, W, R.rank, R.bmask, R.hmask, R.hcnt, R.htot, R.hlist));
         G_CUDA(g, cudaMemcpyAsync(R.cnt_d + (size_t)R.rank * W, R.htot, W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
     }
     pass_mark(g, "halo_lists");
@@ -640,6 +693,53 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
     }
     pass_mark(g, "halo_exchange_cells");
 
+    // 6a. gravity sources: all-gather of (x,y,z,m) in global sorted order; tree gravity also all-gathers the keys, builds the LBVH
+    // nodes of the own range, all-gathers the packed nodes and finishes the nodes that straddle rank boundaries.  None of it
+    // depends on the neighbor pass: it is issued first, on the auxiliary stream and communicator, and runs behind pass 5.
+    const char* gname = impl == SPH_GRAVITY_TREE ? "gravity_tree" : impl == SPH_GRAVITY_PARTICLE ? "gravity_allpairs" : "gravity_none";
+    auto gravity_sources = [&]() -> int {
+        FOR_RANKS(g, R) {
+            G_CUDA(g, cudaSetDevice(R.device));
+            sphb200_ctx* c = R.c;
+            G_CUDA(g, cudaMemcpyAsync(R.posm_g + g->g0[R.rank], c->posm + R.own0, (size_t)R.n_own * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
+            if (impl == SPH_GRAVITY_TREE)
+                G_CUDA(g, cudaMemcpyAsync(R.keys_g + g->g0[R.rank], c->keys[0] + R.own0, (size_t)R.n_own * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
+            c->gsrc = R.posm_g; c->gsrc_n = N;
+        }
+        { auto b = ptrs(g, [](GroupRank& R) { return R.posm_g; }); if ((rc = g_allgatherv(g, b.data(), g->g0.data(), 16))) return rc; }
+        if (impl != SPH_GRAVITY_TREE) return SPH_OK;
+        { auto b = ptrs(g, [](GroupRank& R) { return R.keys_g; }); if ((rc = g_allgatherv(g, b.data(), g->g0.data(), 4))) return rc; }
+        FOR_RANKS(g, R) {
+            G_CUDA(g, cudaSetDevice(R.device));
+            sphb200_ctx* c = R.c;
+            c->tkeys = R.keys_g; c->tree_n = N; c->tree_g0 = g->g0[R.rank]; c->tree_g1 = g->g0[R.rank + 1];
+            c->tree_off = R.own0 - g->g0[R.rank];
+            if (W > 1) G_CUDA(g, cudaMemsetAsync(c->top_counts + 4 * R.rank, 0, 4 * sizeof(int32_t), c->stream));
+            G_RC(g, R, sph_launch_tree_build(c, dt, c->stream));
+            if (W > 1) G_RC(g, R, grk_boundary(c, c->posh[0] + R.own0, c->velm[0] + R.own0, (int)R.n_own, R.bnd + (size_t)R.rank * 2 * SPH_TOP_LEAF * 2));
+        }
+        if (W > 1) {
+            // packed walk nodes of every rank's range: internal nodes [g0, g1) (ids < N-1) and leaves N-1+[g0, g1)
+            std::vector<int64_t> oi(W + 1), ol(W + 1);
+            for (int r = 0; r <= W; r++) { oi[r] = std::min<int64_t>(g->g0[r], N - 1); ol[r] = N - 1 + g->g0[r]; }
+            { auto b = ptrs(g, [](GroupRank& R) { return R.c->packed; }); if ((rc = g_allgatherv(g, b.data(), oi.data(), 32))) return rc; }
+            { auto b = ptrs(g, [](GroupRank& R) { return R.c->packed; }); if ((rc = g_allgatherv(g, b.data(), ol.data(), 32))) return rc; }
+            { auto b = ptrs(g, [](GroupRank& R) { return R.c->top_nodes; }); if ((rc = g_allgather(g, b.data(), SPH_TOP_CAP * sizeof(TopNode)))) return rc; }
+            { auto b = ptrs(g, [](GroupRank& R) { return R.c->front_nodes; }); if ((rc = g_allgather(g, b.data(), SPH_TOP_CAP * sizeof(FrontNode)))) return rc; }
+            { auto b = ptrs(g, [](GroupRank& R) { return R.c->top_counts; }); if ((rc = g_allgather(g, b.data(), 4 * sizeof(int32_t)))) return rc; }
+            { auto b = ptrs(g, [](GroupRank& R) { return R.bnd; }); if ((rc = g_allgather(g, b.data(), 2 * SPH_TOP_LEAF * 2 * sizeof(float4)))) return rc; }
+            FOR_RANKS(g, R) { G_CUDA(g, cudaSetDevice(R.device)); G_RC(g, R, sph_launch_top_tree(R.c, W, R.bnd, R.split_d, dt)); }
+        }
+        return SPH_OK;
+    };
+    const bool overlap = impl != SPH_GRAVITY_NONE && aux_available(g);
+    if (overlap) {
+        if ((rc = aux_begin(g))) return rc;
+        const int rcg = gravity_sources();
+        if ((rc = aux_end(g))) return rc;       // always restores the main stream / communicator
+        if (rcg) return rcg;
+    }
+
     // 5. neighbor rows + density + EOS for the own targets; (m/rho)P of the halo follows
     FOR_RANKS(g, R) {
         G_CUDA(g, cudaSetDevice(R.device));
@@ -655,8 +755,7 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
     }
     pass_mark(g, "neighbors_density_eos");
 
-    // 6. gravity
-    const char* gname = impl == SPH_GRAVITY_TREE ? "gravity_tree" : impl == SPH_GRAVITY_PARTICLE ? "gravity_allpairs" : "gravity_none";
+    // 6b. gravity of the own targets
     if (impl == SPH_GRAVITY_NONE) {
         FOR_RANKS(g, R) {
             G_CUDA(g, cudaSetDevice(R.device));
@@ -666,44 +765,13 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
             G_CUDA(g, cudaMemsetAsync(c->napprox, 0, (size_t)c->n * sizeof(int32_t), c->stream));
         }
     } else {
+        if (overlap) { if ((rc = aux_join(g))) return rc; }
+        else if ((rc = gravity_sources())) return rc;
         FOR_RANKS(g, R) {
             G_CUDA(g, cudaSetDevice(R.device));
-            sphb200_ctx* c = R.c;
-            G_CUDA(g, cudaMemcpyAsync(R.posm_g + g->g0[R.rank], c->posm + R.own0, (size_t)R.n_own * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
-            if (impl == SPH_GRAVITY_TREE)
-                G_CUDA(g, cudaMemcpyAsync(R.keys_g + g->g0[R.rank], c->keys[0] + R.own0, (size_t)R.n_own * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
-            c->gsrc = R.posm_g; c->gsrc_n = N;
-        }
-        { auto b = ptrs(g, [](GroupRank& R) { return R.posm_g; }); if ((rc = g_allgatherv(g, b.data(), g->g0.data(), 16))) return rc; }
-        if (impl == SPH_GRAVITY_PARTICLE) {
-            FOR_RANKS(g, R) {
-                G_CUDA(g, cudaSetDevice(R.device));
-                if (R.n_own > 0) { G_RC(g, R, sph_launch_gravity_allpairs(R.c)); G_RC(g, R, sph_launch_gravity_near(R.c)); }
-            }
-        } else {
-            { auto b = ptrs(g, [](GroupRank& R) { return R.keys_g; }); if ((rc = g_allgatherv(g, b.data(), g->g0.data(), 4))) return rc; }
-            FOR_RANKS(g, R) {
-                G_CUDA(g, cudaSetDevice(R.device));
-                sphb200_ctx* c = R.c;
-                c->tkeys = R.keys_g; c->tree_n = N; c->tree_g0 = g->g0[R.rank]; c->tree_g1 = g->g0[R.rank + 1];
-                c->tree_off = R.own0 - g->g0[R.rank];
-                if (W > 1) G_CUDA(g, cudaMemsetAsync(c->top_counts + 4 * R.rank, 0, 4 * sizeof(int32_t), c->stream));
-                G_RC(g, R, sph_launch_tree_build(c, dt, c->stream));
-                if (W > 1) G_RC(g, R, grk_boundary(c, c->posh[0] + R.own0, c->velm[0] + R.own0, (int)R.n_own, R.bnd + (size_t)R.rank * 2 * SPH_TOP_LEAF * 2));
-            }
-            if (W > 1) {
-                // packed walk nodes of every rank's range: internal nodes [g0, g1) (ids < N-1) and leaves N-1+[g0, g1)
-                std::vector<int64_t> oi(W + 1), ol(W + 1);
-                for (int r = 0; r <= W; r++) { oi[r] = std::min<int64_t>(g->g0[r], N - 1); ol[r] = N - 1 + g->g0[r]; }
-                { auto b = ptrs(g, [](GroupRank& R) { return R.c->packed; }); if ((rc = g_allgatherv(g, b.data(), oi.data(), 32))) return rc; }
-                { auto b = ptrs(g, [](GroupRank& R) { return R.c->packed; }); if ((rc = g_allgatherv(g, b.data(), ol.data(), 32))) return rc; }
-                { auto b = ptrs(g, [](GroupRank& R) { return R.c->top_nodes; }); if ((rc = g_allgather(g, b.data(), SPH_TOP_CAP * sizeof(TopNode)))) return rc; }
-                { auto b = ptrs(g, [](GroupRank& R) { return R.c->front_nodes; }); if ((rc = g_allgather(g, b.data(), SPH_TOP_CAP * sizeof(FrontNode)))) return rc; }
-                { auto b = ptrs(g, [](GroupRank& R) { return R.c->top_counts; }); if ((rc = g_allgather(g, b.data(), 4 * sizeof(int32_t)))) return rc; }
-                { auto b = ptrs(g, [](GroupRank& R) { return R.bnd; }); if ((rc = g_allgather(g, b.data(), 2 * SPH_TOP_LEAF * 2 * sizeof(float4)))) return rc; }
-                FOR_RANKS(g, R) { G_CUDA(g, cudaSetDevice(R.device)); G_RC(g, R, sph_launch_top_tree(R.c, W, R.bnd, R.split_d, dt)); }
-            }
-            FOR_RANKS(g, R) { G_CUDA(g, cudaSetDevice(R.device)); if (R.n_own > 0) G_RC(g, R, sph_launch_tree_walk(R.c)); }
+            if (R.n_own <= 0) continue;
+            if (impl == SPH_GRAVITY_PARTICLE) { G_RC(g, R, sph_launch_gravity_allpairs(R.c)); G_RC(g, R, sph_launch_gravity_near(R.c)); }
+            else G_RC(g, R, sph_launch_tree_walk(R.c));
         }
     }
     pass_mark(g, gname);

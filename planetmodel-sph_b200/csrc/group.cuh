@@ -9,12 +9,12 @@ enum { GR_U32 = 0, GR_U64 = 1, GR_F64 = 2 };
 enum { GR_SUM = 0, GR_MIN = 1, GR_MAX = 2 };
 
 int grk_bin_hist(sphb200_ctx* c, const uint32_t* keys, const int32_t* ncount, const int32_t* npart, const int32_t* napprox, int n, uint32_t* hist);
-int grk_splitters(sphb200_ctx* c, const uint32_t* hist, int world, int64_t* split);
+int grk_splitters(sphb200_ctx* c, const uint32_t* hist, int world, int64_t* split, unsigned long long* part, uint32_t* bmask);
 int grk_dest(sphb200_ctx* c, const uint32_t* keys, int n, const int64_t* split, int world, uint8_t* dest);
 int grk_mig_pack(sphb200_ctx* c, const float4* posh, const float4* velm, const uint32_t* orig, const int32_t* nown, const uint32_t* keys,
                  const uint32_t* perm, int n, uint4* rec);
 int grk_mig_keys(sphb200_ctx* c, const uint4* rec, int n, uint32_t* keys);
-int grk_halo_lists(sphb200_ctx* c, const uint32_t* keys, int n, const int64_t* split, int world, int me, uint32_t* mask, uint32_t* cnt,
+int grk_halo_lists(sphb200_ctx* c, const uint32_t* keys, int n, const int64_t* split, int world, int me, const uint32_t* bmask, uint32_t* mask, uint32_t* cnt,
                    uint32_t* total, uint32_t* list);
 size_t grk_halo_cnt_words(int64_t cap);
 int grk_halo_pack(sphb200_ctx* c, const uint4* rec, const uint32_t* idx, const uint32_t* keys, const uint32_t* list, int n, uint4* out);

@@ -50,40 +50,91 @@ __global__ void __launch_bounds__(256) k_bin_hist(const uint32_t* __restrict__ k
     }
 }
 
-// One block.  Splitter r (1..world-1) = the first bin b whose exclusive work prefix reaches r/world of the total work;
-// rank r owns bins [sbin[r], sbin[r+1]) and global sorted slots [g0[r], g0[r+1]).  out: g0[0..world], sbin[0..world].
-__global__ void __launch_bounds__(1024) k_splitters(const uint32_t* __restrict__ hist, int world, int64_t* __restrict__ out) {
-    constexpr int PER = SPH_NBINS / 1024;
-    __shared__ unsigned long long sw[1024], sc[1024];
-    __shared__ unsigned long long total_w;
-    const int tx = threadIdx.x, b0 = tx * PER;
-    unsigned long long w = 0ull, c = 0ull;
-    for (int b = b0; b < b0 + PER; b++) { c += hist[b]; w += hist[SPH_NBINS + b]; }
-    sw[tx] = w; sc[tx] = c;
+// Splitter r (1..world-1) = the first bin b whose exclusive work prefix reaches r/world of the total work; rank r owns bins
+// [sbin[r], sbin[r+1]) and global sorted slots [g0[r], g0[r+1]).  out: g0[0..world], sbin[0..world].
+// Two levels: k_bin_partials sums runs of 1024 bins (coalesced, 256 blocks); k_splitters scans the 256 run sums, locates the
+// run every splitter falls into and scans only that run.
+constexpr int SPL_RUN = 1024, SPL_NRUN = SPH_NBINS / SPL_RUN;
+
+__global__ void __launch_bounds__(SPL_RUN) k_bin_partials(const uint32_t* __restrict__ hist, unsigned long long* __restrict__ part) {
+    __shared__ unsigned long long sc[32], sw[32];
+    const int b = blockIdx.x * SPL_RUN + threadIdx.x, lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    unsigned long long c = hist[b], wk = hist[SPH_NBINS + b];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(FULL, c, o); wk += __shfl_xor_sync(FULL, wk, o); }
+    if (lane == 0) { sc[w] = c; sw[w] = wk; }
     __syncthreads();
-    for (int o = 1; o < 1024; o <<= 1) {     // inclusive scan (Hillis-Steele)
-        const unsigned long long aw = tx >= o ? sw[tx - o] : 0ull, ac = tx >= o ? sc[tx - o] : 0ull;
-        __syncthreads();
-        sw[tx] += aw; sc[tx] += ac;
-        __syncthreads();
+    if (w == 0) {
+        c = sc[lane]; wk = sw[lane];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { c += __shfl_xor_sync(FULL, c, o); wk += __shfl_xor_sync(FULL, wk, o); }
+        if (lane == 0) { part[blockIdx.x] = c; part[SPL_NRUN + blockIdx.x] = wk; }
     }
-    if (tx == 1023) total_w = sw[1023];
+}
+
+__global__ void __launch_bounds__(SPL_RUN) k_splitters(const uint32_t* __restrict__ hist, const unsigned long long* __restrict__ part,
+                                                       int world, int64_t* __restrict__ out) {
+    __shared__ unsigned long long rw[SPL_NRUN + 1], rc[SPL_NRUN + 1];   // exclusive prefixes of the runs
+    __shared__ unsigned long long wsum_w[32], wsum_c[32];
+    __shared__ int run_of;
+    const int tx = threadIdx.x, lane = tx & 31, wp = tx >> 5;
     if (tx == 0) {
+        unsigned long long aw = 0ull, ac = 0ull;
+        for (int k = 0; k < SPL_NRUN; k++) { rc[k] = ac; rw[k] = aw; ac += part[k]; aw += part[SPL_NRUN + k]; }
+        rc[SPL_NRUN] = ac; rw[SPL_NRUN] = aw;
         for (int r = 0; r < world; r++) { out[r] = 0; out[world + 1 + r] = 0; }
-        out[world] = (int64_t)sc[1023]; out[2 * world + 1] = SPH_NBINS;
+        out[world] = (int64_t)ac; out[2 * world + 1] = SPH_NBINS;
     }
     __syncthreads();
-    unsigned long long pw = sw[tx] - w, pc = sc[tx] - c;   // exclusive prefixes at bin b0
-    const unsigned long long tot = total_w;
-    // splitter b in (b0, b0+PER]: prefix(b) = work of bins < b
-    for (int b = b0; b < b0 + PER; b++) {
-        const unsigned long long before = pw;
-        pw += hist[SPH_NBINS + b]; pc += hist[b];
-        for (int r = 1; r < world; r++) {
-            const unsigned long long target = tot / (unsigned long long)world * r + (tot % (unsigned long long)world) * r / world;
-            if (before < target && target <= pw) { out[r] = (int64_t)pc; out[world + 1 + r] = b + 1; }
+    const unsigned long long tot = rw[SPL_NRUN];
+    for (int r = 1; r < world; r++) {
+        const unsigned long long target = tot / (unsigned long long)world * r + (tot % (unsigned long long)world) * r / world;
+        if (target == 0ull) continue;                       // block-uniform
+        if (tx < SPL_NRUN && rw[tx] < target && target <= rw[tx + 1]) run_of = tx;   // exactly one run
+        __syncthreads();
+        const int k = run_of, b = k * SPL_RUN + tx;
+        const unsigned long long w = hist[SPH_NBINS + b], c = hist[b];
+        unsigned long long iw = w, ic = c;                   // inclusive scan over the run
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long vw = __shfl_up_sync(FULL, iw, o), vc = __shfl_up_sync(FULL, ic, o);
+            if (lane >= o) { iw += vw; ic += vc; }
         }
+        if (lane == 31) { wsum_w[wp] = iw; wsum_c[wp] = ic; }
+        __syncthreads();
+        unsigned long long bw = rw[k], bc = rc[k];
+        for (int j = 0; j < wp; j++) { bw += wsum_w[j]; bc += wsum_c[j]; }
+        const unsigned long long pw = bw + iw, before = pw - w;
+        if (before < target && target <= pw) { out[r] = (int64_t)(bc + ic); out[world + 1 + r] = b + 1; }
+        __syncthreads();
     }
+}
+
+// Owners found among the bins within `sb` bins of every bin (bit q: rank q): a particle whose bin sees only its own rank
+// cannot be in any halo (k_halo_mask skips it).  sb = stencil cells rounded up to whole bins.
+__global__ void __launch_bounds__(256) k_bin_owner_mask(const sph_GridParams* __restrict__ g, const int64_t* __restrict__ split, int world,
+                                                        uint32_t* __restrict__ bmask) {
+    __shared__ int sbin[SPH_MAX_RANKS + 1];
+    if (threadIdx.x <= world) sbin[threadIdx.x] = (int)split[world + 1 + threadIdx.x];
+    __syncthreads();
+    const int bb = bin_bits(g->bits);                 // a multiple of 3: bins are cubes of 2^(bits - bb/3) cells
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= (1 << bb)) return;
+    const int per_axis = bb / 3, bdim = 1 << per_axis, cells = 1 << (g->bits - per_axis);
+    const int sb = (g->stencil + cells - 1) / cells;
+    const int bx = (int)compact10((uint32_t)b), by = (int)compact10((uint32_t)b >> 1), bz = (int)compact10((uint32_t)b >> 2);
+    uint32_t m = 0u;
+    for (int oz = -sb; oz <= sb; oz++)
+        for (int oy = -sb; oy <= sb; oy++)
+            for (int ox = -sb; ox <= sb; ox++) {
+                const int nx = bx + ox, ny = by + oy, nz = bz + oz;
+                if (nx < 0 || ny < 0 || nz < 0 || nx >= bdim || ny >= bdim || nz >= bdim) continue;
+                const int nb = (int)(expand10((uint32_t)nx) | (expand10((uint32_t)ny) << 1) | (expand10((uint32_t)nz) << 2));
+                int r = 0;
+                for (int q = 1; q < world; q++) r += sbin[q] <= nb ? 1 : 0;
+                m |= 1u << r;
+            }
+    bmask[b] = m;
 }
 
 __global__ void __launch_bounds__(256) k_dest(const uint32_t* __restrict__ keys, int n, const sph_GridParams* __restrict__ g,
@@ -123,7 +174,8 @@ __global__ void __launch_bounds__(256) k_mig_keys(const uint4* __restrict__ rec,
 // axis (S * cell >= 2.002 h_max, k_grid_setup), so this is a superset of what rank q's neighbor search can reach.
 // The lanes of a warp that share a cell split its stencil among themselves.
 __global__ void __launch_bounds__(256) k_halo_mask(const uint32_t* __restrict__ keys, int n, const sph_GridParams* __restrict__ g,
-                                                   const int64_t* __restrict__ split, int world, int me, uint32_t* __restrict__ mask) {
+                                                   const int64_t* __restrict__ split, int world, int me, const uint32_t* __restrict__ bmask,
+                                                   uint32_t* __restrict__ mask) {
     __shared__ int sbin[SPH_MAX_RANKS + 1];
     if (threadIdx.x <= world) sbin[threadIdx.x] = (int)split[world + 1 + threadIdx.x];
     __syncthreads();
@@ -132,6 +184,9 @@ __global__ void __launch_bounds__(256) k_halo_mask(const uint32_t* __restrict__ 
     const int bits = g->bits, S = g->stencil, dim = 1 << bits, nst = 2 * S + 1, nst3 = nst * nst * nst;
     const int cshift = 3 * (10 - bits), bshift = 3 * bits - bin_bits(bits);
     const bool live = i < n;
+    // interior particles (the bins around theirs all belong to this rank) are most of the domain: whole warps leave here
+    const bool maybe = live && (bmask[keys[i] >> (30 - bin_bits(bits))] & ~(1u << me)) != 0u;
+    if (!__any_sync(FULL, maybe)) { if (live) mask[i] = 0u; return; }
     const uint32_t ck = live ? keys[i] >> cshift : 0xffffff00u + lane;
     const unsigned peers = __match_any_sync(FULL, ck);
     const int np = __popc(peers), pr = __popc(peers & ((1u << lane) - 1u));
@@ -396,8 +451,10 @@ int grk_bin_hist(sphb200_ctx* c, const uint32_t* keys, const int32_t* ncount, co
     if (n > 0) { k_bin_hist<<<sph_div_up(n, 256), 256, 0, c->stream>>>(keys, ncount, npart, napprox, n, c->grid_d, hist); GL(c); }
     return SPH_OK;
 }
-int grk_splitters(sphb200_ctx* c, const uint32_t* hist, int world, int64_t* split) {
-    k_splitters<<<1, 1024, 0, c->stream>>>(hist, world, split); GL(c);
+int grk_splitters(sphb200_ctx* c, const uint32_t* hist, int world, int64_t* split, unsigned long long* part, uint32_t* bmask) {
+    k_bin_partials<<<SPL_NRUN, SPL_RUN, 0, c->stream>>>(hist, part); GL(c);
+    k_splitters<<<1, SPL_RUN, 0, c->stream>>>(hist, part, world, split); GL(c);
+    k_bin_owner_mask<<<SPH_NBINS / 256, 256, 0, c->stream>>>(c->grid_d, split, world, bmask); GL(c);
     return SPH_OK;
 }
 int grk_dest(sphb200_ctx* c, const uint32_t* keys, int n, const int64_t* split, int world, uint8_t* dest) {
@@ -414,12 +471,12 @@ int grk_mig_keys(sphb200_ctx* c, const uint4* rec, int n, uint32_t* keys) {
     return SPH_OK;
 }
 // halo lists of the sorted own particles: mask -> per-destination stable compaction; total[q] = particles for rank q
-int grk_halo_lists(sphb200_ctx* c, const uint32_t* keys, int n, const int64_t* split, int world, int me, uint32_t* mask,
+int grk_halo_lists(sphb200_ctx* c, const uint32_t* keys, int n, const int64_t* split, int world, int me, const uint32_t* bmask, uint32_t* mask,
                    uint32_t* cnt, uint32_t* total, uint32_t* list) {
     SPH_CK(c, cudaMemsetAsync(total, 0, 256 * sizeof(uint32_t), c->stream));
     if (n <= 0 || world <= 1) return SPH_OK;
     const int ntiles = sph_div_up(n, HC_TILE);
-    k_halo_mask<<<sph_div_up(n, 256), 256, 0, c->stream>>>(keys, n, c->grid_d, split, world, me, mask); GL(c);
+    k_halo_mask<<<sph_div_up(n, 256), 256, 0, c->stream>>>(keys, n, c->grid_d, split, world, me, bmask, mask); GL(c);
     k_halo_count<<<ntiles, HC_THREADS, 0, c->stream>>>(mask, n, world, ntiles, cnt); GL(c);
     int rc = sph_launch_rowscan(c, cnt, ntiles, world, total, c->stream);
     if (rc) return rc;

@@ -71,7 +71,6 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_neighbors_density(
     __shared__ Surv survq[K1_WARPS][K1_SURVQ];
     if (g->hmax < kHugeH) return;   // the cell-centric kernel below owns the normal case
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int warp = blockIdx.x * K1_WARPS + w;
     const int bits = g->bits, S = g->stencil;
     const int shift = 3 * (10 - bits), dim = 1 << bits;
     const float fs = g->fine_scale, cw = (float)(1 << (10 - bits));  // cell width in fine units
@@ -80,9 +79,11 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_neighbors_density(
     const int grp = lane >> 3, sl = lane & 7;
     const unsigned lt = (1u << lane) - 1u;
 
+    // persistent warps (the launch is a few blocks per SM: when the cell-centric kernel owns the step this one costs ~2 us)
+    for (int warp = blockIdx.x * K1_WARPS + w; t0 + warp * K1_TPW < t1; warp += gridDim.x * K1_WARPS)
     for (int tt = 0; tt < K1_TPW; tt++) {
         const int t = t0 + warp * K1_TPW + tt;
-        if (t >= t1) return;
+        if (t >= t1) break;
         const float4 pi = posh[t];
         const float hi = pi.w, hi2 = __fmul_rn(hi, 2.0f), hinv_i = 1.0f / hi;
         // scaled (fine-grid) coordinates of the target, same ops as the key kernel
@@ -607,7 +608,7 @@ int sph_launch_neighbors_density(sphb200_ctx* c) {
     SPH_LAUNCH_CHECK(c);
     // literal-kernel variant: exits at once unless h_max >= 1e5 (decided on the device: no host sync)
     int per_block = K1_WARPS * K1_TPW;
-    k_neighbors_density<<<sph_div_up(nt, per_block), K1_WARPS * 32, 0, c->stream>>>(
+    k_neighbors_density<<<min(sph_div_up(nt, per_block), c->sm_count * 4), K1_WARPS * 32, 0, c->stream>>>(
         c->posh[c->cur], c->posm, c->skeys, c->cell_start, c->cell_end, c->cell_hmax, c->grid_d, t0, t1, (int)c->row_base, c->p.max_neighbors,
         c->p.K, c->nlist, c->ncount, c->nown, c->rho, c->press, c->cvol, c->err_d);
     SPH_LAUNCH_CHECK(c);
