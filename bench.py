@@ -382,16 +382,26 @@ def measure_e2e(eng, impl, steps, barrier):
     h2d = n * (12 + 12 + 4 + 28)                  # Translation, PhysicsVelocity.linear, ParticleMass, ParticleSmoothing records
     d2h = n * (12 + 12 + 4 + 4 + 12 + 24 + 28)    # ... + density, pressure, pressure gradient, GravityField, ParticleSmoothing
 
+    phases = {"upload": 0.0, "step": 0.0, "download": 0.0, "host_writeback": 0.0}
+
     def one():
+        ta = time.perf_counter()
         eng.upload(host["pos"].numpy().reshape(cnt, 3), host["vel"].numpy().reshape(cnt, 3), host["mass"].numpy(), sm)
+        tb = time.perf_counter()
         eng.step(DT, impl)
+        tc = time.perf_counter()                  # asynchronous: the step's device time shows up in the first download
         for f, buf in outs.items():
             w = buf.numel() // max(cnt, 1)
             sim.download(f, buf.numpy().reshape(cnt, w) if w > 1 else buf.numpy(), allow_overflow=True)
         sim.download(sphb200.FIELD_SMOOTHING, sm, allow_overflow=True)
+        td_ = time.perf_counter()
         # feed the results back as next step's host state (what the ECS write-back does)
         host["pos"].copy_(outs[sphb200.FIELD_TRANSLATION]); host["vel"].copy_(outs[sphb200.FIELD_VELOCITY])
+        te = time.perf_counter()
+        phases["upload"] += tb - ta; phases["step"] += tc - tb; phases["download"] += td_ - tc; phases["host_writeback"] += te - td_
     one()
+    for k in phases:
+        phases[k] = 0.0
     barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
@@ -400,6 +410,7 @@ def measure_e2e(eng, impl, steps, barrier):
     dt = time.perf_counter() - t0
     return {"value": n * steps / dt, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
             "steps": steps, "ms_per_step": 1e3 * dt / steps,
+            "host_phase_ms": {k: round(1e3 * v / steps, 3) for k, v in phases.items()},
             "path": "sphb200%s_upload + _step + _download x7 per process; every process moves its body slice (1/%d of the bytes) "
                     "between pinned host component arrays and its GPU, one DMA per component array" % ("_group" if eng.world > 1 else "", eng.world)}
 

@@ -56,11 +56,11 @@ __device__ __forceinline__ float kernel_deriv_exact(float distance, float size, 
 //   q < 1 : (lead + 2.25 q) / h * c4 ;   1 <= q < 2 : -0.75 (2-q)^2 / r * c4 ;  0 beyond -- branch-free via t = max(2-q, 0).
 // Rows beyond max_neighbors (an error state the caller is told about) contribute their stored part only.
 // ------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ float dwr_shape(float q, float hinv, float rinv, float lead) {
+__device__ __forceinline__ float dwr_shape(float q, bool inside, float hinv, float rinv, float lead) {
     const float t = fmaxf(2.0f - q, 0.0f);
     const float outer = (-0.75f * t) * (t * rinv);
     const float inner = fmaf(2.25f, q, lead) * hinv;
-    return q < 1.0f ? inner : outer;
+    return inside ? inner : outer;
 }
 
 constexpr int K2_WARPS = 4;   // 7.6 KB of stream state per warp
@@ -68,7 +68,7 @@ constexpr int K2_WARPS = 4;   // 7.6 KB of stream state per warp
 __global__ void __launch_bounds__(K2_WARPS * 32, 6) k_pressure_grad(const float4* __restrict__ posh, const float* __restrict__ cvol,
                                                                     const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
                                                                     int t0, int t1, int rowbase, int kmax, float lead, float4* __restrict__ gradp) {
-    __shared__ RowStreamSmem<3> smem[K2_WARPS];   // tg[0]: x, y, z, 1/h   tg[1]: 1/(pi h^4), -, -, -
+    __shared__ RowStreamSmem<3> smem[K2_WARPS];   // tg[0]: x, y, z, 1/h   tg[1]: 1/(pi h^4), h, -, -
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int base = t0 + (blockIdx.x * K2_WARPS + w) * 32;
     if (base >= t1) return;
@@ -80,7 +80,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 6) k_pressure_grad(const float4
     if (live) { pi = posh[t]; cnt = min(ncount[t], kmax); }
     const float hinv_i = 1.0f / pi.w, h2 = hinv_i * hinv_i;
     S.tg[0][lane] = make_float4(pi.x, pi.y, pi.z, hinv_i);
-    S.tg[1][lane] = make_float4(h2 * h2 * kInvPI, 0.f, 0.f, 0.f);
+    S.tg[1][lane] = make_float4(h2 * h2 * kInvPI, pi.w, 0.f, 0.f);
     float acc[3];
     int unused;
     row_stream<3, false>(S, nlist + (size_t)(base - rowbase) * kmax, (uint32_t)base, kmax, cnt,
@@ -94,7 +94,15 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 6) k_pressure_grad(const float4
             const float r = r2 * rinv;
             const float hinv_j = rs_rcp(pj.w), g2 = hinv_j * hinv_j;
             const float c4_j = g2 * g2 * kInvPI;
-            const float s = fmaf(B.x, dwr_shape(r * A.w, A.w, rinv, lead), c4_j * dwr_shape(r * hinv_j, hinv_j, rinv, lead)) * cj;
+            const float qi = r * A.w, qj = r * hinv_j;
+            bool in_i = qi < 1.0f, in_j = qj < 1.0f;
+            if (fabsf(qi - 1.0f) < 4.0e-6f || fabsf(qj - 1.0f) < 4.0e-6f) {
+                // within a few ulps of the spline's breakpoint, where the reference's inner branch (quirk Q1) makes dW/dr jump:
+                // decide as the reference does, "distance < size" on the IEEE distance (SplineKernel.cs:115-148)
+                const float re = __fsqrt_rn(dot3_rn(__fsub_rn(A.x, pj.x), __fsub_rn(A.y, pj.y), __fsub_rn(A.z, pj.z)));
+                in_i = re < B.y; in_j = re < pj.w;
+            }
+            const float s = fmaf(B.x, dwr_shape(qi, in_i, A.w, rinv, lead), c4_j * dwr_shape(qj, in_j, hinv_j, rinv, lead)) * cj;
             v[0] = dx * s; v[1] = dy * s; v[2] = dz * s;
             flag = false;
         }, acc, unused);

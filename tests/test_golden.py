@@ -38,7 +38,7 @@ def test_gpu_matches_golden(name):
     np.testing.assert_array_equal(off, g["offsets"]); np.testing.assert_array_equal(nbr, g["nbr"])
     np.testing.assert_array_equal(out["n_own"], g["n_own"])
     np.testing.assert_allclose(out["rho"], g["rho"], rtol=1e-5)
-    np.testing.assert_allclose(out["P"], g["P"], rtol=2e-5)
+    np.testing.assert_allclose(out["P"], g["P"], rtol=1e-5)
     gn = np.linalg.norm(g["grav"][:, :3], axis=1, keepdims=True)
     assert np.all(np.abs(out["grav"][:, :3] - g["grav"][:, :3]) <= 1e-5 * gn + 1e-6 * np.median(gn))
     pn = np.linalg.norm(g["gradP"], axis=1, keepdims=True)

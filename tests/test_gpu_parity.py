@@ -49,7 +49,7 @@ def compare_step(orc, sim, ref, gravity):
     np.testing.assert_array_equal(got["n_own"], ref.n_own)
     np.testing.assert_array_equal(got["h"], ref.h)                    # controller is bit-exact by construction
     np.testing.assert_allclose(got["rho"], ref.rho, rtol=RTOL)
-    np.testing.assert_allclose(got["P"], ref.P, rtol=2 * RTOL)
+    np.testing.assert_allclose(got["P"], ref.P, rtol=RTOL)
     vec_close(got["gradP"], ref.gradP, what="gradP", floor=1e-7 * np.abs(ref.gradP).max())
     if gravity == "tree":
         # identical MAC decisions: every particle sums exactly the oracle's set of bodies and node approximations
@@ -63,7 +63,7 @@ def compare_step(orc, sim, ref, gravity):
         np.testing.assert_allclose(got["grav"][:, 3], ref.grav[:, 3], rtol=RTOL)
     np.testing.assert_allclose(got["pos"], ref.pos, rtol=1e-6, atol=1e-6)
     acc_scale = np.abs(ref.vel - 0).max() + 1e-12
-    np.testing.assert_allclose(got["vel"], ref.vel, rtol=RTOL, atol=2e-5 * acc_scale)
+    np.testing.assert_allclose(got["vel"], ref.vel, rtol=RTOL, atol=RTOL * acc_scale)
     return got
 
 
@@ -283,6 +283,41 @@ def test_c2_multistep_drift_matches_oracle(orc):
     # most particles still agree closely after 20 steps (a few diverge once a neighbor flips at an edge)
     rel = np.linalg.norm(got["pos"] - ref.pos, axis=1) / 50.0
     assert np.median(rel) < 1e-6
+
+
+def test_c2_100_steps_10k_drift(orc):
+    """BASELINE.json config C2 as stated: 10 000 particles, variable smoothing lengths, tree gravity, 100 steps.  Momentum and
+    energy DRIFT must be the oracle's: |p| (not conserved by the reference, quirk Q5), E_kin, E_pot, E_int after 100 steps to
+    1e-5 relative; the smoothing lengths and neighbor counts of all 10 000 particles stay IDENTICAL (no neighbor set ever
+    flipped) and the trajectories stay within 1e-6 R."""
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_config("c2")
+    n = len(c["h"])
+    dt = 1.0 / 60.0
+    sim = make_sim(n)
+    sim.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    p = sim.effective_params()
+    ref = orc.State(c["pos"], c["vel"], c["mass"], c["h"])
+    for _ in range(100):
+        sim.step(dt, sphb200.GRAVITY_TREE)
+        orc.step(ref, dt, gravity="tree", max_bits=p.max_grid_bits, leaf_max=p.leaf_max, aabb_mode=p.aabb_mode)
+    got = sim.download_all()
+    m = ref.mass.astype(np.float64)
+
+    def agg(pos, vel, rho, grav):
+        return dict(p=np.linalg.norm((m[:, None] * vel).sum(0)), ekin=0.5 * (m * (vel.astype(np.float64) ** 2).sum(1)).sum(),
+                    epot=0.5 * (m * grav[:, 3]).sum(), eint=(m * p.K * rho).sum())
+    a, b = agg(got["pos"], got["vel"], got["rho"], got["grav"]), agg(ref.pos, ref.vel, ref.rho, ref.grav)
+    for k in a:
+        assert a[k] == pytest.approx(b[k], rel=1e-5), k
+    d = sim.diagnostics()
+    assert d["e_kin"] == pytest.approx(b["ekin"], rel=1e-5) and d["e_pot"] == pytest.approx(b["epot"], rel=1e-5)
+    assert b["ekin"] > 100 * agg(c["pos"], c["vel"], ref.rho, ref.grav)["ekin"] + 1.0      # the sphere really moved
+    np.testing.assert_array_equal(got["h"], ref.h)
+    np.testing.assert_array_equal(got["count"], np.diff(ref.offsets))
+    np.testing.assert_array_equal(got["n_own"], ref.n_own)
+    assert np.linalg.norm(got["pos"] - ref.pos, axis=1).max() < 1e-6 * 50.0
 
 
 def test_resync_per_step_error_does_not_grow(orc):
