@@ -285,6 +285,14 @@ def measure_workload(args, workload, world, rank, local, headline):
     except sphb200.SphError as ex:
         errors = str(ex)
     info = sim.info() if world > 1 else None
+    rank_ms = None
+    if world > 1:      # per-rank times of the heaviest passes (load balance of the decomposition)
+        import torch.distributed as td
+        names = sorted(pass_ms)
+        mine = torch.tensor([float(np.mean(pass_ms[k])) for k in names], device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        td.all_gather(allr, mine)
+        rank_ms = {k: [round(float(a[i]), 3) for a in allr] for i, k in enumerate(names)}
     if rank == 0:
         print("[bench] %s: %d steps, %.3f ms/step, passes %s%s" % (workload, args.steps, ms_per_step,
               {k: round(float(np.mean(v)), 3) for k, v in pass_ms.items()},
@@ -352,6 +360,8 @@ def measure_workload(args, workload, world, rank, local, headline):
             "e2e": e2e, "gpu_launches": int(launches), "errors": errors, "roofline": roof, "hbm_passes": hbm_passes,
             "pass_ms": mean, "mean_neighbors": kbar, "fp32_peak_tflops_measured": fp32_peak,
             "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}}
+    if rank_ms is not None:
+        line["pass_ms_per_rank"] = {k: v for k, v in rank_ms.items() if max(v) > 0.5}
     if info is not None:
         line["decomposition"] = {"rank0_own": info["n_own"], "rank0_halo": info["n_halo"], "migrated_last_step": info["migrated_last_step"],
                                  "transport": info["transport"]}
@@ -377,12 +387,14 @@ def measure_e2e(eng, impl, steps, barrier):
     sm = host["sm"].numpy().view(sphb200.ParticleSmoothing)
     sm["influenceArea"] = sl["h"]
     outs = {f: torch.empty(cnt * w, dtype=torch.float32).pin_memory() for f, w in
-            ((sphb200.FIELD_TRANSLATION, 3), (sphb200.FIELD_VELOCITY, 3), (sphb200.FIELD_DENSITY, 1), (sphb200.FIELD_PRESSURE, 1),
-             (sphb200.FIELD_PRESSURE_GRAD, 3), (sphb200.FIELD_GRAVITY, 6))}
+            ((sphb200.FIELD_DENSITY, 1), (sphb200.FIELD_PRESSURE, 1), (sphb200.FIELD_PRESSURE_GRAD, 3), (sphb200.FIELD_GRAVITY, 6))}
+    # Translation / PhysicsVelocity / ParticleSmoothing are read AND written by the step (ExportPhysicsWorld writes the components
+    # in place): the download lands in the very arrays the next step uploads
+    outs[sphb200.FIELD_TRANSLATION] = host["pos"]; outs[sphb200.FIELD_VELOCITY] = host["vel"]
     h2d = n * (12 + 12 + 4 + 28)                  # Translation, PhysicsVelocity.linear, ParticleMass, ParticleSmoothing records
     d2h = n * (12 + 12 + 4 + 4 + 12 + 24 + 28)    # ... + density, pressure, pressure gradient, GravityField, ParticleSmoothing
 
-    phases = {"upload": 0.0, "step": 0.0, "download": 0.0, "host_writeback": 0.0}
+    phases = {"upload": 0.0, "step": 0.0, "download": 0.0}
 
     def one():
         ta = time.perf_counter()
@@ -395,10 +407,7 @@ def measure_e2e(eng, impl, steps, barrier):
             sim.download(f, buf.numpy().reshape(cnt, w) if w > 1 else buf.numpy(), allow_overflow=True)
         sim.download(sphb200.FIELD_SMOOTHING, sm, allow_overflow=True)
         td_ = time.perf_counter()
-        # feed the results back as next step's host state (what the ECS write-back does)
-        host["pos"].copy_(outs[sphb200.FIELD_TRANSLATION]); host["vel"].copy_(outs[sphb200.FIELD_VELOCITY])
-        te = time.perf_counter()
-        phases["upload"] += tb - ta; phases["step"] += tc - tb; phases["download"] += td_ - tc; phases["host_writeback"] += te - td_
+        phases["upload"] += tb - ta; phases["step"] += tc - tb; phases["download"] += td_ - tc
     one()
     for k in phases:
         phases[k] = 0.0
