@@ -229,9 +229,21 @@ __device__ __forceinline__ u64 pk2(float a, float b) { u64 r; asm("mov.b64 %0, {
 __device__ __forceinline__ void upk2(u64 v, float& a, float& b) { asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
 __device__ __forceinline__ u64 sub2(u64 a, u64 b) { u64 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 __device__ __forceinline__ u64 mul2(u64 a, u64 b) { u64 r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
 
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
+
+// Pair law inside the softening radius a = h_i (GravityFieldSystem.cs:340-347, Dyer & Ip) MINUS the Newtonian value capped at
+// r = a that the packed loop has already added for this body: g = (m/a^3)(8 - 9x + 2x^3) - m/a^3, Phi likewise.
+__device__ __forceinline__ void p2p_soft_minus_capped(WalkAcc& w, float ex, float ey, float ez, float r2, float m, float ainv) {
+    const float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
+    const float x = r * ainv, x2 = x * x, x3 = x2 * x;
+    const float ma = m * ainv;
+    const float g = ma * ainv * ainv * (7.0f - 9.0f * x + 2.0f * x3);
+    w.gx = fmaf(ex, g, w.gx); w.gy = fmaf(ey, g, w.gy); w.gz = fmaf(ez, g, w.gz);
+    w.gp -= ma * (1.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
+}
 
 // softened pair law inside a = h_i (GravityFieldSystem.cs:340-347, Dyer & Ip)
 __device__ __forceinline__ void p2p_soft(WalkAcc& w, float ex, float ey, float ez, float r2, float m, float ainv) {
@@ -258,14 +270,14 @@ __device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
 // are slots [t0, t1) and the resident arrays (posh, grav, ...) hold slot t at t + off.
 __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __restrict__ posh, const float4* __restrict__ posm,
                                                              const float4* __restrict__ packed, int n, int t0, int t1, int off, float G,
-                                                             float4* __restrict__ grav, int32_t* __restrict__ npart,
+                                                             float negzero, float4* __restrict__ grav, int32_t* __restrict__ npart,
                                                              int32_t* __restrict__ napprox, int32_t* __restrict__ err) {
     __shared__ int2 stack[TW_WARPS][TW_STACK];
     __shared__ ulonglong2 tgxy[TW_WARPS][16];  // target positions as pairs: (x0,x1), (y0,y1)   (lanes = nodes phase)
     __shared__ u64 tgzz[TW_WARPS][16];         //                           (z0,z1)
     __shared__ float4 bcm[TW_WARPS][32];     // batch nodes: (cm, M)            (lanes = targets phase)
     __shared__ __align__(16) float sbodyf[TW_WARPS][128 * 4];   // flattened bodies of the shared buckets, as pairs: (x0,x1,y0,y1),(z0,z1,m0,m1)
-    __shared__ __align__(8) unsigned sbodym[TW_WARPS][128 + 2];  // ... and the lane mask of each body
+    __shared__ __align__(8) unsigned sbodym[TW_WARPS][128 + 2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     // Warps are aligned to absolute multiples of 32 sorted slots and every slot < n walks, whether or not it lies in this
     // rank's target range [t0,t1): the order in which a lane adds its contributions depends on its 31 companions, so a
@@ -312,20 +324,22 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
         const float4 X = __ldg(&packed[2 * (size_t)e.x + 1]);
         // exact MAC, 2 targets per packed subtract / multiply (FADD2 / FMUL2 are IEEE round-to-nearest per half): the
         // reference's (dx*dx + dy*dy) + dz*dz bit for bit
+        // Squares as fma(d, d, -0) with a -0 the compiler cannot see (a kernel argument): ptxas contracts mul.rn.f32x2 +
+        // add.rn.f32x2 into one FFMA2 (a single rounding) even with explicit .rn, but it cannot contract two fma results, so
+        // (dx*dx + dy*dy) + dz*dz keeps the reference's three roundings while every operation stays packed.
         unsigned amask = 0u;
-        const u64 nx = pk2(N.x, N.x), ny = pk2(N.y, N.y), nz = pk2(N.z, N.z);
+        const u64 nx = pk2(N.x, N.x), ny = pk2(N.y, N.y), nz = pk2(N.z, N.z), tw = pk2(N.w, N.w), z2 = pk2(negzero, negzero);
 #pragma unroll
         for (int tp = 15; tp >= 0; tp--) {         // descending: every result is shifted in at bit 0
             const ulonglong2 P = tgp[tp];          // (x0,x1), (y0,y1)
             const u64 Z = tgz[tp];                 // (z0,z1)
             const u64 dx = sub2(P.x, nx), dy = sub2(P.y, ny), dz = sub2(Z, nz);
-            // the sums stay scalar: ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2, which would round once
-            float xa, xb, ya, yb, za, zb;
-            upk2(mul2(dx, dx), xa, xb); upk2(mul2(dy, dy), ya, yb); upk2(mul2(dz, dz), za, zb);
-            const float ra = __fadd_rn(__fadd_rn(xa, ya), za), rb = __fadd_rn(__fadd_rn(xb, yb), zb);
+            const u64 r2 = add2(add2(fma2(dx, dx, z2), fma2(dy, dy, z2)), fma2(dz, dz, z2));
             // AcceptApproximation, exact: r_sq > T <=> T - r_sq < 0 (a difference of distinct floats never rounds to zero)
-            amask = __funnelshift_l(__float_as_uint(__fsub_rn(N.w, rb)), amask, 1);
-            amask = __funnelshift_l(__float_as_uint(__fsub_rn(N.w, ra)), amask, 1);
+            float sa, sb;
+            upk2(sub2(tw, r2), sa, sb);
+            amask = __funnelshift_l(__float_as_uint(sb), amask, 1);
+            amask = __funnelshift_l(__float_as_uint(sa), amask, 1);
         }
         const unsigned mask = (unsigned)e.y;
         const unsigned acc = amask & mask, rej = mask & ~amask;
@@ -610,7 +624,7 @@ int sph_launch_tree_walk(sphb200_ctx* c) {
     if (n <= 0 || nt <= 0) return SPH_OK;
     t0 -= off; t1 -= off;
     k_tree_walk<<<sph_div_up(t1 - (t0 & ~31), TW_WARPS * 32), TW_WARPS * 32, 0, c->stream>>>(c->posh[c->cur], c->gsrc, c->packed, n, t0, t1, off,
-                                                                               c->p.G, c->grav, c->npart, c->napprox, c->err_d);
+                                                                               c->p.G, -0.0f, c->grav, c->npart, c->napprox, c->err_d);
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;
 }

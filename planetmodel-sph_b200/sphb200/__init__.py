@@ -100,7 +100,7 @@ def load_library():
     if not os.path.exists(LIB_PATH):
         raise ImportError("libsphb200.so is not built (run `python __graft_entry__.py` or `make -C planetmodel-sph_b200/csrc`); "
                           "there is no CPU fallback")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(os.environ.get("SPHB200_LIB") or LIB_PATH)    # SPHB200_LIB: another build of the same library (A/B timing of kernel variants)
     H = C.c_void_p
     L.sphb200_default_params.argtypes = [C.POINTER(Params)]
     L.sphb200_create.argtypes = [C.POINTER(Params), C.c_int64, C.c_int, C.POINTER(H)]
