@@ -234,17 +234,6 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0,
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 
-// Pair law inside the softening radius a = h_i (GravityFieldSystem.cs:340-347, Dyer & Ip) MINUS the Newtonian value capped at
-// r = a that the packed loop has already added for this body: g = (m/a^3)(8 - 9x + 2x^3) - m/a^3, Phi likewise.
-__device__ __forceinline__ void p2p_soft_minus_capped(WalkAcc& w, float ex, float ey, float ez, float r2, float m, float ainv) {
-    const float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
-    const float x = r * ainv, x2 = x * x, x3 = x2 * x;
-    const float ma = m * ainv;
-    const float g = ma * ainv * ainv * (7.0f - 9.0f * x + 2.0f * x3);
-    w.gx = fmaf(ex, g, w.gx); w.gy = fmaf(ey, g, w.gy); w.gz = fmaf(ez, g, w.gz);
-    w.gp -= ma * (1.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
-}
-
 // softened pair law inside a = h_i (GravityFieldSystem.cs:340-347, Dyer & Ip)
 __device__ __forceinline__ void p2p_soft(WalkAcc& w, float ex, float ey, float ez, float r2, float m, float ainv) {
     const float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
