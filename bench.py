@@ -79,74 +79,115 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU baseline
-def cpu_reference_sample(c, grav, seconds_budget=20.0):
-    """Time the oracle (CPU port of the reference job path) on a bounded sample of the workload and extrapolate the
-    per-step time: SPH passes on a contiguous subset of particles' worth of work, gravity on a sample of targets
-    against ALL sources.  Returns (particle_steps_per_sec, cores, sample_description, seconds_spent)."""
-    from oracle import oracle as orc
+def settled_h_estimate(c, target=50.0):
+    """Smoothing length the reference's controller converges to on a sphere of this number density: 50 particles inside 2h
+    (ParticleSmoothingSystem.cs:18).  The CPU arm cannot afford the ~10 steps the controller needs at 1M, so it starts there;
+    the GPU arm's in-line baseline uses the state the GPU itself settled (same workload on both sides)."""
     n = len(c["h"])
-    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: override it for the CPU arm)
-    orc.lib().orc_set_num_threads(len(os.sched_getaffinity(0)))
+    R = float(np.linalg.norm(c["pos"], axis=1).max())
+    dens = n / (4.0 / 3.0 * np.pi * R ** 3)
+    return float(0.5 * (3.0 * target / (4.0 * np.pi * dens)) ** (1.0 / 3.0))
+
+
+def cpu_reference_sample(state, grav, seconds_budget=20.0):
+    """Time the reference JOB PATH (oracle/sph_oracle.cpp orc_reference_step: Unity-shaped BVH build, dual-tree candidate
+    pairs, FilterPairs, flatten, the two single-thread counting sorts, interaction buffers with both kernels evaluated on
+    either side, density, EOS, pressure gradient, integration) on a bounded sample of the workload and extrapolate per
+    particle: the SPH passes on a central ball of the state (same number density and h), gravity on a sample of targets
+    against ALL sources.  `state` = dict(pos, vel, mass, h, n_own) with SETTLED smoothing lengths.
+    Returns (particle_steps_per_sec, cores, description, detail dict)."""
+    from oracle import oracle as orc
+    n = len(state["h"])
+    orc.lib().orc_set_num_threads(len(os.sched_getaffinity(0)))   # torchrun exports OMP_NUM_THREADS=1: override for the CPU arm
     cores = orc.lib().orc_num_threads()
-    t_start = time.time()
-    # -- SPH passes (neighbor search via cell list = labelled variant of the reference's BVH broadphase, then the
-    #    literal filter/interaction/density/EOS/pressure-gradient arithmetic) on up to 262 144 particles
-    ns = min(n, 262144)
+    # ~40 us of job path per particle and thread at ~50 neighbors (measured): size the ball for ~60 % of the budget
+    ns = int(min(n, max(20000, 0.6 * seconds_budget * cores / 40e-6)))
     if ns < n:
-        r = np.linalg.norm(c["pos"], axis=1)
-        sel = np.argsort(r)[:ns]                      # a central ball: same number density, no extra surface
+        r = np.linalg.norm(state["pos"] - state["pos"].mean(0), axis=1)
+        sel = np.argpartition(r, ns)[:ns]
+        sel.sort()
     else:
         sel = np.arange(n)
-    pos, h, m = c["pos"][sel].copy(), c["h"][sel].copy(), c["mass"][sel].copy()
-    t0 = time.time()
-    off, nbr = orc.neighbors(pos, h, "grid" if ns > 4096 else "brute")
-    rho, own = orc.density(pos, h, m, off, nbr)
-    P = orc.eos(rho)
-    gp = orc.pressure_grad(pos, h, m, rho, P, off, nbr)
-    t_sph = (time.time() - t0) / ns                   # seconds per particle
+    st = orc.State(state["pos"][sel], state["vel"][sel], state["mass"][sel], state["h"][sel], state["n_own"][sel])
+    # n_own = 50 keeps h as it is in the sample step (radius ratio 1): the sample is timed AT the settled h
+    st.n_own[:] = 50
+    info = orc.reference_step(st, DT, gravity="none", want_lists=False)
+    t_sph = sum(info["stage_sec"].values()) / ns
+    kbar = info["interactions"] / ns
     # -- gravity sample
     if grav == "particle":
-        nt = max(64, min(n, int(2.0e9 * max(cores, 1) / 8 / n)))   # ~ a few seconds of pair work
+        nt = int(max(64, min(n, 0.3 * seconds_budget * cores * 2.5e8 / n)))   # ~4 ns per pair and thread
         t0 = time.time()
-        orc.gravity_direct(c["pos"], c["h"], c["mass"], i0=0, i1=nt)
+        orc.gravity_direct(state["pos"], state["h"], state["mass"], i0=0, i1=nt)
         t_grav = (time.time() - t0) / nt
-        gdesc = "direct gravity for %d targets x %d sources" % (nt, n)
+        gdesc = "direct gravity for %d targets x %d sources (x N/targets)" % (nt, n)
     else:
-        t0 = time.time()
-        nt = min(n, 200000)
-        g, _, _, _, _ = orc.tree_gravity(c["pos"], c["vel"], c["h"], c["mass"], DT)
-        t_grav = (time.time() - t0) / n
-        gdesc = "LBVH build + tree walk for all %d particles" % n
-    # integrate + smoothing update are O(N) trivial; timed on the subset
-    t0 = time.time()
-    orc.smoothing_update(h, own)
-    orc.integrate(pos, np.zeros_like(pos), rho, gp, np.zeros((ns, 4), np.float32), DT)
-    t_int = (time.time() - t0) / ns
-    per_particle = t_sph + t_grav + t_int
-    desc = "oracle (C++ port, OpenMP): neighbor+density+EOS+pressure on %d particles (%.1f neighbors avg), %s; per-particle " \
-           "times extrapolated to N=%d" % (ns, len(nbr) / ns, gdesc, n)
-    return 1.0 / per_particle, cores, desc, time.time() - t_start
+        ng = int(min(n, max(50000, 0.3 * seconds_budget * cores / 60e-6)))
+        selg = sel[:ng] if ng <= len(sel) else np.arange(min(n, ng))
+        sg = orc.State(state["pos"][selg], state["vel"][selg], state["mass"][selg], state["h"][selg], None)
+        sg.n_own[:] = 50
+        ig = orc.reference_step(sg, DT, gravity="tree", want_lists=False)
+        t_grav = ig["stage_sec"]["gravity"] / len(selg) * (np.log(max(n, 2)) / np.log(max(len(selg), 2)))
+        gdesc = "Unity-shaped 4-ary BVH moments + walk on %d particles (x log N / log n)" % len(selg)
+    per_particle = t_sph + t_grav
+    desc = ("EXTRAPOLATED from a bounded sample: reference job path (oracle C++ port, OpenMP; BVH dual-tree candidates x%.1f of "
+            "the kept pairs, 2 serial counting sorts, 4 kernel evaluations per pair) on a central ball of %d of %d particles at "
+            "settled h (%.1f neighbors avg), %s; per-particle times scaled to N=%d"
+            % (info["candidates"] / max(info["pairs"], 1), ns, n, kbar, gdesc, n))
+    detail = {"sample_particles": ns, "mean_neighbors": kbar, "candidates_per_pair": info["candidates"] / max(info["pairs"], 1),
+              "stage_us_per_particle": {k: round(1e6 * v / ns, 4) for k, v in info["stage_sec"].items()},
+              "gravity_us_per_particle": 1e6 * t_grav, "extrapolated": True}
+    return 1.0 / per_particle, cores, desc, detail
+
+
+def cpu_reference_own_cases():
+    """The reference's own CPU-runnable cases IN FULL (BASELINE.json configs[0] and [1]): C1 = 3 000 particles, direct gravity;
+    C2 = 10 000 particles, tree gravity, 100 steps.  Whole job path, every particle, wall clock per step."""
+    from oracle import oracle as orc
+    from sphb200 import ic
+    orc.lib().orc_set_num_threads(len(os.sched_getaffinity(0)))
+    out = {}
+    for name, grav, steps in (("c1", "direct", 20), ("c2", "tree", 100)):
+        c = ic.make_config(name)
+        st = orc.State(c["pos"], c["vel"], c["mass"], c["h"])
+        t = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            info = orc.reference_step(st, DT, gravity=grav, want_lists=False)
+            t.append(time.perf_counter() - t0)
+        last = float(np.mean(t[-max(steps // 2, 1):]))        # settled half of the run
+        out[name] = {"particles": len(c["h"]), "gravity": grav, "steps": steps, "ms_per_step_settled": 1e3 * last,
+                     "ms_per_step_first": 1e3 * t[0], "particle_steps_per_sec": len(c["h"]) / last,
+                     "mean_neighbors_final": info["interactions"] / len(c["h"]), "kind": "port, run in full"}
+    return out
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU job path (oracle port) on the host cores, bounded sample per step."""
+    """--impl reference: the reference's CPU job path (oracle port: the C# cannot be built here) on the host cores; every step
+    is a bounded sample of the workload, extrapolated per particle (stated in the line)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     args.workload = args.workload or "c3"
     c, grav = workload_config(args.workload, args.particles)
-    vals = []
-    for k in range(args.warmup + args.steps):
-        v, cores, desc, _ = cpu_reference_sample(c, grav, 10.0)
-        if k >= args.warmup:
-            vals.append(v)
-    v = float(np.mean(vals))
     n = len(c["h"])
+    state = dict(pos=c["pos"], vel=c["vel"], mass=c["mass"], h=np.full(n, settled_h_estimate(c), np.float32),
+                 n_own=np.full(n, 50, np.int32))
+    budget = max(1.0, min(20.0, 150.0 / max(args.warmup + args.steps, 1)))     # the whole run ends within a few minutes
+    vals, wall = [], []
+    for k in range(args.warmup + args.steps):
+        t0 = time.time()
+        v, cores, desc, detail = cpu_reference_sample(state, grav, budget)
+        if k >= args.warmup:
+            vals.append(v); wall.append(time.time() - t0)
+    v = float(np.mean(vals))
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * n / v, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "warmup": args.warmup, "ms_per_step": 1e3 * n / v, "ms_per_step_is": "extrapolated from the sample (not wall clock)",
+            "sample_wall_s_per_step": float(np.mean(wall)), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_desc(args.workload, n, grav, args.gpus),
-            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
-            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "detail": detail},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0,
+            "reference_own_cases": cpu_reference_own_cases()}
     emit(line)
 
 
@@ -299,12 +340,17 @@ def measure_workload(args, workload, world, rank, local, headline):
               "" if info is None else ", rank 0 owns %s + halo %s, %d migrated last step" % (info["n_own"], info["n_halo"], info["migrated_last_step"])),
               file=sys.stderr)
 
+    diag = sim.diagnostics()            # collective in a group; the state the timed steps ran on (settled h)
+    # ---- the settled state as the host holds it (every process: its body slice): input of the e2e leg and of the CPU baseline
+    state = None
+    if not args.kernels_only:
+        smr = sim.download(sphb200.FIELD_SMOOTHING, allow_overflow=True)
+        state = dict(pos=sim.download(sphb200.FIELD_TRANSLATION, allow_overflow=True), vel=sim.download(sphb200.FIELD_VELOCITY, allow_overflow=True),
+                     mass=sim.download(sphb200.FIELD_MASS, allow_overflow=True), sm=smr)
     # ---- e2e: host component arrays in, host component arrays out, every step
     e2e = None
     if not args.kernels_only:
-        e2e = measure_e2e(eng, impl, max(1, min(args.steps, 3)), barrier)
-
-    diag = sim.diagnostics()            # collective in a group
+        e2e = measure_e2e(eng, state, impl, max(1, min(args.steps, 3)), barrier)
     if rank != 0:
         eng.close()
         return None
@@ -349,17 +395,23 @@ def measure_workload(args, workload, world, rank, local, headline):
                 "achieved": hbm_passes["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm_passes["frac"], "traffic": None,
                 "note": "tree walk is L2-latency/FP32 mixed (no single roof, SURVEY 8d): %.2f ms of the step" % gms, "ms": sph_ms,
                 "share_of_step": sph_ms / ms_per_step}
+    cpu_detail = None
     if args.kernels_only or world > 1 or not headline:
         cpu_v, cores, desc = None, 0, "skipped (%s)" % ("--kernels-only profiling run" if args.kernels_only else
                                                         "reported at N=1 for the headline workload only; see --impl reference")
     else:
-        cpu_v, cores, desc, _ = cpu_reference_sample(c, grav)
+        # the very state the GPU arm was timed on (settled h), as the host holds it
+        cst = dict(pos=state["pos"], vel=state["vel"], mass=state["mass"], h=state["sm"]["influenceArea"].copy(),
+                   n_own=state["sm"]["neighbors"].copy())
+        cpu_v, cores, desc, cpu_detail = cpu_reference_sample(cst, grav)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_desc(workload, n, grav, world), "clocks": sampler.summary(),
             "e2e": e2e, "gpu_launches": int(launches), "errors": errors, "roofline": roof, "hbm_passes": hbm_passes,
             "pass_ms": mean, "mean_neighbors": kbar, "fp32_peak_tflops_measured": fp32_peak,
-            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc}}
+            "cpu_baseline": {"value": cpu_v, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc, "detail": cpu_detail}}
+    if cpu_detail is not None:
+        line["cpu_baseline"]["reference_own_cases"] = cpu_reference_own_cases()
     if rank_ms is not None:
         line["pass_ms_per_rank"] = {k: v for k, v in rank_ms.items() if max(v) > 0.5}
     if info is not None:
@@ -369,7 +421,7 @@ def measure_workload(args, workload, world, rank, local, headline):
     return line
 
 
-def measure_e2e(eng, impl, steps, barrier):
+def measure_e2e(eng, state, impl, steps, barrier):
     """Drop-in usage: ECS owns the components on the host; every step uploads them (pinned) and reads all results back.
     In a group every process moves only its body slice (1/N of the state) over PCIe; the particles travel between the
     GPUs over NVLink inside the step.  Wall clock between two barriers."""
@@ -377,15 +429,15 @@ def measure_e2e(eng, impl, steps, barrier):
     import sphb200
     sim = eng.sim
     n, cnt = eng.n, eng.cnt
-    sl = eng.slice
+    # host component arrays (pinned), holding the settled state the timed steps ended on
     host = {
-        "pos": torch.from_numpy(sl["pos"].copy().reshape(-1)).pin_memory(),
-        "vel": torch.from_numpy(sl["vel"].copy().reshape(-1)).pin_memory(),
-        "mass": torch.from_numpy(sl["mass"].copy()).pin_memory(),
+        "pos": torch.from_numpy(state["pos"].copy().reshape(-1)).pin_memory(),
+        "vel": torch.from_numpy(state["vel"].copy().reshape(-1)).pin_memory(),
+        "mass": torch.from_numpy(state["mass"].copy()).pin_memory(),
         "sm": torch.from_numpy(np.zeros(cnt * 7, np.float32)).pin_memory(),
     }
     sm = host["sm"].numpy().view(sphb200.ParticleSmoothing)
-    sm["influenceArea"] = sl["h"]
+    sm[:] = state["sm"]
     outs = {f: torch.empty(cnt * w, dtype=torch.float32).pin_memory() for f, w in
             ((sphb200.FIELD_DENSITY, 1), (sphb200.FIELD_PRESSURE, 1), (sphb200.FIELD_PRESSURE_GRAD, 3), (sphb200.FIELD_GRAVITY, 6))}
     # Translation / PhysicsVelocity / ParticleSmoothing are read AND written by the step (ExportPhysicsWorld writes the components

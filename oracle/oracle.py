@@ -78,6 +78,10 @@ def lib():
                                     C.c_float, C.c_float, C.c_int64, C.c_int64, C.c_int, f32p, i32p, i32p]
         L.orc_tree4_gravity.argtypes = [C.c_int64, f32p, f32p, f32p, f32p, C.c_float, C.c_float, C.c_float, C.c_int, f32p, i32p, i32p,
                                         C.POINTER(C.c_int32)]
+        L.orc_reference_step.restype = C.c_int64
+        L.orc_reference_step.argtypes = [C.c_int64, f32p, f32p, f32p, f32p, i32p, C.c_float, C.c_int, C.c_float, C.c_float, C.c_float,
+                                         C.c_float, C.c_int, f32p, f32p, f32p, f32p, i32p, i32p, i64p, C.c_void_p, C.c_int64, i64p,
+                                         np.ctypeslib.ndpointer(np.float64, flags="C_CONTIGUOUS")]
         L.orc_num_threads.restype = C.c_int
         L.orc_set_num_threads.argtypes = [C.c_int]
         _LIB = L
@@ -271,3 +275,30 @@ def step(s, dt, gravity="direct", K=1000.0, G=1.0, theta=0.7, target=50.0, leaf_
     # 5f + 9. x += v_n dt ; v += a dt
     s.pos, s.vel = integrate(s.pos, s.vel, s.rho, s.gradP, s.grav, dt, kick_drift)
     return s
+
+
+# ---------------------------------------------------------------- the reference JOB PATH (CPU baseline, bench.py)
+REFERENCE_STAGES = ("smoothing", "aabb_bvh_build", "tree_overlap_candidates", "filter_pairs", "flatten_pairs", "counting_sorts_x2",
+                    "calculate_interactions", "gravity", "integrate_position", "density", "eos_pressure_gradient", "velocity_cleanup")
+
+
+def reference_step(s, dt, gravity="direct", K=1000.0, G=1.0, theta=0.7, target=50.0, fix_q1=0, want_lists=True):
+    """One step of the reference's job path with its own structure (orc_reference_step): candidate pairs from the dual-tree
+    self-overlap of the Unity-shaped 4-ary BVH, FilterPairs, flatten, the two single-thread counting sorts, the interaction
+    buffers with both kernels evaluated on either side, then gravity / density / pressure / integration.  Updates the State
+    in place like step(); returns {"stage_sec": {...}, "candidates", "pairs", "interactions"}.  Lists come back in the
+    reference's emission order (not ascending)."""
+    n = len(s.h)
+    offsets = np.zeros(n + 1, np.int64)
+    counts = np.zeros(3, np.int64); sec = np.zeros(12, np.float64)
+    cap = max(96 * n, 1) if want_lists else 0
+    nbr = np.zeros(cap, np.int32) if want_lists else None
+    gcode = {"none": 0, "direct": 1, "tree": 2}[gravity]
+    s.rho = np.zeros(n, np.float32); s.P = np.zeros(n, np.float32); s.gradP = np.zeros((n, 3), np.float32)
+    s.grav = np.zeros((n, 4), np.float32)
+    tot = lib().orc_reference_step(n, s.pos, s.vel, s.mass, s.h, s.n_own, dt, gcode, K, G, theta, target, fix_q1, s.rho, s.P, s.gradP,
+                                   s.grav, s.num_particles, s.num_approx, offsets, nbr.ctypes.data if want_lists else None, cap, counts, sec)
+    s.offsets = offsets
+    s.nbr = nbr[:tot].copy() if (want_lists and tot <= cap) else None
+    return {"stage_sec": dict(zip(REFERENCE_STAGES, sec.tolist())), "candidates": int(counts[0]), "pairs": int(counts[1]),
+            "interactions": int(counts[2])}

@@ -838,3 +838,290 @@ ORC_API void orc_tree4_gravity(int64_t n, const float* pos, const float* vel, co
         }
     }
 }
+
+// ------------------------------------------------------------------------------------------------
+// The reference JOB PATH, stage by stage, with the reference's own parallel / serial structure -- the CPU baseline that
+// bench.py times.  Same fp32 arithmetic as the functions above; what differs from
+// orc_neighbors_* + orc_density + ... is HOW the pairs are found and stored, i.e. what the reference really pays for:
+//   0  ParticleSmoothingSystem (A/Systems/ParticleSmoothingSystem.cs:19-87)                         parallel over bodies
+//   1  collider AABBs + 4-ary BVH build + refit (UP/Collision/World/Broadphase.cs:725-782,
+//      UP/Collision/Geometry/BoundingVolumeHierarchyBuilder.cs:372-401, 558-600)                     AABBs parallel, build serial
+//      (the reference builds the top levels on one thread and <= 64 branches in parallel: a serial build is the conservative stand-in)
+//   2  candidate pairs: dual-tree self-overlap of the BVH (Broadphase.cs:275-351,
+//      BoundingVolumeHierarchy.cs:107-299): every pair of bodies whose collider AABBs overlap       parallel over tree tasks
+//   3  FilterPairs: SplineKernel.Interacts on every candidate (A/Systems/KernelSystem.cs:583-633)   parallel over candidates
+//   4  FlattenPairsPrePass (one thread) + FlattenPairs (KernelSystem.cs:539-568, 638-663)            prefix serial, copy parallel
+//   5  two stable counting sorts, by body A and by body B, each ONE thread, side by side
+//      (ScheduleSortPairsJob / SortPairsSTJob, KernelSystem.cs:339-464)
+//   6  CalculateInteractionJob: per body, every pair it is in, BOTH kernels evaluated again on either side (4 kernel
+//      evaluations per undirected pair), 40-byte records into the body's buffer (KernelSystem.cs:234-335)   parallel over bodies
+//   7  GravityFieldSystem: direct sum, or moments on ONE thread (GenerateMomentsSTJob, GravityFieldSystem.cs:453-555) + the
+//      per-particle walk of the 4-ary BVH (:133-215)                                                parallel over bodies
+//   8  Integrator.IntegratePosition (UP/Dynamics/Integrator/Integrator.cs:98-101)                  parallel
+//   9  DensityFieldSystem (A/Systems/DensityFieldSystem.cs:38-56)                                   parallel over bodies
+//  10  PressureFieldSystem: EOS + gradient (A/Systems/PressureFieldSystem.cs:30-70)                 parallel over bodies
+//  11  VelocitySystem (A/Systems/VelocitySystem.cs:24-36) + KernelSystem.Cleanup on the main thread (KernelSystem.cs:50-91)
+// It is a stand-in for Burst + ECS and FASTER than the real thing: arrays instead of ComponentDataFromEntity lookups, no
+// chunk fragmentation, no job-scheduling overhead.
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct BodyPair { int a, b; };
+struct IRec { int other; F4 kthis; F4 ksym; };   // ParticleInteraction (A/Components/Kernel.cs:5-16), 36 of its 40 bytes
+
+inline bool Overlap(const Aabb& p, const Aabb& q) {
+    return p.lo.x <= q.hi.x && q.lo.x <= p.hi.x && p.lo.y <= q.hi.y && q.lo.y <= p.hi.y && p.lo.z <= q.hi.z && q.lo.z <= p.hi.z;
+}
+struct OverlapTask { int a, b; };   // b < 0: self-overlap of node a; else node a against node b
+
+struct DualTree {
+    const Tree4& T; const std::vector<Aabb>& boxes;
+    void emit(std::vector<BodyPair>& out, int x, int y) const { if (Overlap(boxes[x], boxes[y])) out.push_back(x < y ? BodyPair{x, y} : BodyPair{y, x}); }
+    void cross(int a, int b, std::vector<BodyPair>& out) const {
+        const Node4 &A = T.nodes[a], &B = T.nodes[b];
+        if (!Overlap(A.box, B.box)) return;
+        if (A.leaf && B.leaf) { for (int c = 0; c < A.nchild; c++) for (int d = 0; d < B.nchild; d++) emit(out, A.child[c], B.child[d]); }
+        else if (A.leaf) { for (int d = 0; d < B.nchild; d++) cross(a, B.child[d], out); }
+        else if (B.leaf) { for (int c = 0; c < A.nchild; c++) cross(A.child[c], b, out); }
+        else for (int c = 0; c < A.nchild; c++) for (int d = 0; d < B.nchild; d++) cross(A.child[c], B.child[d], out);
+    }
+    void self(int a, std::vector<BodyPair>& out) const {
+        const Node4& A = T.nodes[a];
+        if (A.leaf) { for (int c = 0; c < A.nchild; c++) for (int d = c + 1; d < A.nchild; d++) emit(out, A.child[c], A.child[d]); return; }
+        for (int c = 0; c < A.nchild; c++) self(A.child[c], out);
+        for (int c = 0; c < A.nchild; c++) for (int d = c + 1; d < A.nchild; d++) cross(A.child[c], A.child[d], out);
+    }
+    // one level of a task, as tasks (keeps the emission order of the recursion)
+    void expand(const OverlapTask& t, std::vector<OverlapTask>& out) const {
+        const Node4& A = T.nodes[t.a];
+        if (t.b < 0) {
+            if (A.leaf) { out.push_back(t); return; }
+            for (int c = 0; c < A.nchild; c++) out.push_back({A.child[c], -1});
+            for (int c = 0; c < A.nchild; c++) for (int d = c + 1; d < A.nchild; d++) out.push_back({A.child[c], A.child[d]});
+        } else {
+            const Node4& B = T.nodes[t.b];
+            if (!Overlap(A.box, B.box)) return;
+            if (A.leaf || B.leaf) { out.push_back(t); return; }
+            for (int c = 0; c < A.nchild; c++) for (int d = 0; d < B.nchild; d++) out.push_back({A.child[c], B.child[d]});
+        }
+    }
+};
+
+inline double now_sec() {
+#ifdef _OPENMP
+    return omp_get_wtime();
+#else
+    return (double)clock() / CLOCKS_PER_SEC;
+#endif
+}
+
+void tree4_refit_moments(Tree4& T, const std::vector<Aabb>& boxes, const float* pos, const float* m, bool moments) {
+    for (int k = (int)T.nodes.size() - 1; k >= 0; k--) {   // children have larger ids than their parent
+        Node4& nd = T.nodes[k];
+        if (!moments) nd.box = {{INFINITY, INFINITY, INFINITY}, {-INFINITY, -INFINITY, -INFINITY}};
+        else nd.mom = Moment();
+        for (int c = 0; c < nd.nchild; c++) {
+            if (nd.leaf) { int b = nd.child[c]; if (!moments) nd.box = Union(nd.box, boxes[b]); else nd.mom.Accumulate(ld3(pos, b), m[b]); }
+            else { const Node4& ch = T.nodes[nd.child[c]]; if (!moments) nd.box = Union(nd.box, ch.box); else nd.mom.Accumulate(ch.mom.cm, ch.mom.m); }
+        }
+    }
+}
+}  // namespace
+
+// gravity: 0 none, 1 direct, 2 tree (4-ary BVH).  pos / vel / h / n_own are updated in place; outputs rho, P, gradP[3n], grav4[4n],
+// offsets[n+1] + nbr (the interaction buffers as CSR, in the reference's emission order: pairs where the body is A, then where
+// it is B; nbr may be null / nbr_cap too small: only the counts are returned).  counts[0..2] = candidate pairs, filtered
+// pairs, directed interactions kept.  stage_sec[12] as listed above.  Returns the number of directed interactions.
+ORC_API int64_t orc_reference_step(int64_t n64, float* pos, float* vel, const float* m, float* h, int32_t* n_own, float dt, int gravity,
+                                   float K, float G, float theta, float target, int fix_q1, float* rho, float* P, float* gradP,
+                                   float* grav4, int32_t* num_particles, int32_t* num_approx, int64_t* offsets, int32_t* nbr,
+                                   int64_t nbr_cap, int64_t* counts, double* stage_sec) {
+    const int n = (int)n64;
+    double t0 = now_sec();
+    auto lap = [&](int k) { double t = now_sec(); stage_sec[k] = t - t0; t0 = t; };
+    for (int k = 0; k < 12; k++) stage_sec[k] = 0;
+    // 0. smoothing lengths from last step's own-support counts
+    {
+        std::vector<float> hn(n);
+        orc_smoothing_update(n, h, n_own, target, hn.data());
+        memcpy(h, hn.data(), (size_t)n * 4);
+    }
+    lap(0);
+    // 1. collider AABBs, BVH over their centres, refit
+    std::vector<Aabb> boxes(n);
+    std::vector<float> cen(3 * (size_t)n);
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        boxes[i] = ParticleBox(ld3(pos, i), h[i], ld3(vel, i), dt, 0);
+        cen[3 * (size_t)i] = 0.5f * (boxes[i].lo.x + boxes[i].hi.x); cen[3 * (size_t)i + 1] = 0.5f * (boxes[i].lo.y + boxes[i].hi.y);
+        cen[3 * (size_t)i + 2] = 0.5f * (boxes[i].lo.z + boxes[i].hi.z);
+    }
+    Tree4 T; T.cen = cen.data(); T.idx.resize(n); std::iota(T.idx.begin(), T.idx.end(), 0);
+    T.nodes.reserve(n);
+    const int root = n > 0 ? T.build(0, n) : -1;
+    tree4_refit_moments(T, boxes, pos, m, false);
+    lap(1);
+    // 2. candidate pairs: dual-tree self-overlap, parallel over a few thousand sub-tasks
+    std::vector<OverlapTask> tasks;
+    DualTree D{T, boxes};
+    if (root >= 0) tasks.push_back({root, -1});
+    for (int round = 0; round < 12 && tasks.size() < 4096; round++) {
+        std::vector<OverlapTask> next;
+        for (const auto& t : tasks) D.expand(t, next);
+        if (next.size() == tasks.size()) break;
+        tasks.swap(next);
+    }
+    std::vector<std::vector<BodyPair>> found(tasks.size());
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t k = 0; k < (int64_t)tasks.size(); k++) {
+        if (tasks[k].b < 0) D.self(tasks[k].a, found[k]); else D.cross(tasks[k].a, tasks[k].b, found[k]);
+    }
+    std::vector<int64_t> toff(tasks.size() + 1, 0);
+    for (size_t k = 0; k < tasks.size(); k++) toff[k + 1] = toff[k] + (int64_t)found[k].size();
+    const int64_t ncand = toff[tasks.size()];
+    lap(2);
+    // 3. FilterPairs: the exact interaction predicate, per candidate (the stream keeps its order)
+    std::vector<std::vector<BodyPair>> kept(tasks.size());
+#pragma omp parallel for schedule(dynamic, 1)
+    for (int64_t k = 0; k < (int64_t)tasks.size(); k++) {
+        kept[k].reserve(found[k].size() / 8 + 4);
+        for (const BodyPair& p : found[k])
+            if (Interacts(ld3(pos, p.a), ld3(pos, p.b), h[p.a], h[p.b])) kept[k].push_back(p);
+        std::vector<BodyPair>().swap(found[k]);
+    }
+    lap(3);
+    // 4. flatten: offsets on one thread, copy in parallel
+    std::vector<int64_t> koff(tasks.size() + 1, 0);
+    for (size_t k = 0; k < tasks.size(); k++) koff[k + 1] = koff[k] + (int64_t)kept[k].size();
+    const int64_t npair = koff[tasks.size()];
+    std::vector<BodyPair> pairs((size_t)npair);
+#pragma omp parallel for schedule(dynamic, 8)
+    for (int64_t k = 0; k < (int64_t)tasks.size(); k++)
+        if (!kept[k].empty()) memcpy(&pairs[(size_t)koff[k]], kept[k].data(), kept[k].size() * sizeof(BodyPair));
+    kept.clear();
+    lap(4);
+    // 5. two stable counting sorts (key = body A, key = body B), each on ONE thread, side by side
+    std::vector<BodyPair> byA((size_t)npair), byB((size_t)npair);
+    std::vector<int64_t> offA((size_t)n + 1, 0), offB((size_t)n + 1, 0);
+#pragma omp parallel sections num_threads(2)
+    {
+#pragma omp section
+        {
+            for (int64_t e = 0; e < npair; e++) offA[(size_t)pairs[(size_t)e].a + 1]++;
+            for (int i = 0; i < n; i++) offA[(size_t)i + 1] += offA[i];
+            std::vector<int64_t> cur(offA.begin(), offA.end() - 1);
+            for (int64_t e = 0; e < npair; e++) byA[(size_t)cur[pairs[(size_t)e].a]++] = pairs[(size_t)e];
+        }
+#pragma omp section
+        {
+            for (int64_t e = 0; e < npair; e++) offB[(size_t)pairs[(size_t)e].b + 1]++;
+            for (int i = 0; i < n; i++) offB[(size_t)i + 1] += offB[i];
+            std::vector<int64_t> cur(offB.begin(), offB.end() - 1);
+            for (int64_t e = 0; e < npair; e++) byB[(size_t)cur[pairs[(size_t)e].b]++] = pairs[(size_t)e];
+        }
+    }
+    lap(5);
+    // 6. interaction buffers: per body, both kernels of every pair it is in (the partner evaluates them again)
+    std::vector<int64_t> boff((size_t)n + 1, 0);
+    for (int i = 0; i < n; i++) boff[(size_t)i + 1] = boff[i] + (offA[(size_t)i + 1] - offA[i]) + (offB[(size_t)i + 1] - offB[i]);
+    std::vector<IRec> buf((size_t)boff[n]);
+    std::vector<int32_t> bcnt(n, 0);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < n; i++) {
+        IRec* out = buf.data() + boff[i];
+        int c = 0;
+        const F3 ri = ld3(pos, i);
+        for (int64_t e = offA[i]; e < offA[(size_t)i + 1]; e++) {
+            const int j = byA[(size_t)e].b;
+            Interaction it = CalculateInteraction(ri, ld3(pos, j), h[i], h[j], fix_q1);
+            if (it.ksym.w > 0.0f) out[c++] = IRec{j, it.kthis, it.ksym};
+        }
+        for (int64_t e = offB[i]; e < offB[(size_t)i + 1]; e++) {
+            const int j = byB[(size_t)e].a;
+            Interaction it = CalculateInteraction(ri, ld3(pos, j), h[i], h[j], fix_q1);
+            if (it.ksym.w > 0.0f) out[c++] = IRec{j, it.kthis, it.ksym};
+        }
+        bcnt[i] = c;
+    }
+    lap(6);
+    // 7. gravity at x_n
+    if (gravity == 1) {
+        orc_gravity_direct(n, pos, h, m, G, 0, n, 0, grav4);
+        if (num_particles) memset(num_particles, 0, (size_t)n * 4);
+        if (num_approx) memset(num_approx, 0, (size_t)n * 4);
+    } else if (gravity == 2) {
+        tree4_refit_moments(T, boxes, pos, m, true);   // GenerateMomentsSTJob: one thread
+#pragma omp parallel
+        {
+            std::vector<int> stack; stack.reserve(256);
+#pragma omp for schedule(dynamic, 64)
+            for (int t = 0; t < n; t++) {
+                const F3 ri = ld3(pos, t); const float a = h[t];
+                F4 g{0, 0, 0, 0}; int np = 0, na = 0;
+                auto add = [&](F4 c) { g.x += c.x; g.y += c.y; g.z += c.z; g.w += c.w; };
+                stack.clear(); stack.push_back(root);
+                do {
+                    const int k = stack.back(); stack.pop_back();
+                    const Node4& nd = T.nodes[k];
+                    if (AcceptApproximation(ri, nd.mom, nd.box, theta)) { add(nd.mom.GravityContribution(ri, G)); na++; }
+                    else if (nd.leaf) { for (int c = 0; c < nd.nchild; c++) { const int b = nd.child[c]; add(GravityContributionParticle(ri, ld3(pos, b), m[b], a, G)); np++; } }
+                    else for (int c = 0; c < nd.nchild; c++) stack.push_back(nd.child[c]);
+                } while (!stack.empty());
+                memcpy(grav4 + 4 * (size_t)t, &g, 16);
+                if (num_particles) num_particles[t] = np;
+                if (num_approx) num_approx[t] = na;
+            }
+        }
+    } else {
+        memset(grav4, 0, (size_t)n * 16);
+        if (num_particles) memset(num_particles, 0, (size_t)n * 4);
+        if (num_approx) memset(num_approx, 0, (size_t)n * 4);
+    }
+    lap(7);
+    // 8. x += v dt (old v); the interaction buffers keep the kernels of x_n
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) { pos[3 * (size_t)i] += vel[3 * (size_t)i] * dt; pos[3 * (size_t)i + 1] += vel[3 * (size_t)i + 1] * dt; pos[3 * (size_t)i + 2] += vel[3 * (size_t)i + 2] * dt; }
+    lap(8);
+    // 9. density + own-support count
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < n; i++) {
+        const IRec* b = buf.data() + boff[i];
+        float d = m[i] * Kernel(0.0f, h[i]);
+        int own = 0;
+        for (int k = 0; k < bcnt[i]; k++) { d += m[b[k].other] * b[k].ksym.w; own += b[k].kthis.w > 0.0f ? 1 : 0; }
+        rho[i] = d; n_own[i] = own;
+    }
+    lap(9);
+    // 10. EOS + pressure gradient
+    orc_eos(n, rho, K, P);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int i = 0; i < n; i++) {
+        const IRec* b = buf.data() + boff[i];
+        F3 g{0, 0, 0};
+        for (int k = 0; k < bcnt[i]; k++) {
+            const int j = b[k].other;
+            const float f = m[j] / rho[j] * P[j];
+            g.x += f * b[k].ksym.x; g.y += f * b[k].ksym.y; g.z += f * b[k].ksym.z;
+        }
+        gradP[3 * (size_t)i] = g.x; gradP[3 * (size_t)i + 1] = g.y; gradP[3 * (size_t)i + 2] = g.z;
+    }
+    lap(10);
+    // 11. v += (-gradP/rho - gradPhi) dt; buffers returned / cleared on one thread (KernelSystem.Cleanup)
+#pragma omp parallel for schedule(static)
+    for (int i = 0; i < n; i++) {
+        for (int c = 0; c < 3; c++) {
+            const float a = -gradP[3 * (size_t)i + c] / rho[i] - grav4[4 * (size_t)i + c];
+            vel[3 * (size_t)i + c] += a * dt;
+        }
+    }
+    int64_t total = 0;
+    offsets[0] = 0;
+    for (int i = 0; i < n; i++) {
+        if (nbr && total + bcnt[i] <= nbr_cap) for (int k = 0; k < bcnt[i]; k++) nbr[total + k] = buf[(size_t)boff[i] + k].other;
+        total += bcnt[i];
+        offsets[(size_t)i + 1] = total;
+        bcnt[i] = 0;
+    }
+    lap(11);
+    if (counts) { counts[0] = ncand; counts[1] = npair; counts[2] = total; }
+    return total;
+}

@@ -403,3 +403,36 @@ def test_accuracy_envelope_lbvh_vs_reference_shaped_tree(orc):
     w4, wl = (np4 + na4).mean(), (npl + nal).mean()
     assert 0.5 < wl / w4 < 2.0                                            # comparable interaction counts
     assert nodes4 < 6000
+
+
+# ------------------------------------------------------------------ the reference JOB PATH (bench.py's CPU baseline)
+def test_reference_job_path_equals_the_oracle_step(orc):
+    """orc_reference_step -- candidate pairs from the dual-tree self-overlap of the Unity-shaped BVH, FilterPairs, flatten, the
+    two counting sorts, interaction buffers -- must produce what the plain oracle step produces from its cell lists: the same
+    neighbor SETS (emission order differs), the same h, rho / grad P to summation-order noise, the same direct-sum gravity;
+    and its candidate stream is the superset the reference's broadphase hands to FilterPairs (~10-15x the kept pairs)."""
+    from sphb200 import ic
+    c = ic.make_sphere(2500, seed=5)
+    a = orc.State(c["pos"], c["vel"], c["mass"], c["h"]); b = a.copy()
+    for k in range(6):
+        orc.step(a, 1 / 60, gravity="direct")
+        info = orc.reference_step(b, 1 / 60, gravity="direct")
+        np.testing.assert_array_equal(np.diff(a.offsets), np.diff(b.offsets))
+        for i in range(0, len(a.h), 7):
+            np.testing.assert_array_equal(a.nbr[a.offsets[i]:a.offsets[i + 1]], np.sort(b.nbr[b.offsets[i]:b.offsets[i + 1]]))
+        np.testing.assert_array_equal(a.h, b.h)
+        np.testing.assert_array_equal(a.n_own, b.n_own)
+        np.testing.assert_allclose(a.rho, b.rho, rtol=3e-6)
+        assert np.abs(a.gradP - b.gradP).max() <= 1e-5 * np.abs(a.gradP).max()
+        np.testing.assert_array_equal(a.grav, b.grav)            # same pair arithmetic, same (index) order
+        np.testing.assert_allclose(a.pos, b.pos, rtol=0, atol=1e-5)
+        assert info["interactions"] == 2 * info["pairs"] == len(b.nbr)
+        assert info["candidates"] >= info["pairs"]
+    assert 5 < info["candidates"] / info["pairs"] < 25
+    assert set(info["stage_sec"]) == set(orc.REFERENCE_STAGES)
+    # tree gravity on the Unity-shaped tree: the same walk as orc_tree4_gravity
+    t = orc.State(c["pos"], c["vel"], c["mass"], c["h"])
+    orc.reference_step(t, 1 / 60, gravity="tree")
+    g4, npart, napp, _ = orc.tree4_gravity(c["pos"], c["vel"], c["h"], c["mass"], 1 / 60)
+    np.testing.assert_array_equal(t.grav, g4)
+    np.testing.assert_array_equal(t.num_particles, npart)
