@@ -187,6 +187,16 @@ SPH_API int sphb200_download_tree(sph_handle h, int32_t* child, int32_t* range, 
  * [7]=E_kin, [8]=E_pot=0.5 sum m Phi, [9]=E_int=sum m K rho, [10]=mean symmetric neighbor count, [11]=max count */
 SPH_API int sphb200_diagnostics(sph_handle h, double* out12);
 
+/* Field statistics (README.md:50-52 roadmap: "Average/max/min: Temp, Pressure, Density, Grav Field"): for q = rho, P,
+ * |grad Phi|, u = K rho (specific internal energy of the P = K rho^2 gas, the model's temperature proxy), in this order:
+ * out[3q] = min, out[3q+1] = max, out[3q+2] = mean over all particles. */
+SPH_API int sphb200_field_stats(sph_handle h, double* out12);
+/* Snapshot dump / restore of the host-visible state (positions, velocities, masses, smoothing lengths, own-support counts)
+ * in body order: checkpoint / resume, and the format fixtures travel in.  One binary file, 64-byte header.  Restoring and
+ * stepping continues the run bit-identically (the resident order is rebuilt from the body order by the next sort). */
+SPH_API int sphb200_snapshot_save(sph_handle h, const char* path);
+SPH_API int sphb200_snapshot_load(sph_handle h, const char* path);
+
 /* ---- introspection ------------------------------------------------------------------------------------------ */
 SPH_API int sphb200_count(sph_handle h, int64_t* n, int64_t* capacity);
 SPH_API int sphb200_get_params(sph_handle h, sph_Params* out);
@@ -249,6 +259,13 @@ SPH_API int sphb200_group_download(sph_group g, int field, void* dst, int stride
 SPH_API int sphb200_group_sync(sph_group g);
 /* As sphb200_diagnostics, reduced over the group. */
 SPH_API int sphb200_group_diagnostics(sph_group g, double* out12);
+/* As sphb200_field_stats, reduced over the group. */
+SPH_API int sphb200_group_field_stats(sph_group g, double* out12);
+/* As sphb200_snapshot_save / _load for this process's body slice.  A process that drives the whole group writes one complete
+ * file (a single handle can load it, and vice versa); one process per GPU writes / reads its part `path`.rNNN, and also
+ * accepts a complete file at `path` on load (every process reads its slice of it). */
+SPH_API int sphb200_group_snapshot_save(sph_group g, const char* path);
+SPH_API int sphb200_group_snapshot_load(sph_group g, const char* path);
 SPH_API int sphb200_group_info(sph_group g, sph_GroupInfo* out);
 SPH_API int sphb200_group_enable_timing(sph_group g, int enable);
 SPH_API int sphb200_group_get_timings(sph_group g, const char** names, float* ms, int cap);

@@ -1,5 +1,6 @@
 // abi.cu -- the C ABI of libsphb200 (see include/sphb200.h for the contract and the reference citations).
 #include "ctx.cuh"
+#include <stdio.h>
 #include <math.h>
 #include <string.h>
 #include <algorithm>
@@ -661,6 +662,99 @@ int sphb200_diagnostics(sph_handle c, double* out12) {
     ARG_CHECK(c, out12, "null out");
     if (c->n == 0) { for (int k = 0; k < 12; k++) out12[k] = 0; return SPH_OK; }
     return sph_launch_diagnostics(c, out12);
+}
+
+int sphb200_field_stats(sph_handle c, double* out12) {
+    NEED_RESIDENT(c);
+    ARG_CHECK(c, out12, "null out");
+    for (int k = 0; k < 12; k++) out12[k] = 0;
+    if (c->n == 0) return SPH_OK;
+    if (!c->lists_valid) { c->err = "no fields yet: run a step (or build_neighbors) first"; return SPH_ERR_STATE; }
+    int rc = sph_launch_field_stats_range(c, 0, (int)c->n);
+    if (rc) return rc;
+    double tmp[8];
+    SPH_CK(c, cudaMemcpyAsync(tmp, c->diag_d + 16, sizeof(tmp), cudaMemcpyDeviceToHost, c->stream));
+    SPH_CK(c, cudaStreamSynchronize(c->stream));
+    sph_finish_field_stats(tmp, (const uint32_t*)(tmp + 4), c->n, out12);
+    return SPH_OK;
+}
+
+// ---- snapshots: the host-visible state in body order, one binary file ------------------------------------------------
+// header (64 bytes): magic "SPHB200S", u32 version, u32 reserved, i64 n_total, i64 body0, i64 count, i64 steps, pad;
+// then pos[3 count] f32, vel[3 count] f32, mass[count] f32, h[count] f32, n_own[count] i32.
+static const char kSnapMagic[8] = {'S', 'P', 'H', 'B', '2', '0', '0', 'S'};
+struct SnapHeader { char magic[8]; uint32_t version, reserved; int64_t n_total, body0, count, steps, pad[2]; };
+static_assert(sizeof(SnapHeader) == 64, "snapshot header is 64 bytes");
+
+extern "C++" int sph_snapshot_write(const char* path, int64_t n_total, int64_t body0, int64_t count, int64_t steps, const float* pos, const float* vel,
+                                    const float* mass, const float* h, const int32_t* nown, std::string& err) {
+    FILE* f = fopen(path, "wb");
+    if (!f) { err = std::string("cannot open ") + path + " for writing"; return SPH_ERR_INVALID_ARG; }
+    SnapHeader hd{};
+    memcpy(hd.magic, kSnapMagic, 8); hd.version = 1; hd.n_total = n_total; hd.body0 = body0; hd.count = count; hd.steps = steps;
+    const size_t c = (size_t)count;
+    bool ok = fwrite(&hd, sizeof(hd), 1, f) == 1;
+    ok = ok && (c == 0 || (fwrite(pos, 12, c, f) == c && fwrite(vel, 12, c, f) == c && fwrite(mass, 4, c, f) == c && fwrite(h, 4, c, f) == c &&
+                           fwrite(nown, 4, c, f) == c));
+    ok = (fclose(f) == 0) && ok;
+    if (!ok) { err = std::string("short write to ") + path; return SPH_ERR_INVALID_ARG; }
+    return SPH_OK;
+}
+
+// reads the bodies [want0, want0 + want) of a snapshot that covers them
+extern "C++" int sph_snapshot_read(const char* path, int64_t want0, int64_t want, int64_t* n_total, std::vector<float>& pos, std::vector<float>& vel,
+                                   std::vector<float>& mass, std::vector<sph_ParticleSmoothing>& sm, std::string& err) {
+    FILE* f = fopen(path, "rb");
+    if (!f) { err = std::string("cannot open ") + path; return SPH_ERR_INVALID_ARG; }
+    SnapHeader hd{};
+    bool ok = fread(&hd, sizeof(hd), 1, f) == 1 && memcmp(hd.magic, kSnapMagic, 8) == 0 && hd.version == 1 && hd.count >= 0 && hd.body0 >= 0;
+    if (!ok) { fclose(f); err = std::string(path) + " is not a sphb200 snapshot (version 1)"; return SPH_ERR_INVALID_ARG; }
+    if (want < 0) { want0 = hd.body0; want = hd.count; }
+    if (want0 < hd.body0 || want0 + want > hd.body0 + hd.count) { fclose(f); err = std::string(path) + " does not hold the requested bodies"; return SPH_ERR_INVALID_ARG; }
+    *n_total = hd.n_total;
+    const size_t c = (size_t)want, skip = (size_t)(want0 - hd.body0), all = (size_t)hd.count;
+    pos.resize(3 * c); vel.resize(3 * c); mass.resize(c); sm.assign(c, sph_ParticleSmoothing{});
+    std::vector<float> hh(c); std::vector<int32_t> no(c);
+    auto rd = [&](void* dst, size_t elem, size_t base_elems) {
+        return fseek(f, (long)(sizeof(hd) + base_elems + skip * elem), SEEK_SET) == 0 && (c == 0 || fread(dst, elem, c, f) == c);
+    };
+    ok = rd(pos.data(), 12, 0) && rd(vel.data(), 12, all * 12) && rd(mass.data(), 4, all * 24) && rd(hh.data(), 4, all * 28) && rd(no.data(), 4, all * 32);
+    fclose(f);
+    if (!ok) { err = std::string("short read from ") + path; return SPH_ERR_INVALID_ARG; }
+    for (size_t i = 0; i < c; i++) {
+        sm[i].influenceArea = hh[i]; sm[i].supportDomain = 2.0f * hh[i];
+        sm[i].sphereColliderPosRadius[3] = 2.0f * hh[i]; sm[i].neighbors = no[i];
+    }
+    return SPH_OK;
+}
+
+int sphb200_snapshot_save(sph_handle c, const char* path) {
+    NEED_RESIDENT(c);
+    ARG_CHECK(c, path, "null path");
+    const size_t n = (size_t)c->n;
+    std::vector<float> pos(3 * n), vel(3 * n), mass(n), sm2(2 * n), h(n);
+    std::vector<int32_t> no(n);
+    int rc = SPH_OK;
+    if (n) {
+        if ((rc = sphb200_download(c, SPH_FIELD_TRANSLATION, pos.data(), 12)) && rc != SPH_ERR_NEIGHBOR_OVERFLOW) return rc;
+        if ((rc = sphb200_download(c, SPH_FIELD_VELOCITY, vel.data(), 12)) && rc != SPH_ERR_NEIGHBOR_OVERFLOW) return rc;
+        if ((rc = sphb200_download(c, SPH_FIELD_MASS, mass.data(), 4)) && rc != SPH_ERR_NEIGHBOR_OVERFLOW) return rc;
+        std::vector<sph_ParticleSmoothing> sm(n);
+        if ((rc = sphb200_download(c, SPH_FIELD_SMOOTHING, sm.data(), (int)sizeof(sph_ParticleSmoothing))) && rc != SPH_ERR_NEIGHBOR_OVERFLOW) return rc;
+        for (size_t i = 0; i < n; i++) { h[i] = sm[i].influenceArea; no[i] = sm[i].neighbors; }
+    }
+    return sph_snapshot_write(path, c->n, 0, c->n, 0, pos.data(), vel.data(), mass.data(), h.data(), no.data(), c->err);
+}
+
+int sphb200_snapshot_load(sph_handle c, const char* path) {
+    if (!c) return SPH_ERR_INVALID_ARG;
+    ARG_CHECK(c, path, "null path");
+    std::vector<float> pos, vel, mass; std::vector<sph_ParticleSmoothing> sm;
+    int64_t n_total = 0;
+    int rc = sph_snapshot_read(path, 0, -1, &n_total, pos, vel, mass, sm, c->err);
+    if (rc) return rc;
+    if ((int64_t)mass.size() != n_total) { c->err = "the snapshot holds a slice of a group; load it with sphb200_group_snapshot_load"; return SPH_ERR_INVALID_ARG; }
+    return sphb200_upload(c, n_total, pos.data(), 12, vel.data(), 12, mass.data(), 4, sm.data(), (int)sizeof(sph_ParticleSmoothing));
 }
 
 int sphb200_device_ptr(sph_handle c, const char* name, void** ptr, int64_t* bytes) {

@@ -210,6 +210,8 @@ int sph_launch_tree_walk(sphb200_ctx* c);
 int sph_launch_top_tree(sphb200_ctx* c, int world, const float4* bnd, const int64_t* g0_d, float dt);
 int sph_launch_diagnostics(sphb200_ctx* c, double* out12);
 int sph_launch_diagnostics_range(sphb200_ctx* c, int off, int n);
+int sph_launch_field_stats_range(sphb200_ctx* c, int off, int n);
+void sph_finish_field_stats(const double* sums4, const uint32_t* mm8, int64_t n, double* out12);
 int sph_launch_pack_upload(sphb200_ctx* c, int64_t n, int has_nown, uint32_t orig0);
 int sph_upload_core(sphb200_ctx* c, int64_t n, uint32_t orig0, const void* pos, int pos_stride, const void* vel, int vel_stride,
                     const void* mass, int mass_stride, const void* smoothing, int smoothing_stride);
@@ -218,6 +220,10 @@ int sph_launch_unpack_field(sphb200_ctx* c, int field, int* elem_bytes);
 int sph_launch_neighbor_rows_sorted(sphb200_ctx* c, int32_t* rows_d);
 int sph_launch_interactions(sphb200_ctx* c, int64_t total, const int64_t* offsets_d, const int32_t* nbr_d, sph_ParticleInteraction* out_d);
 int sph_fp32_peak(sphb200_ctx* c, double* tflops);
+int sph_snapshot_write(const char* path, int64_t n_total, int64_t body0, int64_t count, int64_t steps, const float* pos, const float* vel,
+                       const float* mass, const float* h, const int32_t* nown, std::string& err);
+int sph_snapshot_read(const char* path, int64_t want0, int64_t want, int64_t* n_total, std::vector<float>& pos, std::vector<float>& vel,
+                      std::vector<float>& mass, std::vector<sph_ParticleSmoothing>& sm, std::string& err);
 size_t sph_sort_hist_words(int64_t cap);
 int sph_launch_radix_sort(sphb200_ctx* c, int n, cudaStream_t stream);
 int sph_launch_digit_pass(sphb200_ctx* c, const uint32_t* keys_in, const uint32_t* vals_in, const uint8_t* bucket, int n, int shift,

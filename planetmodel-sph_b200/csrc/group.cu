@@ -27,6 +27,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 #include <math.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <algorithm>
@@ -919,6 +920,76 @@ int sphb200_group_diagnostics(sph_group g, double* out12) {
     unsigned long long mx; memcpy(&mx, &R.diag_h[12], 8);
     out12[11] = (double)(mx & 0xffffffffull);
     return SPH_OK;
+}
+
+// (min, max, mean) x (rho, P, |grad Phi|, K rho) over the whole group
+int sphb200_group_field_stats(sph_group g, double* out12) {
+    if (!g || !out12) return SPH_ERR_INVALID_ARG;
+    if (!g->resident) G_FAIL(g, SPH_ERR_STATE, "no particles uploaded");
+    for (int k = 0; k < 12; k++) out12[k] = 0;
+    if (g->n_total == 0) return SPH_OK;
+    if (!g->stepped) G_FAIL(g, SPH_ERR_STATE, "no fields yet: run a step first");
+    int rc;
+    FOR_RANKS(g, R) { G_CUDA(g, cudaSetDevice(R.device)); G_RC(g, R, sph_launch_field_stats_range(R.c, (int)R.own0, (int)R.n_own)); }
+    { auto b = ptrs(g, [](GroupRank& R) { return R.c->diag_d + 16; }); if ((rc = g_allreduce(g, b.data(), 4, GR_F64, GR_SUM))) return rc; }
+    { auto b = ptrs(g, [](GroupRank& R) { return R.c->diag_d + 20; }); if ((rc = g_allreduce(g, b.data(), 4, GR_U32, GR_MIN))) return rc; }
+    { auto b = ptrs(g, [](GroupRank& R) { return R.c->diag_d + 22; }); if ((rc = g_allreduce(g, b.data(), 4, GR_U32, GR_MAX))) return rc; }
+    GroupRank& R = g->r[0];
+    G_CUDA(g, cudaSetDevice(R.device));
+    G_CUDA(g, cudaMemcpyAsync(R.diag_h + 16, R.c->diag_d + 16, 8 * sizeof(double), cudaMemcpyDeviceToHost, R.c->stream));
+    if ((rc = sync_all(g))) return rc;
+    sph_finish_field_stats(R.diag_h + 16, (const uint32_t*)(R.diag_h + 20), g->n_total, out12);
+    return SPH_OK;
+}
+
+// Snapshot of this process's body slice.  One process driving the whole group writes one complete file (loadable by a single
+// handle too); one process per GPU writes `path`.rNNN per rank.
+static std::string snap_path(sph_group g, const char* path) {
+    if (g->nlocal == g->world) return path;
+    char suf[16]; snprintf(suf, sizeof(suf), ".r%03d", g->rank0);
+    return std::string(path) + suf;
+}
+
+int sphb200_group_snapshot_save(sph_group g, const char* path) {
+    if (!g || !path) return SPH_ERR_INVALID_ARG;
+    if (!g->resident) G_FAIL(g, SPH_ERR_STATE, "no particles uploaded");
+    int64_t b0 = 0, cnt = 0;
+    sphb200_group_body_range(g, g->n_total, &b0, &cnt);
+    const size_t n = (size_t)cnt;
+    std::vector<float> pos(3 * n), vel(3 * n), mass(n), h(n);
+    std::vector<int32_t> no(n);
+    std::vector<sph_ParticleSmoothing> sm(n);
+    int rc;
+    // collective: every process takes part in the redistribution even if its slice is empty
+    if ((rc = sphb200_group_download(g, SPH_FIELD_TRANSLATION, pos.data() ? (void*)pos.data() : (void*)&b0, 12)) && rc != SPH_ERR_NEIGHBOR_OVERFLOW) return rc;
+    if ((rc = sphb200_group_download(g, SPH_FIELD_VELOCITY, vel.data() ? (void*)vel.data() : (void*)&b0, 12)) && rc != SPH_ERR_NEIGHBOR_OVERFLOW) return rc;
+    if ((rc = sphb200_group_download(g, SPH_FIELD_MASS, mass.data() ? (void*)mass.data() : (void*)&b0, 4)) && rc != SPH_ERR_NEIGHBOR_OVERFLOW) return rc;
+    if ((rc = sphb200_group_download(g, SPH_FIELD_SMOOTHING, sm.data() ? (void*)sm.data() : (void*)&b0, (int)sizeof(sph_ParticleSmoothing))) && rc != SPH_ERR_NEIGHBOR_OVERFLOW) return rc;
+    for (size_t i = 0; i < n; i++) { h[i] = sm[i].influenceArea; no[i] = sm[i].neighbors; }
+    return sph_snapshot_write(snap_path(g, path).c_str(), g->n_total, b0, cnt, g->steps, pos.data(), vel.data(), mass.data(), h.data(), no.data(), g->err);
+}
+
+// Loads this process's body slice from a complete snapshot at `path` (written by a single handle or a one-process group) or,
+// failing that, from its own part `path`.rNNN.  n_total comes from the file.
+int sphb200_group_snapshot_load(sph_group g, const char* path) {
+    if (!g || !path) return SPH_ERR_INVALID_ARG;
+    int64_t n_total = 0;
+    {   // header only: the size of the whole set
+        std::vector<float> a, b, c; std::vector<sph_ParticleSmoothing> d;
+        int rc = sph_snapshot_read(path, 0, 0, &n_total, a, b, c, d, g->err);
+        if (rc) rc = sph_snapshot_read(snap_path(g, path).c_str(), 0, -1, &n_total, a, b, c, d, g->err);
+        if (rc) return rc;
+    }
+    if (n_total > g->cap_total) G_FAIL(g, SPH_ERR_CAPACITY, "the snapshot exceeds the group's capacity");
+    int64_t b0 = 0, cnt = 0;
+    sphb200_group_body_range(g, n_total, &b0, &cnt);
+    std::vector<float> pos, vel, mass; std::vector<sph_ParticleSmoothing> sm;
+    int rc = sph_snapshot_read(path, b0, cnt, &n_total, pos, vel, mass, sm, g->err);
+    if (rc) rc = sph_snapshot_read(snap_path(g, path).c_str(), b0, cnt, &n_total, pos, vel, mass, sm, g->err);
+    if (rc) return rc;
+    int64_t dummy = 0;
+    return sphb200_group_upload(g, n_total, cnt ? (void*)pos.data() : (void*)&dummy, 12, cnt ? (void*)vel.data() : (void*)&dummy, 12,
+                                cnt ? (void*)mass.data() : (void*)&dummy, 4, cnt ? (void*)sm.data() : (void*)&dummy, (int)sizeof(sph_ParticleSmoothing));
 }
 
 int sphb200_group_info(sph_group g, sph_GroupInfo* out) {

@@ -12,6 +12,7 @@
 #include "ctx.cuh"
 #include "rowstream.cuh"
 #include <math.h>
+#include <string.h>
 
 namespace {
 
@@ -344,6 +345,38 @@ __global__ void __launch_bounds__(256) k_diagnostics(const float4* __restrict__ 
     }
 }
 
+// Field statistics (README.md:50-52 roadmap: "Average/max/min: Temp, Pressure, Density, Grav Field"): sum (fp64), min and max
+// (ordered-uint atomics) of rho, P, |grad Phi| and u = K rho (the specific internal energy of the P = K rho^2 gas: the model's
+// temperature proxy).  out[0..3] sums; mm[0..3] ordered minima, mm[4..7] ordered maxima.
+__global__ void __launch_bounds__(256) k_field_stats(const float* __restrict__ rho, const float* __restrict__ press,
+                                                     const float4* __restrict__ grav, int n, float Keos, double* __restrict__ out,
+                                                     uint32_t* __restrict__ mm) {
+    double s[4] = {0, 0, 0, 0};
+    float lo[4] = {INFINITY, INFINITY, INFINITY, INFINITY}, hi[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const float4 g = grav[i];
+        const float d = rho[i];
+        const float q[4] = {d, press[i], sqrtf(g.x * g.x + g.y * g.y + g.z * g.z), Keos * d};
+#pragma unroll
+        for (int k = 0; k < 4; k++) { s[k] += (double)q[k]; lo[k] = fminf(lo[k], q[k]); hi[k] = fmaxf(hi[k], q[k]); }
+    }
+    __shared__ double ss[4][8];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        double x = s[k];
+        for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(FULL, x, o);
+        const uint32_t l = __reduce_min_sync(FULL, f2ord(lo[k])), h = __reduce_max_sync(FULL, f2ord(hi[k]));
+        if (lane == 0) { ss[k][w] = x; atomicMin(&mm[k], l); atomicMax(&mm[4 + k], h); }
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double x = 0;
+        for (int j = 0; j < 8; j++) x += ss[threadIdx.x][j];
+        atomicAdd(&out[threadIdx.x], x);
+    }
+}
+
 }  // namespace
 
 // ---- launchers ------------------------------------------------------------------------------------------------
@@ -454,4 +487,28 @@ int sph_launch_diagnostics(sphb200_ctx* c, double* out12) {
     out12[10] = n > 0 ? tmp[10] / n : 0.0;
     out12[11] = (double)(*(int*)&tmp[12]);
     return SPH_OK;
+}
+
+// sums of rho, P, |grad Phi|, K rho over resident slots [off, off+n) into diag_d[16..19]; ordered-uint minima / maxima into the
+// eight uint32 at diag_d + 20
+int sph_launch_field_stats_range(sphb200_ctx* c, int off, int n) {
+    uint32_t* mm = (uint32_t*)(c->diag_d + 20);
+    SPH_CK(c, cudaMemsetAsync(c->diag_d + 16, 0, 4 * sizeof(double), c->stream));
+    SPH_CK(c, cudaMemsetAsync(mm, 0xff, 4 * sizeof(uint32_t), c->stream));
+    SPH_CK(c, cudaMemsetAsync(mm + 4, 0, 4 * sizeof(uint32_t), c->stream));
+    if (n <= 0) return SPH_OK;
+    int blocks = min(sph_div_up(n, 256), c->sm_count * 4);
+    k_field_stats<<<blocks, 256, 0, c->stream>>>(c->rho + off, c->press + off, c->grav + off, n, c->p.K, c->diag_d + 16, mm);
+    SPH_LAUNCH_CHECK(c);
+    return SPH_OK;
+}
+
+// out12 = (min, max, mean) x (rho, P, |grad Phi|, K rho) from the sums / ordered extrema (host side; n = particles they cover)
+void sph_finish_field_stats(const double* sums4, const uint32_t* mm8, int64_t n, double* out12) {
+    auto ord2f_h = [](uint32_t u) { uint32_t b = (u & 0x80000000u) ? (u & 0x7fffffffu) : ~u; float f; memcpy(&f, &b, 4); return (double)f; };
+    for (int k = 0; k < 4; k++) {
+        out12[3 * k] = n > 0 ? ord2f_h(mm8[k]) : 0.0;
+        out12[3 * k + 1] = n > 0 ? ord2f_h(mm8[4 + k]) : 0.0;
+        out12[3 * k + 2] = n > 0 ? sums4[k] / (double)n : 0.0;
+    }
 }

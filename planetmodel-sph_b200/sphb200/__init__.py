@@ -65,7 +65,8 @@ EXPORTS = [
     "sphb200_group_last_error", "sphb200_group_body_range", "sphb200_group_upload", "sphb200_group_step",
     "sphb200_group_download", "sphb200_group_sync", "sphb200_group_diagnostics", "sphb200_group_info",
     "sphb200_group_enable_timing", "sphb200_group_get_timings", "sphb200_group_rank_handle", "sphb200_group_stream",
-    "sphb200_get_stream",
+    "sphb200_get_stream", "sphb200_field_stats", "sphb200_snapshot_save", "sphb200_snapshot_load",
+    "sphb200_group_field_stats", "sphb200_group_snapshot_save", "sphb200_group_snapshot_load",
 ]
 
 
@@ -149,6 +150,10 @@ def load_library():
     L.sphb200_group_rank_handle.argtypes = [H, C.c_int, C.POINTER(H)]
     L.sphb200_group_stream.argtypes = [H, C.c_int, C.POINTER(C.c_void_p)]
     L.sphb200_get_stream.argtypes = [H, C.POINTER(C.c_void_p)]
+    L.sphb200_field_stats.argtypes = [H, C.c_void_p]
+    L.sphb200_group_field_stats.argtypes = [H, C.c_void_p]
+    for fn in (L.sphb200_snapshot_save, L.sphb200_snapshot_load, L.sphb200_group_snapshot_save, L.sphb200_group_snapshot_load):
+        fn.argtypes = [H, C.c_char_p]
     _lib = L
     return L
 
@@ -331,16 +336,22 @@ class Simulation:
         return dict(mass=out[0], momentum=out[1:4].copy(), angular_momentum=out[4:7].copy(), e_kin=out[7], e_pot=out[8],
                     e_int=out[9], mean_neighbors=out[10], max_neighbors=int(out[11]))
 
-    # -- snapshot I/O (checkpoint/resume and the golden-vector format): body-order arrays in one .npz
+    def field_stats(self):
+        """{"rho" | "P" | "grav" | "u": (min, max, mean)} over all particles (README.md:50-52 roadmap)."""
+        out = np.zeros(12, np.float64)
+        self._ck(self.L.sphb200_field_stats(self.h, _ptr(out)))
+        return {k: tuple(out[3 * i:3 * i + 3]) for i, k in enumerate(("rho", "P", "grav", "u"))}
+
+    # -- snapshot I/O (SURVEY.md 8f3: checkpoint/resume and the fixture format): body-order arrays in one binary file,
+    #    written and read by the library (sphb200_snapshot_save / _load)
     def save_snapshot(self, path):
-        d = self.download_all()
-        np.savez_compressed(path, pos=d["pos"], vel=d["vel"], mass=d["mass"], h=d["h"], n_own=d["n_own"])
+        self._ck(self.L.sphb200_snapshot_save(self.h, os.fsencode(path)), (SPH_ERR_NEIGHBOR_OVERFLOW,))
 
     def load_snapshot(self, path):
-        z = np.load(path)
-        sm = np.zeros(len(z["h"]), ParticleSmoothing)
-        sm["influenceArea"] = z["h"]; sm["supportDomain"] = 2.0 * z["h"]; sm["neighbors"] = z["n_own"]
-        self.upload(z["pos"], z["vel"], z["mass"], sm)
+        self._ck(self.L.sphb200_snapshot_load(self.h, os.fsencode(path)))
+        n = C.c_int64(0); cap = C.c_int64(0)
+        self._ck(self.L.sphb200_count(self.h, C.byref(n), C.byref(cap)))
+        self.n = n.value
 
     def launch_count(self):
         v = C.c_int64(0)

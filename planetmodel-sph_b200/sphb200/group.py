@@ -166,6 +166,21 @@ class Group:
         return dict(mass=out[0], momentum=out[1:4].copy(), angular_momentum=out[4:7].copy(), e_kin=out[7], e_pot=out[8],
                     e_int=out[9], mean_neighbors=out[10], max_neighbors=int(out[11]))
 
+    def field_stats(self):
+        out = np.zeros(12, np.float64)
+        self._ck(self.L.sphb200_group_field_stats(self.h, _ptr(out)))
+        return {k: tuple(out[3 * i:3 * i + 3]) for i, k in enumerate(("rho", "P", "grav", "u"))}
+
+    def save_snapshot(self, path):
+        self._ck(self.L.sphb200_group_snapshot_save(self.h, os.fsencode(path)), (SPH_ERR_NEIGHBOR_OVERFLOW,))
+
+    def load_snapshot(self, path):
+        self._ck(self.L.sphb200_group_snapshot_load(self.h, os.fsencode(path)))
+        gi = GroupInfo()
+        self._ck(self.L.sphb200_group_info(self.h, C.byref(gi)))
+        self.n_total = int(gi.n_total)
+        self.body0, self.count = self.body_range(self.n_total)
+
     def info(self):
         gi = GroupInfo()
         self._ck(self.L.sphb200_group_info(self.h, C.byref(gi)))

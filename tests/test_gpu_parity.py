@@ -520,7 +520,7 @@ def test_snapshot_roundtrip_resumes_bitwise(tmp_path):
     a.upload(c["pos"], c["vel"], c["mass"], c["h"])
     for _ in range(3):
         a.step(0.01, sphb200.GRAVITY_TREE)
-    path = str(tmp_path / "snap.npz")
+    path = str(tmp_path / "snap.sphb200")
     a.save_snapshot(path)
     b = make_sim(5000)
     b.load_snapshot(path)
@@ -532,6 +532,61 @@ def test_snapshot_roundtrip_resumes_bitwise(tmp_path):
         np.testing.assert_array_equal(da[k], db[k])
     d = a.diagnostics()
     assert abs(d["angular_momentum"][2]) > 0 and d["mass"] == pytest.approx(c["mass"].sum(), rel=1e-6)
+
+
+def test_snapshot_travels_between_a_handle_and_a_group(tmp_path):
+    """The snapshot written through the C ABI by a single handle restores a (one-process, 3-rank) group and vice versa; both
+    continue bit-identically (tree gravity)."""
+    import sphb200
+    from sphb200 import group as sg, ic
+    c = ic.make_rotating_sphere(6001, seed=13)
+    a = make_sim(6001)
+    a.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    for _ in range(2):
+        a.step(0.01, sphb200.GRAVITY_TREE)
+    p1 = str(tmp_path / "from_handle.sphb200")
+    a.save_snapshot(p1)
+    g = sg.Group.single_process(6001, [0, 0, 0])
+    g.load_snapshot(p1)
+    a.load_snapshot(p1)
+    for _ in range(2):
+        a.step(0.01, sphb200.GRAVITY_TREE); g.step(0.01, sphb200.GRAVITY_TREE)
+    da, dg = a.download_all(), g.download_all()
+    for k in ("pos", "vel", "h", "n_own", "rho", "P", "gradP", "grav"):
+        np.testing.assert_array_equal(da[k], dg[k], err_msg=k)
+    p2 = str(tmp_path / "from_group.sphb200")
+    g.save_snapshot(p2)
+    b = make_sim(6001)
+    b.load_snapshot(p2)
+    db = b.download_all()
+    for k in ("pos", "vel", "mass", "h", "n_own"):
+        np.testing.assert_array_equal(db[k], dg[k], err_msg=k)
+    with pytest.raises(sphb200.SphError):
+        b.load_snapshot(str(tmp_path / "missing.sphb200"))
+    g.close()
+
+
+def test_field_stats_min_max_mean(orc):
+    """README.md:50-52 roadmap item: min / max / mean of density, pressure, |grad Phi| and u = K rho, single handle and group."""
+    import sphb200
+    from sphb200 import group as sg, ic
+    c = ic.make_collision(4000, seed=3)
+    sim = run_gpu_step(c, 1 / 60, sphb200.GRAVITY_TREE)
+    d = sim.download_all()
+    st = sim.field_stats()
+    gn = np.linalg.norm(d["grav"][:, :3].astype(np.float64), axis=1)
+    K = sim.effective_params().K
+    for key, arr in (("rho", d["rho"]), ("P", d["P"]), ("grav", gn), ("u", K * d["rho"])):
+        lo, hi, mean = st[key]
+        assert lo == pytest.approx(float(arr.min()), rel=1e-6) and hi == pytest.approx(float(arr.max()), rel=1e-6)
+        assert mean == pytest.approx(float(arr.astype(np.float64).mean()), rel=1e-6)
+    g = sg.Group.single_process(len(c["h"]), [0, 0])
+    g.upload_global(c["pos"], c["vel"], c["mass"], c["h"])
+    g.step(1 / 60, sphb200.GRAVITY_TREE)
+    sg_ = g.field_stats()
+    for key in st:
+        assert sg_[key] == pytest.approx(st[key], rel=1e-9), key      # bit-identical fields: same extrema, sums to fp64 noise
+    g.close()
 
 
 def test_kick_drift_flag_matches_oracle_and_conserves_energy_better(orc):
