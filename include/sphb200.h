@@ -59,7 +59,9 @@ typedef struct sph_Params {
 
 enum {
     SPH_FLAG_FIX_KERNEL_DERIV_SIGN = 1, /* use -3q in KernelDeriv's inner branch (undo quirk Q1, SplineKernel.cs:135) */
-    SPH_FLAG_KICK_DRIFT = 2             /* v += a dt first, then x += v_new dt (symplectic leapfrog; roadmap README.md:90-93) */
+    SPH_FLAG_KICK_DRIFT = 2,            /* v += a dt first, then x += v_new dt (symplectic leapfrog; roadmap README.md:90-93) */
+    SPH_FLAG_PM07_SOFTENING = 4         /* gravity softened with the spline kernel, symmetric in h_i and h_j (Price & Monaghan 2007;
+                                           roadmap README.md:75-77) instead of the one-sided a = h_i law of GravityFieldSystem.cs:340-347 */
 };
 
 /* ---- byte-exact mirrors of the reference components */
@@ -175,7 +177,9 @@ SPH_API int sphb200_download(sph_handle h, int field, void* dst, int stride);
 /* Neighbor lists as CSR in body-index space, each row ascending (canonical order).  offsets has n+1 entries.
  * If total > cap only *total is set (call again).  Replaces reading DynamicBuffer<ParticleInteraction>.Other. */
 SPH_API int sphb200_download_neighbors(sph_handle h, int64_t* offsets, int32_t* nbr, int64_t cap, int64_t* total);
-/* Interaction records (KernelSystem.cs:305-334) for the same CSR layout; optional debugging/parity surface. */
+/* Interaction records (KernelSystem.cs:305-334) for the same CSR layout; optional debugging/parity surface.
+ * SPH_ERR_STATE unless the lists of build_neighbors still describe the resident positions (integrate / smoothing_update
+ * invalidate them); SPH_ERR_INVALID_ARG for offsets that do not ascend from 0 or an index outside [0, n). */
 SPH_API int sphb200_download_interactions(sph_handle h, const int64_t* offsets, const int32_t* nbr,
                                           sph_ParticleInteraction* out);
 /* Sorted slot -> body index, and the 30-bit Morton keys in sorted order (either pointer may be NULL). */

@@ -66,6 +66,9 @@ def lib():
         L.orc_eos.argtypes = [C.c_int64, f32p, C.c_float, f32p]
         L.orc_pressure_grad.argtypes = [C.c_int64, f32p, f32p, f32p, f32p, f32p, i64p, i32p, C.c_int, f32p]
         L.orc_gravity_direct.argtypes = [C.c_int64, f32p, f32p, f32p, C.c_float, C.c_int64, C.c_int64, C.c_int, f32p]
+        L.orc_gravity_direct_pm07.argtypes = [C.c_int64, f32p, f32p, f32p, C.c_float, C.c_int64, C.c_int64, f32p]
+        L.orc_gravity_pm07_correction.argtypes = [C.c_int64, f32p, f32p, f32p, C.c_float, i64p, i32p, f32p]
+        L.orc_pm07_kernel.argtypes = [C.c_double, C.c_double, C.POINTER(C.c_double)]
         L.orc_integrate.argtypes = [C.c_int64, f32p, f32p, f32p, f32p, f32p, C.c_float]
         L.orc_integrate2.argtypes = [C.c_int64, f32p, f32p, f32p, f32p, f32p, C.c_float, C.c_int]
         L.orc_grid_params.argtypes = [C.c_int64, f32p, f32p, C.c_int, C.POINTER(GridParams)]
@@ -153,6 +156,27 @@ def gravity_direct(pos, h, m, G=1.0, i0=0, i1=None, accum_double=False):
     g = np.zeros((i1 - i0, 4), np.float32)
     lib().orc_gravity_direct(n, _f(pos), _f(h), _f(m), G, i0, i1, int(accum_double), g)
     return g
+
+
+def gravity_direct_pm07(pos, h, m, G=1.0, i0=0, i1=None):
+    """NON-REFERENCE option (README.md:75-77 roadmap): Price & Monaghan 2007 spline-softened gravity, symmetric in h_i, h_j."""
+    n = len(h); i1 = n if i1 is None else i1
+    g = np.zeros((i1 - i0, 4), np.float32)
+    lib().orc_gravity_direct_pm07(n, _f(pos), _f(h), _f(m), G, i0, i1, g)
+    return g
+
+
+def gravity_pm07_correction(pos, h, m, offsets, nbr, G=1.0):
+    """Sum over the neighbor lists of (PM07 pair law - reference pair law): what SPH_FLAG_PM07_SOFTENING adds to a tree walk."""
+    n = len(h); g = np.zeros((n, 4), np.float32)
+    lib().orc_gravity_pm07_correction(n, _f(pos), _f(h), _f(m), G, offsets, nbr, g)
+    return g
+
+
+def pm07_kernel(r, h):
+    out = (C.c_double * 2)()
+    lib().orc_pm07_kernel(r, h, out)
+    return out[0], out[1]
 
 
 def smoothing_update(h, n_own, target=50.0):

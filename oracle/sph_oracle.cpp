@@ -467,6 +467,72 @@ ORC_API void orc_gravity_direct(int64_t n, const float* pos, const float* h, con
 }
 
 // ------------------------------------------------------------------------------------------------
+// NON-REFERENCE OPTION (roadmap A README.md:75-77 "Gravity kernel which conserves energy, see Price & Monaghan 2007"):
+// gravity softened with the cubic-spline kernel of support 2h, symmetrised in the two smoothing lengths,
+//     grad Phi_i = G sum_j m_j (r_i - r_j)/r * 0.5 [phi'(r,h_i) + phi'(r,h_j)],  Phi_i = G sum_j m_j 0.5 [phi(r,h_i) + phi(r,h_j)]
+// with phi, phi' of P&M 2007 appendix A (Newtonian beyond r = 2h).  Evaluated in double: this is the yardstick of
+// SPH_FLAG_PM07_SOFTENING, which the GPU builds as "main gravity kernel + neighbor-list correction" in fp32.
+// ------------------------------------------------------------------------------------------------
+namespace {
+inline void Pm07Kernel(double r, double h, double& dphi_over_r, double& phi) {
+    double q = r / h;
+    if (q < 1.0) {
+        dphi_over_r = (4.0 / 3.0 - 1.2 * q * q + 0.5 * q * q * q) / (h * h * h);
+        phi = (2.0 / 3.0 * q * q - 0.3 * q * q * q * q + 0.1 * q * q * q * q * q - 1.4) / h;
+    } else if (q < 2.0) {
+        dphi_over_r = (8.0 / 3.0 - 3.0 * q + 1.2 * q * q - q * q * q / 6.0 - 1.0 / (15.0 * q * q * q)) / (h * h * h);
+        phi = (4.0 / 3.0 * q * q - q * q * q + 0.3 * q * q * q * q - q * q * q * q * q / 30.0 - 1.6 + 1.0 / (15.0 * q)) / h;
+    } else {
+        dphi_over_r = 1.0 / (r * r * r);
+        phi = -1.0 / r;
+    }
+}
+}  // namespace
+
+ORC_API void orc_pm07_kernel(double r, double h, double* out2) { Pm07Kernel(r, h, out2[0], out2[1]); }
+
+// all sources, targets i0..i1, double accumulation
+ORC_API void orc_gravity_direct_pm07(int64_t n, const float* pos, const float* h, const float* m, float G,
+                                     int64_t i0, int64_t i1, float* grav4) {
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int64_t i = i0; i < i1; i++) {
+        double s[4] = {0, 0, 0, 0};
+        for (int64_t j = 0; j < n; j++) {
+            if (j == i) continue;
+            double d[3] = {(double)pos[3 * i] - pos[3 * j], (double)pos[3 * i + 1] - pos[3 * j + 1], (double)pos[3 * i + 2] - pos[3 * j + 2]};
+            double r = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            if (!(r > 0.0)) { s[3] += m[j] * 0.5 * (-1.4 / h[i] - 1.4 / h[j]); continue; }   // coincident: no force, phi(0)
+            double fi, pi, fj, pj;
+            Pm07Kernel(r, h[i], fi, pi); Pm07Kernel(r, h[j], fj, pj);
+            double f = 0.5 * (fi + fj) * m[j];
+            s[0] += d[0] * f; s[1] += d[1] * f; s[2] += d[2] * f; s[3] += m[j] * 0.5 * (pi + pj);
+        }
+        for (int k = 0; k < 4; k++) grav4[4 * (i - i0) + k] = (float)((double)G * s[k]);
+    }
+}
+
+// Correction over the neighbor lists that turns a reference-law sum into the PM07 sum (what the tree path adds):
+// out4[i] = G sum_{j in list(i)} m_j { PM07 pair - GravityContributionParticle pair }, double accumulation.
+ORC_API void orc_gravity_pm07_correction(int64_t n, const float* pos, const float* h, const float* m, float G,
+                                         const int64_t* offsets, const int32_t* nbr, float* out4) {
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < n; i++) {
+        double s[4] = {0, 0, 0, 0};
+        for (int64_t e = offsets[i]; e < offsets[i + 1]; e++) {
+            int64_t j = nbr[e];
+            double d[3] = {(double)pos[3 * i] - pos[3 * j], (double)pos[3 * i + 1] - pos[3 * j + 1], (double)pos[3 * i + 2] - pos[3 * j + 2]};
+            double r = std::sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+            F4 ref = GravityContributionParticle(ld3(pos, i), ld3(pos, j), m[j], h[i], 1.0f);
+            double fi = 0, pi = -1.4 / h[i], fj = 0, pj = -1.4 / h[j];
+            if (r > 0.0) { Pm07Kernel(r, h[i], fi, pi); Pm07Kernel(r, h[j], fj, pj); }
+            double f = 0.5 * (fi + fj) * m[j];
+            s[0] += d[0] * f - ref.x; s[1] += d[1] * f - ref.y; s[2] += d[2] * f - ref.z; s[3] += m[j] * 0.5 * (pi + pj) - ref.w;
+        }
+        for (int k = 0; k < 4; k++) out4[4 * i + k] = (float)((double)G * s[k]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // Integration: x += v*dt  (UP/Dynamics/Integrator/Integrator.cs:98-101, old v), then
 //              v += (-gradP/rho - gradPhi)*dt  (A/Systems/VelocitySystem.cs:24-36)
 // ------------------------------------------------------------------------------------------------

@@ -66,7 +66,7 @@ int sphb200_destroy(sph_handle c) {
     cudaFree(c->ncount); cudaFree(c->nown); cudaFree(c->rho); cudaFree(c->press); cudaFree(c->cvol); cudaFree(c->gradp);
     cudaFree(c->grav); cudaFree(c->npart); cudaFree(c->napprox); cudaFree(c->gpart); cudaFree(c->tbox); cudaFree(c->child); cudaFree(c->range);
     cudaFree(c->parent); cudaFree(c->flag); cudaFree(c->mom); cudaFree(c->nlo); cudaFree(c->nhi); cudaFree(c->packed); cudaFree(c->bounds);
-    cudaFree(c->grid_d); cudaFree(c->err_d); cudaFree(c->rr_table); cudaFree(c->diag_d); cudaFree(c->stage_d);
+    cudaFree(c->scratch_d); cudaFree(c->grid_d); cudaFree(c->err_d); cudaFree(c->rr_table); cudaFree(c->diag_d); cudaFree(c->stage_d);
     if (c->err_h) cudaFreeHost(c->err_h);
     if (c->stage_h) cudaFreeHost(c->stage_h);
     if (c->ev_created) for (int i = 0; i <= SPH_MAX_PASSES; i++) cudaEventDestroy(c->ev[i]);
@@ -198,6 +198,7 @@ int sphb200_get_stream(sph_handle c, void** s) {
 }
 
 static int check_errflags(sphb200_ctx* c);
+static int join_tree(sphb200_ctx* c);
 
 int sphb200_sync(sph_handle c) {
     if (!c) return SPH_ERR_INVALID_ARG;
@@ -274,9 +275,10 @@ int sph_upload_core(sphb200_ctx* c, int64_t n, uint32_t orig0, const void* pos, 
     c->cur = 0;
     c->resident = true; c->lists_valid = c->pressure_valid = c->gravity_valid = c->tree_valid = c->h_updated = false;
     c->sorted_valid = c->lists_fresh = false;
+    c->nown_aligned = true;
     // asynchronous error flags are sticky from one upload to the next (results after an overflow are tainted)
     SPH_CK(c, cudaMemsetAsync(c->err_d, 0, ERR_SLOTS * sizeof(int32_t), c->stream));
-    const uint32_t mm0[2] = {0xffffffffu, 0u};
+    const uint32_t mm0[3] = {0xffffffffu, 0u, 0u};
     SPH_CK(c, cudaMemcpyAsync(c->bounds + 12, mm0, sizeof(mm0), cudaMemcpyHostToDevice, c->stream));
     if (n == 0) return SPH_OK;
     // Staging layout (device): pos[3n] vel[3n] mass[n] h[n] nown[n].  Arrays with their natural stride are copied
@@ -309,12 +311,13 @@ int sph_upload_core(sphb200_ctx* c, int64_t n, uint32_t orig0, const void* pos, 
 
 // Blocks; equal masses (the reference spawner, ParticleAuthoring.cs:208) select the kernels that hoist the mass multiply.
 int sph_upload_finish(sphb200_ctx* c) {
-    SPH_CK(c, cudaMemcpyAsync(c->err_h + 4, c->bounds + 12, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    SPH_CK(c, cudaMemcpyAsync(c->err_h + 4, c->bounds + 12, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     SPH_CK(c, cudaStreamSynchronize(c->stream));
     const uint32_t lo = (uint32_t)c->err_h[4], hi = (uint32_t)c->err_h[5];
     c->equal_mass = lo == hi;
     const uint32_t bits = (lo & 0x80000000u) ? (lo & 0x7fffffffu) : ~lo;   // ord2f on the host
     memcpy(&c->common_mass, &bits, 4);
+    memcpy(&c->h_bound, &c->err_h[6], 4);   // non-negative floats order like their bit patterns
     return SPH_OK;
 }
 
@@ -358,8 +361,17 @@ static int check_errflags(sphb200_ctx* c) {
 int sphb200_smoothing_update(sph_handle c) {
     NEED_RESIDENT(c);
     if (c->n == 0) return SPH_OK;
-    int rc = sph_launch_smoothing_bounds(c, true);
+    if (!c->nown_aligned) {
+        c->err = "smoothing_update after a sort without a neighbor pass: the own-support counts are in the previous slot order "
+                 "(call it first in a step, as ParticleSmoothingSystem runs, or after build_neighbors)";
+        return SPH_ERR_STATE;
+    }
+    int rc = join_tree(c);   // a pending LBVH build on the auxiliary stream reads posh.w
     if (rc) return rc;
+    rc = sph_launch_smoothing_bounds(c, true);
+    if (rc) return rc;
+    // h <- 0.5 h (1 + (target/n_own)^(1/3)), n_own >= 1 (ParticleSmoothingSystem.cs:46-59): the largest growth of one update
+    c->h_bound *= 0.5f * (1.0f + cbrtf(fmaxf(c->p.target_neighbors, 1.0f))) * 1.001f;
     c->h_updated = true;
     c->sorted_valid = c->lists_fresh = c->pressure_valid = c->gravity_valid = false;
     return SPH_OK;
@@ -399,6 +411,7 @@ static int ensure_sorted(sphb200_ctx* c) {
     if (rc) return rc;
     c->sorted_valid = true;
     c->lists_valid = c->lists_fresh = c->tree_valid = c->tree_fresh = false;  // slot indices changed
+    c->nown_aligned = false;
     return SPH_OK;
 }
 
@@ -410,7 +423,7 @@ int sphb200_build_neighbors(sph_handle c) {
     if ((rc = maybe_fork_tree(c))) return rc;
     rc = sph_launch_neighbors_density(c);
     if (rc) return rc;
-    c->lists_valid = c->lists_fresh = true;
+    c->lists_valid = c->lists_fresh = c->nown_aligned = true;
     c->pressure_valid = false;
     return SPH_OK;
 }
@@ -430,7 +443,7 @@ int sphb200_gravity(sph_handle c, int impl, float dt) {
         if (!c->lists_fresh) { c->err = "direct gravity needs this step's neighbor lists (softened near-pair correction): call build_neighbors first"; return SPH_ERR_STATE; }
         int rc = sph_launch_gravity_allpairs(c);
         if (rc) return rc;
-        rc = sph_launch_gravity_near(c);
+        rc = sph_launch_gravity_near(c, SPH_GRAVITY_PARTICLE);
         if (rc) return rc;
         c->gravity_valid = true;
         return SPH_OK;
@@ -448,6 +461,10 @@ int sphb200_gravity(sph_handle c, int impl, float dt) {
         }
         rc = sph_launch_tree_walk(c);
         if (rc) return rc;
+        if (c->p.flags & SPH_FLAG_PM07_SOFTENING) {
+            if (!c->lists_fresh) { c->err = "SPH_FLAG_PM07_SOFTENING needs this step's neighbor lists: call build_neighbors first"; return SPH_ERR_STATE; }
+            if ((rc = sph_launch_gravity_near(c, SPH_GRAVITY_TREE))) return rc;
+        }
         c->gravity_valid = true;
         return SPH_OK;
     }
@@ -504,7 +521,7 @@ int sphb200_step(sph_handle c, float dt, int impl) {
     pass_mark(c, "keys_sort_permute_cells");
     if ((rc = maybe_fork_tree(c))) return rc;
     if ((rc = sph_launch_neighbors_density(c))) return rc;
-    c->lists_valid = c->lists_fresh = true;
+    c->lists_valid = c->lists_fresh = c->nown_aligned = true;
     pass_mark(c, "neighbors_density_eos");
     if ((rc = sphb200_gravity(c, impl, dt))) return rc;
     pass_mark(c, impl == SPH_GRAVITY_TREE ? "gravity_tree" : (impl == SPH_GRAVITY_PARTICLE ? "gravity_allpairs" : "gravity_none"));
@@ -566,6 +583,21 @@ int sphb200_download(sph_handle c, int field, void* dst, int stride) {
     return rc;
 }
 
+}  // extern "C"
+
+// grow-only scratch (the previous contents are not kept)
+static int scratch_reserve(sphb200_ctx* c, size_t bytes) {
+    if (bytes <= c->scratch_bytes) return SPH_OK;
+    SPH_CK(c, cudaStreamSynchronize(c->stream));
+    cudaFree(c->scratch_d); c->scratch_d = nullptr; c->scratch_bytes = 0;
+    bytes += bytes / 8;
+    if (cudaMalloc(&c->scratch_d, bytes) != cudaSuccess) { cudaGetLastError(); c->err = "allocation failed (download scratch)"; return SPH_ERR_CUDA; }
+    c->scratch_bytes = bytes;
+    return SPH_OK;
+}
+
+extern "C" {
+
 int sphb200_download_neighbors(sph_handle c, int64_t* offsets, int32_t* nbr, int64_t cap, int64_t* total) {
     NEED_RESIDENT(c);
     ARG_CHECK(c, offsets && total, "null argument");
@@ -585,42 +617,44 @@ int sphb200_download_neighbors(sph_handle c, int64_t* offsets, int32_t* nbr, int
     if (*total > cap || !nbr) return check_errflags(c);
     memcpy(c->stage_h, offsets, (size_t)(n + 1) * 8);
     SPH_CK(c, cudaMemcpyAsync(c->stage_d, c->stage_h, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
-    int32_t* rows_d = nullptr;
-    SPH_CK(c, cudaMalloc((void**)&rows_d, std::max<int64_t>(*total, 1) * 4));
+    if ((rc = scratch_reserve(c, (size_t)std::max<int64_t>(*total, 1) * 4))) return rc;
+    int32_t* rows_d = (int32_t*)c->scratch_d;
     rc = sph_launch_neighbor_rows_sorted(c, rows_d);
     if (rc == SPH_OK) {
         cudaError_t e = cudaMemcpyAsync(nbr, rows_d, (size_t)*total * 4, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
         if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = SPH_ERR_CUDA; }
     }
-    cudaFree(rows_d);
     if (rc) return rc;
     return check_errflags(c);
 }
 
 int sphb200_download_interactions(sph_handle c, const int64_t* offsets, const int32_t* nbr, sph_ParticleInteraction* out) {
     NEED_RESIDENT(c);
-    ARG_CHECK(c, offsets && (nbr || offsets[c->n] == 0) && (out || offsets[c->n] == 0), "null argument");
-    int64_t n = c->n, total = offsets[n];
-    if (n == 0 || total == 0) return SPH_OK;
-    int64_t* off_d = nullptr; int32_t* nbr_d = nullptr; sph_ParticleInteraction* out_d = nullptr;
-    int rc = SPH_OK;
-    if (cudaMalloc((void**)&off_d, (n + 1) * 8) != cudaSuccess || cudaMalloc((void**)&nbr_d, total * 4) != cudaSuccess ||
-        cudaMalloc((void**)&out_d, total * sizeof(sph_ParticleInteraction)) != cudaSuccess) {
-        c->err = "allocation failed"; rc = SPH_ERR_CUDA;
-    }
-    if (!rc) {
-        cudaMemcpyAsync(off_d, offsets, (n + 1) * 8, cudaMemcpyHostToDevice, c->stream);
-        cudaMemcpyAsync(nbr_d, nbr, total * 4, cudaMemcpyHostToDevice, c->stream);
-        rc = sph_launch_interactions(c, total, off_d, nbr_d, out_d);
-    }
-    if (!rc) {
-        cudaError_t e = cudaMemcpyAsync(out, out_d, total * sizeof(sph_ParticleInteraction), cudaMemcpyDeviceToHost, c->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-        if (e != cudaSuccess) { c->err = cudaGetErrorString(e); rc = SPH_ERR_CUDA; }
-    }
-    cudaFree(off_d); cudaFree(nbr_d); cudaFree(out_d);
-    return rc;
+    ARG_CHECK(c, offsets, "null argument");
+    const int64_t n = c->n;
+    if (n == 0) return SPH_OK;
+    // the records are W / grad W at the positions the lists were built for (KernelSystem.cs:290-334): after integrate or a
+    // smoothing update they would describe other positions than the lists do
+    if (!c->lists_fresh) { c->err = "interaction records need this step's neighbor lists (call build_neighbors; integrate invalidates them)"; return SPH_ERR_STATE; }
+    ARG_CHECK(c, offsets[0] == 0, "offsets[0] != 0");
+    for (int64_t i = 0; i < n; i++) ARG_CHECK(c, offsets[i + 1] >= offsets[i], "offsets not ascending");
+    const int64_t total = offsets[n];
+    if (total == 0) return SPH_OK;
+    ARG_CHECK(c, nbr && out, "null argument");
+    for (int64_t e = 0; e < total; e++) ARG_CHECK(c, nbr[e] >= 0 && nbr[e] < n, "neighbor index out of range");
+    const size_t off_b = ((size_t)(n + 1) * 8 + 255) & ~(size_t)255, nbr_b = ((size_t)total * 4 + 255) & ~(size_t)255;
+    int rc = scratch_reserve(c, off_b + nbr_b + (size_t)total * sizeof(sph_ParticleInteraction));
+    if (rc) return rc;
+    int64_t* off_d = (int64_t*)c->scratch_d;
+    int32_t* nbr_d = (int32_t*)((char*)c->scratch_d + off_b);
+    sph_ParticleInteraction* out_d = (sph_ParticleInteraction*)((char*)c->scratch_d + off_b + nbr_b);
+    SPH_CK(c, cudaMemcpyAsync(off_d, offsets, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, c->stream));
+    SPH_CK(c, cudaMemcpyAsync(nbr_d, nbr, (size_t)total * 4, cudaMemcpyHostToDevice, c->stream));
+    if ((rc = sph_launch_interactions(c, total, off_d, nbr_d, out_d))) return rc;
+    SPH_CK(c, cudaMemcpyAsync(out, out_d, (size_t)total * sizeof(sph_ParticleInteraction), cudaMemcpyDeviceToHost, c->stream));
+    SPH_CK(c, cudaStreamSynchronize(c->stream));
+    return SPH_OK;
 }
 
 int sphb200_download_sort(sph_handle c, uint32_t* order, uint32_t* keys, sph_GridParams* grid) {
@@ -765,7 +799,7 @@ int sphb200_device_ptr(sph_handle c, const char* name, void** ptr, int64_t* byte
         {"orig", c->orig[c->cur], 4}, {"ncount", c->ncount, 4}, {"npart", c->npart, 4}, {"napprox", c->napprox, 4},
     };
     for (auto& t : tab)
-        if (strcmp(t.nm, name) == 0) { *ptr = t.p; if (bytes) *bytes = (int64_t)(t.el * (size_t)c->cap); return SPH_OK; }
+        if (strcmp(t.nm, name) == 0) { *ptr = t.p; if (t.p == (void*)c->posh[c->cur]) c->h_bound = INFINITY;   /* the caller may write h */ if (bytes) *bytes = (int64_t)(t.el * (size_t)c->cap); return SPH_OK; }
     c->err = std::string("unknown array name: ") + name;
     return SPH_ERR_INVALID_ARG;
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <math.h>
 #include <string>
 #include <vector>
 #include "../../include/sphb200.h"
@@ -61,6 +62,8 @@ struct sphb200_ctx {
     float4* tbox = nullptr;      // all-pairs: bounding box (lo, hi) of every 256-source tile
     bool equal_mass = false;     // every uploaded particle has the same mass (ParticleAuthoring.cs:208)
     float common_mass = 0.f;
+    float h_bound = INFINITY;    // host-side upper bound of every resident h (upload value x the controller's largest growth per update):
+                                 // below 1e5 the literal-kernel neighbor pass (k_neighbors_density) cannot be needed and is not launched
     float4* gpart = nullptr;     // all-pairs partial sums [splits][n]
     int gpart_splits = 0;
     float4* gsrc = nullptr;      // gravity sources (x,y,z,m) in GLOBAL sorted order: posm for a single handle, the all-gathered
@@ -95,11 +98,15 @@ struct sphb200_ctx {
     void* stage_d = nullptr;     // upload/download staging (device)
     void* stage_h = nullptr;     // pinned host staging
     size_t stage_bytes = 0;
+    void* scratch_d = nullptr;   // grow-only device scratch of the list/record downloads (no cudaMalloc per call once sized)
+    size_t scratch_bytes = 0;
 
     bool resident = false, lists_valid = false, pressure_valid = false, gravity_valid = false, tree_valid = false;
     bool h_updated = false;      // bounds/grid params computed for the current positions and h
     bool sorted_valid = false;   // sort + cell table match the current positions and h
     bool lists_fresh = false;    // neighbor lists/density belong to the current positions and h
+    bool nown_aligned = false;   // nown[] is index-aligned with posh[cur] (true after upload and after the density pass; a sort
+                                 // permutes the slots but not nown, which the next density pass rewrites)
     // overlapped LBVH build (sphb200_prepare_gravity): built on aux_stream while the neighbor pass runs on `stream`
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
@@ -202,7 +209,7 @@ int sph_launch_keys(sphb200_ctx* c, const float4* posh, int n, uint32_t* keys);
 int sph_launch_rowscan(sphb200_ctx* c, uint32_t* rows_d, int nblocks, int rows, uint32_t* totals, cudaStream_t stream);
 int sph_launch_neighbors_density(sphb200_ctx* c);
 int sph_launch_pressure(sphb200_ctx* c);
-int sph_launch_gravity_near(sphb200_ctx* c);
+int sph_launch_gravity_near(sphb200_ctx* c, int impl);
 int sph_launch_integrate(sphb200_ctx* c, float dt);
 int sph_launch_gravity_allpairs(sphb200_ctx* c);
 int sph_launch_tree_build(sphb200_ctx* c, float dt, cudaStream_t stream);

@@ -691,6 +691,7 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
         c->skeys = c->keys[0];
         c->cur = 0;
         c->resident = true;
+        c->h_bound = grid.hmax;   // the global maximum of this step (all-reduced bounds): exact, covers the halo too
     }
     pass_mark(g, "halo_exchange_cells");
 
@@ -771,8 +772,9 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
         FOR_RANKS(g, R) {
             G_CUDA(g, cudaSetDevice(R.device));
             if (R.n_own <= 0) continue;
-            if (impl == SPH_GRAVITY_PARTICLE) { G_RC(g, R, sph_launch_gravity_allpairs(R.c)); G_RC(g, R, sph_launch_gravity_near(R.c)); }
+            if (impl == SPH_GRAVITY_PARTICLE) G_RC(g, R, sph_launch_gravity_allpairs(R.c));
             else G_RC(g, R, sph_launch_tree_walk(R.c));
+            G_RC(g, R, sph_launch_gravity_near(R.c, impl));
         }
     }
     pass_mark(g, gname);

@@ -606,7 +606,9 @@ int sph_launch_neighbors_density(sphb200_ctx* c) {
                                                                          (int)c->row_base, c->p.max_neighbors, c->p.K, c->nown, c->rho, c->press, c->cvol);
     }
     SPH_LAUNCH_CHECK(c);
-    // literal-kernel variant: exits at once unless h_max >= 1e5 (decided on the device: no host sync)
+    // literal-kernel variant: needed only when h_max >= 1e5 (decided on the device: no host sync); not launched at all while the
+    // host-side bound of h (ctx.cuh h_bound) rules that out
+    if (c->h_bound < kHugeH) return SPH_OK;
     int per_block = K1_WARPS * K1_TPW;
     k_neighbors_density<<<min(sph_div_up(nt, per_block), c->sm_count * 4), K1_WARPS * 32, 0, c->stream>>>(
         c->posh[c->cur], c->posm, c->skeys, c->cell_start, c->cell_end, c->cell_hmax, c->grid_d, t0, t1, (int)c->row_base, c->p.max_neighbors,

@@ -110,11 +110,38 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 6) k_pressure_grad(const float4
     if (live) gradp[t] = make_float4(0.5f * acc[0], 0.5f * acc[1], 0.5f * acc[2], 0.f);
 }
 
-// Near-pair correction of the all-pairs gravity kernel (kernels_gravity.cu): for neighbors with r < a = h_i add
-// "Dyer & Ip softened law minus the capped Newtonian value the all-pairs kernel already summed"
-// (GravityFieldSystem.cs:340-347).  Every such pair is in i's list because r < h_i < 2 max(h_i,h_j).
+// Near-pair correction of the gravity kernels, from the neighbor lists: adds, for every listed neighbor j of i,
+//     [pair law that should hold]  -  [what the main gravity kernel has already summed for the pair].
+// BASE (what was summed): CAPPED = the all-pairs kernel's Newtonian value with r capped at a = h_i (kernels_gravity.cu);
+//                         DYER   = the tree walk's P2P law (Dyer & Ip inside a = h_i, Newtonian outside).
+// LAW  (what should hold): reference = Dyer & Ip softened inside a = h_i, Newtonian outside (GravityFieldSystem.cs:340-347) --
+//     with CAPPED this is non-zero only for r < h_i, and every such pair is in i's list because r < h_i < 2 max(h_i,h_j);
+//     SPH_FLAG_PM07_SOFTENING (off by default; roadmap README.md:75-77 "Gravity kernel which conserves energy, see Price &
+//     Monaghan 2007") = the force softened with the cubic-spline kernel itself, symmetrised in the two smoothing lengths:
+//         grad Phi_i += G m_j (r_i - r_j)/r * 0.5 [phi'(r,h_i) + phi'(r,h_j)],   Phi_i += G m_j 0.5 [phi(r,h_i) + phi(r,h_j)]
+//     (P&M 2007 appendix A; phi' = 1/r^2 and phi = -1/r beyond 2h).  It differs from Newton exactly for r < 2 max(h_i,h_j): the
+//     neighbor list.  Pairwise antisymmetric (gravity then conserves momentum, unlike the one-sided a = h_i law) and
+//     derivable from a potential for fixed h; P&M's extra term for h that varies in time (their zeta / Omega) is not included.
+//     In tree mode a listed neighbor that the walk absorbed into an accepted node (possible only under extreme h contrast) is
+//     corrected as if it had been summed as a point mass.
+__device__ __forceinline__ void pm07_kernel(float r, float hinv, float rinv, float& fr, float& phi) {   // phi'/r and phi of one h
+    const float q = r * hinv, q2 = q * q, h3 = hinv * hinv * hinv;
+    if (q < 1.0f) {
+        fr = h3 * (4.0f / 3.0f + q2 * (-1.2f + 0.5f * q));
+        phi = hinv * (q2 * (2.0f / 3.0f + q2 * (-0.3f + 0.1f * q)) - 1.4f);
+    } else if (q < 2.0f) {
+        const float qi = rinv / hinv;   // 1/q
+        fr = h3 * (8.0f / 3.0f - 3.0f * q + q2 * (1.2f - q * (1.0f / 6.0f)) - (1.0f / 15.0f) * qi * qi * qi);
+        phi = hinv * (q2 * (4.0f / 3.0f - q + q2 * (0.3f - q * (1.0f / 30.0f))) - 1.6f + (1.0f / 15.0f) * qi);
+    } else {
+        fr = rinv * rinv * rinv;
+        phi = -rinv;
+    }
+}
+
 constexpr int K2_LPT = 16;
 
+template <bool BASE_CAPPED, bool PM07>
 __global__ void __launch_bounds__(256) k_gravity_near(const float4* __restrict__ posh, const float4* __restrict__ posm,
                                                       const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
                                                       int t0, int t1, int rowbase, int kmax, float G, float4* __restrict__ grav) {
@@ -133,13 +160,37 @@ __global__ void __launch_bounds__(256) k_gravity_near(const float4* __restrict__
             float4 pj = posm[j];
             float dx = pi.x - pj.x, dy = pi.y - pj.y, dz = pi.z - pj.z;
             float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));   // same expression as the all-pairs kernel
-            if (r2 < a2) {
-                float r = r2 > 0.f ? r2 * rsqrtf(r2) : 0.f;
-                float x = r * hinv_i, x2 = x * x, x3 = x2 * x;
-                float ma = pj.w * hinv_i;
-                float mg = ma * hinv_i * hinv_i * (7.0f - 9.0f * x + 2.0f * x3);
+            if (!PM07) {
+                if (BASE_CAPPED && r2 < a2) {
+                    float r = r2 > 0.f ? r2 * rsqrtf(r2) : 0.f;
+                    float x = r * hinv_i, x2 = x * x, x3 = x2 * x;
+                    float ma = pj.w * hinv_i;
+                    float mg = ma * hinv_i * hinv_i * (7.0f - 9.0f * x + 2.0f * x3);
+                    gx = fmaf(dx, mg, gx); gy = fmaf(dy, mg, gy); gz = fmaf(dz, mg, gz);
+                    gp -= ma * (1.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
+                }
+            } else {
+                const float hj = posh[j].w;
+                const float rinv = rsqrtf(fmaxf(r2, 1.0e-37f));
+                const float r = r2 * rinv;
+                float fi, pi_, fj, pj_;
+                pm07_kernel(r, hinv_i, rinv, fi, pi_);
+                pm07_kernel(r, 1.0f / hj, rinv, fj, pj_);
+                float f = 0.5f * (fi + fj), p = 0.5f * (pi_ + pj_);
+                // minus what the main kernel summed
+                if (BASE_CAPPED) {
+                    const float ci = rsqrtf(fmaxf(r2, a2));
+                    f -= ci * ci * ci; p += ci;
+                } else if (r2 < a2) {
+                    const float x = r * hinv_i, x2 = x * x, x3 = x2 * x;
+                    f -= hinv_i * hinv_i * hinv_i * (8.0f - 9.0f * x + 2.0f * x3);
+                    p += hinv_i * (2.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
+                } else {
+                    f -= rinv * rinv * rinv; p += rinv;
+                }
+                const float mg = pj.w * f;
                 gx = fmaf(dx, mg, gx); gy = fmaf(dy, mg, gy); gz = fmaf(dz, mg, gz);
-                gp -= ma * (1.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
+                gp = fmaf(pj.w, p, gp);
             }
         }
     }
@@ -200,6 +251,11 @@ __global__ void __launch_bounds__(256) k_pack_upload(const float* __restrict__ s
         const uint32_t mo = i < n ? f2ord(st[6 * (size_t)n + i]) : 0u;
         const uint32_t lo = __reduce_min_sync(FULL, i < n ? mo : 0xffffffffu), hi = __reduce_max_sync(FULL, mo);
         if ((threadIdx.x & 31) == 0 && lo <= hi) { atomicMin(&mm[0], lo); atomicMax(&mm[1], hi); }
+        // largest uploaded h (NaN and negative values count as +inf: the host then keeps the literal-kernel pass armed)
+        float hv = 0.f;
+        if (i < n) { hv = has_nown == 2 ? st[7 * (size_t)n + 7 * (size_t)i] : st[7 * (size_t)n + i]; if (!(hv >= 0.f)) hv = INFINITY; }
+        const uint32_t hm = __reduce_max_sync(FULL, __float_as_uint(hv));
+        if ((threadIdx.x & 31) == 0) atomicMax(&mm[2], hm);
     }
     if (i >= n) return;
     const float* pos = st;
@@ -398,13 +454,19 @@ int sph_launch_pressure(sphb200_ctx* c) {
     return SPH_OK;
 }
 
-int sph_launch_gravity_near(sphb200_ctx* c) {
+// impl = the gravity kernel that has just run (SPH_GRAVITY_PARTICLE / SPH_GRAVITY_TREE); see k_gravity_near
+int sph_launch_gravity_near(sphb200_ctx* c, int impl) {
     int t0, t1; target_range(c, t0, t1);
     int nt = t1 - t0;
     if (nt <= 0) return SPH_OK;
+    const bool pm07 = (c->p.flags & SPH_FLAG_PM07_SOFTENING) != 0;
+    if (impl == SPH_GRAVITY_TREE && !pm07) return SPH_OK;      // the walk applies the reference's softened law itself
     int tpb = 256 / K2_LPT;
-    k_gravity_near<<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->posm, c->nlist, c->ncount, t0, t1,
-                                                               (int)c->row_base, c->p.max_neighbors, c->p.G, c->grav);
+#define NEAR_LAUNCH(B, P) k_gravity_near<B, P><<<sph_div_up(nt, tpb), 256, 0, c->stream>>>(c->posh[c->cur], c->posm, c->nlist, c->ncount, t0, t1, \
+                                                                                        (int)c->row_base, c->p.max_neighbors, c->p.G, c->grav)
+    if (impl == SPH_GRAVITY_PARTICLE) { if (pm07) NEAR_LAUNCH(true, true); else NEAR_LAUNCH(true, false); }
+    else NEAR_LAUNCH(false, true);
+#undef NEAR_LAUNCH
     SPH_LAUNCH_CHECK(c);
     return SPH_OK;
 }

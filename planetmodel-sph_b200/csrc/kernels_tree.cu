@@ -234,14 +234,29 @@ __device__ __forceinline__ u64 add2(u64 a, u64 b) { u64 r; asm("add.rn.f32x2 %0,
 __device__ __forceinline__ u64 fma2(u64 a, u64 b, u64 c) { u64 r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
 
 
-// softened pair law inside a = h_i (GravityFieldSystem.cs:340-347, Dyer & Ip)
+// Inside a = h_i the pair law is Dyer & Ip's (GravityFieldSystem.cs:340-347): g = (m/a^3)(8 - 9x + 2x^3), phi = -(m/a)(2.4 - 4x^2 +
+// 3x^3 - 0.4x^5), x = r/a.  The packed loop has already summed the capped Newtonian value (m/a^3, -m/a) for the pair: this adds the rest.
 __device__ __forceinline__ void p2p_soft(WalkAcc& w, float ex, float ey, float ez, float r2, float m, float ainv) {
     const float r = r2 > 0.f ? r2 * rsqrt_approx(r2) : 0.f;
     const float x = r * ainv, x2 = x * x, x3 = x2 * x;
     const float ma = m * ainv;
-    const float g = ma * ainv * ainv * (8.0f - 9.0f * x + 2.0f * x3);
+    const float g = ma * ainv * ainv * (7.0f - 9.0f * x + 2.0f * x3);
     w.gx = fmaf(ex, g, w.gx); w.gy = fmaf(ey, g, w.gy); w.gz = fmaf(ez, g, w.gz);
-    w.gp -= ma * (2.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
+    w.gp -= ma * (1.4f - 4.0f * x2 + 3.0f * x3 - 0.4f * x2 * x3);
+}
+
+// One body of the packed P2P sequence: m <- (W & BIT) ? m : 0, and BIT is recorded in `soft` when the body is the lane's and lies
+// inside the softening radius.  PTX so that the bit test stays one LOP3 with a predicate result (the compiler's own lowering of
+// (W & BIT) != 0 is a shift, a mask and a compare per body).
+template <unsigned BIT>
+__device__ __forceinline__ void tw_mask_body(unsigned W, float& m, float r2, float a2, unsigned& soft) {
+    asm("{\n\t.reg .pred p, q;\n\t.reg .b32 t;\n\t"
+        "and.b32 t, %2, %5;\n\t"
+        "setp.ne.u32 p, t, 0;\n\t"
+        "selp.f32 %0, %0, 0f00000000, p;\n\t"
+        "setp.lt.and.f32 q, %3, %4, p;\n\t"
+        "@q or.b32 %1, %1, %5;\n\t}"
+        : "+f"(m), "+r"(soft) : "r"(W), "f"(r2), "f"(a2), "n"(BIT));
 }
 
 // 32x32 bit-matrix transpose across the warp: in: lane i holds row i, out: lane j holds column j
@@ -380,28 +395,62 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
                 bfirst += c4; brem -= c4;
                 __syncwarp();
                 const ulonglong2* recs = reinterpret_cast<const ulonglong2*>(sbf);
-#pragma unroll 2
-                for (int k = 0; k < total; k += 2) {
-                    const ulonglong2 A = recs[k], B = recs[k + 1];   // (x0,x1),(y0,y1) | (z0,z1),(m0,m1)
-                    const uint2 mk = *reinterpret_cast<const uint2*>(sbm + k);
-                    const bool m0 = (mk.x >> lane) & 1u, m1 = (mk.y >> lane) & 1u;
-                    const u64 ex = sub2(pix, A.x), ey = sub2(piy, A.y), ez = sub2(piz, B.x);
-                    const u64 r2 = fma2(ez, ez, fma2(ey, ey, mul2(ex, ex)));
-                    float ra, rb, ma, mb;
-                    upk2(r2, ra, rb);
-                    upk2(B.y, ma, mb);
-                    const bool s0 = m0 && ra < a2, s1 = m1 && rb < a2;   // inside the softening radius: scalar law below
-                    const u64 rinv = pk2(rsqrt_approx(fmaxf(ra, a2)), rsqrt_approx(fmaxf(rb, a2)));
-                    const u64 mr = mul2(pk2(m0 && !s0 ? ma : 0.f, m1 && !s1 ? mb : 0.f), rinv);
-                    const u64 g = mul2(mr, mul2(rinv, rinv));
-                    gx2 = fma2(ex, g, gx2); gy2 = fma2(ey, g, gy2); gz2 = fma2(ez, g, gz2);
-                    gp2 = sub2(gp2, mr);
-                    w.np += (m0 ? 1 : 0) + (m1 ? 1 : 0);
-                    if (s0 || s1) {
-                        float exa, exb, eya, eyb, eza, ezb;
-                        upk2(ex, exa, exb); upk2(ey, eya, eyb); upk2(ez, eza, ezb);
-                        if (s0) p2p_soft(w, exa, eya, eza, ra, ma, ainv);
-                        if (s1) p2p_soft(w, exb, eyb, ezb, rb, mb, ainv);
+                // The (body x lane) mask matrix is turned sideways 32 bodies at a time: lane = target then holds one word whose
+                // bit k says "body k of the chunk is mine" -- no mask load or variable shift per body, and numParticles is one
+                // popc per chunk.  Every listed body is summed with the all-pairs kernel's capped Newtonian law (r capped at
+                // a = h_i, kernels_gravity.cu); the few bodies inside a get "Dyer & Ip minus capped" in the branch below.
+                for (int c0 = 0; c0 < total; c0 += 32) {
+                    unsigned W = transpose32(c0 + lane < total ? sbm[c0 + lane] : 0u, lane);
+                    w.np += __popc(W);
+                    // The chunk's pairs run through one straight-line sequence of 16 pair evaluations entered at 16 - npair
+                    // (fall-through switch: no exit test and no shift per pair); pair q of the sequence is the chunk's pair
+                    // q - (16 - npair), so the mask word and the record pointer are aligned to the END of the sequence.
+                    const int npair = (min(total - c0, 32) + 1) >> 1, skip = 16 - npair;
+                    const ulonglong2* rp = recs + c0 - 2 * skip;
+                    W <<= 2 * skip;
+                    unsigned soft = 0u;   // bodies inside the softening radius (rare: finished after the sequence)
+#define TW_PAIR(q)                                                                                                              \
+                    {                                                                                                           \
+                        const ulonglong2 A = rp[2 * (q)], B = rp[2 * (q) + 1]; /* (x0,x1),(y0,y1) | (z0,z1),(m0,m1) */          \
+                        const u64 ex = sub2(pix, A.x), ey = sub2(piy, A.y), ez = sub2(piz, B.x);                                \
+                        const u64 r2 = fma2(ez, ez, fma2(ey, ey, mul2(ex, ex)));                                                \
+                        float ra, rb, ma, mb;                                                                                   \
+                        upk2(r2, ra, rb);                                                                                       \
+                        upk2(B.y, ma, mb);                                                                                      \
+                        tw_mask_body<(1u << (2 * (q)))>(W, ma, ra, a2, soft);                                                   \
+                        tw_mask_body<(2u << (2 * (q)))>(W, mb, rb, a2, soft);                                                   \
+                        const u64 rinv = pk2(rsqrt_approx(fmaxf(ra, a2)), rsqrt_approx(fmaxf(rb, a2)));                         \
+                        const u64 mr = mul2(pk2(ma, mb), rinv);                                                                 \
+                        const u64 g = mul2(mr, mul2(rinv, rinv));                                                               \
+                        gx2 = fma2(ex, g, gx2); gy2 = fma2(ey, g, gy2); gz2 = fma2(ez, g, gz2);                                 \
+                        gp2 = sub2(gp2, mr);                                                                                    \
+                    }
+                    switch (skip) {
+                        case 0: TW_PAIR(0)
+                        case 1: TW_PAIR(1)
+                        case 2: TW_PAIR(2)
+                        case 3: TW_PAIR(3)
+                        case 4: TW_PAIR(4)
+                        case 5: TW_PAIR(5)
+                        case 6: TW_PAIR(6)
+                        case 7: TW_PAIR(7)
+                        case 8: TW_PAIR(8)
+                        case 9: TW_PAIR(9)
+                        case 10: TW_PAIR(10)
+                        case 11: TW_PAIR(11)
+                        case 12: TW_PAIR(12)
+                        case 13: TW_PAIR(13)
+                        case 14: TW_PAIR(14)
+                        default: TW_PAIR(15)
+                    }
+#undef TW_PAIR
+                    soft >>= 2 * skip;
+                    while (soft) {
+                        const int b = __ffs(soft) - 1;
+                        soft &= soft - 1u;
+                        const float* rec = sbf + ((c0 + b) >> 1) * 8 + (b & 1);
+                        const float ex = pi.x - rec[0], ey = pi.y - rec[2], ez = pi.z - rec[4];
+                        p2p_soft(w, ex, ey, ez, fmaf(ez, ez, fmaf(ey, ey, ex * ex)), rec[6], ainv);
                     }
                 }
                 __syncwarp();

@@ -27,6 +27,7 @@ SPH_ERR_NCCL = -7
 GRAVITY_TREE, GRAVITY_PARTICLE, GRAVITY_NONE = 0, 1, 2
 FLAG_FIX_KERNEL_DERIV_SIGN = 1
 FLAG_KICK_DRIFT = 2
+FLAG_PM07_SOFTENING = 4     # Price & Monaghan 2007 spline-softened, h-symmetric gravity (reference roadmap README.md:75-77)
 
 (FIELD_TRANSLATION, FIELD_VELOCITY, FIELD_MASS, FIELD_SMOOTHING, FIELD_DENSITY, FIELD_PRESSURE, FIELD_PRESSURE_GRAD,
  FIELD_GRAVITY, FIELD_NEIGHBOR_COUNT) = range(9)

@@ -612,3 +612,47 @@ def test_kick_drift_flag_matches_oracle_and_conserves_energy_better(orc):
             e0 = e if e0 is None else e0
         drift[flags] = abs(e - e0) / abs(e0)
     assert drift[sphb200.FLAG_KICK_DRIFT] <= drift[0] * 1.05
+
+
+def test_pm07_softening_flag_direct_and_tree_vs_oracle_and_momentum(orc):
+    """SPH_FLAG_PM07_SOFTENING (off by default; reference roadmap README.md:75-77): gravity softened with the spline kernel,
+    symmetric in h_i and h_j.  The GPU builds it as main kernel + neighbor-list correction in fp32; the oracle sums the pair law
+    from scratch in double (direct) or adds the same correction to its own tree walk (tree).  Tolerance 1e-5 |g_i| (+ the
+    ill-conditioned-centre floor of compare_step).  Pairwise antisymmetry: sum m_i g_i vanishes to fp32 rounding, which the
+    reference's one-sided a = h_i law does not do."""
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_sphere(4000, seed=12)
+    rng = np.random.default_rng(5)
+    c["h"] = (c["h"] * rng.uniform(0.7, 1.6, len(c["h"]))).astype(np.float32)      # unequal h: the symmetrisation matters
+    c["mass"] = (c["mass"] * rng.uniform(0.5, 2.0, len(c["h"]))).astype(np.float32)
+    res = {}
+    for impl, name in ((sphb200.GRAVITY_PARTICLE, "direct"), (sphb200.GRAVITY_TREE, "tree")):
+        sim = run_gpu_step(c, 1 / 60, impl, flags=sphb200.FLAG_PM07_SOFTENING)
+        got = sim.download_all()
+        h = got["h"]                                                                # h after the controller (bit-exact, tested elsewhere)
+        off, nbr = sim.download_neighbors()
+        if name == "direct":
+            ref = orc.gravity_direct_pm07(c["pos"], h, c["mass"])
+        else:
+            p = sim.effective_params()
+            base, npart, napprox, _, _ = orc.tree_gravity(c["pos"], c["vel"], h, c["mass"], 1 / 60, p.theta, p.G, p.leaf_max, p.aabb_mode,
+                                                          p.max_grid_bits, True)
+            np.testing.assert_array_equal(got["num_particles"], npart)
+            ref = base + orc.gravity_pm07_correction(c["pos"], h, c["mass"], off.astype(np.int64), nbr)
+        gfloor = 1e-6 * np.median(np.linalg.norm(ref[:, :3], axis=1))
+        vec_close(got["grav"][:, :3], ref[:, :3], what="PM07 gradPhi " + name, floor=gfloor)
+        np.testing.assert_allclose(got["grav"][:, 3], ref[:, 3], rtol=RTOL)
+        res[name] = got["grav"].copy()
+        sim.close()
+    # the tree answer approaches the direct one (theta = 0.7 monopoles: per cent level) -- same law on both paths
+    rel = np.linalg.norm(res["tree"][:, :3] - res["direct"][:, :3], axis=1) / np.linalg.norm(res["direct"][:, :3], axis=1).mean()
+    assert np.median(rel) < 2e-2
+    # momentum: |sum m g| / sum m |g|
+    m = c["mass"][:, None].astype(np.float64)
+    sim = run_gpu_step(c, 1 / 60, sphb200.GRAVITY_PARTICLE)
+    g_ref_law = sim.download_all()["grav"][:, :3].astype(np.float64); sim.close()
+    g_pm = res["direct"][:, :3].astype(np.float64)
+    net = lambda g: np.linalg.norm((m * g).sum(0)) / (m * np.linalg.norm(g, axis=1, keepdims=True)).sum()
+    assert net(g_pm) < 2e-6
+    assert net(g_pm) < net(g_ref_law)

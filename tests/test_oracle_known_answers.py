@@ -436,3 +436,39 @@ def test_reference_job_path_equals_the_oracle_step(orc):
     g4, npart, napp, _ = orc.tree4_gravity(c["pos"], c["vel"], c["h"], c["mass"], 1 / 60)
     np.testing.assert_array_equal(t.grav, g4)
     np.testing.assert_array_equal(t.num_particles, npart)
+
+
+# ------------------------------------------------------------------ non-reference option: P&M 2007 softening (roadmap README.md:75-77)
+def test_pm07_kernel_is_continuous_newtonian_outside_and_a_gradient(orc):
+    """phi and phi'/r of the spline-softened potential: continuous at q = 1 and q = 2, Newtonian beyond 2h, phi' = d phi / dr
+    (central differences), phi(0) = -7/(5h)."""
+    for h in (0.3, 1.0, 2.5):
+        for rb in (h, 2 * h):
+            lo = orc.pm07_kernel(rb * (1 - 1e-12), h); hi = orc.pm07_kernel(rb * (1 + 1e-12), h)
+            assert lo[0] == pytest.approx(hi[0], rel=1e-9) and lo[1] == pytest.approx(hi[1], rel=1e-9)
+        f, p = orc.pm07_kernel(3.0 * h, h)
+        assert f == pytest.approx(1 / (3 * h) ** 3) and p == pytest.approx(-1 / (3 * h))
+        assert orc.pm07_kernel(1e-9, h)[1] == pytest.approx(-1.4 / h)
+        for r in np.linspace(0.05, 2.4, 48) * h:
+            e = 1e-6 * h
+            dphi = (orc.pm07_kernel(r + e, h)[1] - orc.pm07_kernel(r - e, h)[1]) / (2 * e)
+            assert orc.pm07_kernel(r, h)[0] * r == pytest.approx(dphi, rel=2e-6)
+
+
+def test_pm07_direct_sum_is_antisymmetric_and_newtonian_for_far_pairs(orc):
+    rng = np.random.default_rng(3)
+    n = 300
+    pos = rng.uniform(-1, 1, (n, 3)).astype(np.float32); h = rng.uniform(0.05, 0.4, n).astype(np.float32)
+    m = rng.uniform(0.5, 2, n).astype(np.float32)
+    g = orc.gravity_direct_pm07(pos, h, m).astype(np.float64)
+    net = (m[:, None] * g[:, :3]).sum(0)
+    assert np.abs(net).max() <= 1e-6 * (m[:, None] * np.abs(g[:, :3])).sum()
+    # two far particles: exactly Newton
+    pos2 = np.array([[0, 0, 0], [3, 0, 0]], np.float32); h2 = np.array([0.5, 1.0], np.float32); m2 = np.array([2.0, 5.0], np.float32)
+    g2 = orc.gravity_direct_pm07(pos2, h2, m2)
+    assert g2[0, 0] == pytest.approx(-5.0 / 9.0, rel=1e-6) and g2[0, 3] == pytest.approx(-5.0 / 3.0, rel=1e-6)
+    # correction over lists + reference law == PM07 from scratch
+    off, nbr = orc.neighbors(pos, h, "brute")
+    base = orc.gravity_direct(pos, h, m, accum_double=True)
+    corr = orc.gravity_pm07_correction(pos, h, m, off, nbr)
+    np.testing.assert_allclose(base + corr, g, rtol=2e-5, atol=2e-5 * np.abs(g).max())
