@@ -416,7 +416,7 @@ def measure_workload(args, workload, world, rank, local, headline):
         line["pass_ms_per_rank"] = {k: v for k, v in rank_ms.items() if max(v) > 0.5}
     if info is not None:
         line["decomposition"] = {"rank0_own": info["n_own"], "rank0_halo": info["n_halo"], "migrated_last_step": info["migrated_last_step"],
-                                 "transport": info["transport"]}
+                                 "tree_nodes_received_last_step": info.get("tree_nodes_last_step"), "transport": info["transport"]}
     eng.close()
     return line
 

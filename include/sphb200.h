@@ -236,6 +236,8 @@ typedef struct sph_GroupInfo {
     int64_t halo_last_step;       /* halo particles received in the last step (this process's ranks) */
     int64_t cap_own, cap_halo;    /* per-rank capacities: own slots, halo slots on either side */
     int64_t launches;             /* kernels launched by this process's ranks since create */
+    int64_t tree_nodes_last_step; /* walk-node records received in the last tree-gravity step (locally essential tree; this process's
+                                     ranks); -1 = the whole node array was all-gathered (records beyond the exchange capacity) */
     int64_t n_own[32], n_halo[32];/* per local rank */
 } sph_GroupInfo;
 

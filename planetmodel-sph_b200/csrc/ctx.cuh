@@ -72,6 +72,11 @@ struct sphb200_ctx {
     // resident slot of global slot s is s + tree_off
     uint32_t* tkeys = nullptr;
     int64_t tree_n = 0, tree_g0 = 0, tree_g1 = 0, tree_off = 0;
+    // particle records the LBVH build reads: slot s of the tree at tree_posh[s + tree_src_off] (null: the resident posh / velm at
+    // s + tree_off).  A group rank builds from the sorted own records before its extended resident set is assembled.
+    const float4* tree_posh = nullptr;
+    const float4* tree_velm = nullptr;
+    int64_t tree_src_off = 0;
     TopNode* top_nodes = nullptr;     // [world][SPH_TOP_CAP] (own segment filled by the build, the rest all-gathered)
     FrontNode* front_nodes = nullptr; // [world][SPH_TOP_CAP]
     int32_t* top_counts = nullptr;    // [world][4]: top nodes, frontier nodes

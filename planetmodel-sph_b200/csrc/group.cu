@@ -94,6 +94,11 @@ struct GroupRank {
     float4* posm_g = nullptr;
     uint32_t* keys_g = nullptr;
     float4* bnd = nullptr;           // [world][2][SPH_TOP_LEAF][2]
+    // locally essential tree exchange (kernels_group.cu k_let_*)
+    uint32_t *let_mask = nullptr, *let_cnt = nullptr, *let_cursor = nullptr, *let_soff = nullptr, *let_box = nullptr, *lcnt_d = nullptr;
+    float4 *let_send = nullptr, *let_recv = nullptr;
+    float4 *tposh = nullptr, *tvelm = nullptr;   // own particles in sorted order (what the LBVH build reads)
+    uint32_t* lcnt_h = nullptr;      // pinned [world][world]
     void* red_scratch = nullptr;     // in-process transport
     size_t red_bytes = 0;
     // pinned host mirrors
@@ -113,7 +118,8 @@ struct sphb200_group {
     sph_Params p{};
     int world = 1, nlocal = 1, rank0 = 0;
     bool local = false;               // in-process transport (every rank is local)
-    int64_t cap_total = 0, cap_own = 0, cap_halo = 0, cap_ext = 0;
+    int64_t cap_total = 0, cap_own = 0, cap_halo = 0, cap_ext = 0, cap_let = 0;
+    int64_t last_let = 0;             // walk-node records received by the local ranks in the last tree step (-1: full all-gather)
     int64_t n_total = 0, chunk = 0;
     std::vector<GroupRank> r;
     std::vector<int64_t> g0;          // global slot ranges of the ranks, world+1 (after the first step)
@@ -126,6 +132,10 @@ struct sphb200_group {
     const char* pass_name[SPH_MAX_PASSES];
     cudaEvent_t tev[SPH_MAX_PASSES + 1];
     bool tev_created = false;
+    // the auxiliary lane of the step (gravity sources / tree exchange): events on the first local rank's auxiliary stream
+    int naux = 0, aux_fork_pass = 0;
+    const char* aux_name[12];
+    cudaEvent_t aev[13];
     std::string err;
 };
 
@@ -313,6 +323,19 @@ int aux_begin(sphb200_group* g) {
     }
     return SPH_OK;
 }
+// leave the auxiliary lane without closing it (no join event): the lane is resumed later in the step
+int aux_pause(sphb200_group* g) {
+    FOR_RANKS(g, R) { R.c->stream = R.main_stream; R.comm = R.comm_main; }
+    return SPH_OK;
+}
+int aux_resume(sphb200_group* g) {
+    FOR_RANKS(g, R) {
+        R.main_stream = R.c->stream;
+        R.c->stream = R.c->aux_stream;
+        if (!g->local) R.comm = R.comm_aux;
+    }
+    return SPH_OK;
+}
 int aux_end(sphb200_group* g) {
     FOR_RANKS(g, R) {
         G_CUDA(g, cudaSetDevice(R.device));
@@ -341,10 +364,21 @@ void pass_begin(sphb200_group* g) {
     cudaSetDevice(R.device);
     if (!g->tev_created) {
         for (int i = 0; i <= SPH_MAX_PASSES; i++) cudaEventCreate(&g->tev[i]);
+        for (int i = 0; i < 13; i++) cudaEventCreate(&g->aev[i]);
         g->tev_created = true;
     }
     g->npass = 0;
+    g->naux = 0;
     cudaEventRecord(g->tev[0], R.c->stream);
+}
+// a mark on whatever stream rank 0 currently issues to (the auxiliary lane between aux_begin/aux_resume and aux_pause/aux_end)
+void aux_mark(sphb200_group* g, const char* name) {
+    if (!g->timing || g->naux >= 12) return;
+    GroupRank& R = g->r[0];
+    cudaSetDevice(R.device);
+    if (g->naux == 0) g->aux_fork_pass = g->npass;   // lane time is counted from the last main-lane mark (the fork point)
+    g->aux_name[g->naux++] = name;
+    cudaEventRecord(g->aev[g->naux], R.c->stream);
 }
 void pass_mark(sphb200_group* g, const char* name) {
     if (!g->timing || g->npass >= SPH_MAX_PASSES) return;
@@ -360,6 +394,8 @@ void free_rank(GroupRank& R) {
     if (R.c) cudaSetDevice(R.device);
     cudaFree(R.mig_send); cudaFree(R.mig_recv); cudaFree(R.dest); cudaFree(R.perm); cudaFree(R.tot256); cudaFree(R.hmask); cudaFree(R.hlist);
     cudaFree(R.hcnt); cudaFree(R.htot); cudaFree(R.halo_send); cudaFree(R.halo_recv); cudaFree(R.cv_send); cudaFree(R.hist); cudaFree(R.bpart); cudaFree(R.bmask);
+    cudaFree(R.tposh); cudaFree(R.tvelm); cudaFree(R.let_mask); cudaFree(R.let_cnt); cudaFree(R.let_cursor); cudaFree(R.let_soff); cudaFree(R.let_box); cudaFree(R.lcnt_d); cudaFree(R.let_send); cudaFree(R.let_recv);
+    if (R.lcnt_h) cudaFreeHost(R.lcnt_h);
     cudaFree(R.split_d); cudaFree(R.cnt_d); cudaFree(R.posm_g); cudaFree(R.keys_g); cudaFree(R.bnd); cudaFree(R.red_scratch);
     if (R.c) { cudaFree(R.c->top_nodes); cudaFree(R.c->front_nodes); cudaFree(R.c->top_counts); R.c->top_nodes = nullptr; R.c->front_nodes = nullptr; R.c->top_counts = nullptr; }
     if (R.cnt_h) cudaFreeHost(R.cnt_h);
@@ -388,6 +424,10 @@ int alloc_rank(sphb200_group* g, GroupRank& R) {
          dal(&R.hist, 2 * (size_t)SPH_NBINS) == cudaSuccess && dal(&R.bpart, 2 * (size_t)SPH_NBINS / 1024) == cudaSuccess && dal(&R.bmask, (size_t)SPH_NBINS) == cudaSuccess && dal(&R.split_d, 2 * (size_t)(W + 1)) == cudaSuccess &&
          dal(&R.cnt_d, (size_t)W * W) == cudaSuccess && dal(&R.posm_g, N) == cudaSuccess && dal(&R.keys_g, N) == cudaSuccess &&
          dal(&R.bnd, (size_t)W * 2 * SPH_TOP_LEAF * 2) == cudaSuccess &&
+         dal(&R.tposh, own) == cudaSuccess && dal(&R.tvelm, own) == cudaSuccess && dal(&R.let_mask, 2 * own) == cudaSuccess && dal(&R.let_cnt, (size_t)W) == cudaSuccess && dal(&R.let_cursor, (size_t)W) == cudaSuccess &&
+         dal(&R.let_soff, (size_t)W) == cudaSuccess && dal(&R.let_box, (size_t)W * 8) == cudaSuccess && dal(&R.lcnt_d, (size_t)W * W) == cudaSuccess &&
+         (W == 1 || (dal(&R.let_send, 3 * (size_t)g->cap_let) == cudaSuccess && dal(&R.let_recv, 3 * (size_t)g->cap_let) == cudaSuccess)) &&
+         cudaMallocHost((void**)&R.lcnt_h, (size_t)W * W * sizeof(uint32_t)) == cudaSuccess &&
          (!g->local || cudaMalloc(&R.red_scratch, R.red_bytes) == cudaSuccess) &&
          dal(&R.c->top_nodes, (size_t)W * SPH_TOP_CAP) == cudaSuccess && dal(&R.c->front_nodes, (size_t)W * SPH_TOP_CAP) == cudaSuccess &&
          dal(&R.c->top_counts, (size_t)W * 4) == cudaSuccess &&
@@ -418,6 +458,7 @@ int create_common(const sph_Params* params, int64_t capacity, int world, int ran
     g->cap_own = world == 1 ? capacity : std::min<int64_t>(capacity, 2 * share + 4096);
     g->cap_halo = world == 1 ? 0 : std::min<int64_t>(capacity, g->cap_own / 2 + 65536);
     g->cap_ext = g->cap_own + 2 * g->cap_halo;
+    g->cap_let = 2 * g->cap_own;      // walk-node records a rank may send / receive per step (beyond it: the full all-gather)
     g->r.resize(nlocal);
     for (int l = 0; l < nlocal; l++) { g->r[l].rank = rank0 + l; g->r[l].device = devices[l]; }
     for (int l = 0; l < nlocal; l++)
@@ -634,6 +675,128 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
         if ((rc = g_alltoallv(g, s.data(), d.data(), roff, M, 48))) return rc;
     }
     pass_mark(g, "migrate");
+    // 6a. gravity sources: all-gather of (x,y,z,m) in global sorted order; tree gravity also all-gathers the keys, builds the LBVH
+    // nodes of the own range, all-gathers the packed nodes and finishes the nodes that straddle rank boundaries.  None of it
+    // depends on the neighbor pass: it is issued first, on the auxiliary stream and communicator, and runs behind pass 5.
+    const char* gname = impl == SPH_GRAVITY_TREE ? "gravity_tree" : impl == SPH_GRAVITY_PARTICLE ? "gravity_allpairs" : "gravity_none";
+    // Part A (before the neighbor pass is issued): source / key all-gathers, LBVH build of the own range, top lists, and -- the
+    // walk nodes being far too many to all-gather (64 B x N per step) -- the selection of the nodes every other rank can reach
+    // (locally essential tree, kernels_group.cu k_let_*) with its count matrix on the way to the host.
+    const bool let_on = impl == SPH_GRAVITY_TREE && W > 1 && getenv("SPHB200_GROUP_NO_LET") == nullptr;
+    const GroupRank* l0 = &g->r[0];
+    auto gravity_part_a = [&]() -> int {
+        FOR_RANKS(g, R) {
+            G_CUDA(g, cudaSetDevice(R.device));
+            sphb200_ctx* c = R.c;
+            // from the sorted migration records: the extended resident set (posm, keys[0]) does not exist yet
+            G_RC(g, R, grk_sorted_sources(c, R.mig_recv, c->idx[1], c->keys[1], (int)R.n_own, R.posm_g + g->g0[R.rank],
+                                          impl == SPH_GRAVITY_TREE ? R.keys_g + g->g0[R.rank] : nullptr, R.tposh, R.tvelm));
+            c->gsrc = R.posm_g; c->gsrc_n = N;
+        }
+        { auto b = ptrs(g, [](GroupRank& R) { return R.posm_g; }); if ((rc = g_allgatherv(g, b.data(), g->g0.data(), 16))) return rc; }
+        if (impl != SPH_GRAVITY_TREE) { aux_mark(g, "gravity_aux_sources"); return SPH_OK; }
+        { auto b = ptrs(g, [](GroupRank& R) { return R.keys_g; }); if ((rc = g_allgatherv(g, b.data(), g->g0.data(), 4))) return rc; }
+        FOR_RANKS(g, R) {
+            G_CUDA(g, cudaSetDevice(R.device));
+            sphb200_ctx* c = R.c;
+            c->tkeys = R.keys_g; c->tree_n = N; c->tree_g0 = g->g0[R.rank]; c->tree_g1 = g->g0[R.rank + 1];
+            c->tree_posh = R.tposh; c->tree_velm = R.tvelm; c->tree_src_off = -g->g0[R.rank];
+            if (W > 1) G_CUDA(g, cudaMemsetAsync(c->top_counts + 4 * R.rank, 0, 4 * sizeof(int32_t), c->stream));
+            if (l0 == &R) aux_mark(g, "gravity_aux_sources_keys");
+            G_RC(g, R, sph_launch_tree_build(c, dt, c->stream));
+            if (W > 1) G_RC(g, R, grk_boundary(c, R.tposh, R.tvelm, (int)R.n_own, R.bnd + (size_t)R.rank * 2 * SPH_TOP_LEAF * 2));
+            if (l0 == &R) aux_mark(g, "gravity_aux_lbvh_build");
+        }
+        if (W > 1) {
+            { auto b = ptrs(g, [](GroupRank& R) { return R.c->top_nodes; }); if ((rc = g_allgather(g, b.data(), SPH_TOP_CAP * sizeof(TopNode)))) return rc; }
+            { auto b = ptrs(g, [](GroupRank& R) { return R.c->front_nodes; }); if ((rc = g_allgather(g, b.data(), SPH_TOP_CAP * sizeof(FrontNode)))) return rc; }
+            { auto b = ptrs(g, [](GroupRank& R) { return R.c->top_counts; }); if ((rc = g_allgather(g, b.data(), 4 * sizeof(int32_t)))) return rc; }
+            { auto b = ptrs(g, [](GroupRank& R) { return R.bnd; }); if ((rc = g_allgather(g, b.data(), 2 * SPH_TOP_LEAF * 2 * sizeof(float4)))) return rc; }
+            aux_mark(g, "gravity_aux_top_lists");
+        }
+        if (let_on) {
+            FOR_RANKS(g, R) {
+                G_CUDA(g, cudaSetDevice(R.device));
+                // the slots this rank walks: its targets and the companions that complete its first and last 32-slot group
+                const int64_t lo = g->g0[R.rank] & ~(int64_t)31, hi = std::min<int64_t>(N, (g->g0[R.rank + 1] + 31) & ~(int64_t)31);
+                G_RC(g, R, grk_let_box(R.c, R.posm_g, (int)lo, R.n_own > 0 ? (int)hi : (int)lo, R.let_box + 8 * (size_t)R.rank));
+            }
+            { auto b = ptrs(g, [](GroupRank& R) { return R.let_box; }); if ((rc = g_allgather(g, b.data(), 8 * sizeof(uint32_t)))) return rc; }
+            FOR_RANKS(g, R) {
+                G_CUDA(g, cudaSetDevice(R.device));
+                G_RC(g, R, grk_let_mask(R.c, R.let_box, W, R.rank, R.let_mask, R.let_cnt));
+                G_CUDA(g, cudaMemcpyAsync(R.lcnt_d + (size_t)R.rank * W, R.let_cnt, W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, R.c->stream));
+            }
+            { auto b = ptrs(g, [](GroupRank& R) { return R.lcnt_d; }); if ((rc = g_allgather(g, b.data(), W * sizeof(uint32_t)))) return rc; }
+            FOR_RANKS(g, R) {
+                G_CUDA(g, cudaSetDevice(R.device));
+                G_CUDA(g, cudaMemcpyAsync(R.lcnt_h, R.lcnt_d, (size_t)W * W * sizeof(uint32_t), cudaMemcpyDeviceToHost, R.c->stream));
+            }
+            aux_mark(g, "gravity_aux_let_select");
+        }
+        return SPH_OK;
+    };
+    // Part B (issued once the host has the count matrix; the device is busy with the neighbor pass meanwhile): the selected walk
+    // nodes travel to the ranks that can reach them and the straddling nodes are finished.
+    auto gravity_part_b = [&]() -> int {
+        if (impl != SPH_GRAVITY_TREE || W == 1) return SPH_OK;
+        bool let = let_on;
+        std::vector<std::vector<int64_t>> loff(g->nlocal, std::vector<int64_t>(W + 1, 0));
+        const uint32_t* L = g->r[0].lcnt_h;
+        if (let) {
+            FOR_RANKS(g, R) { G_CUDA(g, cudaSetDevice(R.device)); G_CUDA(g, cudaStreamSynchronize(R.c->stream)); }   // ---- host sync 3 (this lane only)
+            // every rank takes the same decision from the same matrix
+            for (int p = 0; p < W && let; p++) {
+                int64_t out = 0, in = 0;
+                for (int q = 0; q < W; q++) { out += L[p * W + q]; in += L[q * W + p]; }
+                if (out > g->cap_let || in > g->cap_let) let = false;
+            }
+        }
+        if (let) {
+            g->last_let = 0;
+            for (int l = 0; l < g->nlocal; l++) {
+                GroupRank& R = g->r[l];
+                const int me = R.rank;
+                uint32_t soff[SPH_MAX_RANKS];
+                uint32_t acc = 0;
+                for (int q = 0; q < W; q++) { soff[q] = acc; acc += L[me * W + q]; }
+                for (int p = 0; p < W; p++) loff[l][p + 1] = loff[l][p] + L[p * W + me];
+                g->last_let += loff[l][W];
+                G_CUDA(g, cudaSetDevice(R.device));
+                G_CUDA(g, cudaMemcpyAsync(R.let_soff, soff, W * sizeof(uint32_t), cudaMemcpyHostToDevice, R.c->stream));
+                G_RC(g, R, grk_let_pack(R.c, R.let_mask, W, R.let_soff, R.let_cursor, R.let_send));
+            }
+            {
+                auto sd = ptrs(g, [](GroupRank& R) { return R.let_send; });
+                auto rv = ptrs(g, [](GroupRank& R) { return R.let_recv; });
+                if ((rc = g_alltoallv(g, sd.data(), rv.data(), loff, L, 48))) return rc;
+            }
+            for (int l = 0; l < g->nlocal; l++) {
+                GroupRank& R = g->r[l];
+                G_CUDA(g, cudaSetDevice(R.device));
+                if (getenv("SPHB200_GROUP_LET_POISON")) {
+                    // test aid: every node record this rank neither built nor received reads as NaN / child -1, so a walk that
+                    // stepped outside its locally essential tree could not go unnoticed
+                    const int64_t a0 = g->g0[R.rank], a1 = g->g0[R.rank + 1];
+                    const int64_t seg[3][2] = {{0, a0}, {std::min<int64_t>(a1, N - 1), N - 1 + a0}, {N - 1 + a1, 2 * N - 1}};
+                    for (auto& sg : seg)
+                        if (sg[1] > sg[0]) G_CUDA(g, cudaMemsetAsync(R.c->packed + 2 * sg[0], 0xff, (size_t)(sg[1] - sg[0]) * 2 * sizeof(float4), R.c->stream));
+                }
+                G_RC(g, R, grk_let_scatter(R.c, R.let_recv, loff[l][W]));
+            }
+        } else {
+            // packed walk nodes of every rank's range: internal nodes [g0, g1) (ids < N-1) and leaves N-1+[g0, g1)
+            g->last_let = -1;
+            std::vector<int64_t> oi(W + 1), ol(W + 1);
+            for (int r = 0; r <= W; r++) { oi[r] = std::min<int64_t>(g->g0[r], N - 1); ol[r] = N - 1 + g->g0[r]; }
+            { auto b = ptrs(g, [](GroupRank& R) { return R.c->packed; }); if ((rc = g_allgatherv(g, b.data(), oi.data(), 32))) return rc; }
+            { auto b = ptrs(g, [](GroupRank& R) { return R.c->packed; }); if ((rc = g_allgatherv(g, b.data(), ol.data(), 32))) return rc; }
+        }
+        aux_mark(g, "gravity_aux_node_exchange");
+        FOR_RANKS(g, R) { G_CUDA(g, cudaSetDevice(R.device)); G_RC(g, R, sph_launch_top_tree(R.c, W, R.bnd, R.split_d, dt)); }
+        aux_mark(g, "gravity_aux_top_tree");
+        return SPH_OK;
+    };
     // 3. local stable sort of the received set
     for (int l = 0; l < g->nlocal; l++) {
         GroupRank& R = g->r[l];
@@ -643,6 +806,21 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
         G_RC(g, R, grk_mig_keys(c, R.mig_recv, (int)R.n_own, c->keys[1]));
         G_RC(g, R, sph_launch_radix_sort(c, (int)R.n_own, c->stream));
         if (l == 0) pass_mark(g, "sort");
+    }
+    // 3b. the own particles are final: the gravity lane (source / key all-gathers, LBVH build of the own range, selection of the
+    // walk nodes the other ranks can reach) starts here, on the auxiliary stream and communicator, behind the halo exchange and
+    // the neighbor pass
+    const bool overlap = impl != SPH_GRAVITY_NONE && aux_available(g);
+    if (overlap) {
+        if ((rc = aux_begin(g))) return rc;
+        const int rcg = gravity_part_a();
+        if ((rc = aux_pause(g))) return rc;     // always restores the main stream / communicator
+        if (rcg) return rcg;
+    }
+    for (int l = 0; l < g->nlocal; l++) {
+        GroupRank& R = g->r[l];
+        G_CUDA(g, cudaSetDevice(R.device));
+        sphb200_ctx* c = R.c;
         // 4. halo lists
         G_RC(g, R, grk_halo_lists(c, c->keys[1], (int)R.n_own, R.split_d, W, R.rank, R.bmask, R.hmask, R.hcnt, R.htot, R.hlist));
         G_CUDA(g, cudaMemcpyAsync(R.cnt_d + (size_t)R.rank * W, R.htot, W * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
@@ -688,59 +866,13 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
         sphb200_ctx* c = R.c;
         G_RC(g, R, grk_assemble_ext(c, R.mig_recv, c->idx[1], c->keys[1], R.halo_recv, (int)R.own0, (int)R.n_own, (int)R.n_ext, c->keys[0], ncell));
         c->n = R.n_ext; c->t0 = R.own0; c->t1 = R.own0 + R.n_own; c->row_base = R.own0;
+        c->tree_off = R.own0 - g->g0[R.rank];   // resident slot of global slot s (the walk's targets)
         c->skeys = c->keys[0];
         c->cur = 0;
         c->resident = true;
         c->h_bound = grid.hmax;   // the global maximum of this step (all-reduced bounds): exact, covers the halo too
     }
     pass_mark(g, "halo_exchange_cells");
-
-    // 6a. gravity sources: all-gather of (x,y,z,m) in global sorted order; tree gravity also all-gathers the keys, builds the LBVH
-    // nodes of the own range, all-gathers the packed nodes and finishes the nodes that straddle rank boundaries.  None of it
-    // depends on the neighbor pass: it is issued first, on the auxiliary stream and communicator, and runs behind pass 5.
-    const char* gname = impl == SPH_GRAVITY_TREE ? "gravity_tree" : impl == SPH_GRAVITY_PARTICLE ? "gravity_allpairs" : "gravity_none";
-    auto gravity_sources = [&]() -> int {
-        FOR_RANKS(g, R) {
-            G_CUDA(g, cudaSetDevice(R.device));
-            sphb200_ctx* c = R.c;
-            G_CUDA(g, cudaMemcpyAsync(R.posm_g + g->g0[R.rank], c->posm + R.own0, (size_t)R.n_own * sizeof(float4), cudaMemcpyDeviceToDevice, c->stream));
-            if (impl == SPH_GRAVITY_TREE)
-                G_CUDA(g, cudaMemcpyAsync(R.keys_g + g->g0[R.rank], c->keys[0] + R.own0, (size_t)R.n_own * sizeof(uint32_t), cudaMemcpyDeviceToDevice, c->stream));
-            c->gsrc = R.posm_g; c->gsrc_n = N;
-        }
-        { auto b = ptrs(g, [](GroupRank& R) { return R.posm_g; }); if ((rc = g_allgatherv(g, b.data(), g->g0.data(), 16))) return rc; }
-        if (impl != SPH_GRAVITY_TREE) return SPH_OK;
-        { auto b = ptrs(g, [](GroupRank& R) { return R.keys_g; }); if ((rc = g_allgatherv(g, b.data(), g->g0.data(), 4))) return rc; }
-        FOR_RANKS(g, R) {
-            G_CUDA(g, cudaSetDevice(R.device));
-            sphb200_ctx* c = R.c;
-            c->tkeys = R.keys_g; c->tree_n = N; c->tree_g0 = g->g0[R.rank]; c->tree_g1 = g->g0[R.rank + 1];
-            c->tree_off = R.own0 - g->g0[R.rank];
-            if (W > 1) G_CUDA(g, cudaMemsetAsync(c->top_counts + 4 * R.rank, 0, 4 * sizeof(int32_t), c->stream));
-            G_RC(g, R, sph_launch_tree_build(c, dt, c->stream));
-            if (W > 1) G_RC(g, R, grk_boundary(c, c->posh[0] + R.own0, c->velm[0] + R.own0, (int)R.n_own, R.bnd + (size_t)R.rank * 2 * SPH_TOP_LEAF * 2));
-        }
-        if (W > 1) {
-            // packed walk nodes of every rank's range: internal nodes [g0, g1) (ids < N-1) and leaves N-1+[g0, g1)
-            std::vector<int64_t> oi(W + 1), ol(W + 1);
-            for (int r = 0; r <= W; r++) { oi[r] = std::min<int64_t>(g->g0[r], N - 1); ol[r] = N - 1 + g->g0[r]; }
-            { auto b = ptrs(g, [](GroupRank& R) { return R.c->packed; }); if ((rc = g_allgatherv(g, b.data(), oi.data(), 32))) return rc; }
-            { auto b = ptrs(g, [](GroupRank& R) { return R.c->packed; }); if ((rc = g_allgatherv(g, b.data(), ol.data(), 32))) return rc; }
-            { auto b = ptrs(g, [](GroupRank& R) { return R.c->top_nodes; }); if ((rc = g_allgather(g, b.data(), SPH_TOP_CAP * sizeof(TopNode)))) return rc; }
-            { auto b = ptrs(g, [](GroupRank& R) { return R.c->front_nodes; }); if ((rc = g_allgather(g, b.data(), SPH_TOP_CAP * sizeof(FrontNode)))) return rc; }
-            { auto b = ptrs(g, [](GroupRank& R) { return R.c->top_counts; }); if ((rc = g_allgather(g, b.data(), 4 * sizeof(int32_t)))) return rc; }
-            { auto b = ptrs(g, [](GroupRank& R) { return R.bnd; }); if ((rc = g_allgather(g, b.data(), 2 * SPH_TOP_LEAF * 2 * sizeof(float4)))) return rc; }
-            FOR_RANKS(g, R) { G_CUDA(g, cudaSetDevice(R.device)); G_RC(g, R, sph_launch_top_tree(R.c, W, R.bnd, R.split_d, dt)); }
-        }
-        return SPH_OK;
-    };
-    const bool overlap = impl != SPH_GRAVITY_NONE && aux_available(g);
-    if (overlap) {
-        if ((rc = aux_begin(g))) return rc;
-        const int rcg = gravity_sources();
-        if ((rc = aux_end(g))) return rc;       // always restores the main stream / communicator
-        if (rcg) return rcg;
-    }
 
     // 5. neighbor rows + density + EOS for the own targets; (m/rho)P of the halo follows
     FOR_RANKS(g, R) {
@@ -757,6 +889,10 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
     }
     pass_mark(g, "neighbors_density_eos");
 
+    // 6. pressure gradient (independent of gravity: it runs first, more cover for the gravity lane)
+    FOR_RANKS(g, R) { G_CUDA(g, cudaSetDevice(R.device)); G_RC(g, R, sph_launch_pressure(R.c)); }
+    pass_mark(g, "pressure_grad");
+
     // 6b. gravity of the own targets
     if (impl == SPH_GRAVITY_NONE) {
         FOR_RANKS(g, R) {
@@ -767,8 +903,17 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
             G_CUDA(g, cudaMemsetAsync(c->napprox, 0, (size_t)c->n * sizeof(int32_t), c->stream));
         }
     } else {
-        if (overlap) { if ((rc = aux_join(g))) return rc; }
-        else if ((rc = gravity_sources())) return rc;
+        if (overlap) {
+            if ((rc = aux_resume(g))) return rc;
+            const int rcg = gravity_part_b();
+            if ((rc = aux_end(g))) return rc;
+            if (rcg) return rcg;
+            if ((rc = aux_join(g))) return rc;
+        } else {
+            if ((rc = gravity_part_a())) return rc;
+            if ((rc = gravity_part_b())) return rc;
+        }
+        pass_mark(g, "gravity_exchange_wait");   // what the source / tree exchange takes beyond the neighbor pass it runs behind
         FOR_RANKS(g, R) {
             G_CUDA(g, cudaSetDevice(R.device));
             if (R.n_own <= 0) continue;
@@ -779,9 +924,7 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
     }
     pass_mark(g, gname);
 
-    // 7. pressure gradient, integration
-    FOR_RANKS(g, R) { G_CUDA(g, cudaSetDevice(R.device)); G_RC(g, R, sph_launch_pressure(R.c)); }
-    pass_mark(g, "pressure_grad");
+    // 7. integration
     FOR_RANKS(g, R) { G_CUDA(g, cudaSetDevice(R.device)); G_RC(g, R, sph_launch_integrate(R.c, dt)); }
     pass_mark(g, "integrate");
     g->stepped = true;
@@ -998,7 +1141,7 @@ int sphb200_group_info(sph_group g, sph_GroupInfo* out) {
     if (!g || !out) return SPH_ERR_INVALID_ARG;
     memset(out, 0, sizeof(*out));
     out->world = g->world; out->nlocal = g->nlocal; out->rank0 = g->rank0; out->transport = g->local ? 1 : (g->world > 1 ? 0 : 2);
-    out->n_total = g->n_total; out->steps = g->steps; out->migrated_last_step = g->last_migrated; out->halo_last_step = g->last_halo;
+    out->n_total = g->n_total; out->steps = g->steps; out->migrated_last_step = g->last_migrated; out->halo_last_step = g->last_halo; out->tree_nodes_last_step = g->last_let;
     out->cap_own = g->cap_own; out->cap_halo = g->cap_halo;
     for (int l = 0; l < g->nlocal && l < 32; l++) { out->n_own[l] = g->r[l].n_own; out->n_halo[l] = g->r[l].n_ext - g->r[l].n_own; }
     int64_t launches = 0;
@@ -1023,6 +1166,14 @@ int sphb200_group_get_timings(sph_group g, const char** names, float* ms, int ca
         if (names) names[k] = g->pass_name[k];
         float t = 0;
         cudaEventElapsedTime(&t, g->tev[k], g->tev[k + 1]);
+        if (ms) ms[k] = t;
+    }
+    // auxiliary lane: time of every stage since the previous one (the first: since the fork point on the main lane)
+    for (int a = 0; a < g->naux && k < cap; a++, k++) {
+        if (names) names[k] = g->aux_name[a];
+        float t = 0;
+        cudaEventSynchronize(g->aev[a + 1]);
+        cudaEventElapsedTime(&t, a == 0 ? g->tev[g->aux_fork_pass] : g->aev[a], g->aev[a + 1]);
         if (ms) ms[k] = t;
     }
     return k;

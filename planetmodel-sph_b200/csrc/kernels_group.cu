@@ -14,6 +14,7 @@
 //   k_assemble_ext                      resident "extended" set = [halo of lower ranks | own | halo of higher ranks] -- a sorted
 //                                       subsequence of the global order -- with its SoA arrays and cell table
 //   k_boundary                          first / last particles of the rank (buckets that straddle a rank boundary)
+//   k_let_box / mask / pack / scatter   locally essential tree: only the walk nodes another rank can reach travel to it
 //   k_result_* / k_body_dest            redistribution of the results to body-order slices for the download
 //   k_reduce_ranks                      all-reduce of the in-process transport (single process, ranks on one or more devices)
 #include "ctx.cuh"
@@ -162,6 +163,22 @@ __global__ void __launch_bounds__(256) k_mig_pack(const float4* __restrict__ pos
     rec[3 * (size_t)k] = make_uint4(__float_as_uint(p.x), __float_as_uint(p.y), __float_as_uint(p.z), __float_as_uint(p.w));
     rec[3 * (size_t)k + 1] = make_uint4(__float_as_uint(v.x), __float_as_uint(v.y), __float_as_uint(v.z), __float_as_uint(v.w));
     rec[3 * (size_t)k + 2] = make_uint4(orig[i], (uint32_t)nown[i], keys[i], 0u);
+}
+
+// the own particles in sorted order, as soon as the local sort is done: gravity sources and keys straight into the rank's segment of
+// the global arrays (what the all-gather publishes) and the (posh, velm) records the LBVH build reads
+__global__ void __launch_bounds__(256) k_sorted_sources(const uint4* __restrict__ rec, const uint32_t* __restrict__ idx, const uint32_t* __restrict__ keys,
+                                                        int n, float4* __restrict__ posm, uint32_t* __restrict__ keys_out, float4* __restrict__ tposh,
+                                                        float4* __restrict__ tvelm) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const size_t s = idx[i];
+    const uint4 a = rec[3 * s], b = rec[3 * s + 1];
+    const float4 p = make_float4(__uint_as_float(a.x), __uint_as_float(a.y), __uint_as_float(a.z), __uint_as_float(a.w));
+    const float4 v = make_float4(__uint_as_float(b.x), __uint_as_float(b.y), __uint_as_float(b.z), __uint_as_float(b.w));
+    posm[i] = make_float4(p.x, p.y, p.z, v.w);
+    if (keys_out) keys_out[i] = keys[i];
+    tposh[i] = p; tvelm[i] = v;
 }
 
 __global__ void __launch_bounds__(256) k_mig_keys(const uint4* __restrict__ rec, int n, uint32_t* __restrict__ keys) {
@@ -340,6 +357,111 @@ __global__ void k_boundary(const float4* __restrict__ posh, const float4* __rest
     bnd[2 * (size_t)k + 1] = velm[i];
 }
 
+
+// ---- locally essential tree (LET): which of this rank's finished walk nodes the other ranks can reach ------------------------
+// A walk reads node k only after a target of the walking rank has opened k's parent p (rejected it: r_sq <= T_p, kernels_tree.cu).
+// With B_r = the box of the positions rank r walks (its own targets plus the <= 31 companions that fill its first and last
+// 32-slot group), "some target of r opens p" implies dist^2(cm_p, B_r) <= T_p: the sender evaluates this superset test for every
+// one of its nodes against every other rank's box and ships only those records instead of all-gathering the whole node array.
+// Nodes inside buckets are unreachable (mask 0); nodes hanging below a straddling (top) node are needed by everybody.
+
+// box of posm[lo, hi) into 8 ordered uints (lo.xyz, -, hi.xyz, -), pre-set to (0xffffffff x4, 0 x4)
+__global__ void __launch_bounds__(256) k_let_box(const float4* __restrict__ posm, int lo, int hi, uint32_t* __restrict__ box) {
+    float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+    for (int i = lo + blockIdx.x * blockDim.x + threadIdx.x; i < hi; i += gridDim.x * blockDim.x) {
+        const float4 p = posm[i];
+        mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+        mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+    }
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        const uint32_t a = __reduce_min_sync(FULL, f2ord(mn[k])), b = __reduce_max_sync(FULL, f2ord(mx[k]));
+        if ((threadIdx.x & 31) == 0) { atomicMin(&box[k], a); atomicMax(&box[4 + k], b); }
+    }
+}
+
+// mask[u] = ranks that need own node u (u enumerates the internal nodes g0..g1-1, then the leaves of slots g0..g1-1);
+// cnt[r] += number of nodes rank r needs
+__global__ void __launch_bounds__(256) k_let_mask(const int2* __restrict__ range, const int32_t* __restrict__ parent,
+                                                  const float4* __restrict__ packed, int n, int g0, int g1, int leaf_max,
+                                                  const uint32_t* __restrict__ boxes, int world, int me, uint32_t* __restrict__ mask,
+                                                  uint32_t* __restrict__ cnt) {
+    __shared__ float sbox[SPH_MAX_RANKS][6];
+    if (threadIdx.x < world * 6) {
+        const int r = threadIdx.x / 6, k = threadIdx.x % 6;
+        sbox[r][k] = ord2f(boxes[8 * r + (k < 3 ? k : k + 1)]);
+    }
+    __syncthreads();
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, own = g1 - g0;
+    uint32_t m = 0u;
+    if (u < 2 * own) {
+        const int k = u < own ? g0 + u : n - 1 + g0 + (u - own);
+        if (!(u < own && k >= n - 1)) {
+            const int2 rg = range[k];
+            const bool top = rg.x < g0 || rg.y >= g1;            // straddles a rank boundary: finished by k_top_tree on every rank
+            const int p = parent[k];
+            const uint32_t all = (world >= 32 ? 0xffffffffu : ((1u << world) - 1u)) & ~(1u << me);
+            if (!top) {
+                if (p < 0) m = all;                                // root, or the parent is built elsewhere: below a top node
+                else {
+                    const int2 prg = range[p];
+                    if (prg.y - prg.x + 1 > leaf_max) {            // else: strictly inside a bucket, unreachable
+                        if (prg.x < g0 || prg.y >= g1) m = all;    // the parent is a top node
+                        else {
+                            const float4 N = packed[2 * (size_t)p];   // (cm, T)
+                            for (int r = 0; r < world; r++) {
+                                if (r == me) continue;
+                                const float dx = fmaxf(fmaxf(sbox[r][0] - N.x, N.x - sbox[r][3]), 0.f);
+                                const float dy = fmaxf(fmaxf(sbox[r][1] - N.y, N.y - sbox[r][4]), 0.f);
+                                const float dz = fmaxf(fmaxf(sbox[r][2] - N.z, N.z - sbox[r][5]), 0.f);
+                                // an empty box (a rank without targets) has lo = +inf: d = inf, never needed
+                                if ((dx * dx + dy * dy + dz * dz) * 0.99999f <= N.w) m |= 1u << r;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        mask[u] = m;
+    }
+    for (int r = 0; r < world; r++) {
+        const unsigned b = __ballot_sync(FULL, (m >> r) & 1u);
+        if ((threadIdx.x & 31) == 0 && b) atomicAdd(&cnt[r], (uint32_t)__popc(b));
+    }
+}
+
+// records (cm,T | M,a,b,Bmax^2 | id) of the needed nodes, grouped by destination: segment of rank r starts at soff[r];
+// cursor[r] counts what has been placed (the order inside a segment is irrelevant: the receiver scatters by id)
+__global__ void __launch_bounds__(256) k_let_pack(const uint32_t* __restrict__ mask, const float4* __restrict__ packed, int n, int g0, int g1,
+                                                  int world, const uint32_t* __restrict__ soff, uint32_t* __restrict__ cursor,
+                                                  float4* __restrict__ out) {
+    const int u = blockIdx.x * blockDim.x + threadIdx.x, own = g1 - g0;
+    const int lane = threadIdx.x & 31;
+    uint32_t m = u < 2 * own ? mask[u] : 0u;
+    const int k = u < own ? g0 + u : n - 1 + g0 + (u - own);
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+    if (m) { a = packed[2 * (size_t)k]; b = packed[2 * (size_t)k + 1]; }
+    for (int r = 0; r < world; r++) {
+        const unsigned bal = __ballot_sync(FULL, (m >> r) & 1u);
+        if (!bal) continue;
+        uint32_t base = 0u;
+        if (lane == 0) base = atomicAdd(&cursor[r], (uint32_t)__popc(bal));
+        base = __shfl_sync(FULL, base, 0);
+        if ((m >> r) & 1u) {
+            float4* o = out + 3 * ((size_t)soff[r] + base + __popc(bal & ((1u << lane) - 1u)));
+            o[0] = a; o[1] = b; o[2] = make_float4(__int_as_float(k), 0.f, 0.f, 0.f);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) k_let_scatter(const float4* __restrict__ rec, int nrec, float4* __restrict__ packed) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nrec) return;
+    const int k = __float_as_int(rec[3 * (size_t)i + 2].x);
+    packed[2 * (size_t)k] = rec[3 * (size_t)i];
+    packed[2 * (size_t)k + 1] = rec[3 * (size_t)i + 1];
+}
+
 // ---- download: results travel back to the rank that holds the particle's body-order slice
 __global__ void __launch_bounds__(256) k_body_dest(const uint32_t* __restrict__ orig, int n, int64_t chunk, uint8_t* __restrict__ dest) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -502,6 +624,11 @@ int grk_assemble_ext(sphb200_ctx* c, const uint4* rec, const uint32_t* idx, cons
     }
     return SPH_OK;
 }
+int grk_sorted_sources(sphb200_ctx* c, const uint4* rec, const uint32_t* idx, const uint32_t* keys, int n, float4* posm, uint32_t* keys_out,
+                       float4* tposh, float4* tvelm) {
+    if (n > 0) { k_sorted_sources<<<sph_div_up(n, 256), 256, 0, c->stream>>>(rec, idx, keys, n, posm, keys_out, tposh, tvelm); GL(c); }
+    return SPH_OK;
+}
 int grk_gather_f32(sphb200_ctx* c, const float* src, const uint32_t* list, int n, float* out) {
     if (n > 0) { k_gather_f32<<<sph_div_up(n, 256), 256, 0, c->stream>>>(src, list, n, out); GL(c); }
     return SPH_OK;
@@ -509,6 +636,33 @@ int grk_gather_f32(sphb200_ctx* c, const float* src, const uint32_t* list, int n
 int grk_boundary(sphb200_ctx* c, const float4* posh, const float4* velm, int n, float4* bnd) {
     SPH_CK(c, cudaMemsetAsync(bnd, 0, 2 * SPH_TOP_LEAF * 2 * sizeof(float4), c->stream));
     if (n > 0) { k_boundary<<<1, 2 * SPH_TOP_LEAF, 0, c->stream>>>(posh, velm, n, bnd); GL(c); }
+    return SPH_OK;
+}
+
+// box[8] (ordered uints) of the positions posm[lo, hi); an empty range leaves lo = +inf
+int grk_let_box(sphb200_ctx* c, const float4* posm, int lo, int hi, uint32_t* box) {
+    const uint32_t init[8] = {0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0u, 0u, 0u, 0u};
+    SPH_CK(c, cudaMemcpyAsync(box, init, sizeof(init), cudaMemcpyHostToDevice, c->stream));
+    if (hi > lo) { k_let_box<<<min(sph_div_up(hi - lo, 256), c->sm_count * 4), 256, 0, c->stream>>>(posm, lo, hi, box); GL(c); }
+    return SPH_OK;
+}
+int grk_let_mask(sphb200_ctx* c, const uint32_t* boxes, int world, int me, uint32_t* mask, uint32_t* cnt) {
+    const int n = (int)c->tree_n, g0 = (int)c->tree_g0, g1 = (int)c->tree_g1;
+    SPH_CK(c, cudaMemsetAsync(cnt, 0, (size_t)world * sizeof(uint32_t), c->stream));
+    if (g1 > g0) {
+        k_let_mask<<<sph_div_up(2 * (int64_t)(g1 - g0), 256), 256, 0, c->stream>>>(c->range, c->parent, c->packed, n, g0, g1, c->p.leaf_max, boxes, world, me, mask, cnt);
+        GL(c);
+    }
+    return SPH_OK;
+}
+int grk_let_pack(sphb200_ctx* c, const uint32_t* mask, int world, const uint32_t* soff, uint32_t* cursor, float4* out) {
+    const int n = (int)c->tree_n, g0 = (int)c->tree_g0, g1 = (int)c->tree_g1;
+    SPH_CK(c, cudaMemsetAsync(cursor, 0, (size_t)world * sizeof(uint32_t), c->stream));
+    if (g1 > g0) { k_let_pack<<<sph_div_up(2 * (int64_t)(g1 - g0), 256), 256, 0, c->stream>>>(mask, c->packed, n, g0, g1, world, soff, cursor, out); GL(c); }
+    return SPH_OK;
+}
+int grk_let_scatter(sphb200_ctx* c, const float4* rec, int64_t nrec) {
+    if (nrec > 0) { k_let_scatter<<<sph_div_up(nrec, 256), 256, 0, c->stream>>>(rec, (int)nrec, c->packed); GL(c); }
     return SPH_OK;
 }
 int grk_body_dest(sphb200_ctx* c, const uint32_t* orig, int n, int64_t chunk, uint8_t* dest) {

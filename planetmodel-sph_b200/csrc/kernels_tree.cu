@@ -633,7 +633,10 @@ int sph_launch_tree_build(sphb200_ctx* c, float dt, cudaStream_t stream) {
     }
     k_lbvh_topology<<<sph_div_up(own, 256), 256, 0, stream>>>(c->tkeys, n, g0, g1, c->child, c->range, c->parent, top, tcount, c->err_d);
     SPH_LAUNCH_CHECK(c);
-    k_lbvh_nodes<<<sph_div_up(2 * (int64_t)own, 256), 256, 0, stream>>>(c->posh[c->cur], c->velm[c->cur], n, g0, g1, (int)c->tree_off,
+    const float4* bposh = c->tree_posh ? c->tree_posh : c->posh[c->cur];
+    const float4* bvelm = c->tree_posh ? c->tree_velm : c->velm[c->cur];
+    const int boff = (int)(c->tree_posh ? c->tree_src_off : c->tree_off);
+    k_lbvh_nodes<<<sph_div_up(2 * (int64_t)own, 256), 256, 0, stream>>>(bposh, bvelm, n, g0, g1, boff,
                                                                        c->child, c->range, c->parent, c->p.leaf_max, c->p.aabb_mode, dt,
                                                                        c->p.theta * c->p.theta /* fp32 product, as k_Theta*k_Theta (GravityFieldSystem.cs:246) */,
                                                                        c->flag, c->mom, c->nlo, c->nhi, c->packed, front, tcount, c->err_d);

@@ -74,7 +74,7 @@ EXPORTS = [
 class GroupInfo(C.Structure):
     _fields_ = [("world", C.c_int32), ("nlocal", C.c_int32), ("rank0", C.c_int32), ("transport", C.c_int32),
                 ("n_total", C.c_int64), ("steps", C.c_int64), ("migrated_last_step", C.c_int64), ("halo_last_step", C.c_int64),
-                ("cap_own", C.c_int64), ("cap_halo", C.c_int64), ("launches", C.c_int64),
+                ("cap_own", C.c_int64), ("cap_halo", C.c_int64), ("launches", C.c_int64), ("tree_nodes_last_step", C.c_int64),
                 ("n_own", C.c_int64 * 32), ("n_halo", C.c_int64 * 32)]
 
 

@@ -186,7 +186,7 @@ class Group:
         self._ck(self.L.sphb200_group_info(self.h, C.byref(gi)))
         return dict(world=gi.world, nlocal=gi.nlocal, rank0=gi.rank0, transport=("nccl", "local", "none")[gi.transport],
                     n_total=gi.n_total, steps=gi.steps, migrated_last_step=gi.migrated_last_step, halo_last_step=gi.halo_last_step,
-                    cap_own=gi.cap_own, cap_halo=gi.cap_halo, launches=gi.launches, n_own=list(gi.n_own[:gi.nlocal]),
+                    cap_own=gi.cap_own, cap_halo=gi.cap_halo, launches=gi.launches, tree_nodes_last_step=gi.tree_nodes_last_step, n_own=list(gi.n_own[:gi.nlocal]),
                     n_halo=list(gi.n_halo[:gi.nlocal]))
 
     def launch_count(self):

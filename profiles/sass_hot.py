@@ -4,6 +4,7 @@ import csv, sys, re
 rows = list(csv.reader(open(sys.argv[1])))
 hdr = rows[1]
 ia = hdr.index('Instructions Executed'); isrc = hdr.index('Source'); ist = hdr.index('# Samples'); ith = hdr.index('Avg. Threads Executed')
+rows = rows[:2] + [r for r in rows[2:] if len(r) > max(ia, isrc, ist, ith)]
 tot = sum(int(r[ia]) for r in rows[2:] if r[ia].isdigit())
 print('total warp instructions', tot)
 # group consecutive instructions with identical execution count (basic-block proxy)

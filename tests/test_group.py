@@ -89,6 +89,34 @@ def test_group_tree_gravity_bit_identical_to_single_handle(world):
         assert abs(gd[k] - wd[k]) <= 1e-9 * abs(wd[k]) + 1e-12, k
 
 
+def test_group_locally_essential_tree_is_a_superset_of_what_the_walk_reads(monkeypatch):
+    """Tree gravity of a group ships only the walk nodes another rank can reach (k_let_*): with every other node record
+    poisoned (NaN moments, child -1) the step is still bit-identical to the single handle, far fewer records travel than the
+    all-gather moved, and the all-gather fallback (SPHB200_GROUP_NO_LET) gives the same bits."""
+    import sphb200
+    c = _sphere(120011, seed=11)
+    want, _ = _single(c, 3, sphb200.GRAVITY_TREE)
+    monkeypatch.setenv("SPHB200_GROUP_LET_POISON", "1")
+    got, _, info = _group(c, 3, sphb200.GRAVITY_TREE, [0, 0, 0, 0])
+    _compare(got, want, exact=True)
+    n = len(c["h"])
+    # the all-gather moved (world-1)/world of 2n-1 records to every rank
+    assert 0 < info["tree_nodes_last_step"] < 0.6 * 4 * (0.75 * 2 * n), info["tree_nodes_last_step"]
+    monkeypatch.delenv("SPHB200_GROUP_LET_POISON")
+    monkeypatch.setenv("SPHB200_GROUP_NO_LET", "1")
+    got2, _, info2 = _group(c, 3, sphb200.GRAVITY_TREE, [0, 0, 0, 0])
+    assert info2["tree_nodes_last_step"] == -1
+    _compare(got2, want, exact=True)
+    # collision geometry (two separated bodies, S > 1 stencil, unequal masses), poisoned
+    monkeypatch.delenv("SPHB200_GROUP_NO_LET")
+    monkeypatch.setenv("SPHB200_GROUP_LET_POISON", "1")
+    from sphb200 import ic
+    c5 = ic.make_collision(30000, seed=4)
+    want5, _ = _single(c5, 2, sphb200.GRAVITY_TREE)
+    got5, _, _ = _group(c5, 2, sphb200.GRAVITY_TREE, [0, 0, 0])
+    _compare(got5, want5, exact=True)
+
+
 @pytest.mark.parametrize("world", [2, 4])
 def test_group_allpairs_gravity_matches_single_handle(world):
     import sphb200
