@@ -20,13 +20,16 @@
 // source splits -- deterministic, and ~sqrt(256) times tighter than one 10^6-term fp32 chain.
 #include "ctx.cuh"
 #include <math.h>
+#include <algorithm>
 
 namespace {
 
 constexpr int AP_THREADS = 256;
-constexpr int AP_TPT = 4;     // targets per thread (2, 3, 4 and 6 measure within 3 %: profiles/r01_tune_allpairs.txt)
+constexpr int AP_TPT = 6;     // targets per thread: 6 x unroll 2 (160 registers, ONE 8-warp CTA per SM, 12 independent pair chains per thread)
+                              // measures 421 ms at 1M against 442 ms for 4 x 4 (128 registers, two CTAs); 3x4 440, 5x2 455, 8x2 464, 10x1 429,
+                              // 6x1 489, 6x4 487, 7x2 534 (profiles/README.md, round 2): ILP per warp beats resident warps here
 constexpr int AP_TILE = 256;  // sources per shared-memory tile (inner fp32 partial sums: 2 interleaved chains of 128)
-constexpr int AP_UNROLL = 4;  // source pairs per unrolled inner-loop body
+constexpr int AP_UNROLL = 2;  // source pairs per unrolled inner-loop body
 constexpr unsigned FULL = 0xffffffffu;
 
 __device__ __forceinline__ float rsqrt_approx(float x) {
@@ -246,18 +249,32 @@ int sph_launch_gravity_allpairs(sphb200_ctx* c) {
     int n = (int)c->gsrc_n;          // sources: every particle of the (global) sorted order
     const float4* src = c->gsrc;
     int tblocks = sph_div_up(nt, AP_THREADS * AP_TPT);
-    // enough blocks for >= ~12 waves of 3 resident CTAs/SM, bounded by the partial-sum buffer (cap * gpart_splits float4)
-    int want = c->sm_count * 3 * 12;
-    int splits = sph_div_up(want, tblocks);
-    int64_t mem_splits = (int64_t)c->cap_rows * c->gpart_splits / nt;
-    if (splits > mem_splits) splits = (int)mem_splits;
-    int max_by_src = sph_div_up(n, AP_TILE);
-    if (splits > max_by_src) splits = max_by_src;
-    if (splits > 65535) splits = 65535;
-    if (splits < 1) splits = 1;
-    int per = sph_div_up(n, splits);
-    per = sph_div_up(per, AP_TILE) * AP_TILE;
-    splits = sph_div_up(n, per);
+    // Source splits: the grid (target blocks x splits) should fill whole waves of resident CTAs (one 8-warp CTA per SM at 160
+    // registers: asked from the occupancy calculator once) -- among the split counts the partial-sum buffer (cap * gpart_splits
+    // float4) and the tile granularity allow, take the one with the least idle tail, preferring >= 12 waves.
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+        int a = 0, b = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, k_gravity_allpairs<AP_TPT, true>, AP_THREADS, 0);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, k_gravity_allpairs<AP_TPT, false>, AP_THREADS, 0);
+        ctas_per_sm = std::max(1, std::min(a, b));
+    }
+    const int resident = c->sm_count * ctas_per_sm;
+    int64_t smax = (int64_t)c->cap_rows * c->gpart_splits / nt;
+    smax = std::min<int64_t>(smax, sph_div_up(n, AP_TILE));
+    smax = std::max<int64_t>(std::min<int64_t>(smax, 65535), 1);
+    int splits = 1, per = 0;
+    double best = -1.0;
+    for (int sp = (int)smax; sp >= 1; sp--) {
+        int pr = sph_div_up(sph_div_up(n, sp), AP_TILE) * AP_TILE;   // sources per split: whole tiles
+        int ns = sph_div_up(n, pr);                                   // splits that are not empty
+        const int64_t grid = (int64_t)tblocks * ns;
+        const int64_t waves = (grid + resident - 1) / resident;
+        double eff = (double)grid / (double)(waves * resident);
+        if (waves < 12) eff *= 0.5 + 0.5 * (double)waves / 12.0;     // too few waves: the last one weighs more, tiles load less often
+        if (eff > best + 1e-9) { best = eff; splits = ns; per = pr; }
+        if (grid < resident && sp < smax) break;                      // fewer splits only shrink the grid further
+    }
     k_tile_boxes<<<sph_div_up(n, AP_TILE), AP_TILE, 0, c->stream>>>(src, n, c->tbox);
     SPH_LAUNCH_CHECK(c);
     dim3 grid(tblocks, splits);
