@@ -506,7 +506,8 @@ __global__ void __launch_bounds__(RS_WARPS * 32, 4) k_density(const float4* __re
     float acc[1];
     int own;
     row_stream<1, true>(S, nlist + (size_t)(base - rowbase) * kmax, (uint32_t)base, kmax, ovf ? 0 : cnt,
-        [&](const float4 A, const float4 B, uint32_t j, float (&v)[1], bool& in_i) {
+        [&](const float4 A, const float4* Bp, uint32_t j, float (&v)[1], bool& in_i) {
+            const float2 B = *reinterpret_cast<const float2*>(Bp);   // t(h_i), 1/(pi h_i^3)
             const float4 pj = posh[j];
             const float dx = __fsub_rn(A.x, pj.x), dy = __fsub_rn(A.y, pj.y), dz = __fsub_rn(A.z, pj.z);
             const float d2 = dot3_rn(dx, dy, dz);

@@ -69,7 +69,7 @@ constexpr int K2_WARPS = 4;   // 7.6 KB of stream state per warp
 __global__ void __launch_bounds__(K2_WARPS * 32, 6) k_pressure_grad(const float4* __restrict__ posh, const float* __restrict__ cvol,
                                                                     const uint32_t* __restrict__ nlist, const int32_t* __restrict__ ncount,
                                                                     int t0, int t1, int rowbase, int kmax, float lead, float4* __restrict__ gradp) {
-    __shared__ RowStreamSmem<3> smem[K2_WARPS];   // tg[0]: x, y, z, 1/h   tg[1]: 1/(pi h^4), h, -, -
+    __shared__ RowStreamSmem<3> smem[K2_WARPS];   // tg[0]: x, y, z, 1/h   tg[1]: -, h, -, - (read at the spline breakpoint only)
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int base = t0 + (blockIdx.x * K2_WARPS + w) * 32;
     if (base >= t1) return;
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 6) k_pressure_grad(const float4
     float acc[3];
     int unused;
     row_stream<3, false>(S, nlist + (size_t)(base - rowbase) * kmax, (uint32_t)base, kmax, cnt,
-        [&](const float4 A, const float4 B, uint32_t j, float (&v)[3], bool& flag) {
+        [&](const float4 A, const float4* Bp, uint32_t j, float (&v)[3], bool& flag) {
             const float4 pj = posh[j];
             const float cj = cvol[j];
             const float dx = A.x - pj.x, dy = A.y - pj.y, dz = A.z - pj.z;
@@ -101,9 +101,10 @@ __global__ void __launch_bounds__(K2_WARPS * 32, 6) k_pressure_grad(const float4
                 // within a few ulps of the spline's breakpoint, where the reference's inner branch (quirk Q1) makes dW/dr jump:
                 // decide as the reference does, "distance < size" on the IEEE distance (SplineKernel.cs:115-148)
                 const float re = __fsqrt_rn(dot3_rn(__fsub_rn(A.x, pj.x), __fsub_rn(A.y, pj.y), __fsub_rn(A.z, pj.z)));
-                in_i = re < B.y; in_j = re < pj.w;
+                in_i = re < Bp->y; in_j = re < pj.w;
             }
-            const float s = fmaf(B.x, dwr_shape(qi, in_i, A.w, rinv, lead), c4_j * dwr_shape(qj, in_j, hinv_j, rinv, lead)) * cj;
+            const float a2 = A.w * A.w;
+            const float s = fmaf(a2 * a2 * kInvPI, dwr_shape(qi, in_i, A.w, rinv, lead), c4_j * dwr_shape(qj, in_j, hinv_j, rinv, lead)) * cj;
             v[0] = dx * s; v[1] = dy * s; v[2] = dz * s;
             flag = false;
         }, acc, unused);

@@ -27,7 +27,9 @@ struct RowStreamSmem {
 
 // Runs the stream for one warp.  `clen` = length of the lane's own row (0: no row), `wrow` = row of the warp's first target (row q
 // at wrow + q * kmax), `fallback` = any resident particle (what a padding lane evaluates; its result is dropped).
-// pair(A, B, j, v, flag): one pair of the target with records (A, B) with particle j -> NV values and a flag to count.
+// pair(A, Bp, j, v, flag): one pair of the target with records (A, *Bp) with particle j -> NV values and a flag to count
+// (the second record stays in shared memory until the callee reads it: a 128-bit shared load is four wavefronts of the L1 data
+// pipe, which is what bounds these kernels).
 // On return sum[0..NV) / count hold the lane's own target's totals.
 template <int NV, bool COUNT, typename PairFn>
 __device__ __forceinline__ void row_stream(RowStreamSmem<NV>& S, const uint32_t* __restrict__ wrow, uint32_t fallback, int kmax, int clen,
@@ -59,9 +61,9 @@ __device__ __forceinline__ void row_stream(RowStreamSmem<NV>& S, const uint32_t*
     };
     auto eval = [&](uint32_t m, uint32_t j, float (&v)[NV], bool& flag) {
         const float4 A = *reinterpret_cast<const float4*>(tgw + (m & 0x1f0u));
-        const float4 B = *reinterpret_cast<const float4*>(tgw + (m & 0x1f0u) + 32 * sizeof(float4));
+        const float4* Bp = reinterpret_cast<const float4*>(tgw + (m & 0x1f0u) + 32 * sizeof(float4));   // read by the callee, if at all
         const bool ok = sub < (int)((m >> 9) & 0xfu);
-        pair(A, B, j, v, flag);
+        pair(A, Bp, j, v, flag);
         flag = flag && ok;
 #pragma unroll
         for (int k = 0; k < NV; k++) v[k] = ok ? v[k] : 0.0f;
