@@ -34,7 +34,7 @@ UNIT = "particle-steps/s"
 DT = 1.0 / 60.0
 FLOP_PER_PAIR = 20.0          # conventional N-body count per ordered pair
 SPH_BYTES_BASE, SPH_BYTES_PER_NEIGHBOR = 368.0, 12.0   # algorithmic HBM bytes / particle-step
-NCU_TRAFFIC_ALLPAIRS_C3 = 179.1e6   # profiles/r01_allpairs_full.txt: 69.2 MB read + 109.9 MB written per launch at C3
+NCU_TRAFFIC_ALLPAIRS_C3 = 136.4e6   # dram__bytes_read.sum + dram__bytes_write.sum of k_gravity_allpairs<6, equal-mass> at C3 (profiles/r02_allpairs_full.txt)
 
 
 def workload_config(name, particles=None):

@@ -190,6 +190,11 @@ SPH_API int sphb200_download_tree(sph_handle h, int32_t* child, int32_t* range, 
 /* Conserved-quantity diagnostics (README.md:50-52 roadmap): out[0]=sum m, [1..3]=sum m v, [4..6]=sum m x cross v,
  * [7]=E_kin, [8]=E_pot=0.5 sum m Phi, [9]=E_int=sum m K rho, [10]=mean symmetric neighbor count, [11]=max count */
 SPH_API int sphb200_diagnostics(sph_handle h, double* out12);
+/* SPH_DEBUG_BOUNDS build (make -C csrc debug -> libsphb200_dbg.so; the release library answers *allocations = -1): every device
+ * allocation of the library carries guard zones, every data-dependent index in the kernels is asserted (a violation traps and the
+ * next synchronising call fails).  *bad_bytes = guard bytes overwritten so far, over *allocations live allocations.  Stands in
+ * for the reference's job-safety checks (KernelSystem.cs:247, 475, 546 [NativeDisableContainerSafetyRestriction] opt-outs). */
+SPH_API int sphb200_debug_check_guards(int64_t* bad_bytes, int64_t* allocations);
 
 /* Field statistics (README.md:50-52 roadmap: "Average/max/min: Temp, Pressure, Density, Grav Field"): for q = rho, P,
  * |grad Phi|, u = K rho (specific internal energy of the P = K rho^2 gas, the model's temperature proxy), in this order:

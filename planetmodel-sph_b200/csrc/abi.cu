@@ -33,14 +33,95 @@ static void pass_mark(sphb200_ctx* c, const char* name) {
     cudaEventRecord(c->ev[c->npass], c->stream);
 }
 
+// ---- device allocations (guarded in the SPH_DEBUG_BOUNDS build, see ctx.cuh) ----------------------------------------------
+#ifdef SPH_DEBUG_BOUNDS
+#include <map>
+#include <mutex>
+namespace {
+constexpr size_t DBG_GUARD = 256;
+struct DbgAlloc { char* base; size_t bytes; int device; };
+std::map<void*, DbgAlloc> g_dbg_allocs;
+std::mutex g_dbg_mutex;
+}
+cudaError_t sph_dev_malloc(void** p, size_t bytes) {
+    char* base = nullptr;
+    const size_t body = (bytes + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc((void**)&base, body + 2 * DBG_GUARD);
+    if (e != cudaSuccess) return e;
+    e = cudaMemset(base, 0xA5, body + 2 * DBG_GUARD);
+    if (e != cudaSuccess) return e;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    *p = base + DBG_GUARD;
+    std::lock_guard<std::mutex> lk(g_dbg_mutex);
+    g_dbg_allocs[*p] = DbgAlloc{base, bytes, dev};
+    return cudaSuccess;
+}
+cudaError_t sph_dev_free(void* p) {
+    if (!p) return cudaSuccess;
+    std::lock_guard<std::mutex> lk(g_dbg_mutex);
+    auto it = g_dbg_allocs.find(p);
+    if (it == g_dbg_allocs.end()) return cudaFree(p);
+    char* base = it->second.base;
+    g_dbg_allocs.erase(it);
+    return cudaFree(base);
+}
+// guard bytes (the 256 before every allocation and everything from its last requested byte to the end of the rear guard)
+// that no longer hold the fill pattern
+int sph_debug_guard_errors(long long* bad_bytes, long long* allocations) {
+    std::lock_guard<std::mutex> lk(g_dbg_mutex);
+    long long bad = 0;
+    int cur = 0;
+    cudaGetDevice(&cur);
+    std::vector<unsigned char> h;
+    for (auto& kv : g_dbg_allocs) {
+        const DbgAlloc& a = kv.second;
+        cudaSetDevice(a.device);
+        if (cudaDeviceSynchronize() != cudaSuccess) { cudaSetDevice(cur); return SPH_ERR_CUDA; }
+        const size_t body = (a.bytes + 255) & ~(size_t)255;
+        h.resize(DBG_GUARD);
+        if (cudaMemcpy(h.data(), a.base, DBG_GUARD, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaSetDevice(cur); return SPH_ERR_CUDA; }
+        for (unsigned char b : h) bad += b != 0xA5;
+        const size_t tail = body - a.bytes + DBG_GUARD;
+        h.resize(tail);
+        if (cudaMemcpy(h.data(), a.base + DBG_GUARD + a.bytes, tail, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaSetDevice(cur); return SPH_ERR_CUDA; }
+        for (unsigned char b : h) bad += b != 0xA5;
+    }
+    cudaSetDevice(cur);
+    if (bad_bytes) *bad_bytes = bad;
+    if (allocations) *allocations = (long long)g_dbg_allocs.size();
+    return SPH_OK;
+}
+#else
+cudaError_t sph_dev_malloc(void** p, size_t bytes) { return cudaMalloc(p, bytes); }
+cudaError_t sph_dev_free(void* p) { return cudaFree(p); }
+int sph_debug_guard_errors(long long* bad_bytes, long long* allocations) {
+    if (bad_bytes) *bad_bytes = 0;
+    if (allocations) *allocations = -1;   // not a debug build
+    return SPH_OK;
+}
+#endif
+
 template <typename T>
 static cudaError_t dalloc(T** p, size_t count) {
-    return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
+    return sph_dev_malloc((void**)p, std::max<size_t>(count, 1) * sizeof(T));
 }
 
 extern "C" {
 
+#ifdef SPH_DEBUG_BOUNDS
+const char* sphb200_version(void) { return "sphb200 0.1 (sm_100a, SPH_DEBUG_BOUNDS)"; }
+#else
 const char* sphb200_version(void) { return "sphb200 0.1 (sm_100a)"; }
+#endif
+
+int sphb200_debug_check_guards(int64_t* bad_bytes, int64_t* allocations) {
+    long long b = 0, a = 0;
+    int rc = sph_debug_guard_errors(&b, &a);
+    if (bad_bytes) *bad_bytes = b;
+    if (allocations) *allocations = a;
+    return rc;
+}
 
 int sphb200_default_params(sph_Params* p) {
     if (!p) return SPH_ERR_INVALID_ARG;
@@ -61,12 +142,12 @@ int sphb200_destroy(sph_handle c) {
     if (!c) return SPH_ERR_INVALID_ARG;
     cudaSetDevice(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-    for (int k = 0; k < 2; k++) { cudaFree(c->posh[k]); cudaFree(c->velm[k]); cudaFree(c->orig[k]); cudaFree(c->keys[k]); cudaFree(c->idx[k]); }
-    cudaFree(c->posm); cudaFree(c->posc); cudaFree(c->chunk_counter); cudaFree(c->sort_hist); cudaFree(c->cell_start); cudaFree(c->cell_end); cudaFree(c->cell_hmax); cudaFree(c->nlist);
-    cudaFree(c->ncount); cudaFree(c->nown); cudaFree(c->rho); cudaFree(c->press); cudaFree(c->cvol); cudaFree(c->gradp);
-    cudaFree(c->grav); cudaFree(c->npart); cudaFree(c->napprox); cudaFree(c->gpart); cudaFree(c->tbox); cudaFree(c->child); cudaFree(c->range);
-    cudaFree(c->parent); cudaFree(c->flag); cudaFree(c->mom); cudaFree(c->nlo); cudaFree(c->nhi); cudaFree(c->packed); cudaFree(c->bounds);
-    cudaFree(c->scratch_d); cudaFree(c->grid_d); cudaFree(c->err_d); cudaFree(c->rr_table); cudaFree(c->diag_d); cudaFree(c->stage_d);
+    for (int k = 0; k < 2; k++) { sph_dev_free(c->posh[k]); sph_dev_free(c->velm[k]); sph_dev_free(c->orig[k]); sph_dev_free(c->keys[k]); sph_dev_free(c->idx[k]); }
+    sph_dev_free(c->posm); sph_dev_free(c->posc); sph_dev_free(c->chunk_counter); sph_dev_free(c->sort_hist); sph_dev_free(c->cell_start); sph_dev_free(c->cell_end); sph_dev_free(c->cell_hmax); sph_dev_free(c->nlist);
+    sph_dev_free(c->ncount); sph_dev_free(c->nown); sph_dev_free(c->rho); sph_dev_free(c->press); sph_dev_free(c->cvol); sph_dev_free(c->gradp);
+    sph_dev_free(c->grav); sph_dev_free(c->npart); sph_dev_free(c->napprox); sph_dev_free(c->gpart); sph_dev_free(c->tbox); sph_dev_free(c->child); sph_dev_free(c->range);
+    sph_dev_free(c->parent); sph_dev_free(c->flag); sph_dev_free(c->mom); sph_dev_free(c->nlo); sph_dev_free(c->nhi); sph_dev_free(c->packed); sph_dev_free(c->bounds);
+    sph_dev_free(c->scratch_d); sph_dev_free(c->grid_d); sph_dev_free(c->err_d); sph_dev_free(c->rr_table); sph_dev_free(c->diag_d); sph_dev_free(c->stage_d);
     if (c->err_h) cudaFreeHost(c->err_h);
     if (c->stage_h) cudaFreeHost(c->stage_h);
     if (c->ev_created) for (int i = 0; i <= SPH_MAX_PASSES; i++) cudaEventDestroy(c->ev[i]);
@@ -142,7 +223,7 @@ int sph_ctx_create(const sph_Params& p, int device, int64_t slots, int64_t rows,
          dalloc(&c->mom, nn) == cudaSuccess && dalloc(&c->nlo, nn) == cudaSuccess && dalloc(&c->nhi, nn) == cudaSuccess && dalloc(&c->packed, 2 * nn) == cudaSuccess &&
          dalloc(&c->bounds, 16) == cudaSuccess && dalloc(&c->grid_d, 1) == cudaSuccess && dalloc(&c->err_d, ERR_SLOTS) == cudaSuccess &&
          dalloc(&c->rr_table, SPH_RR_TABLE) == cudaSuccess && dalloc(&c->diag_d, 32) == cudaSuccess &&
-         cudaMalloc(&c->stage_d, c->stage_bytes) == cudaSuccess && cudaMallocHost((void**)&c->err_h, 2 * ERR_SLOTS * sizeof(int32_t)) == cudaSuccess &&
+         sph_dev_malloc(&c->stage_d, c->stage_bytes) == cudaSuccess && cudaMallocHost((void**)&c->err_h, 2 * ERR_SLOTS * sizeof(int32_t)) == cudaSuccess &&
          cudaMallocHost(&c->stage_h, c->stage_bytes) == cudaSuccess;
     if (!ok) {
         err = std::string("allocation failed: ") + cudaGetErrorString(cudaGetLastError());
@@ -589,9 +670,9 @@ int sphb200_download(sph_handle c, int field, void* dst, int stride) {
 static int scratch_reserve(sphb200_ctx* c, size_t bytes) {
     if (bytes <= c->scratch_bytes) return SPH_OK;
     SPH_CK(c, cudaStreamSynchronize(c->stream));
-    cudaFree(c->scratch_d); c->scratch_d = nullptr; c->scratch_bytes = 0;
+    sph_dev_free(c->scratch_d); c->scratch_d = nullptr; c->scratch_bytes = 0;
     bytes += bytes / 8;
-    if (cudaMalloc(&c->scratch_d, bytes) != cudaSuccess) { cudaGetLastError(); c->err = "allocation failed (download scratch)"; return SPH_ERR_CUDA; }
+    if (sph_dev_malloc(&c->scratch_d, bytes) != cudaSuccess) { cudaGetLastError(); c->err = "allocation failed (download scratch)"; return SPH_ERR_CUDA; }
     c->scratch_bytes = bytes;
     return SPH_OK;
 }

@@ -7,6 +7,29 @@
 #include <vector>
 #include "../../include/sphb200.h"
 
+// ---- SPH_DEBUG_BOUNDS build (make debug -> libsphb200_dbg.so): stands in for compute-sanitizer, which the GPU pool refuses.
+//   * every data-dependent shared-memory / row / stack / list index in the kernels is asserted (SPH_DBG_IDX): a violation
+//     prints file:line, the index and its limit, and traps -- the next synchronising ABI call fails;
+//   * every device allocation of the library carries 256-byte guard zones on both sides, filled with 0xA5;
+//     sphb200_debug_check_guards counts the guard bytes that no longer hold the pattern (out-of-bounds WRITES of any kernel).
+// In the release build SPH_DBG_IDX compiles to nothing and allocations are plain cudaMalloc / cudaFree.
+#ifdef SPH_DEBUG_BOUNDS
+#include <stdio.h>
+#define SPH_DBG_IDX(i, n)                                                                                                     \
+    do {                                                                                                                      \
+        if (!((long long)(i) >= 0 && (long long)(i) < (long long)(n))) {                                                      \
+            printf("SPH_DEBUG_BOUNDS %s:%d: index %lld outside [0, %lld) (block %d thread %d)\n", __FILE__, __LINE__,           \
+                   (long long)(i), (long long)(n), (int)blockIdx.x, (int)threadIdx.x);                                        \
+            __trap();                                                                                                         \
+        }                                                                                                                     \
+    } while (0)
+#else
+#define SPH_DBG_IDX(i, n) ((void)0)
+#endif
+cudaError_t sph_dev_malloc(void** p, size_t bytes);   // abi.cu
+cudaError_t sph_dev_free(void* p);
+int sph_debug_guard_errors(long long* bad_bytes, long long* allocations);
+
 #define SPH_MAX_PASSES 24
 #define SPH_RR_TABLE 4096          // radius-ratio table entries (own-support count 1..4095)
 #define SPH_MAX_RANKS 32           // ranks of one group (halo masks are 32-bit)

@@ -13,14 +13,19 @@
 //   2. keys; histogram over 2^18 key-prefix bins, all-reduced; work-balanced splitters; particles that left the rank's key
 //      range migrate (all-to-all of 48-byte records over NVLink; a handful per step once the run is settled)
 //   3. local stable radix sort of the received set (source-rank order + stable sort = the global stable order)
+//   3b. the GRAVITY LANE starts here on the auxiliary stream / communicator and runs behind passes 4-6: gravity sources and keys of
+//      the own range straight from the sorted records, all-gathered in global sorted order; tree gravity builds the LBVH nodes of
+//      the own range, all-gathers the few records that describe the nodes straddling rank boundaries (k_top_tree finishes them
+//      identically on every rank) and exchanges a LOCALLY ESSENTIAL TREE: the sender tests every finished node's parent against
+//      the box of the positions each other rank walks and ships only the records a walk of that rank can reach (k_let_*,
+//      kernels_group.cu: ~8 % of the nodes at 8 ranks x 2 M) -- all-gathering the node array would move 64 B x N per step
 //   4. halo: own particles whose cell stencil touches another rank's cells go to that rank (32-byte records);
 //      extended set [low halo | own | high halo] = a sorted subsequence of the global order, with its own cell table
 //   5. neighbor rows + density for the own targets; (m/rho)P of the halo particles follows through the same lists
-//   6. gravity sources: all-gather of (x,y,z,m) in global sorted order; tree gravity also all-gathers the keys, builds the
-//      LBVH nodes of the own range, all-gathers the packed nodes and finishes the few nodes that straddle rank boundaries
-//      from all-gathered frontier moments (k_top_tree) -- the identical tree on every rank
-//   7. pressure gradient, integration of the own particles
-// Two host synchronisations per step (migration counts, halo counts): NCCL needs the message sizes on the host.
+//   6. pressure gradient; then the gravity lane is joined and the own targets walk the tree (or run the all-pairs kernel)
+//   7. integration of the own particles
+// Three host synchronisations per step (migration counts, halo counts and -- on the gravity lane only, while the device runs the
+// neighbor pass -- the tree-node counts): NCCL needs the message sizes on the host.
 // Results are bit-identical to the single-GPU step for tree gravity (tests/test_group.py), <= 1e-6 for all-pairs (the
 // source-split partial sums depend on the number of targets per rank).
 #include "group.cuh"
@@ -388,16 +393,16 @@ void pass_mark(sphb200_group* g, const char* name) {
     cudaEventRecord(g->tev[g->npass], R.c->stream);
 }
 
-template <typename T> cudaError_t dal(T** p, size_t count) { return cudaMalloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)); }
+template <typename T> cudaError_t dal(T** p, size_t count) { return sph_dev_malloc((void**)p, std::max<size_t>(count, 1) * sizeof(T)); }
 
 void free_rank(GroupRank& R) {
     if (R.c) cudaSetDevice(R.device);
-    cudaFree(R.mig_send); cudaFree(R.mig_recv); cudaFree(R.dest); cudaFree(R.perm); cudaFree(R.tot256); cudaFree(R.hmask); cudaFree(R.hlist);
-    cudaFree(R.hcnt); cudaFree(R.htot); cudaFree(R.halo_send); cudaFree(R.halo_recv); cudaFree(R.cv_send); cudaFree(R.hist); cudaFree(R.bpart); cudaFree(R.bmask);
-    cudaFree(R.tposh); cudaFree(R.tvelm); cudaFree(R.let_mask); cudaFree(R.let_cnt); cudaFree(R.let_cursor); cudaFree(R.let_soff); cudaFree(R.let_box); cudaFree(R.lcnt_d); cudaFree(R.let_send); cudaFree(R.let_recv);
+    sph_dev_free(R.mig_send); sph_dev_free(R.mig_recv); sph_dev_free(R.dest); sph_dev_free(R.perm); sph_dev_free(R.tot256); sph_dev_free(R.hmask); sph_dev_free(R.hlist);
+    sph_dev_free(R.hcnt); sph_dev_free(R.htot); sph_dev_free(R.halo_send); sph_dev_free(R.halo_recv); sph_dev_free(R.cv_send); sph_dev_free(R.hist); sph_dev_free(R.bpart); sph_dev_free(R.bmask);
+    sph_dev_free(R.tposh); sph_dev_free(R.tvelm); sph_dev_free(R.let_mask); sph_dev_free(R.let_cnt); sph_dev_free(R.let_cursor); sph_dev_free(R.let_soff); sph_dev_free(R.let_box); sph_dev_free(R.lcnt_d); sph_dev_free(R.let_send); sph_dev_free(R.let_recv);
     if (R.lcnt_h) cudaFreeHost(R.lcnt_h);
-    cudaFree(R.split_d); cudaFree(R.cnt_d); cudaFree(R.posm_g); cudaFree(R.keys_g); cudaFree(R.bnd); cudaFree(R.red_scratch);
-    if (R.c) { cudaFree(R.c->top_nodes); cudaFree(R.c->front_nodes); cudaFree(R.c->top_counts); R.c->top_nodes = nullptr; R.c->front_nodes = nullptr; R.c->top_counts = nullptr; }
+    sph_dev_free(R.split_d); sph_dev_free(R.cnt_d); sph_dev_free(R.posm_g); sph_dev_free(R.keys_g); sph_dev_free(R.bnd); sph_dev_free(R.red_scratch);
+    if (R.c) { sph_dev_free(R.c->top_nodes); sph_dev_free(R.c->front_nodes); sph_dev_free(R.c->top_counts); R.c->top_nodes = nullptr; R.c->front_nodes = nullptr; R.c->top_counts = nullptr; }
     if (R.cnt_h) cudaFreeHost(R.cnt_h);
     if (R.split_h) cudaFreeHost(R.split_h);
     if (R.grid_h) cudaFreeHost(R.grid_h);
@@ -428,7 +433,7 @@ int alloc_rank(sphb200_group* g, GroupRank& R) {
          dal(&R.let_soff, (size_t)W) == cudaSuccess && dal(&R.let_box, (size_t)W * 8) == cudaSuccess && dal(&R.lcnt_d, (size_t)W * W) == cudaSuccess &&
          (W == 1 || (dal(&R.let_send, 3 * (size_t)g->cap_let) == cudaSuccess && dal(&R.let_recv, 3 * (size_t)g->cap_let) == cudaSuccess)) &&
          cudaMallocHost((void**)&R.lcnt_h, (size_t)W * W * sizeof(uint32_t)) == cudaSuccess &&
-         (!g->local || cudaMalloc(&R.red_scratch, R.red_bytes) == cudaSuccess) &&
+         (!g->local || sph_dev_malloc(&R.red_scratch, R.red_bytes) == cudaSuccess) &&
          dal(&R.c->top_nodes, (size_t)W * SPH_TOP_CAP) == cudaSuccess && dal(&R.c->front_nodes, (size_t)W * SPH_TOP_CAP) == cudaSuccess &&
          dal(&R.c->top_counts, (size_t)W * 4) == cudaSuccess &&
          cudaMallocHost((void**)&R.cnt_h, (size_t)W * W * sizeof(uint32_t)) == cudaSuccess &&

@@ -454,10 +454,11 @@ __global__ void __launch_bounds__(256) k_let_pack(const uint32_t* __restrict__ m
     }
 }
 
-__global__ void __launch_bounds__(256) k_let_scatter(const float4* __restrict__ rec, int nrec, float4* __restrict__ packed) {
+__global__ void __launch_bounds__(256) k_let_scatter(const float4* __restrict__ rec, int nrec, long long n_nodes, float4* __restrict__ packed) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nrec) return;
     const int k = __float_as_int(rec[3 * (size_t)i + 2].x);
+    SPH_DBG_IDX(k, 2 * (long long)n_nodes);
     packed[2 * (size_t)k] = rec[3 * (size_t)i];
     packed[2 * (size_t)k + 1] = rec[3 * (size_t)i + 1];
 }
@@ -662,7 +663,7 @@ int grk_let_pack(sphb200_ctx* c, const uint32_t* mask, int world, const uint32_t
     return SPH_OK;
 }
 int grk_let_scatter(sphb200_ctx* c, const float4* rec, int64_t nrec) {
-    if (nrec > 0) { k_let_scatter<<<sph_div_up(nrec, 256), 256, 0, c->stream>>>(rec, (int)nrec, c->packed); GL(c); }
+    if (nrec > 0) { k_let_scatter<<<sph_div_up(nrec, 256), 256, 0, c->stream>>>(rec, (int)nrec, (long long)c->tree_n, c->packed); GL(c); }
     return SPH_OK;
 }
 int grk_body_dest(sphb200_ctx* c, const uint32_t* orig, int n, int64_t chunk, uint8_t* dest) {

@@ -311,6 +311,8 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINB) k_cell_neighbors(
             const int cx = (int)compact10(ck), cy = (int)compact10(ck >> 1), cz = (int)compact10(ck >> 2);
             {
                 const int nt = min(K3_MAXT, e - p0);   // targets of this pass (a cell far denser than its size: several passes)
+                SPH_DBG_IDX(nt - 1, K3_MAXT);
+                SPH_DBG_IDX(p0 - rowbase, 0x7fffffff);
                 __syncwarp();
                 int rh = 0, rt = 0;   // candidate ring head / tail (monotone counters)
                 // stage the targets; box of their positions, their largest keep threshold and largest h
@@ -356,6 +358,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINB) k_cell_neighbors(
                         const bool keep = d2 < fmaxf(Tt.w, c.w) && jrel != tt;
                         const unsigned kb = __ballot_sync(FULL, keep);
                         const int slot = base + __popc(kb & lt);
+                        if (keep) { SPH_DBG_IDX(slot, 1 << 24); SPH_DBG_IDX(j, t1 + (1 << 28)); }
                         if (keep && slot < kmax) rowt[slot] = (uint32_t)j;   // beyond max_neighbors: counted, not stored
                         if (lane == 0) cn_w[tt] = base + __popc(kb);
                     }
@@ -365,6 +368,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINB) k_cell_neighbors(
                 // a candidate enters the ring only if it can reach the box of the targets:
                 // d2(i,j) < max(C_i, C_j) for some target i needs dist^2(p_j, box) (1 - 1e-5) < max(C_max, C_j)
                 auto flush = [&]() {
+                    SPH_DBG_IDX(qn, K3_QCAP + 1);
                     if (lane == 0) qp_w[qn] = (uint32_t)qtotal;
                     __syncwarp();
                     int q0 = 0;   // queue entry holding flattened position f0 of the batch being fetched
@@ -376,6 +380,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINB) k_cell_neighbors(
                         const unsigned starts = __reduce_or_sync(FULL, pos <= 32 ? 1u << (pos - 1) : 0u);
                         const int q = q0 + __popc(starts & lt);
                         const int f = f0 + lane;
+                        if (f < qtotal) SPH_DBG_IDX(q, qn);
                         j = f < qtotal ? (int)(qs_w[q] + ((uint32_t)f - qp_w[q])) : 0;
                         c = posc[j];
                         q0 += __popc(starts);
@@ -447,6 +452,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINB) k_cell_neighbors(
                     }
                     if (ok) {
                         const int pos = qn + __popc(bal & lt);
+                        SPH_DBG_IDX(pos, K3_QCAP);
                         qs_w[pos] = a;
                         qp_w[pos] = (uint32_t)(qtotal + incl - (int)(b - a));
                     }

@@ -144,6 +144,7 @@ __global__ void __launch_bounds__(SORT_THREADS) k_digit_scatter(const uint32_t* 
         if (dig[r] < 0) continue;
         const int i = c0 + r * 32 + lane;
         const uint32_t pos = wcount[w][dig[r]] + rnk[r];
+        SPH_DBG_IDX(pos, n);
         if (keys_out) keys_out[pos] = keys_in[i];
         vals_out[pos] = vals_in ? vals_in[i] : (uint32_t)i;
     }

@@ -73,6 +73,7 @@ __global__ void __launch_bounds__(256) k_lbvh_topology(const uint32_t* __restric
     int lo = min(i, j), hi = max(i, j);
     int lc = (lo == gamma) ? (n - 1 + gamma) : gamma;
     int rc = (hi == gamma + 1) ? (n - 1 + gamma + 1) : (gamma + 1);
+    SPH_DBG_IDX(lc, 2 * (long long)n - 1); SPH_DBG_IDX(rc, 2 * (long long)n - 1);
     child[i] = make_int2(lc, rc);
     range[i] = make_int2(lo, hi);
     parent[lc] = i;
@@ -160,6 +161,7 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
     const int k = u < nown ? g0 + u : n - 1 + g0 + (u - nown);
     if (u < nown && k >= n - 1) return;   // n slots have n-1 internal nodes
     int2 rg = range[k];
+    SPH_DBG_IDX(rg.x, n); SPH_DBG_IDX(rg.y, n);
     if (rg.y - rg.x + 1 > leaf_max) return;
     {   // a small node whose parent is small too lies strictly inside a bucket: the walk never reaches it
         const int p = parent[k];
@@ -181,6 +183,7 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
     float4 cmo = mo, clo = make_float4(lo[0], lo[1], lo[2], 0.f), chi = make_float4(hi[0], hi[1], hi[2], 0.f);
     while (true) {
         int p = parent[cur];
+        SPH_DBG_IDX(p + 1, 2 * (long long)n);
         int2 prg = p >= 0 ? range[p] : make_int2(0, 0);
         if (p < 0 || prg.x < g0 || prg.y >= g1) {
             // the root -- or, on a group rank, a parent that is built elsewhere / straddles the rank boundary: `cur` is a
@@ -322,7 +325,7 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
         if (sp >= TW_STACK) { if (lane == 0) atomicExch(&err[ERR_TREE_STACK], 1); break; }   // unreachable for trees of depth < TW_HEADROOM
         const bool have = lane < nb;
         int2 e = make_int2(0, 0);
-        if (have) e = st[sp - 1 - lane];
+        if (have) { SPH_DBG_IDX(sp - 1 - lane, TW_STACK); e = st[sp - 1 - lane]; SPH_DBG_IDX(e.x, 2 * (long long)n - 1); }
         sp -= nb;
         const float4 N = __ldg(&packed[2 * (size_t)e.x]);
         const float4 X = __ldg(&packed[2 * (size_t)e.x + 1]);
@@ -356,6 +359,8 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
         const unsigned ob = __ballot_sync(FULL, open);
         if (open) {
             const int pos = sp + 2 * __popc(ob & ((1u << lane) - 1u));
+            SPH_DBG_IDX(pos + 1, TW_STACK);
+            SPH_DBG_IDX(ia, 2 * (long long)n - 1); SPH_DBG_IDX(ib, 2 * (long long)n - 1);
             st[pos] = make_int2(ia, (int)rej);
             st[pos + 1] = make_int2(ib, (int)rej);
         }
@@ -382,6 +387,8 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
                 for (int u = 0; u < 4; u++)
                     if (u < c4) {
                         const int pos = incl - c4 + u;
+                        SPH_DBG_IDX(pos, 128);
+                        SPH_DBG_IDX(bfirst + u, n);
                         const float4 pj = __ldg(&posm[bfirst + u]);
                         float* rec = sbf + (pos >> 1) * 8 + (pos & 1);
                         rec[0] = pj.x; rec[2] = pj.y; rec[4] = pj.z; rec[6] = pj.w;

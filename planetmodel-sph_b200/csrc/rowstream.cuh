@@ -13,6 +13,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "ctx.cuh"
 
 constexpr int RS_WARPS = 8;     // warps per block
 constexpr int RS_SLOTS = 320;   // octet sums per warp and round (32 rows x 46 neighbors = 200 octets; longer streams take rounds)
@@ -56,6 +57,7 @@ __device__ __forceinline__ void row_stream(RowStreamSmem<NV>& S, const uint32_t*
     auto entry = [&](uint32_t m) {
         uint32_t j = fallback;
         const uint32_t* ep = wrow + ((m >> 13) + sub);
+        if ((uint32_t)sub < ((m >> 9) & 0xfu)) SPH_DBG_IDX((m >> 13) + sub, 32 * kmax);
         asm("{ .reg .pred p; setp.lt.u32 p, %2, %3; @p ld.global.nc.u32 %0, [%1]; }" : "+r"(j) : "l"(ep), "r"((uint32_t)sub), "r"((m >> 9) & 0xfu));
         return j;
     };
@@ -77,8 +79,10 @@ __device__ __forceinline__ void row_stream(RowStreamSmem<NV>& S, const uint32_t*
         const int no = S.pre[r_hi] - o_lo;
         const bool mine = lane >= r_lo && lane < r_hi;
         if (mine)
-            for (int u = 0; u < noct; u++)
+            for (int u = 0; u < noct; u++) {
+                SPH_DBG_IDX(my_o0 - o_lo + u, RS_SLOTS);
                 S.om[my_o0 - o_lo + u] = (uint32_t)(lane * 16) | ((uint32_t)min(8, clen - 8 * u) << 9) | ((uint32_t)(lane * kmax + 8 * u) << 13);
+            }
         if (lane < 16) S.om[no + lane] = 0u;   // padding of the last iteration and of the look-ahead: no live entries
         __syncwarp();
         uint32_t ma = S.om[grp], mb = S.om[4 + grp];
@@ -117,6 +121,7 @@ __device__ __forceinline__ void row_stream(RowStreamSmem<NV>& S, const uint32_t*
         __syncwarp();
         if (mine)
             for (int u = 0; u < noct; u++) {
+                SPH_DBG_IDX(my_o0 - o_lo + u, RS_SLOTS);
                 const float* v = S.osum[my_o0 - o_lo + u];
 #pragma unroll
                 for (int k = 0; k < NV; k++) sum[k] += v[k];

@@ -67,7 +67,7 @@ EXPORTS = [
     "sphb200_group_download", "sphb200_group_sync", "sphb200_group_diagnostics", "sphb200_group_info",
     "sphb200_group_enable_timing", "sphb200_group_get_timings", "sphb200_group_rank_handle", "sphb200_group_stream",
     "sphb200_get_stream", "sphb200_field_stats", "sphb200_snapshot_save", "sphb200_snapshot_load",
-    "sphb200_group_field_stats", "sphb200_group_snapshot_save", "sphb200_group_snapshot_load",
+    "sphb200_group_field_stats", "sphb200_group_snapshot_save", "sphb200_group_snapshot_load", "sphb200_debug_check_guards",
 ]
 
 
@@ -76,6 +76,16 @@ class GroupInfo(C.Structure):
                 ("n_total", C.c_int64), ("steps", C.c_int64), ("migrated_last_step", C.c_int64), ("halo_last_step", C.c_int64),
                 ("cap_own", C.c_int64), ("cap_halo", C.c_int64), ("launches", C.c_int64), ("tree_nodes_last_step", C.c_int64),
                 ("n_own", C.c_int64 * 32), ("n_halo", C.c_int64 * 32)]
+
+
+def debug_check_guards():
+    """(bad guard bytes, live allocations) of the SPH_DEBUG_BOUNDS build of the library; allocations == -1: release build."""
+    L = load_library()
+    bad = C.c_int64(0); na = C.c_int64(0)
+    rc = L.sphb200_debug_check_guards(C.byref(bad), C.byref(na))
+    if rc:
+        raise RuntimeError("sphb200_debug_check_guards failed: %d" % rc)
+    return int(bad.value), int(na.value)
 
 
 class SphError(RuntimeError):
@@ -133,6 +143,7 @@ def load_library():
     L.sphb200_get_timings.argtypes = [H, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.c_int]
     L.sphb200_fp32_peak.argtypes = [H, C.POINTER(C.c_double)]
     L.sphb200_version.restype = C.c_char_p
+    L.sphb200_debug_check_guards.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
     L.sphb200_group_create.argtypes = [C.POINTER(Params), C.c_int64, C.c_int, C.POINTER(C.c_int), C.POINTER(H)]
     L.sphb200_group_unique_id.argtypes = [C.c_void_p]
     L.sphb200_group_create_rank.argtypes = [C.POINTER(Params), C.c_int64, C.c_void_p, C.c_int, C.c_int, C.c_int, C.POINTER(H)]

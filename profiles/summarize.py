@@ -17,7 +17,7 @@ def launches(path, out):
         for k, (c, v) in sorted(agg.items(), key=lambda x: -x[1][1]):
             f.write('%12.3f %6d %7.2f%%  %s\n' % (v, c, 100 * v / tot, k))
 
-WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+WANT = ['gpu__time_duration.sum', 'l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed', 'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
         'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size', 'launch__waves_per_multiprocessor',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active',
@@ -41,6 +41,7 @@ def full(rep, out):
             f.write('  stall reasons per issue: ' + ', '.join('%s=%.2f' % (n, v) for v, n in st) + '\n')
 
 if __name__ == '__main__':
-    launches('gpurun_out/r01_launches_c3.csv', 'profiles/r01_launches_c3.txt')
-    full('gpurun_out/r01_allpairs.ncu-rep', 'profiles/r01_allpairs_full.txt')
-    full('gpurun_out/r01_tree_sph.ncu-rep', 'profiles/r01_tree_sph_full.txt')
+    rnd = sys.argv[1] if len(sys.argv) > 1 else 'r02'
+    launches('gpurun_out/%s_launches_c3.csv' % rnd, 'profiles/%s_launches_c3.txt' % rnd)
+    full('gpurun_out/%s_allpairs.ncu-rep' % rnd, 'profiles/%s_allpairs_full.txt' % rnd)
+    full('gpurun_out/%s_tree_sph.ncu-rep' % rnd, 'profiles/%s_tree_sph_full.txt' % rnd)
