@@ -12,6 +12,10 @@ public static unsafe class SphB200Native
     public const int SPH_OK = 0, SPH_ERR_INVALID_ARG = -1, SPH_ERR_CAPACITY = -2, SPH_ERR_NEIGHBOR_OVERFLOW = -3,
                      SPH_ERR_CUDA = -4, SPH_ERR_STATE = -5, SPH_ERR_TREE_STACK = -6;
 
+    // sph_Params.flags (all off by default = the reference's behaviour): undo quirk Q1; kick-drift integration (README.md:90-93);
+    // Price & Monaghan 2007 spline-softened, h-symmetric gravity (README.md:75-77)
+    public const int SPH_FLAG_FIX_KERNEL_DERIV_SIGN = 1, SPH_FLAG_KICK_DRIFT = 2, SPH_FLAG_PM07_SOFTENING = 4;
+
     // GravityFieldSystem.GravityImpl (GravityFieldSystem.cs:19-23)
     public const int SPH_GRAVITY_TREE = 0, SPH_GRAVITY_PARTICLE = 1, SPH_GRAVITY_NONE = 2;
 
@@ -43,6 +47,34 @@ public static unsafe class SphB200Native
     [DllImport(Lib)] public static extern int sphb200_download(IntPtr h, int field, void* dst, int stride);
     [DllImport(Lib)] public static extern int sphb200_download_neighbors(IntPtr h, long* offsets, int* nbr, long cap, long* total);
     [DllImport(Lib)] public static extern int sphb200_diagnostics(IntPtr h, double* out12);
+    [DllImport(Lib)] public static extern int sphb200_field_stats(IntPtr h, double* out12);            // min / max / mean rho, P, |grad Phi|, u (README.md:50-52)
+    [DllImport(Lib)] public static extern int sphb200_snapshot_save(IntPtr h, [MarshalAs(UnmanagedType.LPStr)] string path);
+    [DllImport(Lib)] public static extern int sphb200_snapshot_load(IntPtr h, [MarshalAs(UnmanagedType.LPStr)] string path);
+
+    // ---- several GPUs: Morton-range domain decomposition (include/sphb200.h "group" section).  One process -- the Unity player --
+    // drives every GPU of the node through ONE group handle; body indices, strides and fields mean what they mean above.
+    public const int SPH_ERR_NCCL = -7;
+    [DllImport(Lib)] public static extern int sphb200_group_create(Params* p, long capacity, int ndev, int* devices, out IntPtr group);
+    [DllImport(Lib)] public static extern int sphb200_group_destroy(IntPtr g);
+    [DllImport(Lib)] public static extern IntPtr sphb200_group_last_error(IntPtr g);
+    [DllImport(Lib)] public static extern int sphb200_group_upload(IntPtr g, long nTotal, void* pos, int posStride, void* vel, int velStride,
+                                                                  void* mass, int massStride, void* smoothing, int smoothingStride);
+    [DllImport(Lib)] public static extern int sphb200_group_step(IntPtr g, float dt, int gravityImpl);
+    [DllImport(Lib)] public static extern int sphb200_group_download(IntPtr g, int field, void* dst, int stride);
+    [DllImport(Lib)] public static extern int sphb200_group_sync(IntPtr g);
+    [DllImport(Lib)] public static extern int sphb200_group_diagnostics(IntPtr g, double* out12);
+    [DllImport(Lib)] public static extern int sphb200_group_field_stats(IntPtr g, double* out12);
+    [DllImport(Lib)] public static extern int sphb200_group_snapshot_save(IntPtr g, [MarshalAs(UnmanagedType.LPStr)] string path);
+    [DllImport(Lib)] public static extern int sphb200_group_snapshot_load(IntPtr g, [MarshalAs(UnmanagedType.LPStr)] string path);
+
+    public static void CheckGroup(IntPtr g, int rc)
+    {
+        if (rc == SPH_OK) return;
+        string msg = Marshal.PtrToStringAnsi(sphb200_group_last_error(g)) ?? "";
+        if (rc == SPH_ERR_CAPACITY) throw new ArgumentOutOfRangeException("count", msg);
+        if (rc == SPH_ERR_NEIGHBOR_OVERFLOW) throw new OverflowException(msg);
+        throw new InvalidOperationException("sphb200 group error " + rc + ": " + msg);
+    }
 
     // Error mapping of SURVEY.md 8(b): the wrapper rethrows as the exception types the reference throws
     // (KernelSystem.cs:102-105 NotImplementedException, GravityFieldSystem.cs:400-403 InvalidOperationException).

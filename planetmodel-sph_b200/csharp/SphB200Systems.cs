@@ -73,6 +73,53 @@ public unsafe class SphWorldBridge : IDisposable
     public void Dispose() { if (Handle != IntPtr.Zero) { SphB200Native.sphb200_destroy(Handle); Handle = IntPtr.Zero; } }
 }
 
+// Several GPUs (the reference caps a world at 2^24-2 bodies, UP/Dynamics/Simulation/Scheduler.cs:24-41; a group does not): the same
+// bridge over a group handle.  The decomposition fuses the six stages into one call per fixed step (its exchanges sit between
+// them), so with a group the six systems stay registered for their ordering attributes and constants but only VelocitySystem --
+// the last of the step -- makes the native call: SphGroupBridge.Instance != null switches them (see SphSystemBase.Stage).
+public unsafe class SphGroupBridge : IDisposable
+{
+    public IntPtr Group;
+    public int Count;
+    public static SphGroupBridge Instance;
+
+    public SphGroupBridge(int capacity, int[] devices)
+    {
+        SphB200Native.Params p;
+        SphB200Native.sphb200_default_params(&p);
+        p.G = GravityFieldSystem.k_GravConstant; p.theta = GravityFieldSystem.k_Theta; p.target_neighbors = ParticleSmoothingSystem.TARGET_NEIGHBORS;
+        fixed (int* d = devices)
+            SphB200Native.CheckGroup(IntPtr.Zero, SphB200Native.sphb200_group_create(&p, capacity, devices.Length, d, out Group));
+    }
+
+    public void Upload(EntityQuery q)
+    {
+        using (var pos = q.ToComponentDataArray<Translation>(Allocator.TempJob))
+        using (var vel = q.ToComponentDataArray<PhysicsVelocity>(Allocator.TempJob))
+        using (var mass = q.ToComponentDataArray<ParticleMass>(Allocator.TempJob))
+        using (var sm = q.ToComponentDataArray<ParticleSmoothing>(Allocator.TempJob))
+        {
+            Count = pos.Length;
+            SphB200Native.CheckGroup(Group, SphB200Native.sphb200_group_upload(Group, Count,
+                pos.GetUnsafeReadOnlyPtr(), sizeof(Translation), vel.GetUnsafeReadOnlyPtr(), sizeof(PhysicsVelocity),
+                mass.GetUnsafeReadOnlyPtr(), sizeof(ParticleMass), sm.GetUnsafeReadOnlyPtr(), sizeof(ParticleSmoothing)));
+        }
+    }
+
+    public void Step(float dt, int impl) { SphB200Native.CheckGroup(Group, SphB200Native.sphb200_group_step(Group, dt, impl)); }
+
+    public void Export<T>(EntityQuery q, SphB200Native.Field f) where T : struct, IComponentData
+    {
+        using (var a = new NativeArray<T>(Count, Allocator.TempJob))
+        {
+            SphB200Native.CheckGroup(Group, SphB200Native.sphb200_group_download(Group, (int)f, a.GetUnsafePtr(), UnsafeUtility.SizeOf<T>()));
+            q.CopyFromComponentDataArray(a);
+        }
+    }
+
+    public void Dispose() { if (Group != IntPtr.Zero) { SphB200Native.sphb200_group_destroy(Group); Group = IntPtr.Zero; } }
+}
+
 public abstract class SphSystemBase : SystemBase, IPhysicsSystem
 {
     // IPhysicsSystem (UP/ECS/Base/Systems/IPhysicsSystem.cs:6-11): GPU work is stream-ordered, handles stay default.
@@ -81,20 +128,22 @@ public abstract class SphSystemBase : SystemBase, IPhysicsSystem
     public void AddInputDependency(JobHandle jh) => InputDependency = JobHandle.CombineDependencies(jh, InputDependency);
     protected IntPtr H => SphWorldBridge.Instance.Handle;
     protected void Begin() { InputDependency.Complete(); InputDependency = default; }
+    // with a group the whole step is one native call, made by the last system of the step
+    protected static bool Grouped => SphGroupBridge.Instance != null;
 }
 
 [UpdateInGroup(typeof(FixedStepSimulationSystemGroup))]
 public class ParticleSmoothingSystem : SphSystemBase
 {
     public const float TARGET_NEIGHBORS = 50;                        // ParticleSmoothingSystem.cs:18
-    protected override void OnUpdate() { Begin(); SphB200Native.Check(H, SphB200Native.sphb200_smoothing_update(H)); }
+    protected override void OnUpdate() { Begin(); if (Grouped) return; SphB200Native.Check(H, SphB200Native.sphb200_smoothing_update(H)); }
 }
 
 [UpdateInGroup(typeof(FixedStepSimulationSystemGroup))]
 [UpdateAfter(typeof(ParticleSmoothingSystem))]
 public class KernelSystem : SphSystemBase
 {
-    protected override void OnUpdate() { Begin(); SphB200Native.Check(H, SphB200Native.sphb200_build_neighbors(H)); }
+    protected override void OnUpdate() { Begin(); if (Grouped) return; SphB200Native.Check(H, SphB200Native.sphb200_build_neighbors(H)); }
 }
 
 [UpdateInGroup(typeof(FixedStepSimulationSystemGroup))]
@@ -108,6 +157,7 @@ public class GravityFieldSystem : SphSystemBase
     protected override void OnUpdate()
     {
         Begin();
+        if (Grouped) return;
         int impl = k_GravityImpl == GravityImpl.GRAVITY_TREE_CPU ? SphB200Native.SPH_GRAVITY_TREE : SphB200Native.SPH_GRAVITY_PARTICLE;
         SphB200Native.Check(H, SphB200Native.sphb200_gravity(H, impl, World.Time.DeltaTime));
     }
@@ -117,14 +167,14 @@ public class GravityFieldSystem : SphSystemBase
 [UpdateAfter(typeof(GravityFieldSystem))]
 public class DensityFieldSystem : SphSystemBase
 {
-    protected override void OnUpdate() { Begin(); SphB200Native.Check(H, SphB200Native.sphb200_density(H)); }
+    protected override void OnUpdate() { Begin(); if (Grouped) return; SphB200Native.Check(H, SphB200Native.sphb200_density(H)); }
 }
 
 [UpdateInGroup(typeof(FixedStepSimulationSystemGroup))]
 [UpdateAfter(typeof(DensityFieldSystem))]
 public class PressureFieldSystem : SphSystemBase
 {
-    protected override void OnUpdate() { Begin(); SphB200Native.Check(H, SphB200Native.sphb200_pressure(H)); }
+    protected override void OnUpdate() { Begin(); if (Grouped) return; SphB200Native.Check(H, SphB200Native.sphb200_pressure(H)); }
 }
 
 [UpdateInGroup(typeof(FixedStepSimulationSystemGroup))]
@@ -132,5 +182,15 @@ public class PressureFieldSystem : SphSystemBase
 public class VelocitySystem : SphSystemBase
 {
     // x += v dt (Integrator.cs:98-101) and v += (-gradP/rho - gradPhi) dt (VelocitySystem.cs:24-36) in one kernel
-    protected override void OnUpdate() { Begin(); SphB200Native.Check(H, SphB200Native.sphb200_integrate(H, World.Time.DeltaTime)); }
+    protected override void OnUpdate()
+    {
+        Begin();
+        if (Grouped)
+        {
+            int impl = GravityFieldSystem.k_GravityImpl == GravityFieldSystem.GravityImpl.GRAVITY_TREE_CPU ? SphB200Native.SPH_GRAVITY_TREE : SphB200Native.SPH_GRAVITY_PARTICLE;
+            SphGroupBridge.Instance.Step(World.Time.DeltaTime, impl);     // all six stages + the exchanges between them, on every GPU
+            return;
+        }
+        SphB200Native.Check(H, SphB200Native.sphb200_integrate(H, World.Time.DeltaTime));
+    }
 }

@@ -61,6 +61,44 @@ class World {
     }
 };
 
+// Several GPUs: the same component arrays over a GROUP handle (Morton-range domain decomposition, include/sphb200.h); one process
+// drives every GPU.  The decomposition fuses the six stages into one call per fixed step (its exchanges sit between them).
+class GroupWorld {
+  public:
+    std::vector<sph_Translation> Translation;
+    std::vector<sph_PhysicsVelocity> PhysicsVelocity;
+    std::vector<sph_ParticleMass> ParticleMass;
+    std::vector<sph_ParticleSmoothing> ParticleSmoothing;
+    std::vector<sph_ParticleDensity> ParticleDensity;
+    std::vector<sph_GravityField> GravityField;
+    float DeltaTime = 1.0f / 60.0f;
+    sph_group group = nullptr;
+
+    GroupWorld(int64_t count, const std::vector<int>& devices, const sph_Params* params = nullptr) {
+        Translation.resize(count); PhysicsVelocity.resize(count); ParticleMass.resize(count); ParticleSmoothing.resize(count);
+        ParticleDensity.resize(count); GravityField.resize(count);
+        int rc = sphb200_group_create(params, count, (int)devices.size(), devices.data(), &group);
+        if (rc) throw Error(rc, sphb200_group_last_error(nullptr));
+    }
+    ~GroupWorld() { if (group) sphb200_group_destroy(group); }
+    GroupWorld(const GroupWorld&) = delete;
+    GroupWorld& operator=(const GroupWorld&) = delete;
+    void check(int rc) const { if (rc) throw Error(rc, sphb200_group_last_error(group)); }
+    int64_t count() const { return (int64_t)Translation.size(); }
+    void Upload() {
+        check(sphb200_group_upload(group, count(), Translation.data(), sizeof(sph_Translation), PhysicsVelocity.data(), sizeof(sph_PhysicsVelocity),
+                                   ParticleMass.data(), sizeof(sph_ParticleMass), ParticleSmoothing.data(), sizeof(sph_ParticleSmoothing)));
+    }
+    void Step(int gravity_impl) { check(sphb200_group_step(group, DeltaTime, gravity_impl)); }   // one FixedStepSimulationSystemGroup tick
+    void Export() {
+        check(sphb200_group_download(group, SPH_FIELD_TRANSLATION, Translation.data(), sizeof(sph_Translation)));
+        check(sphb200_group_download(group, SPH_FIELD_VELOCITY, PhysicsVelocity.data(), sizeof(sph_PhysicsVelocity)));
+        check(sphb200_group_download(group, SPH_FIELD_SMOOTHING, ParticleSmoothing.data(), sizeof(sph_ParticleSmoothing)));
+        check(sphb200_group_download(group, SPH_FIELD_DENSITY, ParticleDensity.data(), sizeof(sph_ParticleDensity)));
+        check(sphb200_group_download(group, SPH_FIELD_GRAVITY, GravityField.data(), sizeof(sph_GravityField)));
+    }
+};
+
 struct SystemBase {
     World& world;
     explicit SystemBase(World& w) : world(w) {}
