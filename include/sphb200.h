@@ -29,7 +29,9 @@ enum {
     SPH_OK = 0,
     SPH_ERR_INVALID_ARG = -1,
     SPH_ERR_CAPACITY = -2,          /* n > capacity (the reference itself is capped at 2^24-2 bodies, Scheduler.cs:26-31,41; this library is not) */
-    SPH_ERR_NEIGHBOR_OVERFLOW = -3, /* some particle has more than max_neighbors neighbors; lists truncated */
+    SPH_ERR_NEIGHBOR_OVERFLOW = -3, /* some particle has more than max_neighbors neighbors; lists truncated.  Raised asynchronously: reported by
+                                       the next download / sync while the lists in memory are the truncated ones; the next neighbor pass whose
+                                       rows fit clears it (density and the h controller stay complete under overflow, so a run recovers by itself) */
     SPH_ERR_CUDA = -4,
     SPH_ERR_STATE = -5,             /* stage called out of order (e.g. pressure before build_neighbors) */
     SPH_ERR_TREE_STACK = -6,        /* traversal stack / top-tree list overflow in the LBVH gravity */

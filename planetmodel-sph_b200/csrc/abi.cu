@@ -426,7 +426,8 @@ static int check_errflags(sphb200_ctx* c) {
     if (c->err_h[ERR_TREE_STACK]) { c->err = "LBVH traversal stack overflow"; return SPH_ERR_TREE_STACK; }
     if (c->err_h[ERR_NEIGHBOR_OVERFLOW]) {
         c->err = "neighbor list overflow: a particle has " + std::to_string(c->err_h[ERR_NEIGHBOR_OVERFLOW]) +
-                 " neighbors > max_neighbors=" + std::to_string(c->p.max_neighbors) + " (lists truncated)";
+                 " neighbors > max_neighbors=" + std::to_string(c->p.max_neighbors) +
+                 " (lists truncated: the pressure gradient and the softened near-pair gravity of that particle miss the rest; density and h control stay complete)";
         return SPH_ERR_NEIGHBOR_OVERFLOW;
     }
     return SPH_OK;

@@ -36,7 +36,9 @@ int sph_debug_guard_errors(long long* bad_bytes, long long* allocations);
 #define SPH_TOP_LEAF 64            // >= the largest leaf_max: boundary particles published per rank side
 #define SPH_TOP_CAP 512            // per-rank capacity of the top-tree lists (nodes that straddle a rank boundary)
 
-enum { ERR_NEIGHBOR_OVERFLOW = 0, ERR_TREE_STACK = 1, ERR_TOP_TREE = 2, ERR_SLOTS = 4 };
+// ERR_NEIGHBOR_OVERFLOW describes the lists in memory (re-armed by every neighbor pass); ERR_OVERFLOW_EVER keeps the largest count
+// any pass since the upload has seen
+enum { ERR_NEIGHBOR_OVERFLOW = 0, ERR_TREE_STACK = 1, ERR_TOP_TREE = 2, ERR_OVERFLOW_EVER = 3, ERR_SLOTS = 4 };
 
 // Top-tree records of the distributed LBVH build (kernels_tree.cu / kernels_group.cu).  A node whose particle range crosses
 // a rank boundary cannot be finished by one rank: its owner emits its topology, the owners of its finished children emit

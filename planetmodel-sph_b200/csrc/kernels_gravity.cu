@@ -175,17 +175,28 @@ __global__ void __launch_bounds__(AP_THREADS) k_gravity_allpairs(const float4* _
     const int tile0 = s0 / AP_TILE;
     // padding source: zero mass (EQM: weight folded into position), far away: contributes exactly 0
     const float4 pad = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f);
-    float4 nxt = (s0 + tid < s1) ? src[s0 + tid] : pad;
+    constexpr int LPT = AP_TILE / AP_THREADS;   // sources a thread stages per tile
+    static_assert(AP_TILE % AP_THREADS == 0 && AP_TILE % (2 * AP_UNROLL) == 0, "tile shape");
+    float4 nxt[LPT];
+#pragma unroll
+    for (int l = 0; l < LPT; l++) nxt[l] = (s0 + l * AP_THREADS + tid < s1) ? src[s0 + l * AP_THREADS + tid] : pad;
     float4 nbx = tid < 2 ? tbox[2 * tile0 + tid] : pad;
-    const int so = (tid >> 1) * 8 + (tid & 1);   // slot of source `tid` inside its pair record
     for (int it = 0; it < ntiles; it++) {
         float* buf = tile[it & 1];
-        buf[so] = nxt.x; buf[so + 2] = nxt.y; buf[so + 4] = nxt.z; buf[so + 6] = nxt.w;
+#pragma unroll
+        for (int l = 0; l < LPT; l++) {
+            const int sidx = l * AP_THREADS + tid;                 // source `sidx` of the tile
+            const int so = (sidx >> 1) * 8 + (sidx & 1);          // its slot inside its pair record
+            buf[so] = nxt[l].x; buf[so + 2] = nxt[l].y; buf[so + 4] = nxt[l].z; buf[so + 6] = nxt[l].w;
+        }
         if (tid == 0) tb_lo[it & 1] = nbx;
         if (tid == 1) tb_hi[it & 1] = nbx;
         __syncthreads();
-        int nidx = s0 + (it + 1) * AP_TILE + tid;
-        nxt = (nidx < s1) ? src[nidx] : pad;
+#pragma unroll
+        for (int l = 0; l < LPT; l++) {
+            const int nidx = s0 + (it + 1) * AP_TILE + l * AP_THREADS + tid;
+            nxt[l] = (nidx < s1) ? src[nidx] : pad;
+        }
         if (tid < 2 && it + 1 < ntiles) nbx = tbox[2 * (tile0 + it + 1) + tid];
         const float4 lo = tb_lo[it & 1], hi = tb_hi[it & 1];
         const bool far = lo.x > e[3] || lo.y > e[4] || lo.z > e[5] || hi.x < e[0] || hi.y < e[1] || hi.z < e[2];

@@ -222,7 +222,7 @@ __global__ void __launch_bounds__(K1_WARPS * 32) k_neighbors_density(
             cvol[t] = __fmul_rn(__fdiv_rn(mi, d), P);    // m_j / rho_j * P_j (PressureFieldSystem.cs:65)
             ncount[t] = count;
             nown[t] = own;
-            if (count > kmax) atomicMax(&err[ERR_NEIGHBOR_OVERFLOW], count);
+            if (count > kmax) { atomicMax(&err[ERR_NEIGHBOR_OVERFLOW], count); atomicMax(&err[ERR_OVERFLOW_EVER], count); }
         }
     }
 }
@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(K3_WARPS * 32, K3_MINB) k_cell_neighbors(
                 for (int i = lane; i < nt; i += 32) {
                     const int cnt = cn_w[i];
                     ncount[p0 + i] = cnt;
-                    if (cnt > kmax) atomicMax(&err[ERR_NEIGHBOR_OVERFLOW], cnt);
+                    if (cnt > kmax) { atomicMax(&err[ERR_NEIGHBOR_OVERFLOW], cnt); atomicMax(&err[ERR_OVERFLOW_EVER], cnt); }
                 }
             }
         }
@@ -595,6 +595,8 @@ int sph_launch_neighbors_density(sphb200_ctx* c) {
     if (nt <= 0) return SPH_OK;
     // cell-centric kernel (h_max < 1e5): persistent warps pull 32-cell chunks from a counter
     SPH_CK(c, cudaMemsetAsync(c->chunk_counter, 0, sizeof(unsigned int), c->stream));
+    // the overflow flag describes the lists this pass builds: a later pass whose rows fit clears it
+    SPH_CK(c, cudaMemsetAsync(c->err_d + ERR_NEIGHBOR_OVERFLOW, 0, sizeof(int32_t), c->stream));
 #define K3_LAUNCH(E) k_cell_neighbors<E><<<c->sm_count * K3_MINB, K3_WARPS * 32, 0, c->stream>>>(                                        \
         c->posc, c->posh[c->cur], c->posm, c->skeys, c->cell_start, c->cell_end, c->cell_hmax, c->grid_d, t0, t1, (int)c->row_base, c->p.max_neighbors, c->p.K, \
         c->nlist, c->ncount, c->nown, c->rho, c->press, c->cvol, c->err_d, c->chunk_counter)

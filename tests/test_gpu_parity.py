@@ -656,3 +656,53 @@ def test_pm07_softening_flag_direct_and_tree_vs_oracle_and_momentum(orc):
     net = lambda g: np.linalg.norm((m * g).sum(0)) / (m * np.linalg.norm(g, axis=1, keepdims=True)).sum()
     assert net(g_pm) < 2e-6
     assert net(g_pm) < net(g_ref_law)
+
+
+def test_overflow_flag_follows_the_lists_and_stale_states_are_refused(orc):
+    """SPH_ERR_NEIGHBOR_OVERFLOW describes the lists in memory: reported after the step that overflowed, gone once a later
+    neighbor pass fits (density and own-support counts stay complete under overflow, so the h controller recovers by itself).
+    Also: smoothing_update after a sort without a neighbor pass and interaction records after integrate are SPH_ERR_STATE."""
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_sphere(3000, seed=21)
+    c["h"] = (c["h"] * 3.0).astype(np.float32)                  # ~27x the target neighbor count: rows of 64 overflow
+    sim = make_sim(3000, max_neighbors=64)
+    sim.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    sim.step(1e-4, sphb200.GRAVITY_NONE)
+    with pytest.raises(sphb200.SphError) as e:
+        sim.sync()
+    assert e.value.code == sphb200.SPH_ERR_NEIGHBOR_OVERFLOW
+    recovered = False
+    for _ in range(12):                                          # the controller shrinks h towards 50 neighbors
+        sim.step(1e-4, sphb200.GRAVITY_NONE)
+        try:
+            sim.sync()
+            recovered = True
+            break
+        except sphb200.SphError as ex:
+            assert ex.code == sphb200.SPH_ERR_NEIGHBOR_OVERFLOW
+    assert recovered, "the overflow flag stayed set although the rows fit again"
+    out = sim.download_all()
+    assert out["count"].max() <= 64
+    # stale own-support counts: upload, sort through tree gravity, then smoothing_update
+    sim.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    sim.gravity(sphb200.GRAVITY_TREE, 0.01)
+    with pytest.raises(sphb200.SphError) as e:
+        sim.smoothing_update()
+    assert e.value.code == sphb200.SPH_ERR_STATE
+    # interaction records need lists that still describe the resident positions
+    c2 = ic.make_sphere(500, seed=22)
+    s2 = make_sim(500)
+    s2.upload(c2["pos"], c2["vel"], c2["mass"], c2["h"])
+    s2.step(0.01, sphb200.GRAVITY_NONE)
+    off, nbr = s2.download_neighbors()
+    with pytest.raises(sphb200.SphError) as e:
+        s2.download_interactions(off, nbr)
+    assert e.value.code == sphb200.SPH_ERR_STATE
+    s2.build_neighbors()
+    off, nbr = s2.download_neighbors()
+    bad = nbr.copy(); bad[0] = 500
+    with pytest.raises(sphb200.SphError) as e:
+        s2.download_interactions(off, bad)
+    assert e.value.code == sphb200.SPH_ERR_INVALID_ARG
+    s2.download_interactions(off, nbr)
