@@ -771,11 +771,13 @@ int sphb200_group_step(sph_group g, float dt, int impl) {
                 G_CUDA(g, cudaMemcpyAsync(R.let_soff, soff, W * sizeof(uint32_t), cudaMemcpyHostToDevice, R.c->stream));
                 G_RC(g, R, grk_let_pack(R.c, R.let_mask, W, R.let_soff, R.let_cursor, R.let_send));
             }
+            aux_mark(g, "gravity_aux_hostsync_pack");
             {
                 auto sd = ptrs(g, [](GroupRank& R) { return R.let_send; });
                 auto rv = ptrs(g, [](GroupRank& R) { return R.let_recv; });
                 if ((rc = g_alltoallv(g, sd.data(), rv.data(), loff, L, 48))) return rc;
             }
+            aux_mark(g, "gravity_aux_alltoall");
             for (int l = 0; l < g->nlocal; l++) {
                 GroupRank& R = g->r[l];
                 G_CUDA(g, cudaSetDevice(R.device));
