@@ -454,10 +454,17 @@ def measure_e2e(eng, state, impl, steps, barrier):
         tb = time.perf_counter()
         eng.step(DT, impl)
         tc = time.perf_counter()                  # asynchronous: the step's device time shows up in the first download
-        for f, buf in outs.items():
+        # the SPH fields first: they are final behind the pressure pass and their copies run beside the gravity pass
+        # (single handle: sphb200_download moves them on the auxiliary stream); then what the end of the step produces
+        def pull(f):
+            buf = outs[f]
             w = buf.numel() // max(cnt, 1)
             sim.download(f, buf.numpy().reshape(cnt, w) if w > 1 else buf.numpy(), allow_overflow=True)
+        for f in (sphb200.FIELD_DENSITY, sphb200.FIELD_PRESSURE, sphb200.FIELD_PRESSURE_GRAD):
+            pull(f)
         sim.download(sphb200.FIELD_SMOOTHING, sm, allow_overflow=True)
+        for f in (sphb200.FIELD_GRAVITY, sphb200.FIELD_TRANSLATION, sphb200.FIELD_VELOCITY):
+            pull(f)
         td_ = time.perf_counter()
         phases["upload"] += tb - ta; phases["step"] += tc - tb; phases["download"] += td_ - tc
     one()

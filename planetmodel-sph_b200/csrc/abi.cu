@@ -153,6 +153,7 @@ int sphb200_destroy(sph_handle c) {
     if (c->ev_created) for (int i = 0; i <= SPH_MAX_PASSES; i++) cudaEventDestroy(c->ev[i]);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_sph) cudaEventDestroy(c->ev_sph);
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
@@ -205,6 +206,7 @@ int sph_ctx_create(const sph_Params& p, int device, int64_t slots, int64_t rows,
     }
     ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
     ok = ok && cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess;
+    ok = ok && cudaEventCreateWithFlags(&c->ev_sph, cudaEventDisableTiming) == cudaSuccess;
     c->stream = c->own_stream;
     for (int k = 0; k < 2 && ok; k++) {
         if (k == 0 || pingpong)
@@ -357,6 +359,7 @@ int sph_upload_core(sphb200_ctx* c, int64_t n, uint32_t orig0, const void* pos, 
     c->resident = true; c->lists_valid = c->pressure_valid = c->gravity_valid = c->tree_valid = c->h_updated = false;
     c->sorted_valid = c->lists_fresh = false;
     c->nown_aligned = true;
+    c->sph_ready = false;
     // asynchronous error flags are sticky from one upload to the next (results after an overflow are tainted)
     SPH_CK(c, cudaMemsetAsync(c->err_d, 0, ERR_SLOTS * sizeof(int32_t), c->stream));
     const uint32_t mm0[3] = {0xffffffffu, 0u, 0u};
@@ -456,6 +459,7 @@ int sphb200_smoothing_update(sph_handle c) {
     c->h_bound *= 0.5f * (1.0f + cbrtf(fmaxf(c->p.target_neighbors, 1.0f))) * 1.001f;
     c->h_updated = true;
     c->sorted_valid = c->lists_fresh = c->pressure_valid = c->gravity_valid = false;
+    c->sph_ready = false;
     return SPH_OK;
 }
 
@@ -493,6 +497,7 @@ static int ensure_sorted(sphb200_ctx* c) {
     if (rc) return rc;
     c->sorted_valid = true;
     c->lists_valid = c->lists_fresh = c->tree_valid = c->tree_fresh = false;  // slot indices changed
+    c->sph_ready = false;
     c->nown_aligned = false;
     return SPH_OK;
 }
@@ -574,6 +579,8 @@ int sphb200_pressure(sph_handle c) {
     int rc = sph_launch_pressure(c);
     if (rc) return rc;
     c->pressure_valid = true;
+    SPH_CK(c, cudaEventRecord(c->ev_sph, c->stream));
+    c->sph_ready = true;
     return SPH_OK;
 }
 
@@ -605,10 +612,12 @@ int sphb200_step(sph_handle c, float dt, int impl) {
     if ((rc = sph_launch_neighbors_density(c))) return rc;
     c->lists_valid = c->lists_fresh = c->nown_aligned = true;
     pass_mark(c, "neighbors_density_eos");
-    if ((rc = sphb200_gravity(c, impl, dt))) return rc;
-    pass_mark(c, impl == SPH_GRAVITY_TREE ? "gravity_tree" : (impl == SPH_GRAVITY_PARTICLE ? "gravity_allpairs" : "gravity_none"));
+    // the pressure gradient does not depend on gravity: it runs first, so that rho, P and grad P are final early and their
+    // downloads (sphb200_download on the auxiliary stream) run beside the gravity pass
     if ((rc = sphb200_pressure(c))) return rc;
     pass_mark(c, "pressure_grad");
+    if ((rc = sphb200_gravity(c, impl, dt))) return rc;
+    pass_mark(c, impl == SPH_GRAVITY_TREE ? "gravity_tree" : (impl == SPH_GRAVITY_PARTICLE ? "gravity_allpairs" : "gravity_none"));
     if ((rc = sphb200_integrate(c, dt))) return rc;
     pass_mark(c, "integrate");
     return SPH_OK;
@@ -623,12 +632,24 @@ int sphb200_download(sph_handle c, int field, void* dst, int stride) {
     if (field < 0 || field >= SPH_FIELD_COUNT_) { c->err = "unknown field"; return SPH_ERR_INVALID_ARG; }
     // a sph_ParticleSmoothing array with its natural stride is assembled on the device and written by one DMA
     const bool sm_record = field == SPH_FIELD_SMOOTHING && stride == (int)sizeof(sph_ParticleSmoothing);
+    // Fields that are final behind the pressure pass (ev_sph) travel on the auxiliary stream: the call returns when ITS copy is
+    // done, not when the step is -- a host that asks for them first reads them while the gravity pass is still running.  (h sits
+    // in posh.w, which the integrate kernel rewrites with the same value: reading it beside that kernel is harmless.)
+    const bool early = c->sph_ready && (field == SPH_FIELD_DENSITY || field == SPH_FIELD_PRESSURE || field == SPH_FIELD_PRESSURE_GRAD ||
+                                        field == SPH_FIELD_NEIGHBOR_COUNT || field == SPH_FIELD_SMOOTHING);
+    cudaStream_t main_stream = c->stream;
+    if (early) {
+        SPH_CK(c, cudaStreamWaitEvent(c->aux_stream, c->ev_sph, 0));
+        c->stream = c->aux_stream;
+    }
     int rc = sph_launch_unpack_field(c, sm_record ? (int)SPH_FIELD_COUNT_ : field, &eb);
-    if (rc) { if (rc == SPH_ERR_INVALID_ARG) c->err = "unknown field"; return rc; }
+    if (rc) { c->stream = main_stream; if (rc == SPH_ERR_INVALID_ARG) c->err = "unknown field"; return rc; }
     int64_t n = c->n;
     const bool direct = stride == eb && (field != SPH_FIELD_SMOOTHING || sm_record);
-    SPH_CK(c, cudaMemcpyAsync(direct ? dst : c->stage_h, c->stage_d, (size_t)n * eb, cudaMemcpyDeviceToHost, c->stream));
-    rc = check_errflags(c);  // also synchronises
+    cudaError_t ce = cudaMemcpyAsync(direct ? dst : c->stage_h, c->stage_d, (size_t)n * eb, cudaMemcpyDeviceToHost, c->stream);
+    if (ce != cudaSuccess) { c->stream = main_stream; c->err = cudaGetErrorString(ce); return SPH_ERR_CUDA; }
+    rc = check_errflags(c);  // also synchronises (the early path: the auxiliary stream only; the tree flag is reported by a later call)
+    c->stream = main_stream;
     if (direct) return rc;   // natural stride: the DMA wrote the caller's array
     const char* src = (const char*)c->stage_h;
     char* d = (char*)dst;

@@ -140,6 +140,10 @@ struct sphb200_ctx {
     // overlapped LBVH build (sphb200_prepare_gravity): built on aux_stream while the neighbor pass runs on `stream`
     cudaStream_t aux_stream = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // recorded behind the pressure pass: rho, P, grad P, the neighbor counts and h are final from here until the next smoothing
+    // update / neighbor pass, so their downloads run on the auxiliary stream beside whatever the step still has to do (gravity)
+    cudaEvent_t ev_sph = nullptr;
+    bool sph_ready = false;
     bool tree_hint = false, tree_fresh = false, tree_join_pending = false;
     float hint_dt = 0.f, tree_dt = 0.f;
     int64_t t0 = 0, t1 = -1;

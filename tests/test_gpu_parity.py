@@ -706,3 +706,29 @@ def test_overflow_flag_follows_the_lists_and_stale_states_are_refused(orc):
         s2.download_interactions(off, bad)
     assert e.value.code == sphb200.SPH_ERR_INVALID_ARG
     s2.download_interactions(off, nbr)
+
+
+def test_early_field_downloads_beside_the_gravity_pass_equal_the_late_ones():
+    """rho, P, grad P, neighbor counts and the smoothing record are final behind the pressure pass: sphb200_download moves them
+    on the auxiliary stream while the step's gravity pass is still running.  Same bytes as after a full sync."""
+    import sphb200
+    from sphb200 import ic
+    c = ic.make_sphere(200000, seed=31, radius=ic.scaled_radius(200000), total_mass=100.0 * 200000 / 3000)
+    fields = (sphb200.FIELD_DENSITY, sphb200.FIELD_PRESSURE, sphb200.FIELD_PRESSURE_GRAD, sphb200.FIELD_NEIGHBOR_COUNT, sphb200.FIELD_SMOOTHING)
+    sim = make_sim(200000)
+    sim.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    for _ in range(3):
+        sim.step(1 / 60, sphb200.GRAVITY_PARTICLE)          # 200k all-pairs: ~16 ms of gravity behind the pressure pass
+    early = [np.array(sim.download(f), copy=True) for f in fields]      # asked for while gravity runs
+    sim.sync()
+    late = [np.array(sim.download(f), copy=True) for f in fields]
+    for f, a, b in zip(fields, early, late):
+        assert a.tobytes() == b.tobytes(), f
+    # and the same state computed by a handle that syncs before every download
+    ref = make_sim(200000)
+    ref.upload(c["pos"], c["vel"], c["mass"], c["h"])
+    for _ in range(3):
+        ref.step(1 / 60, sphb200.GRAVITY_PARTICLE)
+    ref.sync()
+    for f, a in zip(fields, early):
+        assert a.tobytes() == np.array(ref.download(f)).tobytes(), f
