@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) k_lbvh_nodes(const float4* __restrict__ p
 }
 
 constexpr int TW_WARPS = 4;
-constexpr int TW_STACK = 512;    // per-warp work stack entries (node, lane mask)
+constexpr int TW_STACK = 448;    // per-warp work stack entries (node, lane mask); 448 keeps the block at 30 KB of shared memory = 7 blocks per SM
 constexpr int TW_HEADROOM = 72;  // > the deepest possible LBVH (30 key bits + 32 tie-break bits): once the stack is this close to
                                  // full the walk degrades to one node per step -- plain depth-first, which grows the stack by
                                  // at most one entry per tree level -- instead of failing (clustered / duplicate-key inputs)
@@ -262,6 +262,33 @@ __device__ __forceinline__ void tw_mask_body(unsigned W, float& m, float r2, flo
         : "+f"(m), "+r"(soft) : "r"(W), "f"(r2), "f"(a2), "n"(BIT));
 }
 
+// One M2P iteration of a lane: up to two of its pending nodes, the previous batch's (mask mo, nodes bo) before this batch's (mc, bc).
+__device__ __forceinline__ void tw_m2p_step(unsigned& mo, unsigned& mc, const float4* __restrict__ bo, const float4* __restrict__ bc,
+                                            u64 pix, u64 piy, u64 piz, u64& gx2, u64& gy2, u64& gz2, u64& gp2) {
+    const bool f0 = mo != 0u;
+    unsigned m = f0 ? mo : mc;
+    if (m == 0u) return;
+    const float4* p0 = (f0 ? bo : bc) + (__ffs(m) - 1);
+    m &= m - 1u;
+    if (f0) mo = m; else mc = m;
+    const bool f1 = mo != 0u;
+    m = f1 ? mo : mc;
+    const bool two = m != 0u;
+    const float4* p1 = two ? (f1 ? bo : bc) + (__ffs(m) - 1) : p0;
+    m &= m - 1u;                       // 0 & 0xffffffff = 0 when there was no second node
+    if (f1) mo = m; else mc = m;
+    const float4 A0 = *p0, A1 = *p1;
+    const u64 dx = sub2(pix, pk2(A0.x, A1.x)), dy = sub2(piy, pk2(A0.y, A1.y)), dz = sub2(piz, pk2(A0.z, A1.z));
+    const u64 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
+    float ra, rb;
+    upk2(r2, ra, rb);
+    const u64 rinv = pk2(rsqrt_approx(ra), rsqrt_approx(rb));
+    const u64 mr = mul2(pk2(A0.w, two ? A1.w : 0.f), rinv);
+    const u64 g = mul2(mr, mul2(rinv, rinv));
+    gx2 = fma2(dx, g, gx2); gy2 = fma2(dy, g, gy2); gz2 = fma2(dz, g, gz2);
+    gp2 = sub2(gp2, mr);
+}
+
 // 32x32 bit-matrix transpose across the warp: in: lane i holds row i, out: lane j holds column j
 __device__ __forceinline__ unsigned transpose32(unsigned x, int lane) {
 #pragma unroll
@@ -282,7 +309,7 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
     __shared__ int2 stack[TW_WARPS][TW_STACK];
     __shared__ ulonglong2 tgxy[TW_WARPS][16];  // target positions as pairs: (x0,x1), (y0,y1)   (lanes = nodes phase)
     __shared__ u64 tgzz[TW_WARPS][16];         //                           (z0,z1)
-    __shared__ float4 bcm[TW_WARPS][32];     // batch nodes: (cm, M)            (lanes = targets phase)
+    __shared__ float4 bcm[TW_WARPS][2][32];  // batch nodes: (cm, M) of this batch and of the previous one (lanes = targets phase)
     __shared__ __align__(16) float sbodyf[TW_WARPS][128 * 4];   // flattened bodies of the shared buckets, as pairs: (x0,x1,y0,y1),(z0,z1,m0,m1)
     __shared__ __align__(8) unsigned sbodym[TW_WARPS][128 + 2];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -305,7 +332,9 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
     int2* st = stack[wid];
     ulonglong2* tgp = tgxy[wid];
     u64* tgz = tgzz[wid];
-    float4* bc = bcm[wid];
+    float4* bcb = &bcm[wid][0][0];
+    unsigned mold = 0u;   // accepted nodes of the previous batch this lane has not summed yet (M2P below)
+    int par = 0;
     float* sbf = sbodyf[wid];
     unsigned* sbm = sbodym[wid];
     {
@@ -353,6 +382,8 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
         const int ia = __float_as_int(X.y), ib = __float_as_int(X.z);
         const bool bucket = ib < 0;
         __syncwarp();
+        float4* bc = bcb + 32 * par;            // this batch's nodes; the other half holds the previous batch's
+        const float4* bo = bcb + 32 * (par ^ 1);
         bc[lane] = make_float4(N.x, N.y, N.z, X.x);
         // internal nodes some lane rejected: both children inherit that lane mask
         const bool open = have && !bucket && rej != 0u;
@@ -463,28 +494,24 @@ __global__ void __launch_bounds__(TW_WARPS * 32) k_tree_walk(const float4* __res
                 __syncwarp();
             }
         }
-        // ---- 3b. M2P, lane-private (GravitationalMoment.GravityContribution, :428-442): every lane sums the nodes it accepts,
-        // two per iteration with packed FP32 (an odd last one is paired with a zero-mass copy of itself; r_sq > T >= 0)
-        for (int it = __reduce_max_sync(FULL, (__popc(nmask) + 1) >> 1); it > 0; it--) {
-            if (nmask != 0u) {
-                const int b0 = __ffs(nmask) - 1;
-                nmask &= nmask - 1u;
-                const bool two = nmask != 0u;
-                const int b1 = two ? __ffs(nmask) - 1 : b0;
-                nmask &= nmask - 1u;
-                const float4 A0 = bc[b0], A1 = bc[b1];
-                const u64 dx = sub2(pix, pk2(A0.x, A1.x)), dy = sub2(piy, pk2(A0.y, A1.y)), dz = sub2(piz, pk2(A0.z, A1.z));
-                const u64 r2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));
-                float ra, rb;
-                upk2(r2, ra, rb);
-                const u64 rinv = pk2(rsqrt_approx(ra), rsqrt_approx(rb));
-                const u64 mr = mul2(pk2(A0.w, two ? A1.w : 0.f), rinv);
-                const u64 g = mul2(mr, mul2(rinv, rinv));
-                gx2 = fma2(dx, g, gx2); gy2 = fma2(dy, g, gy2); gz2 = fma2(dz, g, gz2);
-                gp2 = sub2(gp2, mr);
-            }
+        // ---- 3b. M2P, lane-private (GravitationalMoment.GravityContribution, :428-442): every lane sums the nodes it accepts, two
+        // per iteration with packed FP32 (an odd last one is paired with a zero-mass copy of itself; r_sq > T >= 0).  The lanes'
+        // sets differ in size (a batch leaves 49 % of the lane-iterations idle if every lane must finish its own set), so a batch
+        // runs only as many iterations as the AVERAGE lane needs -- and as the previous batch's leftovers need, which go first --
+        // and what a lane has left of this batch waits, with the batch's nodes in the other half of the buffer, for the next one.
+        {
+            const int po = __popc(mold), pn = __popc(nmask);
+            const int T = max((__reduce_max_sync(FULL, po) + 1) >> 1, (__reduce_add_sync(FULL, po + pn) + 63) >> 6);
+            for (int it = T; it > 0; it--) tw_m2p_step(mold, nmask, bo, bc, pix, piy, piz, gx2, gy2, gz2, gp2);
+            mold = nmask;      // T covered every lane's old set
+            par ^= 1;
         }
         __syncwarp();
+    }
+    {   // what is left of the last batch
+        const float4* bo = bcb + 32 * (par ^ 1);
+        unsigned none = 0u;
+        for (int it = (__reduce_max_sync(FULL, __popc(mold)) + 1) >> 1; it > 0; it--) tw_m2p_step(mold, none, bo, bo, pix, piy, piz, gx2, gy2, gz2, gp2);
     }
     if (mine) {
         float a, b;
