@@ -194,7 +194,7 @@ int sph_ctx_create(const sph_Params& p, int device, int64_t slots, int64_t rows,
     c->p = p; c->device = device; c->cap = slots; c->cap_rows = rows; c->sm_count = prop.multiProcessorCount;
     c->grid_bits_max = sph_grid_bits_for(p, total);
     c->ncell_max = (size_t)1 << (3 * c->grid_bits_max);
-    c->gpart_splits = 8;
+    c->gpart_entries = std::max<size_t>(8 * (size_t)rows, std::min<size_t>(32 * (size_t)rows, (size_t)1 << 26));
     size_t cap = (size_t)slots, nr = (size_t)rows, nn = 2 * (size_t)tree;
     bool ok = cudaSetDevice(device) == cudaSuccess;
     ok = ok && cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -220,7 +220,7 @@ int sph_ctx_create(const sph_Params& p, int device, int64_t slots, int64_t rows,
          dalloc(&c->nown, cap) == cudaSuccess && dalloc(&c->rho, cap) == cudaSuccess && dalloc(&c->press, cap) == cudaSuccess &&
          dalloc(&c->cvol, cap) == cudaSuccess && dalloc(&c->gradp, cap) == cudaSuccess && dalloc(&c->grav, cap) == cudaSuccess &&
          dalloc(&c->npart, cap) == cudaSuccess && dalloc(&c->napprox, cap) == cudaSuccess &&
-         dalloc(&c->gpart, nr * (size_t)c->gpart_splits) == cudaSuccess && dalloc(&c->tbox, 2 * ((size_t)tree / 256 + 2)) == cudaSuccess && dalloc(&c->child, nn) == cudaSuccess &&
+         dalloc(&c->gpart, c->gpart_entries) == cudaSuccess && dalloc(&c->tbox, 2 * ((size_t)tree / 256 + 2)) == cudaSuccess && dalloc(&c->child, nn) == cudaSuccess &&
          dalloc(&c->range, nn) == cudaSuccess && dalloc(&c->parent, nn) == cudaSuccess && dalloc(&c->flag, nn) == cudaSuccess &&
          dalloc(&c->mom, nn) == cudaSuccess && dalloc(&c->nlo, nn) == cudaSuccess && dalloc(&c->nhi, nn) == cudaSuccess && dalloc(&c->packed, 2 * nn) == cudaSuccess &&
          dalloc(&c->bounds, 16) == cudaSuccess && dalloc(&c->grid_d, 1) == cudaSuccess && dalloc(&c->err_d, ERR_SLOTS) == cudaSuccess &&

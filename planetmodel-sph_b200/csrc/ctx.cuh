@@ -90,7 +90,7 @@ struct sphb200_ctx {
     float h_bound = INFINITY;    // host-side upper bound of every resident h (upload value x the controller's largest growth per update):
                                  // below 1e5 the literal-kernel neighbor pass (k_neighbors_density) cannot be needed and is not launched
     float4* gpart = nullptr;     // all-pairs partial sums [splits][n]
-    int gpart_splits = 0;
+    size_t gpart_entries = 0;    // capacity of gpart: 32 splits of the target rows where that stays under 1 GB, never fewer than 8
     float4* gsrc = nullptr;      // gravity sources (x,y,z,m) in GLOBAL sorted order: posm for a single handle, the all-gathered
     int64_t gsrc_n = 0;          // array for a group rank
     // LBVH addressing: the tree spans tree_n global slots; this context builds the nodes of slots [tree_g0, tree_g1) and its

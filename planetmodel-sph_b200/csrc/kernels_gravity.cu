@@ -261,7 +261,7 @@ int sph_launch_gravity_allpairs(sphb200_ctx* c) {
     const float4* src = c->gsrc;
     int tblocks = sph_div_up(nt, AP_THREADS * AP_TPT);
     // Source splits: the grid (target blocks x splits) should fill whole waves of resident CTAs (one 8-warp CTA per SM at 160
-    // registers: asked from the occupancy calculator once) -- among the split counts the partial-sum buffer (cap * gpart_splits
+    // registers: asked from the occupancy calculator once) -- among the split counts the partial-sum buffer (gpart_entries
     // float4) and the tile granularity allow, take the one with the least idle tail, preferring >= 12 waves.
     static int ctas_per_sm = 0;
     if (ctas_per_sm == 0) {
@@ -271,20 +271,24 @@ int sph_launch_gravity_allpairs(sphb200_ctx* c) {
         ctas_per_sm = std::max(1, std::min(a, b));
     }
     const int resident = c->sm_count * ctas_per_sm;
-    int64_t smax = (int64_t)c->cap_rows * c->gpart_splits / nt;
+    int64_t smax = (int64_t)(c->gpart_entries / (size_t)nt);
     smax = std::min<int64_t>(smax, sph_div_up(n, AP_TILE));
     smax = std::max<int64_t>(std::min<int64_t>(smax, 65535), 1);
     int splits = 1, per = 0;
-    double best = -1.0;
-    for (int sp = (int)smax; sp >= 1; sp--) {
-        int pr = sph_div_up(sph_div_up(n, sp), AP_TILE) * AP_TILE;   // sources per split: whole tiles
-        int ns = sph_div_up(n, pr);                                   // splits that are not empty
+    auto efficiency = [&](int sp, int& ns, int& pr) {
+        pr = sph_div_up(sph_div_up(n, sp), AP_TILE) * AP_TILE;       // sources per split: whole tiles
+        ns = sph_div_up(n, pr);                                       // splits that are not empty
         const int64_t grid = (int64_t)tblocks * ns;
         const int64_t waves = (grid + resident - 1) / resident;
         double eff = (double)grid / (double)(waves * resident);
         if (waves < 12) eff *= 0.5 + 0.5 * (double)waves / 12.0;     // too few waves: the last one weighs more, tiles load less often
-        if (eff > best + 1e-9) { best = eff; splits = ns; per = pr; }
-        if (grid < resident && sp < smax) break;                      // fewer splits only shrink the grid further
+        return eff;
+    };
+    double best = -1.0;
+    for (int sp = (int)smax; sp >= 1; sp--) { int ns, pr; best = std::max(best, efficiency(sp, ns, pr)); }
+    for (int sp = 1; sp <= (int)smax; sp++) {                         // the fewest splits (least partial-sum traffic) within 0.5 % of the best
+        int ns, pr;
+        if (efficiency(sp, ns, pr) >= best - 0.005) { splits = ns; per = pr; break; }
     }
     k_tile_boxes<<<sph_div_up(n, AP_TILE), AP_TILE, 0, c->stream>>>(src, n, c->tbox);
     SPH_LAUNCH_CHECK(c);
