@@ -92,3 +92,55 @@ def halo_mask(keys, grid_bits, stencil, sbin, me):
                 r = owner_of_bins(nk >> np.uint32(bshift), sbin)
                 mask |= np.where(ok, np.uint32(1) << r.astype(np.uint32), np.uint32(0))
     return mask & ~np.uint32(1 << me) & np.uint32((1 << world) - 1)
+
+
+def walk_box(pos_sorted, g0, rank):
+    """Box of the positions rank `rank` walks (k_let_box): its targets [g0[r], g0[r+1]) plus the companions that complete its
+    first and last 32-slot group.  (lo, hi) float32[3]; an empty rank gets lo = +inf."""
+    n = len(pos_sorted)
+    a, b = int(g0[rank]), int(g0[rank + 1])
+    if b <= a:
+        return np.full(3, np.inf, np.float32), np.full(3, -np.inf, np.float32)
+    lo, hi = a & ~31, min(n, (b + 31) & ~31)
+    p = np.asarray(pos_sorted, np.float32)[lo:hi]
+    return p.min(axis=0), p.max(axis=0)
+
+
+def let_mask(first, last, parent, cm, b_sq, theta, g0, me, boxes, leaf_max):
+    """k_let_mask: for every LBVH node (2n-1; arrays of the oracle's tree) a bit mask of the ranks other than `me` that may read
+    the node's walk record, for the nodes rank `me` finishes (particle range inside [g0[me], g0[me+1])).  A walk reads node k only
+    after one of its targets has opened k's parent p, i.e. NOT accepted it: RN(b_sq[p] / r_sq) >= theta^2.  r_sq is at least the
+    squared distance from cm[p] to the box of the walking rank's positions, so "dist^2(cm[p], box_r) * 0.99999 <= T[p]" with
+    T = b_sq / theta^2 (the device uses the exact ulp-stepped threshold; 1e-5 of slack covers it) is a superset of "some target
+    of rank r opens p".  Nodes strictly inside a bucket are unreachable; nodes whose parent straddles a rank boundary (or is the
+    root of another rank's subtree) are needed by everybody."""
+    first = np.asarray(first, np.int64); last = np.asarray(last, np.int64); parent = np.asarray(parent, np.int64)
+    nn = len(first); world = len(g0) - 1
+    a, b = int(g0[me]), int(g0[me + 1])
+    everyone = ((1 << world) - 1) & ~(1 << me)
+    mask = np.zeros(nn, np.int64)
+    size = last - first + 1
+    theta2 = np.float32(theta) * np.float32(theta)
+    for k in range(nn):
+        if first[k] < a or last[k] >= b:
+            continue                                   # not finished by this rank (another rank's node, or a straddling top node)
+        p = parent[k]
+        if p < 0:
+            mask[k] = everyone
+            continue
+        if size[p] <= leaf_max:
+            continue                                   # strictly inside a bucket
+        if first[p] < a or last[p] >= b:
+            mask[k] = everyone                         # the parent is a top node
+            continue
+        T = np.float32(b_sq[p]) / theta2
+        m = 0
+        for r in range(world):
+            if r == me:
+                continue
+            lo, hi = boxes[r]
+            d = np.maximum(np.maximum(lo - cm[p], cm[p] - hi), 0).astype(np.float32)
+            if float(np.dot(d, d)) * 0.99999 <= float(T):
+                m |= 1 << r
+        mask[k] = m
+    return mask

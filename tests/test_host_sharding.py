@@ -104,3 +104,58 @@ def test_two_rank_decomposition_over_gloo(tmp_path):
     port = 29600 + os.getpid() % 300
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
     assert np.load(tmp_path / "ok0.npy")[0] and np.load(tmp_path / "ok1.npy")[0]
+
+
+def test_locally_essential_tree_rule_covers_every_node_the_oracle_walk_reads():
+    """The sender-side box test of the group's tree exchange (decomp.let_mask = k_let_mask) is a superset of what the walks of
+    the other ranks read: every node the oracle's per-particle walk (orc_tree_walk semantics, AcceptApproximation with the
+    reference's fp32 arithmetic) pops for a target of rank r, and that another rank finished, carries bit r in that rank's mask --
+    for a uniform sphere and for the two-body collision geometry (64x density contrast), 3 and 4 ranks, unequal slot ranges."""
+    from oracle import oracle as orc
+    from sphb200 import decomp, ic
+    f32 = np.float32
+    for c, world, cuts in ((ic.make_sphere(1500, seed=4), 3, (0.0, 0.22, 0.71, 1.0)),
+                           (ic.make_collision(700, seed=5), 4, (0.0, 0.3, 0.5, 0.83, 1.0))):
+        pos, vel, h, m = (np.asarray(c[k], np.float32) for k in ("pos", "vel", "h", "mass"))
+        n = len(h)
+        g = orc.grid_params(pos, h, 5)
+        keys = orc.morton_keys(pos, g)
+        order = orc.sort_order(keys).astype(np.int64)
+        ps, vs, hs, ms = pos[order], vel[order], h[order], m[order]
+        leaf_max, theta, dt = 4, 0.7, 1 / 60
+        t = orc.lbvh_build(keys[order], ps, vs, hs, ms, leaf_max, 0, dt)
+        cm = t.mom[:, :3]
+        bx = np.maximum(t.hi - cm, cm - t.lo).astype(f32)
+        b_sq = ((bx[:, 0] * bx[:, 0] + bx[:, 1] * bx[:, 1]).astype(f32) + bx[:, 2] * bx[:, 2]).astype(f32)    # AcceptApproximation order
+        theta2 = f32(theta) * f32(theta)
+        g0 = np.array([int(round(x * n)) for x in cuts], np.int64)
+        boxes = [decomp.walk_box(ps, g0, r) for r in range(world)]
+        masks = [decomp.let_mask(t.first, t.last, t.parent, cm, b_sq, theta, g0, r, boxes, leaf_max) for r in range(world)]
+        finished_by = np.full(2 * n - 1, -1)
+        for r in range(world):
+            inside = (t.first >= g0[r]) & (t.last < g0[r + 1])
+            finished_by[inside] = r
+        size = t.last - t.first + 1
+        read = 0
+        for r in range(world):
+            # the walking slots of rank r: its targets and the companions of its first / last 32-slot group
+            lo, hi = int(g0[r]) & ~31, min(n, (int(g0[r + 1]) + 31) & ~31)
+            for s in range(lo, hi):
+                stack = [0]
+                while stack:
+                    k = stack.pop()
+                    owner = finished_by[k]
+                    if owner >= 0 and owner != r:
+                        read += 1
+                        assert (masks[owner][k] >> r) & 1, "rank %d reads node %d of rank %d outside its essential tree" % (r, k, owner)
+                    d = (ps[s] - cm[k]).astype(f32)
+                    r_sq = ((d[0] * d[0] + d[1] * d[1]).astype(f32) + d[2] * d[2]).astype(f32)
+                    with np.errstate(divide="ignore", invalid="ignore"):
+                        accept = (b_sq[k] / r_sq) < theta2
+                    if accept or size[k] <= leaf_max:
+                        continue
+                    stack.append(int(t.left[k])); stack.append(int(t.right[k]))
+        assert read > 0
+        # and it is selective: far fewer records than the whole remote tree
+        sent = sum(int(np.count_nonzero(masks[o] & (1 << r))) for o in range(world) for r in range(world) if r != o)
+        assert sent < 0.9 * (world - 1) * (2 * n - 1)
