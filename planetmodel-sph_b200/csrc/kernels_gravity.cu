@@ -15,7 +15,8 @@
 //     the capped self term is removed in k_gravity_reduce;
 //   * when every particle has the same mass (the reference spawner, ParticleAuthoring.cs:208) the mass multiply
 //     leaves the loop (EQM variant) and is applied once in the reduce.
-// Issue slots per pair (SASS): 7.7 far/equal-mass (packed FP32, below); measured rates in profiles/README.md.
+// Issue slots per pair (SASS): 7.4 far/equal-mass (packed FP32, below: per 2 sources x 6 targets 144 packed FMA-pipe instructions,
+// 24 MUFU, 4 LDS, 5 loop instructions -- nothing but the formulation's 12 lane-ops per pair is left); rates in profiles/README.md.
 // Summation: per-tile fp32 partials (256 sources) added into a running sum, then a fixed-order reduction over the
 // source splits -- deterministic, and ~sqrt(256) times tighter than one 10^6-term fp32 chain.
 #include "ctx.cuh"

@@ -5,11 +5,12 @@
 // (A/Util/SplineKernel.cs:47-89) and DensityFieldSystem + the EOS (A/Systems/DensityFieldSystem.cs:38-56,
 // A/Systems/PressureFieldSystem.cs:30-34).
 //
-// Three kernels, all launched every step (which one does the work is decided on the device from the grid's h_max, so
-// the host never synchronises):
+// Three kernels (which one does the work is decided on the device from the grid's h_max, so the host never synchronises; the
+// third is launched only while the host-side bound of h -- ctx.cuh h_bound -- cannot rule h_max >= 1e5 out):
 //   k_cell_neighbors    h_max <  1e5 (every real run): cell-centric list build, one warp per pass of <= 32 targets of one
 //                       cell, sqrt-free exact keep thresholds -- described at its definition below;
-//   k_density           h_max <  1e5: density + EOS + own-support count from the finished rows, 16 lanes per target;
+//   k_density           h_max <  1e5: density + EOS + own-support count from the finished rows, consumed as a flat octet stream
+//                       (rowstream.cuh);
 //   k_neighbors_density h_max >= 1e5 (W(r,h) can underflow, the threshold form is not valid): the warp-per-target kernel
 //                       that evaluates the reference's literal Kernel(r,h) > 0 keep rule, lists + density + EOS in one
 //                       pass.  One warp per target particle, three phases:

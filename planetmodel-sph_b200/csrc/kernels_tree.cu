@@ -16,10 +16,13 @@
 //      exact reference MAC and gets a 32-bit accept mask -- 32x32 exact decisions in ~350 instructions;
 //   2. two 32x32 bit transposes (butterfly shuffles) hand every lane = TARGET the set of batch nodes it accepts and the
 //      set of leaf buckets it must open; internal nodes that some lane rejected push both children with that lane mask;
-//   3. the opened buckets' bodies are flattened into a shared-memory list and summed warp-wide (uniform loads, lanes that
-//      did not open a bucket contribute zero mass): measured faster than lane-private P2P, whose per-batch imbalance left
-//      25 % of the lanes busy; lanes = TARGETS for M2P: every lane sums only the nodes it accepts itself (the shared-walk
-//      union was 4.5x the per-lane M2P work).  Both loops use packed FP32 (two bodies / nodes per instruction).
+//   3. the opened buckets' bodies are flattened into a shared-memory list of body pairs and summed warp-wide (uniform loads; the
+//      (body x lane) mask matrix is transposed 32 bodies at a time, so a lane holds one word of "my bodies" and a chunk is a
+//      straight-line sequence of 16 packed pair evaluations entered by a switch; capped Newtonian law for every listed body, the
+//      few inside a = h_i get the softened remainder afterwards): measured faster than lane-private P2P, whose per-batch imbalance
+//      left 25 % of the lanes busy; lanes = TARGETS for M2P: every lane sums only the nodes it accepts itself (the shared-walk
+//      union was 4.5x the per-lane M2P work), as many per batch as the average lane needs -- leftovers wait, with the batch's
+//      nodes, in the other half of a double buffer.  Both loops use packed FP32 (two bodies / nodes per instruction).
 // Every lane still sees exactly the accepted nodes / opened buckets of its private depth-first walk (per-particle MAC,
 // numParticles / numApprox identical to the oracle); only the order in which a lane adds its contributions differs.
 // The MAC "bmax_sq / r_sq < theta^2" is monotone in r_sq, so the build stores per node the exact threshold T with
