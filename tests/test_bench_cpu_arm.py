@@ -1,0 +1,61 @@
+"""bench.py's CPU legs run without a GPU: the reference arm (`--impl reference`) and the `cpu_baseline` sampler are the
+reference's job path restated in oracle/ and timed on the host cores (row d of SURVEY.md section 8).  These tests run them
+on a scaled-down workload and check the contract of the JSON line the driver parses."""
+import json
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def test_reference_arm_prints_one_contract_line():
+    env = dict(os.environ, OMP_NUM_THREADS="4")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c3",
+                          "--particles", "30000", "--steps", "1", "--warmup", "0"], capture_output=True, env=env, timeout=600)
+    assert out.returncode == 0, out.stderr.decode()[-2000:]
+    lines = [l for l in out.stdout.decode().splitlines() if l.strip()]
+    assert len(lines) == 1                                   # ONE JSON line on stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "sph_particle_steps_per_sec" and d["unit"] == "particle-steps/s"
+    assert d["higher_is_better"] is True and d["n_gpus"] == 1 and d["steps"] == 1 and d["dtype"] == "f32"
+    assert d["value"] > 0 and d["gpu_launches"] == 0
+    assert d["config"]["particles"] == 30000 and d["config"]["gravity"] == "particle"
+    e = d["e2e"]
+    assert e["value"] == d["value"] and e["unit"] == d["unit"] and e["h2d_bytes_per_step"] == 0 and e["d2h_bytes_per_step"] == 0
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] == d["value"] and "EXTRAPOLATED" in c["sample"]
+    det = c["detail"]
+    # the reference's stage structure, stage by stage (KernelSystem.cs:93-231 and the systems after it)
+    assert set(det["stage_us_per_particle"]) == {"smoothing", "aabb_bvh_build", "tree_overlap_candidates", "filter_pairs",
+                                                 "flatten_pairs", "counting_sorts_x2", "calculate_interactions", "gravity",
+                                                 "integrate_position", "density", "eos_pressure_gradient", "velocity_cleanup"}
+    assert det["candidates_per_pair"] > 5.0                  # the broadphase hands ~15x the kept pairs to FilterPairs
+    assert 30.0 < det["mean_neighbors"] < 80.0               # timed at the settled h (~50 own-support neighbors)
+    assert det["cell_list_variant"]["label"].startswith("cell-list candidates") and det["cell_list_variant"]["particle_steps_per_sec"] > 0
+    own = d["reference_own_cases"]                           # BASELINE.json configs[0] and [1], run in full
+    assert own["c1"]["particles"] == 3000 and own["c1"]["gravity"] == "direct" and own["c1"]["particle_steps_per_sec"] > 0
+    assert own["c2"]["particles"] == 10000 and own["c2"]["gravity"] == "tree" and own["c2"]["steps"] == 100
+
+
+def test_non_zero_ranks_of_the_reference_arm_do_nothing():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, env=env, timeout=120)
+    assert out.returncode == 0 and out.stdout.decode().strip() == ""
+
+
+def test_cpu_sample_tree_workload_and_settled_h_estimate():
+    import bench
+    from sphb200 import ic
+    c = ic.make_config("c4", particles=60000)
+    n = len(c["h"])
+    h = bench.settled_h_estimate(c)
+    state = dict(pos=c["pos"], vel=c["vel"], mass=c["mass"], h=np.full(n, h, np.float32), n_own=np.full(n, 50, np.int32))
+    v, cores, desc, det = bench.cpu_reference_sample(state, "tree", seconds_budget=1.0)
+    assert v > 0 and cores >= 1 and "4-ary BVH" in desc and det["extrapolated"] is True
+    # the estimate puts ~50 particles inside 2h: the sample's symmetric count lands near the controller's fixed point
+    assert 35.0 < det["mean_neighbors"] < 70.0
