@@ -44,6 +44,26 @@ def workload_config(name, particles=None):
     return c, grav
 
 
+# SURVEY.md 8(d) per pass (bytes per particle-step; K = mean symmetric neighbor count): the single handle's pass names.
+# keys 24 + sort 68 + permute 68 + cell table 12; list emit 20 + 4K and density 44 + 4K; pressure force 32 + 4K; integrate 100.
+# The h update (16 R + 4 W + 4 R counts) is DESIGN.md's own figure: SURVEY's 368 + 12K total does not count it.
+PASS_BYTES = {"smoothing_bounds": (24.0, 0.0), "keys_sort_permute_cells": (172.0, 0.0), "neighbors_density_eos": (64.0, 8.0),
+              "pressure_grad": (32.0, 4.0), "integrate": (100.0, 0.0)}
+
+
+def per_pass_roofline(mean_ms, kbar, particles, hbm_peak_gbs):
+    """Every non-gravity pass of the single handle against the HBM roof: algorithmic bytes / CUDA-event time of the pass."""
+    out = {}
+    for name, (base, per_k) in PASS_BYTES.items():
+        ms = mean_ms.get(name)
+        if not ms or ms <= 0:
+            continue
+        b = base + per_k * kbar
+        gbs = b * particles / (ms * 1e-3) / 1e9
+        out[name] = {"ms": ms, "bytes_per_particle": b, "achieved": gbs, "frac": gbs / hbm_peak_gbs}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler(threading.Thread):
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -392,6 +412,11 @@ def measure_workload(args, workload, world, rank, local, headline):
     hbm_passes = {"achieved": sph_bytes / (sph_ms * 1e-3) / 1e9 if sph_ms > 0 else None, "peak": hbm_peak, "unit": "GB/s",
                   "frac": (sph_bytes / (sph_ms * 1e-3) / 1e9 / hbm_peak) if sph_ms > 0 else None, "ms": sph_ms,
                   "bytes_per_particle": SPH_BYTES_BASE + SPH_BYTES_PER_NEIGHBOR * kbar, "peak_source": hbm_src}
+    if world == 1:
+        try:
+            hbm_passes["per_pass"] = per_pass_roofline(mean, float(kbar), n, hbm_peak)
+        except Exception as ex:      # a reporting extra must never cost the line
+            hbm_passes["per_pass"] = {"error": str(ex)}
     if grav == "particle":
         gms = mean.get("gravity_allpairs", 0.0)
         flops = FLOP_PER_PAIR * (n / world) * (n - 1)

@@ -59,3 +59,18 @@ def test_cpu_sample_tree_workload_and_settled_h_estimate():
     assert v > 0 and cores >= 1 and "4-ary BVH" in desc and det["extrapolated"] is True
     # the estimate puts ~50 particles inside 2h: the sample's symmetric count lands near the controller's fixed point
     assert 35.0 < det["mean_neighbors"] < 70.0
+
+
+def test_per_pass_bytes_add_up_to_the_survey_total():
+    """368 + 12 K bytes per particle-step over the non-gravity passes; bench.py splits it by pass."""
+    import bench
+    K = 53.5
+    ms = {"smoothing_bounds": 0.04, "keys_sort_permute_cells": 0.19, "neighbors_density_eos": 0.85, "pressure_grad": 0.29,
+          "integrate": 0.018, "gravity_allpairs": 421.0}
+    r = bench.per_pass_roofline(ms, K, 1 << 20, 6547.5)
+    assert set(r) == set(ms) - {"gravity_allpairs"}
+    total = sum(v["bytes_per_particle"] for k, v in r.items() if k != "smoothing_bounds")
+    assert abs(total - (bench.SPH_BYTES_BASE + bench.SPH_BYTES_PER_NEIGHBOR * K)) < 1e-9
+    v = r["integrate"]
+    assert abs(v["achieved"] - 100.0 * (1 << 20) / 0.018e-3 / 1e9) < 1e-6 and abs(v["frac"] - v["achieved"] / 6547.5) < 1e-12
+    assert bench.per_pass_roofline({"integrate": 0.0}, K, 10, 6547.5) == {}      # a pass that did not run is left out
