@@ -175,6 +175,9 @@ def cpu_reference_sample(state, grav, seconds_budget=20.0):
     return 1.0 / per_particle, cores, desc, detail
 
 
+KERNEL_SYSTEM_STAGES = ("filter_pairs", "flatten_pairs", "counting_sorts_x2", "calculate_interactions")
+
+
 def cpu_reference_own_cases():
     """The reference's own CPU-runnable cases IN FULL (BASELINE.json configs[0] and [1]): C1 = 3 000 particles, direct gravity;
     C2 = 10 000 particles, tree gravity, 100 steps.  Whole job path, every particle, wall clock per step."""
@@ -185,15 +188,22 @@ def cpu_reference_own_cases():
     for name, grav, steps in (("c1", "direct", 20), ("c2", "tree", 100)):
         c = ic.make_config(name)
         st = orc.State(c["pos"], c["vel"], c["mass"], c["h"])
-        t = []
+        t, ks = [], []
         for _ in range(steps):
             t0 = time.perf_counter()
             info = orc.reference_step(st, DT, gravity=grav, want_lists=False)
             t.append(time.perf_counter() - t0)
-        last = float(np.mean(t[-max(steps // 2, 1):]))        # settled half of the run
+            ks.append(sum(info["stage_sec"][k] for k in KERNEL_SYSTEM_STAGES))
+        half = max(steps // 2, 1)
+        last = float(np.mean(t[-half:]))        # settled half of the run
         out[name] = {"particles": len(c["h"]), "gravity": grav, "steps": steps, "ms_per_step_settled": 1e3 * last,
                      "ms_per_step_first": 1e3 * t[0], "particle_steps_per_sec": len(c["h"]) / last,
-                     "mean_neighbors_final": info["interactions"] / len(c["h"]), "kind": "port, run in full"}
+                     "mean_neighbors_final": info["interactions"] / len(c["h"]), "kind": "port, run in full",
+                     # KernelSystem.OnUpdate alone (FilterPairs, flatten, the two counting sorts, CalculateInteraction)
+                     "kernel_system_stage_ms_first": 1e3 * ks[0], "kernel_system_stage_ms_settled": 1e3 * float(np.mean(ks[-half:]))}
+    # the one timing the reference publishes: that stage at 3 000 particles on the author's laptop
+    out["c1"]["kernel_system_stage_ms_published"] = 6.5
+    out["c1"]["published_source"] = "reference README.md:33 (unspecified gaming laptop, Unity + Burst); sanity anchor, not a baseline"
     return out
 
 

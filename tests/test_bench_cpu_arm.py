@@ -39,6 +39,10 @@ def test_reference_arm_prints_one_contract_line():
     own = d["reference_own_cases"]                           # BASELINE.json configs[0] and [1], run in full
     assert own["c1"]["particles"] == 3000 and own["c1"]["gravity"] == "direct" and own["c1"]["particle_steps_per_sec"] > 0
     assert own["c2"]["particles"] == 10000 and own["c2"]["gravity"] == "tree" and own["c2"]["steps"] == 100
+    # the reference's one published timing (README.md:33, KernelSystem stage at 3k particles) sits beside the port's time for that stage
+    assert own["c1"]["kernel_system_stage_ms_published"] == 6.5
+    assert 0.0 < own["c1"]["kernel_system_stage_ms_first"] < own["c1"]["ms_per_step_first"]
+    assert 0.0 < own["c1"]["kernel_system_stage_ms_settled"] < own["c1"]["ms_per_step_settled"]
 
 
 def test_non_zero_ranks_of_the_reference_arm_do_nothing():
