@@ -472,3 +472,45 @@ def test_pm07_direct_sum_is_antisymmetric_and_newtonian_for_far_pairs(orc):
     base = orc.gravity_direct(pos, h, m, accum_double=True)
     corr = orc.gravity_pm07_correction(pos, h, m, off, nbr)
     np.testing.assert_allclose(base + corr, g, rtol=2e-5, atol=2e-5 * np.abs(g).max())
+
+
+def test_polytrope_hydrostatic_balance_pins_the_whole_sph_chain(orc):
+    """Closed-form anchor for the chain density sum -> EOS -> pressure gradient -> gravity: the reference's
+    EOS P = K rho^2 (PressureFieldSystem.cs:30-34) is the n = 1 polytrope, whose self-gravitating equilibrium is
+    rho(r) = rho_c sin(xi)/xi with R = pi sqrt(K / 2 pi G) = 39.63 for K = 1000, G = 1 -- whatever the mass.  Particles drawn
+    from that profile, smoothing lengths settled by the reference's controller: in every radial shell the outward pressure
+    acceleration -grad P / rho (VelocitySystem.cs:24-36) must cancel the inward gravity -grad Phi.  That only happens if the
+    kernel normalisation, the symmetrised kernel, the pressure-gradient weights and the softened direct sum are all right.
+    It needs the CORRECT kernel derivative (fix_q1 = 1): with the reference's literal inner-branch sign (quirk Q1,
+    SplineKernel.cs:135) close pairs pull instead of push and the shell-averaged "pressure" force points inward."""
+    from sphb200 import ic
+    n = 20000
+    c = ic.make_polytrope(n, seed=5)
+    R = ic.polytrope_radius(1000.0, 1.0)
+    assert abs(R - 39.633) < 1e-2
+    pos, h, m = c["pos"], c["h"].copy(), c["mass"]
+    for _ in range(12):                                     # ParticleSmoothingSystem.cs:46-59 at fixed positions
+        off, nbr = orc.neighbors(pos, h, "grid")
+        _, own = orc.density(pos, h, m, off, nbr)
+        h = orc.smoothing_update(h, own, 50.0)
+    off, nbr = orc.neighbors(pos, h, "grid")
+    rho, own = orc.density(pos, h, m, off, nbr)
+    assert abs(own.mean() - 50.0) < 1.0                     # the controller's fixed point
+    P = orc.eos(rho)
+    g = orc.gravity_direct(pos, h, m)
+    r = np.linalg.norm(pos, axis=1)
+    rhat = pos / r[:, None]
+    a_g = -(g[:, :3] * rhat).sum(1)                         # radial component of -grad Phi: inward, negative
+    # enclosed-mass check of the gravity sum itself: g(r) = G m(<r) / r^2 with m(r)/M = (sin xi - xi cos xi) / pi
+    shells = ((0.2, 0.35), (0.35, 0.5), (0.5, 0.65), (0.65, 0.8))
+    for lo, hi in shells:
+        s = (r > lo * R) & (r < hi * R)
+        xi = np.pi * r[s] / R
+        g_th = 100.0 * (np.sin(xi) - xi * np.cos(xi)) / np.pi / r[s] ** 2
+        assert abs(a_g[s].mean() / -g_th.mean() - 1.0) < 0.03
+    fixed = -(orc.pressure_grad(pos, h, m, rho, P, off, nbr, fix_q1=1) * rhat).sum(1) / rho
+    literal = -(orc.pressure_grad(pos, h, m, rho, P, off, nbr, fix_q1=0) * rhat).sum(1) / rho
+    for lo, hi in shells:
+        s = (r > lo * R) & (r < hi * R)
+        assert abs(fixed[s].mean() / -a_g[s].mean() - 1.0) < 0.06, (lo, hi, fixed[s].mean(), a_g[s].mean())
+        assert literal[s].mean() < 0.0                      # quirk Q1: the literal derivative cannot hold the sphere up
