@@ -514,3 +514,35 @@ def test_polytrope_hydrostatic_balance_pins_the_whole_sph_chain(orc):
         s = (r > lo * R) & (r < hi * R)
         assert abs(fixed[s].mean() / -a_g[s].mean() - 1.0) < 0.06, (lo, hi, fixed[s].mean(), a_g[s].mean())
         assert literal[s].mean() < 0.0                      # quirk Q1: the literal derivative cannot hold the sphere up
+
+
+def test_lattice_closed_forms_density_and_linear_pressure_gradient(orc):
+    """Closed forms on a cubic lattice (spacing 1, mass m per particle): the density sum (DensityFieldSystem.cs:43-53, self term
+    included) is m / spacing^3, and the reference's gradient estimate sum_j (m_j / rho_j) P_j grad W_sym (PressureFieldSystem.cs:
+    56-66) of a LINEAR field P = a.x + b returns a -- for every smoothing length, once the kernel derivative has the right sign.
+    With the literal inner-branch sign (quirk Q1, SplineKernel.cs:135) the estimate is only right while no pair sits inside
+    r < h (h = spacing: the nearest neighbors are at q = 1 exactly, the outer branch); for larger h it is off by O(1) and can
+    even flip sign -- the quantitative face of Q1 that SPH_FLAG_FIX_KERNEL_DERIV_SIGN undoes."""
+    L = 20
+    g = np.arange(L, dtype=np.float32)
+    pos = np.stack(np.meshgrid(g, g, g, indexing="ij"), -1).reshape(-1, 3).astype(np.float32)
+    n = len(pos)
+    m = np.full(n, 2.0, np.float32)
+    a = np.array([0.3, -0.7, 1.1], np.float32)
+    P = (pos @ a + 5.0).astype(np.float32)
+    rho0 = np.full(n, 2.0, np.float32)                       # m / spacing^3
+    inner = np.all((pos > 4.5) & (pos < 14.5), axis=1)       # more than 2h from every face
+    for hh, shell_count in ((1.0, 26), (1.2, 56), (1.3, 80), (1.5, 92)):
+        h = np.full(n, hh, np.float32)
+        off, nbr = orc.neighbors(pos, h, "grid")
+        rho, own = orc.density(pos, h, m, off, nbr)
+        assert np.all(own[inner] == shell_count)             # lattice points strictly inside r < 2h
+        np.testing.assert_allclose(rho[inner], 2.0, rtol=4e-3)
+        fixed = orc.pressure_grad(pos, h, m, rho0, P, off, nbr, fix_q1=1)[inner]
+        assert np.all(np.abs(fixed.mean(0) / a - 1.0) < 0.025), (hh, fixed.mean(0))
+        assert np.all(fixed.std(0) < 1e-4)                   # translation invariance of the interior
+        literal = orc.pressure_grad(pos, h, m, rho0, P, off, nbr, fix_q1=0)[inner]
+        if hh == 1.0:
+            np.testing.assert_array_equal(literal, fixed)    # no pair inside r < h: the inner branch is never taken
+        else:
+            assert np.all(np.abs(literal.mean(0) / a - 1.0) > 0.9), (hh, literal.mean(0))
