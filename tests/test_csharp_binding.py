@@ -212,3 +212,25 @@ def test_system_classes_keep_the_reference_names_order_and_constants():
     assert "IPhysicsSystem" in src and "GetOutputDependency" in src and "AddInputDependency" in src
     for used in set(re.findall(r"SphB200Native\.(sphb200_\w+)", src)):
         assert used in csharp_imports(), used
+
+
+def test_csharp_sources_are_lexically_well_formed():
+    """No compiler here: at least every bracket closes, no string or comment is left open, and every P/Invoke line ends in ';'."""
+    for path in (NATIVE, SYSTEMS):
+        raw = open(path).read()
+        assert raw.count("/*") == raw.count("*/")
+        src = strip_comments(raw)
+        src = re.sub(r'"(?:\\.|[^"\\\n])*"', '""', src)          # string literals out of the way
+        assert src.count('"') % 2 == 0, path
+        stack = []
+        pairs = {")": "(", "]": "[", "}": "{"}
+        for ln, line in enumerate(src.splitlines(), 1):
+            for ch in line:
+                if ch in "([{":
+                    stack.append((ch, ln))
+                elif ch in ")]}":
+                    assert stack and stack[-1][0] == pairs[ch], "%s:%d unbalanced %r" % (path, ln, ch)
+                    stack.pop()
+        assert not stack, "%s: unclosed %r" % (path, stack[-1])
+    decls = re.findall(r"\[DllImport\(Lib\)\][^;]*;", strip_comments(open(NATIVE).read()))
+    assert len(decls) == len(csharp_imports())
