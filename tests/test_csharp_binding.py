@@ -18,7 +18,11 @@ NATIVE = os.path.join(ROOT, "planetmodel-sph_b200", "csharp", "SphB200Native.cs"
 SYSTEMS = os.path.join(ROOT, "planetmodel-sph_b200", "csharp", "SphB200Systems.cs")
 
 
-def strip_comments(src):
+def strip_comments(src, line_first=False):
+    """C header: block comments, then line comments.  C# sources (line_first): the other way round -- they use // only, and one
+    of those comments mentions "Systems/*.cs"."""
+    if line_first:
+        src = re.sub(r"//[^\n]*", " ", src)
     src = re.sub(r"/\*.*?\*/", " ", src, flags=re.S)
     return re.sub(r"//[^\n]*", " ", src)
 
@@ -80,7 +84,7 @@ def header_enums():
 
 # ---------------------------------------------------------------------------------------------------- C# side
 def csharp_imports():
-    src = strip_comments(open(NATIVE).read())
+    src = strip_comments(open(NATIVE).read(), True)
     out = {}
     for ret, name, args in re.findall(r"\[DllImport\(Lib\)\]\s*public\s+static\s+extern\s+(\w+\*?)\s+(\w+)\s*\(([^;]*)\)\s*;", src):
         params = []
@@ -96,7 +100,7 @@ def csharp_imports():
 
 
 def csharp_structs():
-    src = strip_comments(open(NATIVE).read())
+    src = strip_comments(open(NATIVE).read(), True)
     out = {}
     for name, body in re.findall(r"public\s+struct\s+(\w+)\s*\{([^}]*)\}", src):
         fields = []
@@ -170,7 +174,7 @@ def test_mirrored_structs_have_the_header_fields_in_order():
 
 def test_constants_have_the_header_values():
     en = header_enums()
-    src = strip_comments(open(NATIVE).read())
+    src = strip_comments(open(NATIVE).read(), True)
     consts = {}
     for body in re.findall(r"public\s+const\s+int\s+([^;]*);", src):
         for item in body.split(","):
@@ -191,7 +195,7 @@ def test_constants_have_the_header_values():
 
 
 def test_system_classes_keep_the_reference_names_order_and_constants():
-    src = strip_comments(open(SYSTEMS).read())
+    src = strip_comments(open(SYSTEMS).read(), True)
     order = ["ParticleSmoothingSystem", "KernelSystem", "GravityFieldSystem", "DensityFieldSystem", "PressureFieldSystem",
              "VelocitySystem"]
     call = {"ParticleSmoothingSystem": "sphb200_smoothing_update", "KernelSystem": "sphb200_build_neighbors",
@@ -217,9 +221,9 @@ def test_system_classes_keep_the_reference_names_order_and_constants():
 def test_csharp_sources_are_lexically_well_formed():
     """No compiler here: at least every bracket closes, no string or comment is left open, and every P/Invoke line ends in ';'."""
     for path in (NATIVE, SYSTEMS):
-        raw = open(path).read()
+        raw = re.sub(r"//[^\n]*", " ", open(path).read())        # line comments first: one of them mentions "Systems/*.cs"
         assert raw.count("/*") == raw.count("*/")
-        src = strip_comments(raw)
+        src = re.sub(r"/\*.*?\*/", " ", raw, flags=re.S)
         src = re.sub(r'"(?:\\.|[^"\\\n])*"', '""', src)          # string literals out of the way
         assert src.count('"') % 2 == 0, path
         stack = []
@@ -232,5 +236,5 @@ def test_csharp_sources_are_lexically_well_formed():
                     assert stack and stack[-1][0] == pairs[ch], "%s:%d unbalanced %r" % (path, ln, ch)
                     stack.pop()
         assert not stack, "%s: unclosed %r" % (path, stack[-1])
-    decls = re.findall(r"\[DllImport\(Lib\)\][^;]*;", strip_comments(open(NATIVE).read()))
+    decls = re.findall(r"\[DllImport\(Lib\)\][^;]*;", strip_comments(open(NATIVE).read(), True))
     assert len(decls) == len(csharp_imports())
