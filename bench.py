@@ -64,6 +64,21 @@ def per_pass_roofline(mean_ms, kbar, particles, hbm_peak_gbs):
     return out
 
 
+def tree_walk_stats(gf, walk_ms, fp32_peak_tflops):
+    """SURVEY.md 8(d), tree gravity: interactions per particle from the reference's own counters (GravityField.numParticles =
+    bodies summed directly, .numApprox = accepted node monopoles: GravityField.cs:14-15) x 20 flop, against the walk's time.
+    No single roof is claimed for the walk; the FP32 fraction says how far the useful pair work sits below the FMA pipe."""
+    n = len(gf)
+    direct = float(gf["numParticles"].astype(np.float64).mean()) if n else 0.0
+    approx = float(gf["numApprox"].astype(np.float64).mean()) if n else 0.0
+    out = {"direct_per_particle": direct, "approx_per_particle": approx, "interactions_per_particle": direct + approx, "ms": walk_ms}
+    if walk_ms and walk_ms > 0:
+        out["tflops_at_20_flop_per_interaction"] = FLOP_PER_PAIR * (direct + approx) * n / (walk_ms * 1e-3) / 1e12
+        if fp32_peak_tflops:
+            out["frac_of_fp32_peak"] = out["tflops_at_20_flop_per_interaction"] / fp32_peak_tflops
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ clocks sampler
 class ClockSampler(threading.Thread):
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
@@ -390,6 +405,12 @@ def measure_workload(args, workload, world, rank, local, headline):
               file=sys.stderr)
 
     diag = sim.diagnostics()            # collective in a group; the state the timed steps ran on (settled h)
+    gf_last = None
+    if grav == "tree" and world == 1:   # counters of the last timed step (single handle: no collective involved)
+        try:
+            gf_last = sim.download(sphb200.FIELD_GRAVITY, allow_overflow=True)
+        except Exception:               # a reporting extra must never cost the line
+            gf_last = None
     # ---- the settled state as the host holds it (every process: its body slice): input of the e2e leg and of the CPU baseline
     state = None
     if not args.kernels_only:
@@ -449,6 +470,11 @@ def measure_workload(args, workload, world, rank, local, headline):
                 "achieved": hbm_passes["achieved"], "peak": hbm_peak, "unit": "GB/s", "frac": hbm_passes["frac"], "traffic": None,
                 "note": "tree walk is L2-latency/FP32 mixed (no single roof, SURVEY 8d): %.2f ms of the step" % gms, "ms": sph_ms,
                 "share_of_step": sph_ms / ms_per_step}
+        if gf_last is not None:
+            try:
+                roof["tree_walk"] = tree_walk_stats(gf_last, gms, fp32_peak)
+            except Exception as ex:
+                roof["tree_walk"] = {"error": str(ex)}
     cpu_detail = None
     if args.kernels_only or world > 1 or not headline:
         cpu_v, cores, desc = None, 0, "skipped (%s)" % ("--kernels-only profiling run" if args.kernels_only else

@@ -78,3 +78,15 @@ def test_per_pass_bytes_add_up_to_the_survey_total():
     v = r["integrate"]
     assert abs(v["achieved"] - 100.0 * (1 << 20) / 0.018e-3 / 1e9) < 1e-6 and abs(v["frac"] - v["achieved"] / 6547.5) < 1e-12
     assert bench.per_pass_roofline({"integrate": 0.0}, K, 10, 6547.5) == {}      # a pass that did not run is left out
+
+
+def test_tree_walk_stats_from_the_reference_counters():
+    import bench
+    gf = np.zeros(1000, np.dtype([("value", "f4", 4), ("numParticles", "i4"), ("numApprox", "i4")]))
+    gf["numParticles"] = 1200; gf["numApprox"] = 500
+    r = bench.tree_walk_stats(gf, 2.0, 70.0)
+    assert r["direct_per_particle"] == 1200.0 and r["approx_per_particle"] == 500.0 and r["interactions_per_particle"] == 1700.0
+    assert abs(r["tflops_at_20_flop_per_interaction"] - 20.0 * 1700.0 * 1000 / 2.0e-3 / 1e12) < 1e-12
+    assert abs(r["frac_of_fp32_peak"] - r["tflops_at_20_flop_per_interaction"] / 70.0) < 1e-15
+    assert "tflops_at_20_flop_per_interaction" not in bench.tree_walk_stats(gf, 0.0, 70.0)
+    assert bench.tree_walk_stats(gf[:0], 1.0, None)["interactions_per_particle"] == 0.0
