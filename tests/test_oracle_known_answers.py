@@ -508,6 +508,15 @@ def test_polytrope_hydrostatic_balance_pins_the_whole_sph_chain(orc):
         xi = np.pi * r[s] / R
         g_th = 100.0 * (np.sin(xi) - xi * np.cos(xi)) / np.pi / r[s] ** 2
         assert abs(a_g[s].mean() / -g_th.mean() - 1.0) < 0.03
+    # the Barnes-Hut path (moments GravityFieldSystem.cs:367-443, MAC :229-247, walk :133-215) against the same closed form
+    gt, n_direct, n_approx, _, _ = orc.tree_gravity(pos, c["vel"], h, m, 1.0 / 60.0)
+    a_t = -(gt[:, :3] * rhat).sum(1)
+    assert n_approx.min() > 0 and n_direct.mean() < 0.2 * n                # it did approximate
+    for lo, hi in shells:
+        s = (r > lo * R) & (r < hi * R)
+        xi = np.pi * r[s] / R
+        g_th = 100.0 * (np.sin(xi) - xi * np.cos(xi)) / np.pi / r[s] ** 2
+        assert abs(a_t[s].mean() / -g_th.mean() - 1.0) < 0.03
     fixed = -(orc.pressure_grad(pos, h, m, rho, P, off, nbr, fix_q1=1) * rhat).sum(1) / rho
     literal = -(orc.pressure_grad(pos, h, m, rho, P, off, nbr, fix_q1=0) * rhat).sum(1) / rho
     for lo, hi in shells:
