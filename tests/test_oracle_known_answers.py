@@ -167,6 +167,24 @@ def test_uniform_sphere_field(orc):
     assert np.median(gr / expect) == pytest.approx(1.0, abs=0.05)
 
 
+def test_uniform_sphere_potential_and_binding_energy(orc):
+    """GravityField.Value.w is the potential (GravityFieldSystem.cs:345-356 sums -G m / r outside the softening length): inside a
+    uniform sphere Phi(r) = -G M (3 R^2 - r^2) / (2 R^3), and the binding energy 0.5 sum m Phi -- what sphb200_diagnostics reports
+    as E_pot -- is -(3/5) G M^2 / R.  Direct sum and Barnes-Hut walk."""
+    import sphb200.ic as ic
+    c = ic.make_sphere(12000, radius=50, total_mass=100, seed=5)
+    g = orc.gravity_direct(c["pos"], c["h"], c["mass"], accum_double=True)
+    r = np.linalg.norm(c["pos"], axis=1)
+    phi = -100.0 * (3 * 50.0 ** 2 - r ** 2) / (2 * 50.0 ** 3)
+    sel = r < 40
+    ratio = g[sel, 3] / phi[sel]
+    assert abs(np.median(ratio) - 1.0) < 0.005 and np.all(np.abs(ratio - 1.0) < 0.05)
+    e_pot = 0.5 * np.sum(c["mass"].astype(np.float64) * g[:, 3])
+    assert e_pot == pytest.approx(-0.6 * 100.0 ** 2 / 50.0, rel=0.005)
+    gt = orc.tree_gravity(c["pos"], c["vel"], c["h"], c["mass"], 1.0 / 60.0)[0]
+    assert 0.5 * np.sum(c["mass"].astype(np.float64) * gt[:, 3]) == pytest.approx(e_pot, rel=0.015)
+
+
 # ------------------------------------------------------------------ moments and MAC (GravityFieldSystem.cs:229-247, 398-442)
 def test_moment_accumulate_is_mass_weighted_mean(orc):
     L = orc.lib()
